@@ -1,0 +1,142 @@
+/*
+ * amira_b200.h — C ABI of libamira_b200.so: the B200-native (sm_100a) replacement for the two stages
+ * amira-rust-asr-server owns around its encoder:
+ *   (1) the `preprocessor` front end  (i16 PCM -> f32, pre-emphasis, STFT, 128-mel, log, normalise)
+ *   (2) the `decoder_joint` RNN-T greedy decode loop (LSTM prediction net, joint, argmax, limits)
+ *
+ * This header is the single source of truth for every binding (Rust FFI crate in rust/, ctypes in
+ * amira_b200/_lib.py, the C++ host in csrc/host_pipeline.*).  It follows the FFI conventions of the reference's
+ * own CUDA crate (citations relative to the reference root):
+ *   - plain `extern "C"`, POD arguments, opaque handles with create/destroy pairs
+ *       (src/cuda/mod.rs:371-412, src/cuda/cuda_helper.cu:63-142)
+ *   - every entry returns a status code by value, 0 = success, codes 1..4 keep the reference's meaning
+ *       (`#[repr(C)] enum CudaError`, src/cuda/mod.rs:54-62; C twin src/cuda/cuda_helper.cu:14-20)
+ *   - never throws / aborts across the boundary (release profile is panic="abort", Cargo.toml:134)
+ *   - host input slices are borrowed for the call only; results are copied into caller-owned buffers
+ *       (ReadTestData, src/cuda/cuda_helper.cu:226-264)
+ *
+ * Pointer arguments documented "host or device" are classified at run time (cudaPointerGetAttributes): a
+ * device pointer is used in place (no copy), a host pointer is staged through the context's pinned buffers.
+ * There is NO CPU fallback: every compute entry fails with AMIRA_ERR_NO_DEVICE when no sm_100 GPU is present.
+ */
+#ifndef AMIRA_B200_H
+#define AMIRA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes: 0..4 mirror CudaError (src/cuda/mod.rs:54-62), extended upward ---- */
+typedef enum {
+    AMIRA_OK = 0,
+    AMIRA_ERR_INVALID_VALUE = 1,
+    AMIRA_ERR_OUT_OF_MEMORY = 2,
+    AMIRA_ERR_UNKNOWN = 3,
+    AMIRA_ERR_NOT_READY = 4,
+    AMIRA_ERR_NO_DEVICE = 5,      /* no CUDA device / not sm_100: the product path refuses to run */
+    AMIRA_ERR_DECODE_STEP = 6,    /* "Decode step failed" (src/asr/decoder_optimized.rs:148-152) */
+    AMIRA_ERR_NO_WEIGHTS = 7,     /* decode entry called before amira_ctx_load_weights* */
+    AMIRA_ERR_IO = 8
+} amira_status;
+
+/* ---- model / decode constants (src/constants.rs:133-137; model-repo config.pbtxt) ---- */
+#define AMIRA_VOCAB_SIZE 1030
+#define AMIRA_BLANK_ID 1024
+#define AMIRA_MAX_SYMBOLS_PER_STEP 30
+#define AMIRA_MAX_TOTAL_TOKENS 200
+#define AMIRA_STATE_SIZE 640
+#define AMIRA_ENC_DIM 1024
+#define AMIRA_N_MELS 128
+#define AMIRA_N_PARAMS 8946310u /* Embedding(1025x640)+2xLSTM(640)+joint(1024/640->640->1030) */
+
+typedef struct amira_ctx amira_ctx; /* opaque; one per GPU; thread-safe (internally serialised) */
+
+typedef struct {
+    int32_t device_id;            /* config `cuda_device_id` (src/config.rs:284-290) */
+    int32_t max_symbols_per_step; /* 30  — the reference hard-codes it (SURVEY finding 5-v) */
+    int32_t max_total_tokens;     /* 200 */
+    int32_t blank_id;             /* 1024 */
+    int32_t joint_activation;     /* 0 = tanh (north_star), 1 = relu */
+    int32_t decode_engine;        /* 0 = auto, 1 = fp32 CUDA-core persistent kernel, 2 = tcgen05 split-bf16 */
+    int32_t max_streams;          /* resident stream-state slots for the WebSocket path (default 1024) */
+    int32_t reserved;
+} amira_config;
+
+/* replaces get_cuda_device_count_ffi (src/cuda/cuda_helper.cu:23-30, src/cuda/mod.rs:372) */
+int32_t amira_device_count(int32_t *count);
+int32_t amira_config_default(amira_config *cfg);
+/* replaces CudaAsrPipeline::new + CudaSharedMemoryRegionCreate (src/asr/cuda_pipeline.rs:41-103,
+ * src/cuda/cuda_helper.cu:63-110) */
+int32_t amira_ctx_create(const amira_config *cfg, amira_ctx **out);
+/* replaces CudaSharedMemoryRegionDestroy (src/cuda/cuda_helper.cu:113-142) */
+int32_t amira_ctx_destroy(amira_ctx *ctx);
+/* message of the last failing call on this ctx (NULL ctx: last failing create on this thread); owned by the
+ * library — replaces the Display impl of CudaSharedMemoryError (src/cuda/mod.rs:73-82) */
+const char *amira_last_error(amira_ctx *ctx);
+/* run subsequent work on a caller-provided cudaStream_t (NULL = the context's own stream) */
+int32_t amira_ctx_set_stream(amira_ctx *ctx, void *cuda_stream);
+int32_t amira_ctx_synchronize(amira_ctx *ctx);
+/* number of library kernels launched so far on this ctx (bench.py's gpu_launches) */
+int32_t amira_ctx_launch_count(amira_ctx *ctx, int64_t *count);
+
+/* ---- weights: stand-in for model-repo/decoder_joint/1/model.onnx (absent LFS object) ---- */
+/* flat fp32 blob, order: emb[1025][640]; per layer l=0,1: w_ih[2560][640], w_hh[2560][640], b_ih[2560],
+ * b_hh[2560]; w_enc[640][1024], b_enc[640]; w_pred[640][640], b_pred[640]; w_out[1030][640], b_out[1030]. */
+int32_t amira_weights_random_init(float *blob, size_t n_params, uint64_t seed, float blank_bias); /* host only */
+int32_t amira_ctx_load_weights(amira_ctx *ctx, const float *blob, size_t n_params);
+int32_t amira_ctx_load_weights_file(amira_ctx *ctx, const char *path); /* raw little-endian fp32 blob */
+
+/* ---- stage 1: front end ---- */
+/* features_lens rule of the preprocessor model: floor(n/160)+1 (0 for n = 0) */
+int32_t amira_features_len(int64_t n_samples, int64_t *features_len);
+/* replaces convert_audio + PreprocessorModel::infer_zero_copy (src/asr/pipeline.rs:127-139,283-291;
+ * src/triton/model.rs:71-160).  B utterances packed back to back: utterance b = pcm[offsets[b]..offsets[b+1]).
+ * pcm: host or device.  offsets, features_lens: host.  features: host or device, [B][128][t_stride] fp32,
+ * frames >= features_lens[b] are zero.  t_stride >= max features_len. */
+int32_t amira_preprocess_pcm16(amira_ctx *ctx, const int16_t *pcm, const int64_t *offsets, int32_t B,
+                               float *features, int64_t t_stride, int64_t *features_lens);
+/* Triton contract form (model-repo/preprocessor/config.pbtxt:4-28): waveforms [B][n_stride] fp32 (host or
+ * device), waveforms_lens [B] int64 (host) -> features [B][128][t_stride], features_lens [B] (host). */
+int32_t amira_preprocess_f32(amira_ctx *ctx, const float *waveforms, int64_t n_stride, const int64_t *waveforms_lens,
+                             int32_t B, float *features, int64_t t_stride, int64_t *features_lens);
+/* replaces performance_opts::audio::bytes_to_f32_optimized (src/performance_opts.rs:14-31), including the
+ * odd-trailing-byte rule; drop_odd != 0 gives bytes_to_f32_samples (src/asr/audio.rs:18-26) /
+ * simd::bytes_to_f32_optimized (src/asr/simd.rs:222-248).  bytes, out: host or device. */
+int32_t amira_bytes_to_f32(amira_ctx *ctx, const uint8_t *bytes, size_t n_bytes, int32_t drop_odd, float *out,
+                           size_t *n_out);
+
+/* ---- stage 2: decoder_joint ---- */
+/* Triton contract op (model-repo/decoder_joint/config.pbtxt:4-52; replaces DecoderJointModel::infer,
+ * src/triton/model.rs:581-722).  encoder_outputs [B][1024][T]; targets [B][U] int32; target_length [B]
+ * (nullable => U); input_states_1/2 [2][B][640] (nullable => zeros); outputs [B][U][T][1030];
+ * prednet_lengths [B] (nullable); output_states_1/2 [2][B][640] (nullable).  All host or device. */
+int32_t amira_decoder_joint(amira_ctx *ctx, const float *encoder_outputs, int32_t B, int32_t T, const int32_t *targets,
+                            int32_t U, const int32_t *target_length, const float *input_states_1,
+                            const float *input_states_2, float *outputs, int32_t *prednet_lengths,
+                            float *output_states_1, float *output_states_2);
+/* The fused loop: replaces greedy_decode + the per-step RPC closure (src/asr/decoder_optimized.rs:24-200,
+ * src/asr/pipeline.rs:313-356) for B independent utterances in one persistent kernel.
+ * encoder_outputs [B][1024][T] fp32 (host or device), encoded_lengths [B] int64 host (nullable => T);
+ * states_1/2 [2][B][640] in/out (host or device; nullable => zero initial state, final state dropped);
+ * tokens [B][max_total_tokens] int32, n_tokens [B], n_steps [B] (nullable): host or device. */
+int32_t amira_greedy_decode(amira_ctx *ctx, const float *encoder_outputs, int32_t B, int32_t T,
+                            const int64_t *encoded_lengths, float *states_1, float *states_2, int32_t *tokens,
+                            int32_t *n_tokens, int32_t *n_steps);
+
+/* ---- WebSocket path: device-resident per-stream LSTM state (replaces the DecoderState carried by
+ * IncrementalAsr, src/asr/incremental.rs:45-51,101-105, and process_stream_* in src/asr/pipeline.rs:384-431) */
+int32_t amira_stream_open(amira_ctx *ctx, int32_t *slot);  /* state zeroed (DecoderState::new, types.rs:169-174) */
+int32_t amira_stream_close(amira_ctx *ctx, int32_t slot);
+int32_t amira_stream_get_state(amira_ctx *ctx, int32_t slot, float *states_1, float *states_2); /* [2][1][640] */
+int32_t amira_stream_set_state(amira_ctx *ctx, int32_t slot, const float *states_1, const float *states_2);
+/* one tick: n streams, each with an encoder chunk [n][1024][T]; state read from / written back to the slots. */
+int32_t amira_stream_decode(amira_ctx *ctx, const int32_t *slots, int32_t n, const float *encoder_outputs, int32_t T,
+                            const int64_t *encoded_lengths, int32_t *tokens, int32_t *n_tokens, int32_t *n_steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMIRA_B200_H */
