@@ -1,0 +1,571 @@
+// api.cu — the C ABI of libamira_b200.so (include/amira_b200.h): context lifecycle, host<->device staging and
+// argument validation around the kernels in frontend.cu / decoder.cu.  Conventions follow the reference's own
+// FFI crate (src/cuda/mod.rs:54-62,371-412; src/cuda/cuda_helper.cu): status codes by value, opaque handle,
+// no exception crosses the boundary.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.h"
+
+using namespace amira;
+
+struct amira_ctx : public amira::Ctx {};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int32_t fail(Ctx *c, int32_t code, const std::string &msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+int32_t fail_cuda(Ctx *c, cudaError_t e, const char *what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();  // clear sticky-free errors
+    return fail(c, e == cudaErrorMemoryAllocation ? AMIRA_ERR_OUT_OF_MEMORY : AMIRA_ERR_UNKNOWN, m);
+}
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Input argument: device pointers are used in place, host pointers are copied into staging slot `slot`.
+template <class T>
+cudaError_t stage_in(Ctx *c, int slot, const T *p, size_t count, const T **dev) {
+    if (!p || count == 0) {
+        *dev = p && is_device_ptr(p) ? p : nullptr;
+        if (p && !*dev) {  // zero-length host input: hand the kernels a valid dummy pointer
+            cudaError_t e = c->stage[slot].reserve(16);
+            if (e != cudaSuccess) return e;
+            *dev = c->stage[slot].as<T>();
+        }
+        return cudaSuccess;
+    }
+    if (is_device_ptr(p)) {
+        *dev = p;
+        return cudaSuccess;
+    }
+    cudaError_t e = c->stage[slot].reserve(count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    *dev = c->stage[slot].as<T>();
+    return cudaMemcpyAsync(c->stage[slot].p, p, count * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+}
+
+// Output argument: returns the device pointer kernels should write; finish_out copies back when `p` is host.
+template <class T>
+cudaError_t stage_out(Ctx *c, int slot, T *p, size_t count, T **dev, bool *is_host) {
+    *is_host = false;
+    if (!p) {
+        *dev = nullptr;
+        return cudaSuccess;
+    }
+    if (is_device_ptr(p)) {
+        *dev = p;
+        return cudaSuccess;
+    }
+    *is_host = true;
+    cudaError_t e = c->stage[slot].reserve(count * sizeof(T) + 16);
+    if (e != cudaSuccess) return e;
+    *dev = c->stage[slot].as<T>();
+    return cudaSuccess;
+}
+template <class T>
+cudaError_t finish_out(Ctx *c, T *host, const T *dev, size_t count, bool is_host) {
+    if (!is_host || !host || count == 0) return cudaSuccess;
+    return cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream);
+}
+
+#define CK(call, what)                                      \
+    do {                                                    \
+        cudaError_t _e = (call);                            \
+        if (_e != cudaSuccess) return fail_cuda(c, _e, what); \
+    } while (0)
+
+#define API_BEGIN(c)                                                                   \
+    if (!(c)) return fail(nullptr, AMIRA_ERR_INVALID_VALUE, "null context");           \
+    std::lock_guard<std::mutex> _lock((c)->mu);                                        \
+    try {                                                                              \
+        cudaError_t _se = cudaSetDevice((c)->device);                                  \
+        if (_se != cudaSuccess) return fail_cuda((c), _se, "cudaSetDevice");
+
+#define API_END(c)                                                                     \
+    }                                                                                  \
+    catch (const std::bad_alloc &) { return fail((c), AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed"); } \
+    catch (const std::exception &ex) { return fail((c), AMIRA_ERR_UNKNOWN, ex.what()); } \
+    catch (...) { return fail((c), AMIRA_ERR_UNKNOWN, "unknown exception"); }
+
+}  // namespace
+
+static void prof_collect(Ctx *c) {  // fold finished spans into the per-kernel totals (stream must be idle)
+    for (auto &sp : c->prof_spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.beg, sp.end) == cudaSuccess && sp.kernel >= 0 && sp.kernel < 8) {
+            c->prof_ms[sp.kernel] += ms;
+            c->prof_n[sp.kernel] += 1;
+        }
+        cudaEventDestroy(sp.beg);
+        cudaEventDestroy(sp.end);
+    }
+    cudaGetLastError();
+    c->prof_spans.clear();
+}
+
+extern "C" {
+
+int32_t amira_device_count(int32_t *count) {
+    if (!count) return AMIRA_ERR_INVALID_VALUE;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? AMIRA_OK : AMIRA_ERR_UNKNOWN;
+    }
+    *count = n;
+    return AMIRA_OK;
+}
+
+int32_t amira_config_default(amira_config *cfg) {
+    if (!cfg) return AMIRA_ERR_INVALID_VALUE;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->device_id = 0;
+    cfg->max_symbols_per_step = AMIRA_MAX_SYMBOLS_PER_STEP;
+    cfg->max_total_tokens = AMIRA_MAX_TOTAL_TOKENS;
+    cfg->blank_id = AMIRA_BLANK_ID;
+    cfg->joint_activation = 0;
+    cfg->decode_engine = 0;
+    cfg->max_streams = 1024;
+    return AMIRA_OK;
+}
+
+int32_t amira_ctx_create(const amira_config *cfg, amira_ctx **out) {
+    if (!out) return fail(nullptr, AMIRA_ERR_INVALID_VALUE, "null out pointer");
+    *out = nullptr;
+    amira_config dflt;
+    amira_config_default(&dflt);
+    if (!cfg) cfg = &dflt;
+    if (cfg->max_symbols_per_step <= 0 || cfg->max_total_tokens <= 0 || cfg->blank_id < 0 || cfg->blank_id >= kV ||
+        cfg->max_streams < 0 || cfg->joint_activation < 0 || cfg->joint_activation > 1 || cfg->decode_engine < 0 ||
+        cfg->decode_engine > 2)
+        return fail(nullptr, AMIRA_ERR_INVALID_VALUE, "invalid amira_config");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, AMIRA_ERR_NO_DEVICE, "no CUDA device: libamira_b200 has no CPU path");
+    }
+    if (cfg->device_id < 0 || cfg->device_id >= n) return fail(nullptr, AMIRA_ERR_INVALID_VALUE, "device_id out of range");
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, cfg->device_id) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, AMIRA_ERR_NO_DEVICE, "cannot query device");
+    }
+    if (prop.major != 10)
+        return fail(nullptr, AMIRA_ERR_NO_DEVICE,
+                    std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                        "; this library is built for sm_100a (B200) only");
+    amira_ctx *c = nullptr;
+    try {
+        c = new amira_ctx();
+    } catch (...) {
+        return fail(nullptr, AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+    c->cfg = *cfg;
+    c->device = cfg->device_id;
+    c->sm_count = prop.multiProcessorCount;
+    auto bail = [&](cudaError_t e, const char *what) {
+        int32_t rc = fail_cuda(nullptr, e, what);
+        amira_ctx_destroy(c);
+        return rc;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(c->device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    c->stream = c->own_stream;
+    FrontendTables *ht = new FrontendTables();
+    build_frontend_tables(ht);
+    e = cudaMalloc(&c->tables_dev, sizeof(FrontendTables));
+    if (e == cudaSuccess) e = cudaMemcpy(c->tables_dev, ht, sizeof(FrontendTables), cudaMemcpyHostToDevice);
+    delete ht;
+    if (e != cudaSuccess) return bail(e, "front-end tables");
+    if (cfg->max_streams > 0) {
+        const size_t bytes = sizeof(float) * (size_t)cfg->max_streams * 2 * kH;
+        if ((e = cudaMalloc(&c->slot_s1, bytes)) != cudaSuccess) return bail(e, "stream slots");
+        if ((e = cudaMalloc(&c->slot_s2, bytes)) != cudaSuccess) return bail(e, "stream slots");
+        cudaMemset(c->slot_s1, 0, bytes);
+        cudaMemset(c->slot_s2, 0, bytes);
+        c->slot_used.assign((size_t)cfg->max_streams, 0);
+    }
+    *out = c;
+    return AMIRA_OK;
+}
+
+int32_t amira_ctx_destroy(amira_ctx *c) {
+    if (!c) return AMIRA_OK;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    decoder_release(c);
+    if (c->tables_dev) cudaFree(c->tables_dev);
+    if (c->w_blob) cudaFree(c->w_blob);
+    if (c->slot_s1) cudaFree(c->slot_s1);
+    if (c->slot_s2) cudaFree(c->slot_s2);
+    c->fe_meta.release();
+    c->fe_partials.release();
+    c->fe_meta_pin.release();
+    prof_collect(c);
+    for (auto &b : c->stage) b.release();
+    for (auto &b : c->pin) b.release();
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    cudaGetLastError();
+    delete c;
+    return AMIRA_OK;
+}
+
+const char *amira_last_error(amira_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int32_t amira_ctx_set_stream(amira_ctx *c, void *cuda_stream) {
+    API_BEGIN(c)
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return AMIRA_OK;
+    API_END(c)
+}
+
+int32_t amira_ctx_synchronize(amira_ctx *c) {
+    API_BEGIN(c)
+    CK(cudaStreamSynchronize(c->stream), "synchronize");
+    return AMIRA_OK;
+    API_END(c)
+}
+
+int32_t amira_ctx_launch_count(amira_ctx *c, int64_t *count) {
+    if (!c || !count) return AMIRA_ERR_INVALID_VALUE;
+    *count = c->launches;
+    return AMIRA_OK;
+}
+
+int32_t amira_ctx_profile(amira_ctx *c, int32_t enable) {
+    API_BEGIN(c)
+    CK(cudaStreamSynchronize(c->stream), "profile sync");
+    prof_collect(c);
+    for (int i = 0; i < 8; ++i) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
+    c->profiling = enable != 0;
+    return AMIRA_OK;
+    API_END(c)
+}
+
+int32_t amira_ctx_kernel_ms(amira_ctx *c, int32_t kernel, double *total_ms, int64_t *launches) {
+    API_BEGIN(c)
+    if (kernel < 0 || kernel >= PK_COUNT || !total_ms || !launches) return fail(c, AMIRA_ERR_INVALID_VALUE, "bad kernel id");
+    CK(cudaStreamSynchronize(c->stream), "profile sync");
+    prof_collect(c);
+    *total_ms = c->prof_ms[kernel];
+    *launches = c->prof_n[kernel];
+    return AMIRA_OK;
+    API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------- weights
+int32_t amira_weights_random_init(float *blob, size_t n_params, uint64_t seed, float blank_bias) {
+    if (!blob || n_params != (size_t)AMIRA_N_PARAMS) return AMIRA_ERR_INVALID_VALUE;
+    weights_random_init(blob, seed, blank_bias);
+    return AMIRA_OK;
+}
+
+int32_t amira_ctx_load_weights(amira_ctx *c, const float *blob, size_t n_params) {
+    API_BEGIN(c)
+    if (!blob || n_params != (size_t)AMIRA_N_PARAMS || blob_layout().total != (size_t)AMIRA_N_PARAMS)
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "weight blob must hold exactly AMIRA_N_PARAMS fp32 values");
+    if (!c->w_blob) CK(cudaMalloc(&c->w_blob, sizeof(float) * n_params), "weights alloc");
+    CK(cudaMemcpyAsync(c->w_blob, blob, sizeof(float) * n_params,
+                       is_device_ptr(blob) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream),
+       "weights copy");
+    CK(decoder_prepare_weights(c), "derived weight tables");
+    CK(cudaStreamSynchronize(c->stream), "weights sync");
+    c->has_weights = true;
+    return AMIRA_OK;
+    API_END(c)
+}
+
+int32_t amira_ctx_load_weights_file(amira_ctx *c, const char *path) {
+    if (!c) return AMIRA_ERR_INVALID_VALUE;
+    if (!path) return fail(c, AMIRA_ERR_INVALID_VALUE, "null path");
+    std::vector<float> blob;
+    try {
+        blob.resize(AMIRA_N_PARAMS);
+    } catch (...) {
+        return fail(c, AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return fail(c, AMIRA_ERR_IO, std::string("cannot open ") + path);
+    const size_t got = std::fread(blob.data(), sizeof(float), blob.size(), f);
+    const bool extra = std::fgetc(f) != EOF;
+    std::fclose(f);
+    if (got != blob.size() || extra) return fail(c, AMIRA_ERR_IO, "weight file must hold exactly AMIRA_N_PARAMS fp32 values");
+    return amira_ctx_load_weights(c, blob.data(), blob.size());
+}
+
+// ---------------------------------------------------------------------------------------------- front end
+int32_t amira_features_len(int64_t n_samples, int64_t *features_len) {
+    if (!features_len) return AMIRA_ERR_INVALID_VALUE;
+    *features_len = n_samples <= 0 ? 0 : n_samples / kHop + 1;
+    return AMIRA_OK;
+}
+
+static int32_t preprocess_common(amira_ctx *c, const void *wave, bool pcm16, const int64_t *starts, const int64_t *lens,
+                                 int64_t total_elems, int32_t B, float *features, int64_t t_stride,
+                                 int64_t *features_lens) {
+    int64_t max_len = 0;
+    for (int b = 0; b < B; ++b) {
+        if (lens[b] < 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "negative waveform length");
+        const int64_t L = lens[b] <= 0 ? 0 : lens[b] / kHop + 1;
+        if (features_lens) features_lens[b] = L;
+        max_len = L > max_len ? L : max_len;
+    }
+    if (t_stride < max_len || t_stride <= 0)
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "t_stride smaller than the longest features_len");
+    const size_t esz = pcm16 ? sizeof(int16_t) : sizeof(float);
+    const uint8_t *wave_dev = nullptr;
+    CK(stage_in<uint8_t>(c, 0, static_cast<const uint8_t *>(wave), (size_t)total_elems * esz, &wave_dev), "waveform H2D");
+    float *feat_dev = nullptr;
+    bool feat_host = false;
+    const size_t feat_count = (size_t)B * kMel * (size_t)t_stride;
+    CK(stage_out<float>(c, 1, features, feat_count, &feat_dev, &feat_host), "features staging");
+    CK(launch_frontend(c, wave_dev, pcm16, starts, lens, B, feat_dev, t_stride), "front-end launch");
+    CK(finish_out<float>(c, features, feat_dev, feat_count, feat_host), "features D2H");
+    CK(cudaStreamSynchronize(c->stream), "front-end sync");
+    return AMIRA_OK;
+}
+
+int32_t amira_preprocess_pcm16(amira_ctx *c, const int16_t *pcm, const int64_t *offsets, int32_t B, float *features,
+                               int64_t t_stride, int64_t *features_lens) {
+    API_BEGIN(c)
+    if (B < 0 || !offsets || !features || (B > 0 && !pcm && offsets[B] > 0))
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_preprocess_pcm16: bad arguments");
+    if (B == 0) return AMIRA_OK;
+    std::vector<int64_t> lens((size_t)B);
+    for (int b = 0; b < B; ++b) {
+        lens[b] = offsets[b + 1] - offsets[b];
+        if (lens[b] < 0 || offsets[b] < 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "offsets must be non-decreasing");
+    }
+    return preprocess_common(c, pcm, true, offsets, lens.data(), offsets[B], B, features, t_stride, features_lens);
+    API_END(c)
+}
+
+int32_t amira_preprocess_f32(amira_ctx *c, const float *waveforms, int64_t n_stride, const int64_t *waveforms_lens,
+                             int32_t B, float *features, int64_t t_stride, int64_t *features_lens) {
+    API_BEGIN(c)
+    if (B < 0 || !waveforms_lens || !features || n_stride < 0 || (B > 0 && n_stride > 0 && !waveforms))
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_preprocess_f32: bad arguments");
+    if (B == 0) return AMIRA_OK;
+    std::vector<int64_t> starts((size_t)B);
+    for (int b = 0; b < B; ++b) {
+        starts[b] = (int64_t)b * n_stride;
+        if (waveforms_lens[b] > n_stride) return fail(c, AMIRA_ERR_INVALID_VALUE, "waveforms_lens exceeds n_stride");
+    }
+    return preprocess_common(c, waveforms, false, starts.data(), waveforms_lens, (int64_t)B * n_stride, B, features,
+                             t_stride, features_lens);
+    API_END(c)
+}
+
+int32_t amira_bytes_to_f32(amira_ctx *c, const uint8_t *bytes, size_t n_bytes, int32_t drop_odd, float *out,
+                           size_t *n_out) {
+    API_BEGIN(c)
+    const size_t n = n_bytes / 2 + ((n_bytes & 1) && !drop_odd ? 1 : 0);
+    if (n_out) *n_out = n;
+    if (n_bytes == 0) return AMIRA_OK;
+    if (!bytes || !out) return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_bytes_to_f32: null buffer");
+    const uint8_t *in_dev = nullptr;
+    CK(stage_in<uint8_t>(c, 0, bytes, n_bytes, &in_dev), "bytes H2D");
+    float *out_dev = nullptr;
+    bool out_host = false;
+    CK(stage_out<float>(c, 1, out, n + 4, &out_dev, &out_host), "samples staging");
+    CK(launch_bytes_to_f32(c, in_dev, n_bytes, drop_odd != 0, out_dev), "bytes_to_f32 launch");
+    CK(finish_out<float>(c, out, out_dev, n, out_host), "samples D2H");
+    CK(cudaStreamSynchronize(c->stream), "bytes_to_f32 sync");
+    return AMIRA_OK;
+    API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------- decoder_joint
+int32_t amira_decoder_joint(amira_ctx *c, const float *encoder_outputs, int32_t B, int32_t T, const int32_t *targets,
+                            int32_t U, const int32_t *target_length, const float *input_states_1,
+                            const float *input_states_2, float *outputs, int32_t *prednet_lengths,
+                            float *output_states_1, float *output_states_2) {
+    API_BEGIN(c)
+    if (!c->has_weights) return fail(c, AMIRA_ERR_NO_WEIGHTS, "amira_decoder_joint: no weights loaded");
+    if (B <= 0 || T <= 0 || U <= 0 || !encoder_outputs || !targets || !outputs)
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_decoder_joint: bad arguments");
+    const size_t n_state = (size_t)2 * B * kH;
+    const float *enc_dev, *s1_dev, *s2_dev;
+    const int32_t *tg_dev, *tl_dev;
+    CK(stage_in<float>(c, 0, encoder_outputs, (size_t)B * kEnc * T, &enc_dev), "encoder_outputs H2D");
+    CK(stage_in<int32_t>(c, 1, targets, (size_t)B * U, &tg_dev), "targets H2D");
+    CK(stage_in<int32_t>(c, 2, target_length, (size_t)B, &tl_dev), "target_length H2D");
+    CK(stage_in<float>(c, 3, input_states_1, n_state, &s1_dev), "input_states_1 H2D");
+    CK(stage_in<float>(c, 4, input_states_2, n_state, &s2_dev), "input_states_2 H2D");
+    float *out_dev, *o1_dev, *o2_dev;
+    int32_t *pl_dev;
+    bool out_h, o1_h, o2_h, pl_h;
+    const size_t n_out = (size_t)B * U * T * kV;
+    CK(stage_out<float>(c, 5, outputs, n_out, &out_dev, &out_h), "outputs staging");
+    CK(stage_out<float>(c, 6, output_states_1, n_state, &o1_dev, &o1_h), "output_states_1 staging");
+    CK(stage_out<float>(c, 7, output_states_2, n_state, &o2_dev, &o2_h), "output_states_2 staging");
+    CK(stage_out<int32_t>(c, 8, prednet_lengths, (size_t)B, &pl_dev, &pl_h), "prednet_lengths staging");
+    CK(c->stage[9].reserve(16), "flag alloc");
+    int32_t *flag_dev = c->stage[9].as<int32_t>();
+    CK(cudaMemsetAsync(flag_dev, 0, sizeof(int32_t), c->stream), "flag reset");
+    CK(launch_decoder_joint(c, enc_dev, B, T, tg_dev, U, tl_dev, s1_dev, s2_dev, out_dev, pl_dev, o1_dev, o2_dev, flag_dev),
+       "decoder_joint launch");
+    CK(finish_out<float>(c, outputs, out_dev, n_out, out_h), "outputs D2H");
+    CK(finish_out<float>(c, output_states_1, o1_dev, n_state, o1_h), "output_states_1 D2H");
+    CK(finish_out<float>(c, output_states_2, o2_dev, n_state, o2_h), "output_states_2 D2H");
+    CK(finish_out<int32_t>(c, prednet_lengths, pl_dev, (size_t)B, pl_h), "prednet_lengths D2H");
+    int32_t flag = 0;
+    CK(cudaMemcpyAsync(&flag, flag_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream), "flag D2H");
+    CK(cudaStreamSynchronize(c->stream), "decoder_joint sync");
+    // an out-of-range target is an ONNX Gather failure in the reference => "Decode step failed"
+    if (flag) return fail(c, AMIRA_ERR_DECODE_STEP, "Decode step failed: target id outside the embedding table");
+    return AMIRA_OK;
+    API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------- greedy decode
+static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t B, int32_t T,
+                             const int64_t *encoded_lengths, const int32_t *slots_host, float *states_1, float *states_2,
+                             int32_t *tokens, int32_t *n_tokens, int32_t *n_steps) {
+    if (!c->has_weights) return fail(c, AMIRA_ERR_NO_WEIGHTS, "greedy decode: no weights loaded");
+    if (B < 0 || T < 0 || !tokens || !n_tokens || (B > 0 && T > 0 && !encoder_outputs))
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "greedy decode: bad arguments");
+    if (B == 0) return AMIRA_OK;
+    const int cap = c->cfg.max_total_tokens;
+    // lengths (+ slots) -> one pinned block
+    CK(c->pin[0].reserve(sizeof(int32_t) * 2 * (size_t)B), "lens pin");
+    int32_t *h_lens = c->pin[0].as<int32_t>();
+    int32_t *h_slots = h_lens + B;
+    for (int b = 0; b < B; ++b) {
+        const int64_t L = encoded_lengths ? encoded_lengths[b] : T;
+        if (L < 0 || L > T) return fail(c, AMIRA_ERR_INVALID_VALUE, "encoded_lengths out of range");
+        h_lens[b] = (int32_t)L;
+        if (slots_host) {
+            const int32_t s = slots_host[b];
+            if (s < 0 || s >= c->cfg.max_streams || !c->slot_used[(size_t)s])
+                return fail(c, AMIRA_ERR_INVALID_VALUE, "stream slot not open");
+            for (int q = 0; q < b; ++q)
+                if (h_slots[q] == s) return fail(c, AMIRA_ERR_INVALID_VALUE, "duplicate stream slot in one tick");
+            h_slots[b] = s;
+        }
+    }
+    CK(c->stage[9].reserve(sizeof(int32_t) * 2 * (size_t)B), "lens dev");
+    CK(cudaMemcpyAsync(c->stage[9].p, h_lens, sizeof(int32_t) * 2 * (size_t)B, cudaMemcpyHostToDevice, c->stream), "lens H2D");
+    const int32_t *lens_dev = c->stage[9].as<int32_t>();
+    const int32_t *slots_dev = slots_host ? lens_dev + B : nullptr;
+
+    const float *enc_dev;
+    CK(stage_in<float>(c, 0, encoder_outputs, (size_t)B * kEnc * T, &enc_dev), "encoder_outputs H2D");
+    const size_t n_state = (size_t)2 * B * kH;
+    float *s1_dev = nullptr, *s2_dev = nullptr;
+    bool s1_h = false, s2_h = false;
+    if (!slots_host && states_1 && states_2) {
+        CK(stage_out<float>(c, 1, states_1, n_state, &s1_dev, &s1_h), "states_1 staging");
+        CK(stage_out<float>(c, 2, states_2, n_state, &s2_dev, &s2_h), "states_2 staging");
+        if (s1_h) CK(cudaMemcpyAsync(s1_dev, states_1, sizeof(float) * n_state, cudaMemcpyHostToDevice, c->stream), "states_1 H2D");
+        if (s2_h) CK(cudaMemcpyAsync(s2_dev, states_2, sizeof(float) * n_state, cudaMemcpyHostToDevice, c->stream), "states_2 H2D");
+    } else if (!slots_host && (states_1 || states_2)) {
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "states_1 and states_2 must both be given or both be null");
+    }
+    int32_t *tok_dev, *nt_dev, *ns_dev;
+    bool tok_h, nt_h, ns_h;
+    CK(stage_out<int32_t>(c, 3, tokens, (size_t)B * cap, &tok_dev, &tok_h), "tokens staging");
+    CK(stage_out<int32_t>(c, 4, n_tokens, (size_t)B, &nt_dev, &nt_h), "n_tokens staging");
+    CK(stage_out<int32_t>(c, 5, n_steps, (size_t)B, &ns_dev, &ns_h), "n_steps staging");
+    CK(launch_greedy_decode(c, enc_dev, B, T, lens_dev, slots_dev, s1_dev, s2_dev, tok_dev, nt_dev, ns_dev),
+       "greedy decode launch");
+    CK(finish_out<int32_t>(c, tokens, tok_dev, (size_t)B * cap, tok_h), "tokens D2H");
+    CK(finish_out<int32_t>(c, n_tokens, nt_dev, (size_t)B, nt_h), "n_tokens D2H");
+    CK(finish_out<int32_t>(c, n_steps, ns_dev, (size_t)B, ns_h), "n_steps D2H");
+    CK(finish_out<float>(c, states_1, s1_dev, n_state, s1_h), "states_1 D2H");
+    CK(finish_out<float>(c, states_2, s2_dev, n_state, s2_h), "states_2 D2H");
+    int32_t n_failed = 0;
+    CK(cudaMemcpyAsync(&n_failed, decoder_fail_count_dev(c), sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream), "status D2H");
+    CK(cudaStreamSynchronize(c->stream), "greedy decode sync");
+    // streams whose argmax left the embedding table and needed another step: the reference's next decoder_joint
+    // call fails ("Decode step failed", src/asr/decoder_optimized.rs:148-152); their n_tokens is -1
+    if (n_failed > 0) return fail(c, AMIRA_ERR_DECODE_STEP, "Decode step failed for " + std::to_string(n_failed) + " stream(s)");
+    return AMIRA_OK;
+}
+
+int32_t amira_greedy_decode(amira_ctx *c, const float *encoder_outputs, int32_t B, int32_t T,
+                            const int64_t *encoded_lengths, float *states_1, float *states_2, int32_t *tokens,
+                            int32_t *n_tokens, int32_t *n_steps) {
+    API_BEGIN(c)
+    return greedy_common(c, encoder_outputs, B, T, encoded_lengths, nullptr, states_1, states_2, tokens, n_tokens, n_steps);
+    API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------- stream slots
+int32_t amira_stream_open(amira_ctx *c, int32_t *slot) {
+    API_BEGIN(c)
+    if (!slot) return fail(c, AMIRA_ERR_INVALID_VALUE, "null slot pointer");
+    for (size_t s = 0; s < c->slot_used.size(); ++s)
+        if (!c->slot_used[s]) {
+            const size_t off = s * 2 * kH;
+            CK(cudaMemsetAsync(c->slot_s1 + off, 0, sizeof(float) * 2 * kH, c->stream), "slot reset");
+            CK(cudaMemsetAsync(c->slot_s2 + off, 0, sizeof(float) * 2 * kH, c->stream), "slot reset");
+            c->slot_used[s] = 1;
+            *slot = (int32_t)s;
+            return AMIRA_OK;
+        }
+    return fail(c, AMIRA_ERR_OUT_OF_MEMORY, "all stream slots in use (amira_config.max_streams)");
+    API_END(c)
+}
+
+int32_t amira_stream_close(amira_ctx *c, int32_t slot) {
+    API_BEGIN(c)
+    if (slot < 0 || (size_t)slot >= c->slot_used.size() || !c->slot_used[(size_t)slot])
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "stream slot not open");
+    c->slot_used[(size_t)slot] = 0;
+    return AMIRA_OK;
+    API_END(c)
+}
+
+int32_t amira_stream_get_state(amira_ctx *c, int32_t slot, float *states_1, float *states_2) {
+    API_BEGIN(c)
+    if (slot < 0 || (size_t)slot >= c->slot_used.size() || !c->slot_used[(size_t)slot] || !states_1 || !states_2)
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_stream_get_state: bad arguments");
+    const size_t off = (size_t)slot * 2 * kH;
+    CK(cudaMemcpyAsync(states_1, c->slot_s1 + off, sizeof(float) * 2 * kH, cudaMemcpyDefault, c->stream), "state D2H");
+    CK(cudaMemcpyAsync(states_2, c->slot_s2 + off, sizeof(float) * 2 * kH, cudaMemcpyDefault, c->stream), "state D2H");
+    CK(cudaStreamSynchronize(c->stream), "state sync");
+    return AMIRA_OK;
+    API_END(c)
+}
+
+int32_t amira_stream_set_state(amira_ctx *c, int32_t slot, const float *states_1, const float *states_2) {
+    API_BEGIN(c)
+    if (slot < 0 || (size_t)slot >= c->slot_used.size() || !c->slot_used[(size_t)slot] || !states_1 || !states_2)
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_stream_set_state: bad arguments");
+    const size_t off = (size_t)slot * 2 * kH;
+    CK(cudaMemcpyAsync(c->slot_s1 + off, states_1, sizeof(float) * 2 * kH, cudaMemcpyDefault, c->stream), "state H2D");
+    CK(cudaMemcpyAsync(c->slot_s2 + off, states_2, sizeof(float) * 2 * kH, cudaMemcpyDefault, c->stream), "state H2D");
+    CK(cudaStreamSynchronize(c->stream), "state sync");
+    return AMIRA_OK;
+    API_END(c)
+}
+
+int32_t amira_stream_decode(amira_ctx *c, const int32_t *slots, int32_t n, const float *encoder_outputs, int32_t T,
+                            const int64_t *encoded_lengths, int32_t *tokens, int32_t *n_tokens, int32_t *n_steps) {
+    API_BEGIN(c)
+    if (!slots && n > 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "null slots");
+    return greedy_common(c, encoder_outputs, n, T, encoded_lengths, slots, nullptr, nullptr, tokens, n_tokens, n_steps);
+    API_END(c)
+}
+
+}  // extern "C"

@@ -20,16 +20,20 @@ constexpr int kEmbRows = 1025;
 constexpr int kMel = AMIRA_N_MELS;        // 128
 constexpr int kNfft = 512, kNbin = 257, kWin = 400, kHop = 160;
 
-// ---- front-end tables (built on the host in double precision, weights.cpp) ----
+// ---- front-end tables (built on the host in double precision, tables.cpp) ----
+// Mel weights are stored "lane-transposed": lane l of a warp owns filters m = l + 32*g (g = 0..3); for group g
+// the warp walks rows melRow[g] .. melRow[g+1] of melw_t, row r holding the r-th non-zero weight of each
+// lane's filter (zero padded), so a warp reads one conflict-free 128 B row per step.
+constexpr int kMelRowsMax = 48;
 struct FrontendTables {
-    float win[kNfft];     // Hann(400, symmetric) centred in 512, zeros outside [56,456)
-    float2 tw[256];       // exp(-2*pi*i*e/512), e = 0..255
-    int kstart[kMel];     // first non-zero FFT bin of each mel filter
-    int kcnt[kMel];       // number of non-zero bins
-    int woff[kMel];       // offset of the filter's weights in melw
-    float melw[512];      // packed non-zero Slaney mel weights (504 used)
+    float win[kNfft];               // Hann(400, symmetric) rounded to f32, centred in 512, zeros outside [56,456)
+    int kstart[kMel];               // first non-zero FFT bin of each mel filter
+    int kcnt[kMel];                 // number of non-zero bins
+    int melRow[5];                  // row range of each filter group in melw_t
+    float melw_t[kMelRowsMax][32];  // see above
 };
 void build_frontend_tables(FrontendTables *t);
+void build_mel_filterbank(float *fb /* [128][257] */);
 void weights_random_init(float *blob, uint64_t seed, float blank_bias);
 
 // ---- blob layout (element offsets) ----
@@ -37,23 +41,6 @@ struct BlobLayout {
     size_t emb, w_ih[2], w_hh[2], b_ih[2], b_hh[2], w_enc, b_enc, w_pred, b_pred, w_out, b_out, total;
 };
 BlobLayout blob_layout();
-
-struct Ctx;
-
-// frontend.cu
-cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const int64_t *starts_host,
-                            const int64_t *lens_host, int B, int64_t total_elems, float *features_dev,
-                            int64_t t_stride, int64_t *features_lens_host);
-cudaError_t launch_bytes_to_f32(Ctx *c, const uint8_t *bytes_dev, size_t n_bytes, bool drop_odd, float *out_dev);
-
-// decoder.cu
-cudaError_t decoder_prepare_weights(Ctx *c);
-cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, int B, int T, const int64_t *lens_host,
-                                 const int32_t *slots_dev /*nullable*/, float *s1_dev, float *s2_dev,
-                                 int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev);
-cudaError_t launch_decoder_joint(Ctx *c, const float *enc_dev, int B, int T, const int32_t *targets_dev, int U,
-                                 const int32_t *tlen_dev, const float *in_s1, const float *in_s2, float *outputs,
-                                 int32_t *prednet_lengths, float *out_s1, float *out_s2, int32_t *err_flag_dev);
 
 // a growable device / pinned-host scratch buffer
 struct DevBuf {
@@ -74,6 +61,10 @@ struct DevBuf {
         p = nullptr;
         cap = 0;
     }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
 };
 struct PinBuf {
     void *p = nullptr;
@@ -93,7 +84,13 @@ struct PinBuf {
         p = nullptr;
         cap = 0;
     }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
 };
+
+struct DecoderPriv;  // decoder.cu
 
 struct Ctx {
     amira_config cfg{};
@@ -105,24 +102,66 @@ struct Ctx {
     std::string err;
     int64_t launches = 0;
 
+    // optional per-kernel timing (amira_ctx_profile): CUDA events recorded on `stream` around named launches
+    struct ProfSpan { int kernel; cudaEvent_t beg, end; };
+    bool profiling = false;
+    std::vector<ProfSpan> prof_spans;
+    double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
     // front end
     FrontendTables *tables_dev = nullptr;
-    DevBuf fe_meta;      // starts / lens / tile prefix
-    DevBuf fe_partials;  // per-tile (sum, M2)
-    DevBuf in_stage, out_stage, aux_stage[6];
-    PinBuf pin_in, pin_out;
+    DevBuf fe_meta;      // per call: starts[B], lens[B], tile prefix[B+1]
+    DevBuf fe_partials;  // per tile x mel: (mean, M2) in double
+    PinBuf fe_meta_pin;
+
+    // staging for host-pointer arguments (slot per argument position)
+    DevBuf stage[10];
+    PinBuf pin[10];
 
     // decoder
     bool has_weights = false;
     float *w_blob = nullptr;  // fp32 blob as loaded
-    DevBuf dec_derived;       // G1 table etc. (decoder.cu owns the layout)
-    DevBuf dec_work;          // per-call workspace
-    DevBuf dec_ctrl;
-    void *dec_priv = nullptr; // decoder.cu private struct
+    DecoderPriv *dec = nullptr;
 
-    // stream slots
+    // stream slots (WebSocket path): device-resident LSTM state
     float *slot_s1 = nullptr, *slot_s2 = nullptr;  // [max_streams][2][640]
     std::vector<uint8_t> slot_used;
 };
+
+// kernel ids for amira_ctx_kernel_ms
+enum ProfKernel { PK_FE_LOGMEL = 0, PK_FE_NORMALIZE = 1, PK_ENC_PROJ = 2, PK_GREEDY = 3, PK_BYTES = 4, PK_COUNT = 5 };
+struct ProfScope {  // RAII: records begin/end events around one launch when profiling is on
+    Ctx *c; int idx;
+    ProfScope(Ctx *ctx, int kernel) : c(ctx), idx(-1) {
+        if (!c->profiling) return;
+        Ctx::ProfSpan sp{kernel, nullptr, nullptr};
+        if (cudaEventCreate(&sp.beg) != cudaSuccess || cudaEventCreate(&sp.end) != cudaSuccess) return;
+        cudaEventRecord(sp.beg, c->stream);
+        c->prof_spans.push_back(sp);
+        idx = (int)c->prof_spans.size() - 1;
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(c->prof_spans[(size_t)idx].end, c->stream); }
+};
+
+// frontend.cu --------------------------------------------------------------------------------------------------
+// wave_dev: int16 PCM or float samples; utterance b occupies [starts[b], starts[b]+lens[b]) (element units).
+// features_dev [B][128][t_stride]; frames >= features_len are zero.
+cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const int64_t *starts_host,
+                            const int64_t *lens_host, int B, float *features_dev, int64_t t_stride);
+cudaError_t launch_bytes_to_f32(Ctx *c, const uint8_t *bytes_dev, size_t n_bytes, bool drop_odd, float *out_dev);
+
+// decoder.cu ---------------------------------------------------------------------------------------------------
+cudaError_t decoder_prepare_weights(Ctx *c);  // derived tables from c->w_blob
+void decoder_release(Ctx *c);
+// enc_dev [B][1024][T]; lens_dev int32[B]; slots_dev nullable: when given, states live in c->slot_s1/2 rows
+// slots[b] ([slot][2][640]); otherwise s1/s2 are [2][B][640] in/out (nullable => zero start, result dropped).
+cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, int B, int T, const int32_t *lens_dev,
+                                 const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev,
+                                 int32_t *ntok_dev, int32_t *nsteps_dev);
+const int32_t *decoder_fail_count_dev(Ctx *c);  // failed-stream counter of the last greedy launch
+cudaError_t launch_decoder_joint(Ctx *c, const float *enc_dev, int B, int T, const int32_t *targets_dev, int U,
+                                 const int32_t *tlen_dev, const float *in_s1, const float *in_s2, float *outputs,
+                                 int32_t *prednet_lengths, float *out_s1, float *out_s2, int32_t *err_flag_dev);
 
 }  // namespace amira

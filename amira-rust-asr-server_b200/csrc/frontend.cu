@@ -1,0 +1,499 @@
+// frontend.cu — the `preprocessor` stage on B200 (sm_100a).
+//
+// Replaces, for B utterances per launch, what the reference does with one Triton round trip per utterance:
+//   convert_audio (src/asr/pipeline.rs:127-139 -> src/performance_opts.rs:14-31)  i16 LE PCM -> f32
+//   PreprocessorModel::infer_zero_copy (src/triton/model.rs:71-160)               waveform -> [1,128,T'] features
+// Spec of the (absent, LFS) preprocessor ONNX: SURVEY.md 8(c).
+//
+// Kernel 1 (fe_logmel_kernel, persistent, one warp per frame):
+//   global i16/f32 -> smem (128-bit loads) -> pre-emphasis + reflect padding staged in smem (exact: for PCM the
+//   pre-emphasised sample 100*s[n]-97*s[n-1] is an integer < 2^24) -> Hann window -> 512-point real FFT as a
+//   256-point complex FFT: radix-8 in registers + five radix-2 stages over warp shuffles -> |X|^2 ->
+//   banded mel reduction (each lane owns 4 filters) -> log -> smem tile -> coalesced stores of the un-normalised
+//   log-mel tile + per-tile (mean, M2) partials.
+//   The FFT runs in fp64: an fp32 FFT leaves ~2e-4 max-abs error after normalisation on low mel bins (deep
+//   fades under pre-emphasis), above the 1e-4 contract; B200 has a 1:2 fp64 pipe (DESIGN.md "front end").
+// Kernel 2 (fe_normalize_kernel, one warp per (utterance, mel) row): Chan-merge of the partials in fp64,
+//   (x - mean) / (std + 1e-5) in place with 128-bit accesses, frames >= features_len zeroed.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.h"
+
+namespace amira {
+
+namespace {
+
+constexpr int TF = 32;                             // frames per tile
+constexpr int FE_THREADS = 128;                    // 4 warps, 8 frames each
+constexpr int FE_WARPS = FE_THREADS / 32;
+constexpr int SPAN = (TF - 1) * kHop + kNfft;      // 5472 padded samples per tile
+constexpr int RAW_CAP = SPAN + 16;                 // raw samples staged per tile (+ previous sample, alignment slack)
+constexpr int PPAD = 272;                          // power spectrum row (257 bins, index k + (k >> 5))
+constexpr int OUT_LD = TF + 1;
+
+struct FeMeta {
+    const int64_t *starts;   // [B] first element of each utterance
+    const int64_t *lens;     // [B] samples
+    const int32_t *tile_pfx; // [B+1] prefix sum of tiles per utterance
+    int B;
+    int n_tiles;
+};
+
+__device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
+    if (n <= 1) return 0;
+    const int64_t p = 2 * (n - 1);
+    i %= p;
+    if (i < 0) i += p;
+    return i < n ? i : p - i;
+}
+
+__device__ __forceinline__ int rev5(int x) { return (int)(__brev((unsigned)x) >> 27); }
+
+struct cplx {
+    double x, y;
+};
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cplx mul_mi(cplx a) { return {a.y, -a.x}; }  // a * (-i)
+__device__ __forceinline__ cplx twiddle(int num, int den) {            // exp(-2*pi*i*num/den)
+    double s, c;
+    sincospi(-2.0 * (double)num / (double)den, &s, &c);
+    return {c, s};
+}
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// in-register 8-point DFT (decimation in frequency, output in natural order)
+__device__ __forceinline__ void dft8(cplx (&a)[8]) {
+    const double r = 0.70710678118654752440;
+    cplx b[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        b[j] = cadd(a[j], a[j + 4]);
+        b[j + 4] = csub(a[j], a[j + 4]);
+    }
+    // twiddles W8^j on the odd half
+    b[5] = {r * (b[5].x + b[5].y), r * (b[5].y - b[5].x)};
+    b[6] = mul_mi(b[6]);
+    b[7] = {r * (b[7].y - b[7].x), -r * (b[7].x + b[7].y)};
+    // two 4-point DFTs: even outputs from b[0..3], odd outputs from b[4..7]
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const cplx s0 = cadd(b[4 * h + 0], b[4 * h + 2]), d0 = csub(b[4 * h + 0], b[4 * h + 2]);
+        const cplx s1 = cadd(b[4 * h + 1], b[4 * h + 3]), d1 = mul_mi(csub(b[4 * h + 1], b[4 * h + 3]));
+        a[h + 0] = cadd(s0, s1);
+        a[h + 4] = csub(s0, s1);
+        a[h + 2] = cadd(d0, d1);
+        a[h + 6] = csub(d0, d1);
+    }
+}
+
+template <typename RawT>
+struct Stage;  // staged (pre-emphasised, reflect-padded) sample type per input type
+template <>
+struct Stage<int16_t> {
+    using T = float;  // exact integers 100*s[n] - 97*s[n-1], |.| < 2^24
+    static constexpr double kScale = 1.0 / (100.0 * 32768.0);
+    __device__ static T make(int16_t cur, int16_t prev, bool first) {
+        return (float)(100 * (int)cur - (first ? 0 : 97 * (int)prev));
+    }
+};
+template <>
+struct Stage<float> {
+    using T = double;
+    static constexpr double kScale = 1.0;
+    __device__ static T make(float cur, float prev, bool first) {
+        return first ? (double)cur : (double)cur - 0.97 * (double)prev;
+    }
+};
+
+template <typename RawT>
+__global__ void __launch_bounds__(FE_THREADS, 3)
+fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables *__restrict__ tab,
+                 float *__restrict__ features, int64_t t_stride, double2 *__restrict__ partials) {
+    using StT = typename Stage<RawT>::T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StT *ystage = reinterpret_cast<StT *>(smem_raw);                                  // [SPAN]
+    float *outt = reinterpret_cast<float *>(smem_raw + sizeof(StT) * SPAN);           // [128][OUT_LD]
+    float *pw = outt + kMel * OUT_LD;                                                 // [FE_WARPS][PPAD]
+    float *melw = pw + FE_WARPS * PPAD;                                               // [kMelRowsMax][32]
+    RawT *raw = reinterpret_cast<RawT *>(melw + kMelRowsMax * 32);                    // [RAW_CAP]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- loop-invariant per-lane constants (registers) ----
+    double win[16];  // window at samples 2*(lane+32j), 2*(lane+32j)+1, scaled
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        win[2 * j] = (double)tab->win[2 * (lane + 32 * j)] * Stage<RawT>::kScale;
+        win[2 * j + 1] = (double)tab->win[2 * (lane + 32 * j) + 1] * Stage<RawT>::kScale;
+    }
+    cplx tw2[7];  // W256^(lane*k2), k2 = 1..7
+#pragma unroll
+    for (int k2 = 1; k2 < 8; ++k2) tw2[k2 - 1] = twiddle((lane * k2) & 255, 256);
+    cplx tws[4];  // cross-lane DIF stage twiddles (1 on the lower lane of each pair)
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int h = 16 >> s;
+        tws[s] = (lane & h) ? twiddle((lane & (h - 1)) * (16 / h), 32) : cplx{1.0, 0.0};
+    }
+    const int k1 = rev5(lane);                         // this lane ends up holding Z[k2 + 8*k1]
+    const cplx twl = twiddle(8 * k1, 512);             // W512^(8*k1); W512^k = W512^k2 * twl
+    const int src0 = rev5((32 - k1) & 31);             // lane holding Z[8*((32-k1)%32)]
+    int mk[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) mk[g] = tab->kstart[lane + 32 * g];
+    const int r0 = tab->melRow[0], r1 = tab->melRow[1], r2 = tab->melRow[2], r3 = tab->melRow[3], r4 = tab->melRow[4];
+    for (int i = tid; i < kMelRowsMax * 32; i += FE_THREADS) melw[i] = (&tab->melw_t[0][0])[i];
+    float *mypw = pw + warp * PPAD;
+
+    for (int tile = blockIdx.x; tile < meta.n_tiles; tile += gridDim.x) {
+        // ---- locate (utterance, first frame) ----
+        int lo = 0, hi = meta.B;  // largest b with tile_pfx[b] <= tile
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (meta.tile_pfx[mid] <= tile) lo = mid; else hi = mid;
+        }
+        const int b = lo;
+        const int64_t n = meta.lens[b];
+        const RawT *x = wave + meta.starts[b];
+        const int64_t L = n / kHop + 1;
+        const int f0 = (tile - meta.tile_pfx[b]) * TF;
+        const int nf = (int)min((int64_t)TF, L - f0);
+        const int span = (nf - 1) * kHop + kNfft;
+        const int64_t i0 = (int64_t)f0 * kHop - kNfft / 2;  // signal index of padded sample 0 of the tile
+
+        __syncthreads();  // previous tile fully consumed (ystage/outt/raw reuse); melw visible on first pass
+        // ---- stage the signal span [g_lo, g_hi) needed by this tile ----
+        int64_t g_lo = i0 - 1, g_hi = i0 + span;
+        if (g_lo < 0) { g_lo = 0; g_hi = max(g_hi, (int64_t)(kNfft / 2 + 2)); }
+        if (g_hi > n) { g_hi = n; g_lo = min(g_lo, n - (kNfft / 2 + 2)); }
+        if (g_lo < 0) g_lo = 0;
+        const bool fits = (g_hi - g_lo) <= RAW_CAP;  // false only for pathological tiny signals with long reflections
+        if (fits) {
+            const int cnt = (int)(g_hi - g_lo);
+            // 128-bit path over the 16-byte aligned interior, scalar head/tail
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(x + g_lo);
+            int head = (int)(((16 - (a0 & 15)) & 15) / sizeof(RawT));
+            if (head > cnt) head = cnt;
+            constexpr int PER = 16 / sizeof(RawT);
+            const int nvec = (cnt - head) / PER;
+            for (int i = tid; i < head; i += FE_THREADS) raw[i] = x[g_lo + i];
+            const int4 *src = reinterpret_cast<const int4 *>(x + g_lo + head);
+            for (int v = tid; v < nvec; v += FE_THREADS) {
+                const int4 q = __ldg(src + v);
+                alignas(16) RawT tmp[PER];
+                *reinterpret_cast<int4 *>(tmp) = q;
+#pragma unroll
+                for (int e = 0; e < PER; ++e) raw[head + v * PER + e] = tmp[e];
+            }
+            for (int i = head + nvec * PER + tid; i < cnt; i += FE_THREADS) raw[i] = x[g_lo + i];
+        }
+        __syncthreads();
+        // ---- pre-emphasis (y[0] = x[0]; y[i] = x[i] - 0.97 x[i-1]) + reflect padding ----
+        const bool interior = fits && i0 >= 1 && i0 + span <= n;
+        if (interior) {
+            for (int p = tid; p < span; p += FE_THREADS)  // raw[q] = x[i0 - 1 + q]
+                ystage[p] = Stage<RawT>::make(raw[p + 1], raw[p], false);
+        } else {
+            for (int p = tid; p < span; p += FE_THREADS) {
+                const int64_t r = reflect_index(i0 + p, n);
+                RawT cur, prev = RawT(0);
+                if (fits) {
+                    cur = raw[r - g_lo];
+                    if (r > 0) prev = raw[r - 1 - g_lo];
+                } else {
+                    cur = x[r];
+                    if (r > 0) prev = x[r - 1];
+                }
+                ystage[p] = Stage<RawT>::make(cur, prev, r == 0);
+            }
+        }
+        __syncthreads();
+
+        // ---- one warp per frame ----
+        for (int fl = warp; fl < nf; fl += FE_WARPS) {
+            const StT *fr = ystage + fl * kHop;
+            cplx a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int s = 2 * (lane + 32 * j);
+                a[j].x = (double)fr[s] * win[2 * j];
+                a[j].y = (double)fr[s + 1] * win[2 * j + 1];
+            }
+            dft8(a);  // A[k2] = sum_j z[32j + lane] W8^(j k2)
+#pragma unroll
+            for (int k2 = 1; k2 < 8; ++k2) a[k2] = cmul(a[k2], tw2[k2 - 1]);
+            // 32-point DIF across lanes; lane l ends with C[rev5(l)]
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                const int h = 16 >> s;
+                const bool upper = lane & h;
+#pragma unroll
+                for (int k2 = 0; k2 < 8; ++k2) {
+                    const cplx o = {shfl_xor_d(a[k2].x, h), shfl_xor_d(a[k2].y, h)};
+                    cplx v = upper ? csub(o, a[k2]) : cadd(o, a[k2]);
+                    if (s < 4) v = cmul(v, tws[s]);
+                    a[k2] = v;
+                }
+            }
+            // real-FFT post-processing: X[k] = E + W512^k O with E = (Z[k] + conj Z[256-k]) / 2,
+            // O = (Z[k] - conj Z[256-k]) / (2i); this lane owns k = k2 + 8*k1
+            const double c512r[8] = {1.0, 0.99992470183914454, 0.99969881869620422, 0.99932238458834954,
+                                     0.99879545620517241, 0.99811811290014918, 0.99729045667869021,
+                                     0.99631261218277801};
+            const double c512i[8] = {-0.0, -0.012271538285719925, -0.024541228522912288, -0.036807222941358832,
+                                     -0.049067674327418015, -0.061320736302208578, -0.073564563599667426,
+                                     -0.085797312344439894};
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) {
+                cplx zp;
+                if (k2 == 0) zp = {shfl_d(a[0].x, src0), shfl_d(a[0].y, src0)};
+                else zp = {shfl_xor_d(a[8 - k2].x, 31), shfl_xor_d(a[8 - k2].y, 31)};
+                const cplx z = a[k2];
+                const cplx e = {0.5 * (z.x + zp.x), 0.5 * (z.y - zp.y)};
+                const cplx d = {0.5 * (z.x - zp.x), 0.5 * (z.y + zp.y)};  // (Z[k] - conj Z[N-k]) / 2
+                const cplx o = mul_mi(d);                                 // / i
+                const cplx w = cmul(cplx{c512r[k2], c512i[k2]}, twl);
+                const cplx wo = cmul(w, o);
+                const cplx xk = cadd(e, wo);
+                const int k = k2 + 8 * k1;
+                mypw[k + (k >> 5)] = (float)(xk.x * xk.x + xk.y * xk.y);
+                if (k == 0) {  // Nyquist bin: X[256] = Re Z[0] - Im Z[0]
+                    const double ny = z.x - z.y;
+                    mypw[256 + 8] = (float)(ny * ny);
+                }
+            }
+            __syncwarp();
+            // banded mel reduction: lane owns filters lane + 32 g
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            auto band = [&](int g, int ra, int rb) {
+                for (int r = ra; r < rb; ++r) {
+                    const int k = min(mk[g] + (r - ra), 256);
+                    acc[g] = fmaf(melw[r * 32 + lane], mypw[k + (k >> 5)], acc[g]);
+                }
+            };
+            band(0, r0, r1);
+            band(1, r1, r2);
+            band(2, r2, r3);
+            band(3, r3, r4);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) outt[(lane + 32 * g) * OUT_LD + fl] = logf(acc[g] + 5.9604644775390625e-08f);
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---- per-tile statistics (one thread per mel row) + coalesced store of the tile ----
+        {
+            const int m = tid;  // FE_THREADS == kMel
+            double s = 0.0;
+            for (int f = 0; f < nf; ++f) s += (double)outt[m * OUT_LD + f];
+            const double mean = s / nf;
+            double m2 = 0.0;
+            for (int f = 0; f < nf; ++f) {
+                const double d = (double)outt[m * OUT_LD + f] - mean;
+                m2 += d * d;
+            }
+            partials[(size_t)tile * kMel + m] = make_double2(mean, m2);
+        }
+        float *dst = features + (size_t)b * kMel * t_stride + f0;
+        for (int m = warp; m < kMel; m += FE_WARPS)
+            if (lane < nf) dst[(size_t)m * t_stride + lane] = outt[m * OUT_LD + lane];
+    }
+}
+
+// one warp per (utterance, mel) row
+__global__ void __launch_bounds__(256)
+fe_normalize_kernel(FeMeta meta, float *__restrict__ features, int64_t t_stride, const double2 *__restrict__ partials) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= (int64_t)meta.B * kMel) return;
+    const int b = (int)(row / kMel), m = (int)(row % kMel);
+    const int64_t n = meta.lens[b];
+    const int64_t L = n <= 0 ? 0 : n / kHop + 1;
+    float *p = features + row * t_stride;
+    // Chan et al. pairwise merge of (count, mean, M2)
+    double cn = 0.0, cmean = 0.0, cm2 = 0.0;
+    auto merge = [&](double n2, double mean2, double m22) {
+        if (n2 == 0.0) return;
+        const double nt = cn + n2, d = mean2 - cmean;
+        cmean += d * (n2 / nt);
+        cm2 += m22 + d * d * (cn * n2 / nt);
+        cn = nt;
+    };
+    if (L > 0) {
+        const int t0 = meta.tile_pfx[b], nt = meta.tile_pfx[b + 1] - t0;
+        for (int t = lane; t < nt; t += 32) {
+            const double2 q = partials[(size_t)(t0 + t) * kMel + m];
+            const double cnt = (double)min((int64_t)TF, L - (int64_t)t * TF);
+            merge(cnt, q.x, q.y);
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const double n2 = __shfl_xor_sync(0xffffffffu, cn, o);
+            const double mean2 = __shfl_xor_sync(0xffffffffu, cmean, o);
+            const double m22 = __shfl_xor_sync(0xffffffffu, cm2, o);
+            // symmetric merge so both partners end with identical values
+            const double nt2 = cn + n2;
+            if (nt2 > 0.0) {
+                const double d = mean2 - cmean;
+                const double nm = (cn * cmean + n2 * mean2) / nt2;
+                cm2 = cm2 + m22 + d * d * (cn * n2 / nt2);
+                cmean = nm;
+                cn = nt2;
+            }
+        }
+    }
+    const double sd = L > 1 ? sqrt(cm2 / (double)(L - 1)) : 0.0;
+    const float mu = (float)cmean;
+    const float inv = (float)(1.0 / (sd + 1e-5));
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (t_stride % 4 == 0);
+    if (vec) {
+        float4 *p4 = reinterpret_cast<float4 *>(p);
+        const int64_t n4 = t_stride / 4;
+        for (int64_t i = lane; i < n4; i += 32) {
+            const int64_t t = i * 4;
+            float4 v;
+            if (t + 3 < L) {
+                v = p4[i];
+                v.x = (v.x - mu) * inv; v.y = (v.y - mu) * inv; v.z = (v.z - mu) * inv; v.w = (v.w - mu) * inv;
+            } else if (t >= L) {
+                v = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                v = p4[i];
+                v.x = (v.x - mu) * inv;
+                v.y = t + 1 < L ? (v.y - mu) * inv : 0.f;
+                v.z = t + 2 < L ? (v.z - mu) * inv : 0.f;
+                v.w = 0.f;
+            }
+            p4[i] = v;
+        }
+    } else {
+        for (int64_t t = lane; t < t_stride; t += 32) p[t] = t < L ? (p[t] - mu) * inv : 0.f;
+    }
+}
+
+__global__ void bytes_to_f32_kernel(const uint8_t *__restrict__ in, size_t n_bytes, int drop_odd, float *__restrict__ out) {
+    // src/performance_opts.rs:14-31: LE i16 / 32768; an odd trailing byte b -> (b as i16) / 128 (zero-extended)
+    const size_t n_pairs = n_bytes / 2;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (aligned) {
+        const size_t nvec = n_pairs / 8;
+        const int4 *src = reinterpret_cast<const int4 *>(in);
+        float4 *dst = reinterpret_cast<float4 *>(out);
+        for (size_t v = i0; v < nvec; v += stride) {
+            const int4 q = __ldg(src + v);
+            const int w[4] = {q.x, q.y, q.z, q.w};
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                f[2 * e] = (float)(int16_t)(w[e] & 0xffff) * (1.0f / 32768.0f);
+                f[2 * e + 1] = (float)(int16_t)((unsigned)w[e] >> 16) * (1.0f / 32768.0f);
+            }
+            dst[2 * v] = make_float4(f[0], f[1], f[2], f[3]);
+            dst[2 * v + 1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+        for (size_t i = nvec * 8 + i0; i < n_pairs; i += stride) {
+            const int16_t s = (int16_t)((uint16_t)in[2 * i] | ((uint16_t)in[2 * i + 1] << 8));
+            out[i] = (float)s * (1.0f / 32768.0f);
+        }
+    } else {
+        for (size_t i = i0; i < n_pairs; i += stride) {
+            const int16_t s = (int16_t)((uint16_t)in[2 * i] | ((uint16_t)in[2 * i + 1] << 8));
+            out[i] = (float)s * (1.0f / 32768.0f);
+        }
+    }
+    if (i0 == 0 && (n_bytes & 1) && !drop_odd) out[n_pairs] = (float)(int16_t)in[n_bytes - 1] / 128.0f;
+}
+
+template <typename RawT>
+size_t fe_smem_bytes() {
+    return sizeof(typename Stage<RawT>::T) * SPAN + sizeof(float) * (kMel * OUT_LD + FE_WARPS * PPAD + kMelRowsMax * 32) +
+           sizeof(RawT) * RAW_CAP;
+}
+
+}  // namespace
+
+cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const int64_t *starts_host,
+                            const int64_t *lens_host, int B, float *features_dev, int64_t t_stride) {
+    if (B <= 0) return cudaSuccess;
+    // host metadata: starts, lens, tile prefix -> one pinned block, one async copy
+    const size_t meta_bytes = sizeof(int64_t) * 2 * (size_t)B + sizeof(int32_t) * ((size_t)B + 1);
+    cudaError_t e;
+    if ((e = c->fe_meta_pin.reserve(meta_bytes)) != cudaSuccess) return e;
+    if ((e = c->fe_meta.reserve(meta_bytes)) != cudaSuccess) return e;
+    int64_t *h_starts = c->fe_meta_pin.as<int64_t>();
+    int64_t *h_lens = h_starts + B;
+    int32_t *h_pfx = reinterpret_cast<int32_t *>(h_lens + B);
+    int64_t tiles = 0;
+    for (int b = 0; b < B; ++b) {
+        h_starts[b] = starts_host[b];
+        h_lens[b] = lens_host[b];
+        h_pfx[b] = (int32_t)tiles;
+        const int64_t L = lens_host[b] <= 0 ? 0 : lens_host[b] / kHop + 1;
+        tiles += (L + TF - 1) / TF;
+    }
+    h_pfx[B] = (int32_t)tiles;
+    if (tiles > 0x7fffffff) return cudaErrorInvalidValue;
+    if ((e = cudaMemcpyAsync(c->fe_meta.p, c->fe_meta_pin.p, meta_bytes, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
+        return e;
+    FeMeta meta;
+    meta.starts = c->fe_meta.as<int64_t>();
+    meta.lens = meta.starts + B;
+    meta.tile_pfx = reinterpret_cast<const int32_t *>(meta.lens + B);
+    meta.B = B;
+    meta.n_tiles = (int)tiles;
+    if ((e = c->fe_partials.reserve(sizeof(double2) * (size_t)std::max<int64_t>(tiles, 1) * kMel)) != cudaSuccess) return e;
+
+    if (tiles > 0) {
+        ProfScope prof(c, PK_FE_LOGMEL);
+        const int grid = (int)std::min<int64_t>(tiles, (int64_t)c->sm_count * 3);
+        if (is_pcm16) {
+            const size_t smem = fe_smem_bytes<int16_t>();
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(fe_logmel_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_done = true;
+            }
+            fe_logmel_kernel<int16_t><<<grid, FE_THREADS, smem, c->stream>>>(
+                static_cast<const int16_t *>(wave_dev), meta, c->tables_dev, features_dev, t_stride,
+                c->fe_partials.as<double2>());
+        } else {
+            const size_t smem = fe_smem_bytes<float>();
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(fe_logmel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_done = true;
+            }
+            fe_logmel_kernel<float><<<grid, FE_THREADS, smem, c->stream>>>(
+                static_cast<const float *>(wave_dev), meta, c->tables_dev, features_dev, t_stride,
+                c->fe_partials.as<double2>());
+        }
+        c->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    const int64_t rows = (int64_t)B * kMel;
+    ProfScope prof(c, PK_FE_NORMALIZE);
+    fe_normalize_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, c->stream>>>(meta, features_dev, t_stride,
+                                                                            c->fe_partials.as<double2>());
+    c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bytes_to_f32(Ctx *c, const uint8_t *bytes_dev, size_t n_bytes, bool drop_odd, float *out_dev) {
+    if (n_bytes == 0) return cudaSuccess;
+    const size_t work = n_bytes / 16 + 1;
+    const int grid = (int)std::min<size_t>((work + 255) / 256, (size_t)c->sm_count * 8);
+    ProfScope prof(c, PK_BYTES);
+    bytes_to_f32_kernel<<<grid, 256, 0, c->stream>>>(bytes_dev, n_bytes, drop_odd ? 1 : 0, out_dev);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace amira

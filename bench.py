@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — audio-sec/sec of the amira-rust-asr-server hot path (preprocessor front end + RNN-T greedy decode)
+on N B200s, one process per GPU, no data-path collective (utterances are independent).
+
+    python bench.py --gpus 1 --steps K --warmup W
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the CPU restatement of the reference path on the host cores
+
+A "step" is one pass of the hot path over this rank's shard: BASELINE config 5's per-GPU share — 1024 utterances
+of 5-30 s mixed length (weak scaling: 8192 utterances at 8 GPUs): fused front end on the real PCM, then greedy
+decode over synthetic encoder outputs of the matching encoded lengths (the encoder model is out of scope).
+`value` is timed on the device with inputs resident in HBM; `e2e` goes through the same C-ABI calls with pinned HOST
+buffers (PCM and encoder outputs in, features and tokens out — what the Rust AsrPipeline would hand over).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_STEP = 15_244_800      # flop per (stream, decode step): 2 LSTM layers + pred proj + vocab proj
+F_FRAME = 1_310_720      # flop per (stream, encoder frame): hoisted encoder projection
+BYTES_PER_AUDIO_S = 83_200  # front end, i16 in + f32 [128, T'] out
+
+
+def encoded_len(L: int) -> int:
+    for _ in range(3):
+        L = (L - 1) // 2 + 1 if L > 0 else 0
+    return L
+
+
+def make_workload(n_utt: int, seed: int, min_s: float = 5.0, max_s: float = 30.0):
+    """Seeded synthetic 16 kHz PCM (0.1 N(0,1) + three sines, BASELINE config 2's signal) for n_utt utterances."""
+    rng = np.random.default_rng(seed)
+    secs = rng.uniform(min_s, max_s, size=n_utt)
+    lens = np.round(secs * 16000).astype(np.int64)
+    n_base = min(8, n_utt)
+    base = []
+    t = np.arange(int(max_s * 16000))
+    for _ in range(n_base):
+        x = 0.1 * rng.standard_normal(t.size)
+        for _ in range(3):
+            x += 0.2 * np.sin(2 * np.pi * rng.uniform(100, 4000) * t / 16000)
+        base.append(np.round(np.clip(x, -1, 1) * 32767).astype(np.int16))
+    offsets = np.zeros(n_utt + 1, np.int64)
+    offsets[1:] = np.cumsum(lens)
+    pcm = np.empty(int(offsets[-1]), np.int16)
+    for b in range(n_utt):
+        pcm[offsets[b]:offsets[b + 1]] = base[b % n_base][:lens[b]]
+    return pcm, offsets, lens
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.p = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.p = None
+
+    def _pump(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference(pcm, offsets, lens, sample: int, threads: int):
+    """The CPU restatement of the reference path (oracle/; the reference binary itself needs cargo + Triton + ONNX
+    weights, none of which exist here) on a bounded sample of the workload, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    import amira_b200 as A
+    sample = min(sample, lens.size)
+    t_stride = int(max(l // 160 + 1 for l in lens[:sample]))
+    t0 = time.perf_counter()
+    feats, flens = O.preprocess_pcm16_batch(pcm[:offsets[sample]], offsets[:sample + 1], t_stride, threads)
+    t_fe = time.perf_counter() - t0
+    elens = np.array([encoded_len(int(x)) for x in flens], np.int64)
+    T = int(elens.max())
+    rng = np.random.default_rng(2345)
+    enc = (0.5 * rng.standard_normal((sample, 1024, T))).astype(np.float32)
+    model = O.Model(blob=A.synthetic_weights(3456))
+    t0 = time.perf_counter()
+    r = O.greedy_decode_batch(model, enc, enc_lens=elens, threads=threads)
+    t_dec = time.perf_counter() - t0
+    audio_s = float(lens[:sample].sum()) / 16000.0
+    return {"audio_s": audio_s, "t_fe": t_fe, "t_dec": t_dec, "value": audio_s / (t_fe + t_dec),
+            "steps": int(r["n_steps"].sum()), "tokens": int(r["n_tokens"].sum())}
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    pcm, offsets, lens = make_workload(args.ref_sample, 4567)
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_reference(pcm, offsets, lens, min(2, args.ref_sample), threads)
+    ts, last = [], None
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        last = cpu_reference(pcm, offsets, lens, args.ref_sample, threads)
+        ts.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(ts))
+    val = last["audio_s"] / (ms / 1e3)
+    sample = f"{args.ref_sample} utterances ({last['audio_s']:.0f} audio-s) of the same seeded workload per step"
+    print(json.dumps({
+        "impl": "reference", "metric": "audio-sec/sec (preproc + RNN-T greedy decode)", "value": val, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 fft / f32", "data": "synthetic",
+        "config": {"workload": "cfg5 shard: 5-30 s mixed utterances, front end + greedy decode (CPU restatement of the "
+                               "reference path; no gRPC/Triton cost, so optimistic for the reference)", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--utterances", type=int, default=1024, help="utterances per GPU per step")
+    ap.add_argument("--ref-sample", type=int, default=24)
+    ap.add_argument("--cpu-sample", type=int, default=24)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--engine", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import amira_b200 as A
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: amira_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = A.Context(device_id=local_rank, decode_engine=args.engine)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.load_weights(A.synthetic_weights(3456))
+
+    # ---- this rank's shard: the host-side partition is plain striding over independent utterances ----
+    B = args.utterances
+    pcm, offsets, lens = make_workload(B, 4567 + rank)
+    flens = lens // 160 + 1
+    elens = np.array([encoded_len(int(x)) for x in flens], np.int64)
+    t_stride = int((flens.max() + 31) // 32 * 32)
+    T = int(elens.max())
+    audio_s = float(lens.sum()) / 16000.0
+
+    pcm_pin = torch.from_numpy(pcm).pin_memory()
+    pcm_dev = pcm_pin.to(dev)
+    feats_dev = torch.empty((B, 128, t_stride), dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(2345 + rank)
+    enc_dev = torch.randn((B, 1024, T), generator=g, device=dev, dtype=torch.float32) * 0.5
+    tok_dev = torch.zeros((B, ctx.max_total_tokens), dtype=torch.int32, device=dev)
+    ntok_dev = torch.zeros(B, dtype=torch.int32, device=dev)
+    nsteps_dev = torch.zeros(B, dtype=torch.int32, device=dev)
+    flens_out = np.zeros(B, np.int64)
+    torch.cuda.synchronize()
+
+    def step_device():
+        ctx.preprocess_pcm16_raw(pcm_dev.data_ptr(), offsets, B, feats_dev.data_ptr(), t_stride, flens_out)
+        ctx.greedy_decode_raw(enc_dev.data_ptr(), B, T, elens, tok_dev.data_ptr(), ntok_dev.data_ptr(), nsteps_dev.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    ctx.profile(True)
+    l0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total = timed(step_device, args.steps)
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - l0
+    kms = {k: ctx.kernel_ms(k) for k in ("fe_logmel", "fe_normalize", "enc_proj", "greedy")}
+    ctx.profile(False)
+    ms_step = ms_total / args.steps
+    nsteps = nsteps_dev.cpu().numpy().astype(np.int64)
+    ntok = ntok_dev.cpu().numpy().astype(np.int64)
+
+    total_audio = audio_s
+    if world > 1:
+        t = torch.tensor([audio_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_audio = float(t.item())
+    value = total_audio / (ms_step / 1e3)
+
+    # ---- e2e: same calls, pinned host buffers in and out ----
+    e2e = None
+    if not args.no_e2e:
+        enc_pin = torch.empty((B, 1024, T), dtype=torch.float32).pin_memory()
+        enc_pin.copy_(enc_dev)
+        feats_pin = torch.empty((B, 128, t_stride), dtype=torch.float32).pin_memory()
+        tok_pin = torch.zeros((B, ctx.max_total_tokens), dtype=torch.int32).pin_memory()
+        ntok_pin = torch.zeros(B, dtype=torch.int32).pin_memory()
+        torch.cuda.synchronize()
+
+        def step_host():
+            ctx.preprocess_pcm16_raw(pcm_pin.data_ptr(), offsets, B, feats_pin.data_ptr(), t_stride, flens_out)
+            ctx.greedy_decode_raw(enc_pin.data_ptr(), B, T, elens, tok_pin.data_ptr(), ntok_pin.data_ptr(), None)
+
+        step_host()
+        ms_e2e = timed(step_host, args.steps) / args.steps
+        assert np.array_equal(ntok_pin.numpy().astype(np.int64), ntok), "host-buffer path disagrees with the resident path"
+        e2e = {"value": total_audio / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(pcm.nbytes + enc_pin.numel() * 4 + offsets.nbytes + elens.nbytes),
+               "d2h_bytes_per_step": int(feats_pin.numel() * 4 + tok_pin.numel() * 4 + ntok_pin.numel() * 4)}
+        del enc_pin, feats_pin
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, tf_peak, peak_kind = peaks()
+    # dominant kernel = the persistent decode kernel (tensor-pipe roofline)
+    dec_ms, dec_n = kms["greedy"]
+    flops = float(nsteps.sum()) * F_STEP
+    dec_avg_ms = dec_ms / max(dec_n, 1)
+    ach_tf = flops / (dec_avg_ms / 1e3) / 1e12 if dec_avg_ms > 0 else 0.0
+    fe_ms, fe_n = kms["fe_logmel"]
+    fe_avg_ms = fe_ms / max(fe_n, 1)
+    fe_bytes = 2.0 * float(lens.sum()) + 4.0 * 128 * float(flens.sum()) + 16.0 * B
+    fe_gbs = fe_bytes / (fe_avg_ms / 1e3) / 1e9 if fe_avg_ms > 0 else 0.0
+    share = {k: round(v[0] / args.steps, 3) for k, v in kms.items()}
+
+    out = {
+        "metric": "audio-sec/sec (preproc + RNN-T greedy decode)", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 fft + f32 mel / f32 decode" if args.engine != 2 else "f64 fft + f32 mel / split-bf16 tcgen05 decode",
+        "data": "synthetic",
+        "config": {"workload": f"BASELINE cfg5 per-GPU shard: {B} utterances x U[5,30] s 16 kHz PCM ({audio_s:.0f} audio-s, "
+                               f"{pcm.nbytes / 1e6:.0f} MB PCM in, {4 * 128 * int(flens.sum()) / 1e6:.0f} MB features out) + greedy "
+                               f"decode of {B} streams over synthetic encoder outputs [B,1024,T<={T}], limits 30/200, "
+                               "random-init weights (seeded, blank-calibrated)",
+                   "global_utterances": B * world, "parallelism": f"dp{world} by utterance, no collective",
+                   "cache": "inputs larger than L2 (PCM + encoder outputs > 2 GB per step)",
+                   "decode_steps_per_step": int(nsteps.sum()), "tokens_per_step": int(ntok[ntok > 0].sum()),
+                   "decode_engine": "fp32 persistent cooperative kernel" if args.engine != 2 else "tcgen05 split-bf16"},
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+        "kernel_ms_per_step": share,
+        "roofline": {"kernel": "greedy_persistent_kernel", "bound": "tensor", "achieved": ach_tf, "peak": tf_peak,
+                     "unit": "TFLOP/s", "frac": ach_tf / tf_peak, "traffic": None, "peak_kind": f"bf16 sustained, {peak_kind}",
+                     "flops_per_launch": flops, "avg_launch_ms": dec_avg_ms},
+        "roofline_frontend": {"kernel": "fe_logmel_kernel", "bound": "hbm", "achieved": fe_gbs, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": fe_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind, "bytes_per_launch": fe_bytes,
+                              "avg_launch_ms": fe_avg_ms},
+    }
+    if e2e:
+        out["e2e"] = e2e
+    if not args.no_cpu:
+        threads = os.cpu_count() or 1
+        r = cpu_reference(pcm, offsets, lens, args.cpu_sample, threads)
+        out["cpu_baseline"] = {"value": r["value"], "unit": "audio-s/s", "cores": threads, "kind": "port",
+                               "sample": f"first {min(args.cpu_sample, B)} utterances of this workload ({r['audio_s']:.0f} audio-s): "
+                                         f"front end {r['t_fe']:.2f} s + decode {r['t_dec']:.2f} s, OpenMP over utterances"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

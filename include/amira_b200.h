@@ -82,6 +82,12 @@ int32_t amira_ctx_synchronize(amira_ctx *ctx);
 /* number of library kernels launched so far on this ctx (bench.py's gpu_launches) */
 int32_t amira_ctx_launch_count(amira_ctx *ctx, int64_t *count);
 
+/* per-kernel device timing for bench.py's roofline: CUDA events on the context's stream around each launch.
+ * kernel ids: 0 fe_logmel, 1 fe_normalize, 2 encoder projection GEMM, 3 persistent greedy-decode, 4 bytes_to_f32.
+ * amira_ctx_profile(ctx, 1) resets the totals and starts recording; amira_ctx_kernel_ms reads them. */
+int32_t amira_ctx_profile(amira_ctx *ctx, int32_t enable);
+int32_t amira_ctx_kernel_ms(amira_ctx *ctx, int32_t kernel, double *total_ms, int64_t *launches);
+
 /* ---- weights: stand-in for model-repo/decoder_joint/1/model.onnx (absent LFS object) ---- */
 /* flat fp32 blob, order: emb[1025][640]; per layer l=0,1: w_ih[2560][640], w_hh[2560][640], b_ih[2560],
  * b_hh[2560]; w_enc[640][1024], b_enc[640]; w_pred[640][640], b_pred[640]; w_out[1030][640], b_out[1030]. */
@@ -135,6 +141,50 @@ int32_t amira_stream_set_state(amira_ctx *ctx, int32_t slot, const float *states
 /* one tick: n streams, each with an encoder chunk [n][1024][T]; state read from / written back to the slots. */
 int32_t amira_stream_decode(amira_ctx *ctx, const int32_t *slots, int32_t n, const float *encoder_outputs, int32_t T,
                             const int64_t *encoded_lengths, int32_t *tokens, int32_t *n_tokens, int32_t *n_steps);
+
+/* ---- host pipeline: C++ mirror of `trait AsrPipeline` (src/asr/pipeline.rs:20-67) and of TritonAsrPipeline's
+ * process_audio_zero_copy (src/asr/pipeline.rs:269-380) with the preprocessor and decoder_joint stages on the GPU.
+ * The encoder model is out of scope and stays an injected dependency: the callback receives features
+ * [1][128][features_len] (host) and must return encoder outputs [1][1024][encoded_len] (host, layout f*T+t,
+ * src/asr/zero_copy.rs:61-62) in a buffer it owns until the next call on the same pipeline. ---- */
+typedef struct amira_pipeline amira_pipeline;
+typedef int32_t (*amira_encoder_fn)(void *user, const float *features, int64_t features_len, const float **encoder_outputs,
+                                    int64_t *encoded_len); /* 0 = ok; anything else fails the request */
+/* mirror of `struct Transcription` (src/asr/types.rs:217-232); tokens/text go to caller-owned buffers */
+typedef struct {
+    int64_t audio_length_samples;
+    int64_t features_length;
+    int64_t encoded_length;
+    int32_t n_tokens;
+    int32_t text_len; /* bytes of UTF-8 text (without NUL); truncated to text_cap - 1 */
+} amira_transcription;
+/* vocab_path: `<token> <id>` per line (Vocabulary::load_from_file, src/asr/types.rs:87-108) */
+int32_t amira_pipeline_create(amira_ctx *ctx, const char *vocab_path, amira_encoder_fn encoder, void *encoder_user,
+                              amira_pipeline **out);
+int32_t amira_pipeline_destroy(amira_pipeline *p);
+const char *amira_pipeline_last_error(amira_pipeline *p);
+/* AsrPipeline::process_batch (src/asr/pipeline.rs:403-414): fresh DecoderState */
+int32_t amira_pipeline_process_batch(amira_pipeline *p, const uint8_t *audio_bytes, size_t n_bytes,
+                                     amira_transcription *out, int32_t *tokens, int32_t tokens_cap, char *text,
+                                     size_t text_cap);
+/* AsrPipeline::process_stream_chunk (src/asr/pipeline.rs:384-401): states_1/2 [2][1][640] in/out */
+int32_t amira_pipeline_process_stream_chunk(amira_pipeline *p, const uint8_t *audio_bytes, size_t n_bytes,
+                                            float *states_1, float *states_2, amira_transcription *out,
+                                            int32_t *tokens, int32_t tokens_cap, char *text, size_t text_cap);
+/* AsrPipeline::process_batch_samples / process_stream_samples (src/asr/pipeline.rs:416-443) */
+int32_t amira_pipeline_process_batch_samples(amira_pipeline *p, const float *samples, size_t n_samples,
+                                             amira_transcription *out, int32_t *tokens, int32_t tokens_cap,
+                                             char *text, size_t text_cap);
+int32_t amira_pipeline_process_stream_samples(amira_pipeline *p, const float *samples, size_t n_samples,
+                                              float *states_1, float *states_2, amira_transcription *out,
+                                              int32_t *tokens, int32_t tokens_cap, char *text, size_t text_cap);
+/* Vocabulary::decode_tokens (src/asr/types.rs:111-135): unknown ids skipped, U+2581 prefix -> space, trimmed.
+ * returns the full length in *text_len (may exceed text_cap - 1: output truncated). */
+int32_t amira_vocab_decode(amira_pipeline *p, const int32_t *tokens, int32_t n_tokens, char *text, size_t text_cap,
+                           int32_t *text_len);
+/* Multi-GPU: utterances are independent — longest-processing-time assignment of n utterances with
+ * costs[i] (e.g. samples) to n_shards GPUs; shard_of[i] receives the shard index.  No collective follows. */
+int32_t amira_shard_utterances(const int64_t *costs, int32_t n, int32_t n_shards, int32_t *shard_of);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,166 @@
+"""GPU parity of the persistent greedy-decode kernel and the decoder_joint contract op against the CPU oracle
+(literal restatement of src/asr/decoder_optimized.rs:54-200 around an fp32 LSTM/joint step).
+
+Token IDs must be bit-exact except documented argmax near-ties: a stream may diverge from the oracle only at a step
+whose oracle top-1/top-2 logit margin is below NEAR_TIE (fp32 re-association noise is ~1e-5 on logits of O(1))."""
+import numpy as np
+import pytest
+
+from conftest import calibrated_weights
+
+pytestmark = pytest.mark.gpu
+NEAR_TIE = 2e-4
+
+
+@pytest.fixture(scope="module")
+def model(oracle, ctx):
+    blob = calibrated_weights(oracle)
+    ctx.load_weights(blob)
+    return oracle.Model(blob=blob)
+
+
+def _check_tokens(oracle, model, enc, lens, got_tokens, got_steps, states=None):
+    n_div = 0
+    for b in range(enc.shape[0]):
+        L = int(lens[b])
+        st = None if states is None else (states[0][:, b], states[1][:, b])
+        r = oracle.greedy_decode(np.ascontiguousarray(enc[b, :, :L]), L, model, states=st)
+        assert r.rc == 0
+        if got_tokens[b] == r.tokens:
+            assert got_steps[b] == r.n_steps
+            continue
+        # a diverging stream must contain a near-tie step in the oracle (documented exception)
+        n_div += 1
+        assert r.margins.min() < NEAR_TIE, (b, float(r.margins.min()))
+    return n_div
+
+
+def test_decoder_joint_contract_op(ctx, oracle, model):
+    rng = np.random.default_rng(5)
+    B, T, U = 3, 4, 3
+    enc = (0.5 * rng.standard_normal((B, 1024, T))).astype(np.float32)
+    tg = np.array([[1024, 5, 17], [1024, 1000, 3], [7, 7, 7]], np.int32)
+    s1 = (0.1 * rng.standard_normal((2, B, 640))).astype(np.float32)
+    s2 = (0.1 * rng.standard_normal((2, B, 640))).astype(np.float32)
+    import amira_b200 as A
+    out, pl, st = ctx.decoder_joint(enc, tg, state=A.DecoderState(s1, s2))
+    assert out.shape == (B, U, T, 1030) and pl.tolist() == [U] * B
+    for b in range(B):
+        ref, r1, r2 = model.decoder_joint(enc[b], tg[b], s1[:, b:b + 1], s2[:, b:b + 1])
+        assert np.abs(out[b] - ref).max() < 1e-4
+        assert np.abs(st.states_1[:, b] - r1.reshape(2, 640)).max() < 5e-5
+        assert np.abs(st.states_2[:, b] - r2.reshape(2, 640)).max() < 5e-5
+        assert np.array_equal(out[b].reshape(U, T, 1030).argmax(-1), ref.argmax(-1))
+
+
+def test_decoder_joint_rejects_out_of_table_target(ctx, amira, model):
+    enc = np.zeros((1, 1024, 1), np.float32)
+    with pytest.raises(amira.AmiraError) as e:
+        ctx.decoder_joint(enc, np.array([[1024, 1027]], np.int32))
+    assert e.value.code == 6  # "Decode step failed"
+
+
+def test_greedy_batch_matches_oracle(ctx, oracle, model):
+    rng = np.random.default_rng(2345)
+    B, T = 24, 40
+    enc = (0.5 * rng.standard_normal((B, 1024, T))).astype(np.float32)
+    lens = rng.integers(1, T + 1, size=B)
+    lens[0], lens[1], lens[2] = T, 0, 1
+    toks, st, steps = ctx.greedy_decode(enc, lens)
+    assert toks[1] == [] and steps[1] == 0
+    n_div = _check_tokens(oracle, model, enc, lens, toks, steps)
+    assert n_div <= 1
+    # final state of an un-diverged stream equals the oracle's (carried unconditionally, also on blank)
+    r = oracle.greedy_decode(np.ascontiguousarray(enc[0, :, :T]), T, model)
+    if r.tokens == toks[0]:
+        assert np.abs(st.states_1[:, 0] - r.states_1.reshape(2, 640)).max() < 1e-4
+        assert np.abs(st.states_2[:, 0] - r.states_2.reshape(2, 640)).max() < 1e-4
+    emitted = sum(len(t) for t in toks)
+    assert 0 < emitted < int(lens.sum()) * 30
+
+
+def test_greedy_carried_state_streaming(ctx, oracle, model, amira):
+    """Chunked decode with carried LSTM state == the oracle run chunk by chunk (tokens history is per call)."""
+    rng = np.random.default_rng(77)
+    enc = (0.5 * rng.standard_normal((2, 1024, 12))).astype(np.float32)
+    st = amira.DecoderState.new(2)
+    o_s = [(np.zeros((2, 1, 640), np.float32), np.zeros((2, 1, 640), np.float32)) for _ in range(2)]
+    for c in range(4):
+        chunk = np.ascontiguousarray(enc[:, :, 3 * c:3 * c + 3])
+        toks, st, _ = ctx.greedy_decode(chunk, [3, 3], state=st)
+        for b in range(2):
+            r = oracle.greedy_decode(chunk[b], 3, model, states=o_s[b])
+            o_s[b] = (r.states_1, r.states_2)
+            assert toks[b] == r.tokens or r.margins.min() < NEAR_TIE
+    # resident slots give the same answer as caller-owned state
+    s0, s1 = ctx.stream_open(), ctx.stream_open()
+    got = [[], []]
+    for c in range(4):
+        chunk = np.ascontiguousarray(enc[:, :, 3 * c:3 * c + 3])
+        toks, _ = ctx.stream_decode([s0, s1], chunk)
+        got[0] += toks[0]
+        got[1] += toks[1]
+    fin = ctx.stream_get_state(s1)
+    assert np.abs(fin.states_1[:, 0] - st.states_1[:, 1]).max() < 1e-6
+    ctx.stream_close(s0)
+    ctx.stream_close(s1)
+
+
+def test_limits_max_symbols_and_max_total(oracle, amira):
+    """Mock-model KATs of the reference loop (decoder_optimized.rs:331-366 derived): a model that never predicts blank
+    emits exactly max_symbols tokens per frame and stops at max_total_tokens."""
+    blob = calibrated_weights(oracle, blank_bias=-50.0)  # blank never wins
+    model = oracle.Model(blob=blob)
+    rng = np.random.default_rng(3)
+    enc = (0.5 * rng.standard_normal((2, 1024, 9))).astype(np.float32)
+    with amira.Context(device_id=0) as c:
+        c.load_weights(blob)
+        toks, _, steps = c.greedy_decode(enc, [3, 9])
+        assert len(toks[0]) == 90 and steps[0] == 90       # 3 frames x 30 symbols
+        assert len(toks[1]) == 200 and steps[1] == 200     # capped inside frame 6
+        for b, L in ((0, 3), (1, 9)):
+            r = oracle.greedy_decode(np.ascontiguousarray(enc[b, :, :L]), L, model)
+            assert toks[b] == r.tokens or r.margins.min() < NEAR_TIE
+    with amira.Context(device_id=0, max_symbols_per_step=2, max_total_tokens=5) as c:
+        c.load_weights(blob)
+        toks, _, steps = c.greedy_decode(enc, [2, 9])
+        assert len(toks[0]) == 4 and len(toks[1]) == 5 and steps[1] == 5
+
+
+def test_all_blank_updates_state_every_frame(oracle, amira):
+    blob = calibrated_weights(oracle, blank_bias=50.0)  # blank always wins
+    model = oracle.Model(blob=blob)
+    rng = np.random.default_rng(4)
+    enc = (0.5 * rng.standard_normal((1, 1024, 7))).astype(np.float32)
+    with amira.Context(device_id=0) as c:
+        c.load_weights(blob)
+        toks, st, steps = c.greedy_decode(enc)
+        assert toks[0] == [] and steps[0] == 7
+        r = oracle.greedy_decode(enc[0], 7, model)
+        assert r.n_steps == 7 and np.abs(st.states_1[:, 0] - r.states_1.reshape(2, 640)).max() < 1e-5
+
+
+def test_out_of_table_argmax_fails_the_stream(oracle, amira):
+    """Flat argmax over all 1030 outputs (zero_copy.rs:190-232) can pick 1025..1029; the reference's next step then
+    fails ("Decode step failed").  Same here: n_tokens = -1 for that stream, status AMIRA_ERR_DECODE_STEP."""
+    m = oracle.Model(seed=3456)
+    blob = m.blob.copy()
+    blob[-1030:][1027] += 100.0
+    rng = np.random.default_rng(9)
+    enc = (0.5 * rng.standard_normal((1, 1024, 3))).astype(np.float32)
+    r = oracle.greedy_decode(enc[0], 3, oracle.Model(blob=blob))
+    assert r.rc == -1
+    with amira.Context(device_id=0) as c:
+        c.load_weights(blob)
+        toks, _, _ = c.greedy_decode(enc, allow_failed=True)
+        assert toks[0] is None
+        with pytest.raises(amira.AmiraError) as e:
+            c.greedy_decode(enc)
+        assert e.value.code == 6
+
+
+def test_no_weights_is_an_error(amira):
+    with amira.Context(device_id=0) as c:
+        with pytest.raises(amira.AmiraError) as e:
+            c.greedy_decode(np.zeros((1, 1024, 1), np.float32))
+        assert e.value.code == 7

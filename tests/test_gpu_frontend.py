@@ -1,0 +1,107 @@
+"""GPU parity of the fused front end against the CPU oracle (float64 restatement of the preprocessor spec).
+Tolerance from BASELINE.json north_star: max abs error <= 1e-4 after normalisation."""
+import numpy as np
+import pytest
+
+from conftest import synth_pcm
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _oracle_feats(O, pcm_list, t_stride):
+    out = np.zeros((len(pcm_list), 128, t_stride), np.float32)
+    lens = []
+    for b, p in enumerate(pcm_list):
+        w = p.astype(np.float32) / 32768.0
+        if w.size:
+            f, L = O.preprocess(w, "f64", t_stride=t_stride)
+            out[b] = f
+        else:
+            L = 0
+        lens.append(L)
+    return out, np.array(lens)
+
+
+def _pack(pcm_list):
+    offs = np.zeros(len(pcm_list) + 1, np.int64)
+    offs[1:] = np.cumsum([p.size for p in pcm_list])
+    return (np.concatenate(pcm_list) if offs[-1] else np.zeros(0, np.int16)), offs
+
+
+def test_bytes_to_f32_matches_reference_rule(ctx, oracle):
+    raw = bytes((i * 37 + 11) % 256 for i in range(1001))  # odd length: trailing-byte rule, performance_opts.rs:26-30
+    for data in (raw, raw[:-1], raw[:6], raw[:1], b"", bytes([0, 128, 255, 0, 64, 192])):
+        got = ctx.bytes_to_f32(data)
+        assert np.array_equal(got, oracle.bytes_to_f32_optimized(data))
+        got = ctx.bytes_to_f32(data, drop_odd=True)
+        assert np.array_equal(got, oracle.bytes_to_f32_samples(data))
+
+
+def test_single_utterance_10s(ctx, oracle):
+    pcm = synth_pcm(10.0, 1234)
+    feats, lens = ctx.preprocess_pcm16(pcm, [0, pcm.size])
+    ref, rl = _oracle_feats(oracle, [pcm], feats.shape[2])
+    assert lens.tolist() == rl.tolist() == [1001]
+    assert np.abs(feats - ref).max() <= TOL
+
+
+def test_ragged_batch_with_padding_and_edge_lengths(ctx, oracle):
+    secs = [0.5, 3.21, 1.0, 0.01, 2.0]
+    pcms = [synth_pcm(s, 100 + i) for i, s in enumerate(secs)]
+    pcms += [synth_pcm(1.0, 7)[:n] for n in (1, 2, 159, 160, 161, 255, 256, 257, 300, 511, 513, 5120, 5121)]
+    pcms.insert(3, np.zeros(0, np.int16))  # empty utterance: features_len 0, all-zero row
+    pcm, offs = _pack(pcms)
+    t_stride = 328
+    feats, lens = ctx.preprocess_pcm16(pcm, offs, t_stride=t_stride)
+    ref, rl = _oracle_feats(oracle, pcms, t_stride)
+    assert lens.tolist() == rl.tolist()
+    for b in range(len(pcms)):
+        L = int(lens[b])
+        assert np.all(feats[b, :, L:] == 0.0), b
+        if L > 1:
+            err = np.abs(feats[b] - ref[b]).max()
+            assert err <= TOL, (b, pcms[b].size, err)
+        elif L == 1:
+            # one frame: std = 0, (x - mean) / 1e-5 amplifies rounding; the value is 0 in exact arithmetic
+            assert np.abs(feats[b]).max() <= 1e-2
+
+
+def test_f32_contract_form_matches_pcm_form(ctx, oracle):
+    pcms = [synth_pcm(2.0, 5), synth_pcm(1.3, 6)]
+    N = max(p.size for p in pcms)
+    wav = np.zeros((2, N), np.float32)
+    for b, p in enumerate(pcms):
+        wav[b, :p.size] = p.astype(np.float32) / 32768.0
+    feats, lens = ctx.preprocessor(wav, [p.size for p in pcms])
+    ref, rl = _oracle_feats(oracle, pcms, feats.shape[2])
+    assert lens.tolist() == rl.tolist()
+    assert np.abs(feats - ref).max() <= TOL
+    pcm, offs = _pack(pcms)
+    f2, _ = ctx.preprocess_pcm16(pcm, offs, t_stride=feats.shape[2])
+    assert np.abs(f2 - feats).max() <= 1e-5
+
+
+def test_full_size_properties_64x30s(ctx):
+    """BASELINE config 2 (64 x 30 s): size-independent properties — zero mean / unit variance per (utterance, mel)
+    over valid frames, zero padding, batch invariance (row b equals the same utterance run alone)."""
+    base = [synth_pcm(30.0, 1234 + i) for i in range(4)]
+    pcms = [base[i % 4] for i in range(64)]
+    pcm, offs = _pack(pcms)
+    feats, lens = ctx.preprocess_pcm16(pcm, offs, t_stride=3008)
+    assert np.all(lens == 3001)
+    v = feats[:, :, :3001].astype(np.float64)
+    assert np.abs(v.mean(axis=2)).max() < 1e-4
+    assert np.abs(v.std(axis=2, ddof=1) - 1.0).max() < 1e-3
+    assert np.all(feats[:, :, 3001:] == 0)
+    for i in range(4, 64):
+        assert np.array_equal(feats[i], feats[i % 4])
+    alone, _ = ctx.preprocess_pcm16(base[1], [0, base[1].size], t_stride=3008)
+    assert np.array_equal(alone[0], feats[1])
+
+
+def test_invalid_arguments(ctx, amira):
+    pcm = synth_pcm(1.0, 1)
+    with pytest.raises(amira.AmiraError) as e:
+        ctx.preprocess_pcm16(pcm, [0, pcm.size], t_stride=50)  # features_len is 101
+    assert e.value.code == 1
