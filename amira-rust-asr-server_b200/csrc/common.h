@@ -1,5 +1,6 @@
 // common.h — internal declarations shared by the translation units of libamira_b200.so.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -163,5 +164,14 @@ const int32_t *decoder_fail_count_dev(Ctx *c);  // failed-stream counter of the 
 cudaError_t launch_decoder_joint(Ctx *c, const float *enc_dev, int B, int T, const int32_t *targets_dev, int U,
                                  const int32_t *tlen_dev, const float *in_s1, const float *in_s2, float *outputs,
                                  int32_t *prednet_lengths, float *out_s1, float *out_s2, int32_t *err_flag_dev);
+
+
+// decoder_tc.cu (tcgen05 paths) --------------------------------------------------------------------------------
+cudaError_t launch_tc_gemm(Ctx *c, const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_lo, const __nv_bfloat16 *w_hi,
+                           const __nv_bfloat16 *w_lo, const float *bias, float *C, long long ldc, int M, int N, int K);
+cudaError_t launch_split_rows(Ctx *c, const float *x, size_t ldx, __nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t ldo,
+                              size_t rows, size_t cols);
+cudaError_t launch_split_transpose_enc(Ctx *c, const float *enc, int B, int T, const int *lens_dev, __nv_bfloat16 *hi,
+                                       __nv_bfloat16 *lo);
 
 }  // namespace amira

@@ -88,6 +88,11 @@ int32_t amira_ctx_launch_count(amira_ctx *ctx, int64_t *count);
 int32_t amira_ctx_profile(amira_ctx *ctx, int32_t enable);
 int32_t amira_ctx_kernel_ms(amira_ctx *ctx, int32_t kernel, double *total_ms, int64_t *launches);
 
+/* diagnostics: C[M][N] = A[M][K] W[N][K]^T + bias (nullable) through the tcgen05 split-bf16 GEMM that serves the
+ * hoisted encoder projection; host pointers; K % 8 == 0.  Unit test hook for the UMMA descriptor conventions. */
+int32_t amira_debug_tc_gemm(amira_ctx *ctx, const float *A, const float *W, const float *bias, int32_t M, int32_t N,
+                            int32_t K, float *C);
+
 /* ---- weights: stand-in for model-repo/decoder_joint/1/model.onnx (absent LFS object) ---- */
 /* flat fp32 blob, order: emb[1025][640]; per layer l=0,1: w_ih[2560][640], w_hh[2560][640], b_ih[2560],
  * b_hh[2560]; w_enc[640][1024], b_enc[640]; w_pred[640][640], b_pred[640]; w_out[1030][640], b_out[1030]. */
