@@ -486,7 +486,7 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
     CK(stage_out<int32_t>(c, 3, tokens, (size_t)B * cap, &tok_dev, &tok_h), "tokens staging");
     CK(stage_out<int32_t>(c, 4, n_tokens, (size_t)B, &nt_dev, &nt_h), "n_tokens staging");
     CK(stage_out<int32_t>(c, 5, n_steps, (size_t)B, &ns_dev, &ns_h), "n_steps staging");
-    CK(launch_greedy_decode(c, enc_dev, B, T, lens_dev, slots_dev, s1_dev, s2_dev, tok_dev, nt_dev, ns_dev),
+    CK(launch_greedy_decode(c, enc_dev, B, T, lens_dev, h_lens, slots_dev, s1_dev, s2_dev, tok_dev, nt_dev, ns_dev),
        "greedy decode launch");
     CK(finish_out<int32_t>(c, tokens, tok_dev, (size_t)B * cap, tok_h), "tokens D2H");
     CK(finish_out<int32_t>(c, n_tokens, nt_dev, (size_t)B, nt_h), "n_tokens D2H");

@@ -91,7 +91,14 @@ struct PinBuf {
     }
 };
 
-struct DecoderPriv;  // decoder.cu
+struct TcWeights;  // decoder_tc.cu
+struct DecoderPriv {  // derived weight tables (decoder.cu) + tcgen05 operands (decoder_tc.cu)
+    float *g0p = nullptr, *whh0p = nullptr, *w1p = nullptr, *b1p = nullptr, *bjoint = nullptr, *woutp = nullptr, *boutp = nullptr;
+    DevBuf work;
+    int coop_blocks_per_sm = 0;
+    int *fail_count_dev = nullptr;  // valid after a greedy launch
+    TcWeights *tc = nullptr;
+};
 
 struct Ctx {
     amira_config cfg{};
@@ -158,7 +165,7 @@ void decoder_release(Ctx *c);
 // enc_dev [B][1024][T]; lens_dev int32[B]; slots_dev nullable: when given, states live in c->slot_s1/2 rows
 // slots[b] ([slot][2][640]); otherwise s1/s2 are [2][B][640] in/out (nullable => zero start, result dropped).
 cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, int B, int T, const int32_t *lens_dev,
-                                 const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev,
+                                 const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev,
                                  int32_t *ntok_dev, int32_t *nsteps_dev);
 const int32_t *decoder_fail_count_dev(Ctx *c);  // failed-stream counter of the last greedy launch
 cudaError_t launch_decoder_joint(Ctx *c, const float *enc_dev, int B, int T, const int32_t *targets_dev, int U,
@@ -167,6 +174,11 @@ cudaError_t launch_decoder_joint(Ctx *c, const float *enc_dev, int B, int T, con
 
 
 // decoder_tc.cu (tcgen05 paths) --------------------------------------------------------------------------------
+cudaError_t decoder_tc_prepare_weights(Ctx *c);
+void decoder_tc_release(Ctx *c);
+cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, int B, int T, const int32_t *lens_dev,
+                                    const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev,
+                                    int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev);
 cudaError_t launch_tc_gemm(Ctx *c, const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_lo, const __nv_bfloat16 *w_hi,
                            const __nv_bfloat16 *w_lo, const float *bias, float *C, long long ldc, int M, int N, int K);
 cudaError_t launch_split_rows(Ctx *c, const float *x, size_t ldx, __nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t ldo,

@@ -559,13 +559,6 @@ __global__ void fill_int_kernel(int *p, const int *src, int v, int n) {
 
 }  // namespace
 
-struct DecoderPriv {
-    float *g0p = nullptr, *whh0p = nullptr, *w1p = nullptr, *b1p = nullptr, *bjoint = nullptr, *woutp = nullptr, *boutp = nullptr;
-    DevBuf work;
-    int coop_blocks_per_sm = 0;
-    int *fail_count_dev = nullptr;  // valid after launch_greedy_decode
-};
-
 const int32_t *decoder_fail_count_dev(Ctx *c) { return c->dec ? c->dec->fail_count_dev : nullptr; }
 
 void decoder_release(Ctx *c) {
@@ -573,6 +566,7 @@ void decoder_release(Ctx *c) {
     DecoderPriv *d = c->dec;
     for (float *p : {d->g0p, d->whh0p, d->w1p, d->b1p, d->bjoint, d->woutp, d->boutp})
         if (p) cudaFree(p);
+    decoder_tc_release(c);
     d->work.release();
     delete d;
     c->dec = nullptr;
@@ -619,14 +613,18 @@ cudaError_t decoder_prepare_weights(Ctx *c) {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, greedy_persistent_kernel, DEC_THREADS, 0);
     if (e != cudaSuccess) return e;
     d->coop_blocks_per_sm = nb < 1 ? 1 : nb;
-    return cudaSuccess;
+    return decoder_tc_prepare_weights(c);
 }
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, int B, int T, const int32_t *lens_dev,
-                                 const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev,
-                                 int32_t *ntok_dev, int32_t *nsteps_dev) {
+                                 const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev,
+                                 int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev) {
+    // decode_engine: 1 = fp32 CUDA-core persistent kernel (this file), 2 = tcgen05 split-bf16 (decoder_tc.cu), 0 = auto
+    if (c->cfg.decode_engine == 2 || c->cfg.decode_engine == 0)
+        return launch_greedy_decode_tc(c, enc_dev, B, T, lens_dev, lens_host, slots_dev, s1_dev, s2_dev, tokens_dev, ntok_dev,
+                                       nsteps_dev);
     DecoderPriv *d = c->dec;
     const BlobLayout L = blob_layout();
     const size_t BH = (size_t)B * kH;

@@ -12,6 +12,18 @@ pytestmark = pytest.mark.gpu
 NEAR_TIE = 2e-4
 
 
+ENGINES = {1: "fp32 persistent kernel", 2: "tcgen05 split-bf16 persistent kernel"}
+
+
+@pytest.fixture(scope="module", params=[1, 2], ids=["fp32", "tcgen05"])
+def ctx(request, amira):
+    """One context per decode engine: every test in this module runs against both."""
+    c = amira.Context(device_id=0, decode_engine=request.param)
+    c.engine = request.param
+    yield c
+    c.close()
+
+
 @pytest.fixture(scope="module")
 def model(oracle, ctx):
     blob = calibrated_weights(oracle)
@@ -106,14 +118,15 @@ def test_greedy_carried_state_streaming(ctx, oracle, model, amira):
     ctx.stream_close(s1)
 
 
-def test_limits_max_symbols_and_max_total(oracle, amira):
+@pytest.mark.parametrize("engine", [1, 2])
+def test_limits_max_symbols_and_max_total(oracle, amira, engine):
     """Mock-model KATs of the reference loop (decoder_optimized.rs:331-366 derived): a model that never predicts blank
     emits exactly max_symbols tokens per frame and stops at max_total_tokens."""
     blob = calibrated_weights(oracle, blank_bias=-50.0)  # blank never wins
     model = oracle.Model(blob=blob)
     rng = np.random.default_rng(3)
     enc = (0.5 * rng.standard_normal((2, 1024, 9))).astype(np.float32)
-    with amira.Context(device_id=0) as c:
+    with amira.Context(device_id=0, decode_engine=engine) as c:
         c.load_weights(blob)
         toks, _, steps = c.greedy_decode(enc, [3, 9])
         assert len(toks[0]) == 90 and steps[0] == 90       # 3 frames x 30 symbols
@@ -121,18 +134,19 @@ def test_limits_max_symbols_and_max_total(oracle, amira):
         for b, L in ((0, 3), (1, 9)):
             r = oracle.greedy_decode(np.ascontiguousarray(enc[b, :, :L]), L, model)
             assert toks[b] == r.tokens or r.margins.min() < NEAR_TIE
-    with amira.Context(device_id=0, max_symbols_per_step=2, max_total_tokens=5) as c:
+    with amira.Context(device_id=0, max_symbols_per_step=2, max_total_tokens=5, decode_engine=engine) as c:
         c.load_weights(blob)
         toks, _, steps = c.greedy_decode(enc, [2, 9])
         assert len(toks[0]) == 4 and len(toks[1]) == 5 and steps[1] == 5
 
 
-def test_all_blank_updates_state_every_frame(oracle, amira):
+@pytest.mark.parametrize("engine", [1, 2])
+def test_all_blank_updates_state_every_frame(oracle, amira, engine):
     blob = calibrated_weights(oracle, blank_bias=50.0)  # blank always wins
     model = oracle.Model(blob=blob)
     rng = np.random.default_rng(4)
     enc = (0.5 * rng.standard_normal((1, 1024, 7))).astype(np.float32)
-    with amira.Context(device_id=0) as c:
+    with amira.Context(device_id=0, decode_engine=engine) as c:
         c.load_weights(blob)
         toks, st, steps = c.greedy_decode(enc)
         assert toks[0] == [] and steps[0] == 7
@@ -140,7 +154,8 @@ def test_all_blank_updates_state_every_frame(oracle, amira):
         assert r.n_steps == 7 and np.abs(st.states_1[:, 0] - r.states_1.reshape(2, 640)).max() < 1e-5
 
 
-def test_out_of_table_argmax_fails_the_stream(oracle, amira):
+@pytest.mark.parametrize("engine", [1, 2])
+def test_out_of_table_argmax_fails_the_stream(oracle, amira, engine):
     """Flat argmax over all 1030 outputs (zero_copy.rs:190-232) can pick 1025..1029; the reference's next step then
     fails ("Decode step failed").  Same here: n_tokens = -1 for that stream, status AMIRA_ERR_DECODE_STEP."""
     m = oracle.Model(seed=3456)
@@ -150,7 +165,7 @@ def test_out_of_table_argmax_fails_the_stream(oracle, amira):
     enc = (0.5 * rng.standard_normal((1, 1024, 3))).astype(np.float32)
     r = oracle.greedy_decode(enc[0], 3, oracle.Model(blob=blob))
     assert r.rc == -1
-    with amira.Context(device_id=0) as c:
+    with amira.Context(device_id=0, decode_engine=engine) as c:
         c.load_weights(blob)
         toks, _, _ = c.greedy_decode(enc, allow_failed=True)
         assert toks[0] is None
