@@ -26,7 +26,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + \
-           [os.path.join(INCLUDE, "amira_b200.h")]
+           [os.path.join(INCLUDE, "amira_b200.h"), os.path.join(INCLUDE, "amira_hann400.h")]
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs = []

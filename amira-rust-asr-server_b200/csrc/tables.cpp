@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "amira_hann400.h"
 #include "common.h"
 
 namespace amira {
@@ -37,9 +38,8 @@ void build_mel_filterbank(float *fb) {
 
 void build_frontend_tables(FrontendTables *t) {
     std::memset(t, 0, sizeof(*t));
-    const double pi = 3.14159265358979323846;
-    for (int n = 0; n < kWin; ++n)
-        t->win[(kNfft - kWin) / 2 + n] = (float)(0.5 - 0.5 * std::cos(2.0 * pi * n / (kWin - 1)));
+    // window = the float32 buffer torch.hann_window(400, periodic=False) yields (include/amira_hann400.h)
+    for (int n = 0; n < kWin; ++n) std::memcpy(&t->win[(kNfft - kWin) / 2 + n], &AMIRA_HANN400_BITS[n], sizeof(float));
     std::vector<float> fb((size_t)kMel * kNbin);
     build_mel_filterbank(fb.data());
     for (int m = 0; m < kMel; ++m) {

@@ -310,7 +310,7 @@ def main():
     out = {
         "metric": "audio-sec/sec (preproc + RNN-T greedy decode)", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64 fft + f32 mel / f32 decode" if args.engine != 2 else "f64 fft + f32 mel / split-bf16 tcgen05 decode",
+        "vs_baseline": None, "dtype": "f64 fft + f32 mel / f32 decode" if args.engine == 1 else "f64 fft + f32 mel / split-bf16 tcgen05 decode (f32 accumulate)",
         "data": "synthetic",
         "config": {"workload": f"BASELINE cfg5 per-GPU shard: {B} utterances x U[5,30] s 16 kHz PCM ({audio_s:.0f} audio-s, "
                                f"{pcm.nbytes / 1e6:.0f} MB PCM in, {4 * 128 * int(flens.sum()) / 1e6:.0f} MB features out) + greedy "
@@ -319,11 +319,11 @@ def main():
                    "global_utterances": B * world, "parallelism": f"dp{world} by utterance, no collective",
                    "cache": "inputs larger than L2 (PCM + encoder outputs > 2 GB per step)",
                    "decode_steps_per_step": int(nsteps.sum()), "tokens_per_step": int(ntok[ntok > 0].sum()),
-                   "decode_engine": "fp32 persistent cooperative kernel" if args.engine != 2 else "tcgen05 split-bf16"},
+                   "decode_engine": "fp32 persistent cooperative kernel" if args.engine == 1 else "tcgen05 split-bf16 persistent kernel"},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "kernel_ms_per_step": share,
-        "roofline": {"kernel": "greedy_persistent_kernel", "bound": "tensor", "achieved": ach_tf, "peak": tf_peak,
+        "roofline": {"kernel": "greedy_persistent_kernel" if args.engine == 1 else "greedy_tc_kernel", "bound": "tensor", "achieved": ach_tf, "peak": tf_peak,
                      "unit": "TFLOP/s", "frac": ach_tf / tf_peak, "traffic": None, "peak_kind": f"bf16 sustained, {peak_kind}",
                      "flops_per_launch": flops, "avg_launch_ms": dec_avg_ms},
         "roofline_frontend": {"kernel": "fe_logmel_kernel", "bound": "hbm", "achieved": fe_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -6,6 +6,7 @@
  * compiled with -ffp-contract=off so results do not depend on the host's FMA support.
  */
 #include "amira_oracle.h"
+#include "../include/amira_hann400.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -141,11 +142,15 @@ void orc_mel_filterbank(float *fb) {
     }
 }
 
-/* torch.hann_window(400, periodic=False) placed at offset 56 of a 512 frame (torch.stft window padding). */
+/* torch.hann_window(400, periodic=False) (float32 table, include/amira_hann400.h) placed at offset 56 of a 512
+ * frame (torch.stft window padding). */
 void orc_hann_window_padded(double *w512) {
-    const double pi = 3.14159265358979323846;
     memset(w512, 0, sizeof(double) * ORC_NFFT);
-    for (int n = 0; n < ORC_WIN; ++n) w512[(ORC_NFFT - ORC_WIN) / 2 + n] = 0.5 - 0.5 * cos(2.0 * pi * n / (ORC_WIN - 1));
+    for (int n = 0; n < ORC_WIN; ++n) {
+        float f;
+        memcpy(&f, &AMIRA_HANN400_BITS[n], sizeof(f));
+        w512[(ORC_NFFT - ORC_WIN) / 2 + n] = (double)f;
+    }
 }
 
 /* reflect index (numpy/torch "reflect", repeated for very short signals) */

@@ -32,7 +32,8 @@ N_PARAMS = 8946310
 
 def build(force: bool = False) -> str:
     """Compile the C oracle (gcc; no GPU involved)."""
-    srcs = [os.path.join(_HERE, f) for f in ("amira_oracle.c", "amira_oracle.h", "amira_oracle_frontend.inc")]
+    srcs = [os.path.join(_HERE, f) for f in ("amira_oracle.c", "amira_oracle.h", "amira_oracle_frontend.inc",
+                                             "../include/amira_hann400.h")]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:
         cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
@@ -228,9 +229,7 @@ def preprocess_numpy(wave: np.ndarray) -> tuple[np.ndarray, int]:
     else:
         idx = np.zeros_like(idx)
     ypad = y[idx]
-    win = np.zeros(NFFT)
-    k = np.arange(WIN)
-    win[(NFFT - WIN) // 2:(NFFT - WIN) // 2 + WIN] = (0.5 - 0.5 * np.cos(2 * np.pi * k / (WIN - 1))).astype(np.float32)
+    win = hann_window_padded()  # float32 table of torch.hann_window(400, periodic=False), include/amira_hann400.h
     frames = np.stack([ypad[t * HOP:t * HOP + NFFT] for t in range(L)]) * win[None, :]
     power = np.abs(np.fft.rfft(frames, axis=1)) ** 2  # [L, 257]
     mel = power @ _slaney_fb_numpy().astype(np.float64).T  # [L, 128]

@@ -179,3 +179,36 @@ def test_no_weights_is_an_error(amira):
         with pytest.raises(amira.AmiraError) as e:
             c.greedy_decode(np.zeros((1, 1024, 1), np.float32))
         assert e.value.code == 7
+
+
+def test_golden_fixture(ctx, amira):
+    """Committed golden tokens (tests/golden/make_golden.py, produced by the oracle); min oracle margin there is 7e-3,
+    far above NEAR_TIE, so the comparison is exact."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "decode_golden.npz"))
+    ctx.load_weights(amira.synthetic_weights(int(g["seed"])))
+    toks, _, steps = ctx.greedy_decode(g["enc"].astype(np.float32), g["lens"])
+    for b in range(len(toks)):
+        assert toks[b] == g["tokens"][b, :int(g["n_tokens"][b])].tolist()
+        assert steps[b] == int(g["n_steps"][b])
+    assert float(g["min_margin"].min()) > 10 * NEAR_TIE
+
+
+def test_full_size_batch_256_properties(ctx, amira):
+    """BASELINE config 3 (256 streams, T = 126, limits 30/200): size-independent properties — batch invariance (every
+    stream decodes as it does alone / in a small batch), limits respected, steps = frames visited + tokens."""
+    rng = np.random.default_rng(2345)
+    B, T = 256, 126
+    base = (0.5 * rng.standard_normal((8, 1024, T))).astype(np.float32)
+    enc = np.ascontiguousarray(base[np.arange(B) % 8])
+    lens = np.full(B, T, np.int64)
+    lens[8:16] = 60
+    ctx.load_weights(amira.synthetic_weights(3456))
+    toks, _, steps = ctx.greedy_decode(enc, lens)
+    small, _, ssteps = ctx.greedy_decode(base, np.full(8, T, np.int64))
+    for b in range(B):
+        assert len(toks[b]) <= 200 and 0 <= steps[b] <= 30 * lens[b]
+        if lens[b] == T:
+            assert toks[b] == small[b % 8] and steps[b] == ssteps[b % 8]
+        if len(toks[b]) < 200:
+            assert steps[b] >= lens[b] + len(toks[b]) - 29  # every frame ends with a blank step or the symbol limit

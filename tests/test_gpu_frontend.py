@@ -105,3 +105,12 @@ def test_invalid_arguments(ctx, amira):
     with pytest.raises(amira.AmiraError) as e:
         ctx.preprocess_pcm16(pcm, [0, pcm.size], t_stride=50)  # features_len is 101
     assert e.value.code == 1
+
+
+def test_golden_fixture(ctx):
+    """Committed golden vector (tests/golden/make_golden.py, produced by the float64 oracle)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "frontend_golden.npz"))
+    feats, lens = ctx.preprocess_pcm16(g["pcm"], [0, g["pcm"].size])
+    assert int(lens[0]) == int(g["features_len"])
+    assert np.abs(feats[0, :, :int(lens[0])] - g["features"]).max() <= TOL
