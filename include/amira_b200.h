@@ -60,7 +60,8 @@ typedef struct {
     int32_t max_total_tokens;     /* 200 */
     int32_t blank_id;             /* 1024 */
     int32_t joint_activation;     /* 0 = tanh (north_star), 1 = relu */
-    int32_t decode_engine;        /* 0 = auto, 1 = fp32 CUDA-core persistent kernel, 2 = tcgen05 split-bf16 */
+    int32_t decode_engine;        /* 0 = auto (3); 1 = fp32 CUDA-core persistent kernel; tcgen05 split-bf16 persistent
+                                   * kernels: 2 = grid-synchronised phases, 3 = dataflow (per-M-tile dependency counters) */
     int32_t max_streams;          /* resident stream-state slots for the WebSocket path (default 1024) */
     int32_t reserved;
 } amira_config;
