@@ -21,7 +21,7 @@ STATUS = {0: "AMIRA_OK", 1: "AMIRA_ERR_INVALID_VALUE", 2: "AMIRA_ERR_OUT_OF_MEMO
 # every symbol include/amira_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
 EXPORTS = ["amira_device_count", "amira_config_default", "amira_ctx_create", "amira_ctx_destroy", "amira_last_error",
            "amira_ctx_set_stream", "amira_ctx_synchronize", "amira_ctx_launch_count", "amira_ctx_profile",
-           "amira_ctx_kernel_ms", "amira_debug_tc_gemm", "amira_weights_random_init",
+           "amira_ctx_kernel_ms", "amira_debug_tc_gemm", "amira_debug_ws_trace", "amira_weights_random_init",
            "amira_ctx_load_weights", "amira_ctx_load_weights_file", "amira_features_len", "amira_preprocess_pcm16",
            "amira_preprocess_f32", "amira_bytes_to_f32", "amira_decoder_joint", "amira_greedy_decode",
            "amira_stream_open", "amira_stream_close", "amira_stream_get_state", "amira_stream_set_state",
@@ -73,6 +73,7 @@ def load_library():
     L.amira_ctx_profile.argtypes = [vp, i32]
     L.amira_ctx_kernel_ms.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(i64)]
     L.amira_debug_tc_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    L.amira_debug_ws_trace.argtypes = [vp, vp, i32]
     L.amira_weights_random_init.argtypes = [vp, C.c_size_t, C.c_uint64, C.c_float]
     L.amira_ctx_load_weights.argtypes = [vp, vp, C.c_size_t]
     L.amira_ctx_load_weights_file.argtypes = [vp, C.c_char_p]
@@ -258,6 +259,12 @@ class Context:
         C_ = np.empty((A.shape[0], W.shape[0]), np.float32)
         self._check(self._L.amira_debug_tc_gemm(self._h, _ptr(A), _ptr(W), _ptr(b), A.shape[0], W.shape[0], A.shape[1], _ptr(C_)))
         return C_
+
+    def debug_ws_trace(self, n_its: int = 512) -> np.ndarray:
+        """[n_its][32] globaltimer stamps (ns) of M-tile 0 from the last weight-stationary greedy launch (AMIRA_WS_TRACE=1)."""
+        out = np.zeros((n_its, 32), np.int64)
+        self._check(self._L.amira_debug_ws_trace(self._h, _ptr(out), n_its))
+        return out
 
     # -- weights
     def load_weights(self, blob: np.ndarray):

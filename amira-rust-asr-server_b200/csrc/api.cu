@@ -155,7 +155,7 @@ int32_t amira_ctx_create(const amira_config *cfg, amira_ctx **out) {
     if (!cfg) cfg = &dflt;
     if (cfg->max_symbols_per_step <= 0 || cfg->max_total_tokens <= 0 || cfg->blank_id < 0 || cfg->blank_id >= kV ||
         cfg->max_streams < 0 || cfg->joint_activation < 0 || cfg->joint_activation > 1 || cfg->decode_engine < 0 ||
-        cfg->decode_engine > 3)
+        cfg->decode_engine > 4)
         return fail(nullptr, AMIRA_ERR_INVALID_VALUE, "invalid amira_config");
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {

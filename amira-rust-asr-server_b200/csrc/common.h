@@ -98,6 +98,7 @@ struct DecoderPriv {  // derived weight tables (decoder.cu) + tcgen05 operands (
     int coop_blocks_per_sm = 0;
     int *fail_count_dev = nullptr;  // valid after a greedy launch
     TcWeights *tc = nullptr;
+    long long *ws_trace_dev = nullptr;  // decoder_ws.cu debug trace of the last launch (AMIRA_WS_TRACE=1)
 };
 
 struct Ctx {
@@ -185,5 +186,14 @@ cudaError_t launch_split_rows(Ctx *c, const float *x, size_t ldx, __nv_bfloat16 
                               size_t rows, size_t cols);
 cudaError_t launch_split_transpose_enc(Ctx *c, const float *enc, int B, int T, const int *lens_dev, __nv_bfloat16 *hi,
                                        __nv_bfloat16 *lo);
+
+
+// decoder_ws.cu (weight-stationary dataflow engine, decode_engine = 4) ------------------------------------------
+bool decoder_ws_supported(const Ctx *c);
+cudaError_t decoder_ws_prepare(Ctx *c);
+// work == nullptr: size query (*work_bytes receives the workspace size).  E [B*T][640] and perm_dev [Mpad] from the caller.
+cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t *lens_dev, const int *perm_dev,
+                             const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
+                             int32_t *nsteps_dev, char *work, size_t *work_bytes);
 
 }  // namespace amira

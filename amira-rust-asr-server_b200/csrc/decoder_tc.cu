@@ -1044,13 +1044,6 @@ __global__ void __launch_bounds__(D_THREADS, 1) greedy_df_kernel(const __grid_co
 }  // namespace
 
 // ---- host side of engine 2 ----
-struct TcWeights {
-    __nv_bfloat16 *whh0_hi = nullptr, *whh0_lo = nullptr, *w1_hi = nullptr, *w1_lo = nullptr, *wp_hi = nullptr, *wp_lo = nullptr,
-                  *wo_hi = nullptr, *wo_lo = nullptr, *we_hi = nullptr, *we_lo = nullptr;
-    CUtensorMap m_whh0_hi, m_whh0_lo, m_w1_hi, m_w1_lo, m_wp_hi, m_wp_lo, m_wo_hi, m_wo_lo;
-    int coop_blocks_per_sm = 0;
-};
-
 void decoder_tc_release(Ctx *c) {
     if (!c->dec || !c->dec->tc) return;
     TcWeights *w = c->dec->tc;
@@ -1093,7 +1086,7 @@ cudaError_t decoder_tc_prepare_weights(Ctx *c) {
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, greedy_tc_kernel, T_THREADS, T_SMEM)) != cudaSuccess) return e;
     if (nb < 1) return cudaErrorLaunchOutOfResources;
     w->coop_blocks_per_sm = 1;  // one CTA per SM: the smem ring and 256 TMEM columns are sized for that
-    return cudaSuccess;
+    return decoder_ws_prepare(c);
 }
 
 static size_t tc_align(size_t x) { return (x + 1023) & ~(size_t)1023; }
@@ -1106,18 +1099,28 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, int B, int T, 
     const int Tq = T > 0 ? T : 1;
     const int MT = (B + T_BM - 1) / T_BM, Mpad = MT * T_BM;
     if (MT > MAX_MT) return cudaErrorInvalidValue;
+    // decode_engine 0 (auto) / 4: weight-stationary dataflow kernel (decoder_ws.cu) when the device has the 147 SMs it needs
+    const bool use_ws = (c->cfg.decode_engine == 0 || c->cfg.decode_engine == 4) && decoder_ws_supported(c);
     const size_t MH = (size_t)Mpad * kH;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += tc_align(bytes); return o; };
     const size_t oE = take(sizeof(float) * (size_t)B * Tq * kH);
     const size_t oeh = take(2 * (size_t)B * Tq * kEnc), oel = take(2 * (size_t)B * Tq * kEnc);
-    const size_t oh0h = take(2 * 2 * MH), oh0l = take(2 * 2 * MH), oh1h = take(2 * 2 * MH), oh1l = take(2 * 2 * MH);
-    const size_t ozh = take(2 * MH), ozl = take(2 * MH);
-    const size_t oh0f = take(4 * MH), oh1f = take(4 * MH), oc0 = take(4 * MH), oc1 = take(4 * MH);
-    const size_t opv = take(sizeof(float) * (size_t)Mpad * NPART), opi = take(sizeof(int) * (size_t)Mpad * NPART);
-    const size_t octl = take(sizeof(TCtl) * (size_t)Mpad), operm = take(sizeof(int) * (size_t)Mpad);
-    const size_t ocnt = take(sizeof(int) * (7 * (size_t)MT + 4));
+    const size_t operm = take(sizeof(int) * (size_t)Mpad);
+    size_t ows = 0, ws_bytes = 0;
+    size_t oh0h = 0, oh0l = 0, oh1h = 0, oh1l = 0, ozh = 0, ozl = 0, oh0f = 0, oh1f = 0, oc0 = 0, oc1 = 0, opv = 0, opi = 0, octl = 0, ocnt = 0;
     cudaError_t e;
+    if (use_ws) {
+        if ((e = launch_greedy_ws(c, nullptr, B, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &ws_bytes)) != cudaSuccess) return e;
+        ows = take(ws_bytes);
+    } else {
+        oh0h = take(2 * 2 * MH); oh0l = take(2 * 2 * MH); oh1h = take(2 * 2 * MH); oh1l = take(2 * 2 * MH);
+        ozh = take(2 * MH); ozl = take(2 * MH);
+        oh0f = take(4 * MH); oh1f = take(4 * MH); oc0 = take(4 * MH); oc1 = take(4 * MH);
+        opv = take(sizeof(float) * (size_t)Mpad * NPART); opi = take(sizeof(int) * (size_t)Mpad * NPART);
+        octl = take(sizeof(TCtl) * (size_t)Mpad);
+        ocnt = take(sizeof(int) * (7 * (size_t)MT + 4));
+    }
     if ((e = d->work.reserve(off)) != cudaSuccess) return e;
     char *base = d->work.as<char>();
 
@@ -1128,9 +1131,6 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, int B, int T, 
     std::stable_sort(h_perm, h_perm + B, [&](int a, int b2) { return lens_host[a] > lens_host[b2]; });
     for (int i = B; i < Mpad; ++i) h_perm[i] = 0;
     if ((e = cudaMemcpyAsync(base + operm, h_perm, sizeof(int) * (size_t)Mpad, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(base + ocnt, 0, sizeof(int) * (7 * (size_t)MT + 4), c->stream)) != cudaSuccess) return e;
-    // activation buffers start defined (padding rows feed the MMA too)
-    if ((e = cudaMemsetAsync(base + oh0h, 0, (ozl + tc_align(2 * MH)) - oh0h, c->stream)) != cudaSuccess) return e;
 
     float *E = reinterpret_cast<float *>(base + oE);
     if (T > 0) {  // hoisted encoder projection on tcgen05: E[(b,t)][:] = W_enc enc[b][:, t] + b_enc + b_pred
@@ -1139,6 +1139,13 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, int B, int T, 
         if ((e = launch_split_transpose_enc(c, enc_dev, B, T, lens_dev, eh, el)) != cudaSuccess) return e;
         if ((e = launch_tc_gemm(c, eh, el, w->we_hi, w->we_lo, d->bjoint, E, kH, B * T, kH, kEnc)) != cudaSuccess) return e;
     }
+    if (use_ws)
+        return launch_greedy_ws(c, E, B, T, lens_dev, reinterpret_cast<int *>(base + operm), slots_dev, s1_dev, s2_dev, tokens_dev,
+                                ntok_dev, nsteps_dev, base + ows, &ws_bytes);
+
+    if ((e = cudaMemsetAsync(base + ocnt, 0, sizeof(int) * (7 * (size_t)MT + 4), c->stream)) != cudaSuccess) return e;
+    // activation buffers start defined (padding rows feed the MMA too)
+    if ((e = cudaMemsetAsync(base + oh0h, 0, (ozl + tc_align(2 * MH)) - oh0h, c->stream)) != cudaSuccess) return e;
 
     TcDecParams p;
     std::memset(&p, 0, sizeof(p));

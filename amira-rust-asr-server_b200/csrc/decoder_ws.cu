@@ -1,0 +1,817 @@
+// decoder_ws.cu — weight-stationary dataflow greedy decode on tcgen05 (decode_engine = 4, the default on B200).
+//
+// Same algebra, control flow and split-bf16 arithmetic as decoder_tc.cu (citations there and in decoder.cu: the loop is
+// src/asr/decoder_optimized.rs:54-200, the step is src/asr/pipeline.rs:323-348 + src/triton/model.rs:581-722), but the
+// work is laid out around one observation: the decoder weights split into exactly 147 slices of 64 output features x
+// 640 inputs (layer-0 recurrent 40, layer-1 input 40, layer-1 recurrent 40, prediction projection 10, vocabulary 17),
+// and one slice as split bf16 (hi + lo, 160 KB) fits the shared memory of one SM.  So:
+//   * CTA s owns slice s for the whole kernel: its weights are loaded into shared memory ONCE (TMA, 128B swizzle) and
+//     are never read from L2 again.  Only activations stream: per (128-stream M-tile, decode step) a CTA pulls the
+//     128 x 640 hi/lo activation tile through a 4 x 16 KB TMA ring (measured: that ring sustains the SM's ~131 GB/s L2
+//     ingest port) and issues 80 tcgen05.mma per unit: per k-step a_hi x [w_hi ; w_lo] (M=128, N=128: w_lo sits directly
+//     below w_hi, so one instruction yields both products in two 64-column halves of the accumulator) and a_lo x w_hi
+//     (N=64, into the first half); the epilogue adds the halves.  Four 128-column accumulators live in TMEM.
+//   * Every CTA does exactly one unit of work per (M-tile, step): the schedule is static, perfectly balanced, and each
+//     phase of a step runs on all of its slices' SMs at once (40 SMs per LSTM layer GEMM), which keeps the per-step
+//     dependency chain short: layer-0 epilogue -> layer-1 input GEMM -> joint hidden GEMM -> vocabulary GEMM -> control.
+//   * The two recurrent contractions (h0(t-1) W_hh0 and h1(t-1) W_hh1) do not depend on the token emitted at t-1, so
+//     their CTAs run them one step ahead: layer-0 CTAs hold the accumulator in TMEM until the control update of the
+//     previous step publishes the token (the epilogue adds the G0[token] row), layer-1 recurrent CTAs publish fp32
+//     partial sums that the layer-1 input CTAs add in their epilogue.  Neither is on the critical path.
+//   * Dependencies are per-M-tile monotonic counters in global memory (release: __threadfence + atomicAdd by the
+//     epilogue; acquire: ld.acquire spin by the producer thread, then fence.proxy.async before the TMA loads), so
+//     M-tiles advance independently; rows are sorted by encoded length so whole M-tiles retire early.
+// Spin loops carry a cycle-count watchdog that traps instead of hanging the GPU.
+#include <cooperative_groups.h>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.h"
+#include "tc_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace amira {
+namespace {
+
+using namespace tc;
+
+constexpr int W_SL = 64;                                    // output features per slice (UMMA N)
+constexpr int W_BM = 128;                                   // streams per M-tile (UMMA M)
+constexpr int W_NG = kG / W_SL;                             // 40 slices per gate matrix
+constexpr int W_NC = kH / W_SL;                             // 10
+constexpr int W_ND = (kV + W_SL - 1) / W_SL;                // 17
+constexpr int W_CTAS = 3 * W_NG + W_NC + W_ND;              // 147
+constexpr int W_KC = kH / BK;                               // 10 k-chunks
+constexpr int W_WCHUNK = W_SL * BK * 2;                     // 8 KB: [64 rows][64 k] bf16
+constexpr int W_WBYTES = 2 * W_KC * W_WCHUNK;               // 160 KB: per k-chunk [w_hi rows 0-63 | w_lo rows 64-127]
+constexpr int W_UNIT = W_BM * BK * 2;                       // 16 KB: [128 rows][64 k] bf16
+constexpr int W_RING = 4;
+constexpr int W_CTRL = 2048;
+constexpr int W_SMEM = W_WBYTES + W_RING * W_UNIT + W_CTRL;  // 231424 of the 232448-byte per-CTA maximum
+constexpr int W_ACC_COLS = 2 * W_SL;                        // accumulator = [a_hi w_hi + a_lo w_hi | a_hi w_lo], summed in the epilogue
+constexpr int W_NACC = 4;                                   // TMEM accumulators of 128 columns
+constexpr int W_Q = 8;                                      // descriptor queue depth
+constexpr int W_EPI_WARPS = 8, W_EPI_THREADS = W_EPI_WARPS * 32;
+constexpr int W_THREADS = (2 + W_EPI_WARPS) * 32;           // 320: warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int W_NPART = 2 * W_ND;                           // argmax partials per row (32 columns each)
+constexpr int W_MAX_MT = 256;
+constexpr long long W_SPIN_LIMIT = 6000000000LL;            // ~3 s of SM clocks
+constexpr int W_TRACE_ITS = 512;
+
+enum { R_A = 0, R_BI = 1, R_BH = 2, R_C = 3, R_D = 4 };
+
+struct WCtl {
+    int t, sym, total, last, active, nsteps, failed, pad;
+};
+
+struct WsParams {
+    CUtensorMap h0_hi, h0_lo, h1_hi, h1_lo, z_hi, z_lo;                                    // activations, box {64, 128}
+    CUtensorMap whh0_hi, whh0_lo, w1_hi, w1_lo, wp_hi, wp_lo, wo_hi, wo_lo;                // weights, box {64, 64}
+    const float *g0p, *b1p, *boutp, *E;
+    int B, Mpad, MT, T;
+    const int *lens, *slots, *perm;
+    __nv_bfloat16 *h0b_hi, *h0b_lo, *h1b_hi, *h1b_lo, *zb_hi, *zb_lo;
+    float *h0f, *h1f, *c0, *c1;
+    float *part;        // [MT][40 slices][2 column groups][128 rows][32] fp32: h1(t-1) W_hh1 partial sums
+    float *pval;        // [MT][34][128]
+    int *pidx;
+    WCtl *ctl;
+    int *tile_active, *done_d, *cnt_a, *cnt_b, *cnt_c, *ctl_done, *dead_at, *part_ready /* [MT][40] */, *fail_count;
+    float *s1, *s2;
+    int *tokens, *ntok, *nsteps;
+    int max_sym, max_total, blank, relu;
+    long long *trace;   // nullable: [W_TRACE_ITS][32] globaltimer stamps of M-tile 0 (debug)
+};
+
+struct WsDesc {
+    int mt, it;
+};
+struct WsSmem {
+    uint64_t full[W_RING], empty[W_RING], acc_full[W_NACC], acc_empty[W_NACC], q_full[W_Q], q_empty[W_Q], wfull;
+    uint32_t tmem_slot;
+    int flag, act_cnt;
+    WsDesc q[W_Q];
+    unsigned char dead[W_MAX_MT];
+};
+static_assert(sizeof(WsSmem) <= W_CTRL, "control block exceeds its reservation");
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// activations: exp-based, absolute error ~1e-7 (fp32 rounding level), ex2/rcp on the SFU
+__device__ __forceinline__ float fsig(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) {
+    const float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
+// low word of the K-major SWIZZLE_128B shared-memory descriptor (address >> 4 | LBO 1); the high word is constant
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc, uint32_t accumulate) {
+    // high word: SBO = 1024 B >> 4 in [32,46), version 1 at bit 46, layout type 2 (128B swizzle) in [61,64)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(64u | (1u << 14) | (2u << 29))
+        : "memory");
+}
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// debug trace: slice 0 of every role stamps its events for M-tile `W_TRACE_MT`
+#define WS_TRACE(ev)                                                                                   \
+    do {                                                                                               \
+        if (p.trace && slice == 0 && mt == 0 && it < W_TRACE_ITS) p.trace[it * 32 + role * 6 + (ev)] = gtime(); \
+    } while (0)
+
+// this thread's 32 accumulator columns: (a_hi w_hi + a_lo w_hi) + (a_hi w_lo), the two halves of the 128-column accumulator
+__device__ __forceinline__ void tmem_ld32_sum(uint32_t taddr, uint32_t (&r)[32]) {
+    tmem_ld32(taddr, r);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t t[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9]),
+              "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+            : "r"(taddr + W_SL + h * 16)
+            : "memory");
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[h * 16 + j] = __float_as_uint(__uint_as_float(r[h * 16 + j]) + __uint_as_float(t[j]));
+    }
+}
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void spin_ge(const int *p, int target) {
+    if (ld_acquire(p) >= target) return;
+    const long long t0 = clock64();
+    while (ld_acquire(p) < target) {
+        if (clock64() - t0 > W_SPIN_LIMIT) __trap();
+    }
+}
+// wait until *cnt >= target (returns 0) or the M-tile is known to have ended before iteration `it` (returns 1)
+__device__ __forceinline__ int spin_ge_or_dead(const int *cnt, int target, const int *dead_at, int it) {
+    const long long t0 = clock64();
+    for (;;) {
+        if (ld_acquire(dead_at) <= it) return 1;
+        if (ld_acquire(cnt) >= target) return 0;
+        if (clock64() - t0 > W_SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t n = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++n & 0xfff) == 0 && clock64() - t0 > W_SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ WCtl load_ctl(const WCtl *q) {  // L1-bypassing: written by another SM's control update
+    const int4 a = __ldcg(reinterpret_cast<const int4 *>(q)), b = __ldcg(reinterpret_cast<const int4 *>(q) + 1);
+    WCtl c;
+    c.t = a.x; c.sym = a.y; c.total = a.z; c.last = a.w; c.active = b.x; c.nsteps = b.y; c.failed = b.z; c.pad = b.w;
+    return c;
+}
+__device__ __forceinline__ size_t ws_state_off(const WsParams &p, int layer, int b) {
+    return p.slots ? ((size_t)p.slots[b] * 2 + layer) * kH : ((size_t)layer * p.B + b) * kH;
+}
+
+__global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_constant__ WsParams p) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *w_hi = smem, *ring = smem + W_WBYTES;  // w_hi: [k-chunk][w_hi 8 KB | w_lo 8 KB]
+    WsSmem &sm = *reinterpret_cast<WsSmem *>(smem + W_WBYTES + W_RING * W_UNIT);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // role and slice of this CTA
+    int role, slice;
+    {
+        const int b = blockIdx.x;
+        if (b < W_NG) { role = R_A; slice = b; }
+        else if (b < 2 * W_NG) { role = R_BI; slice = b - W_NG; }
+        else if (b < 3 * W_NG) { role = R_BH; slice = b - 2 * W_NG; }
+        else if (b < 3 * W_NG + W_NC) { role = R_C; slice = b - 3 * W_NG; }
+        else { role = R_D; slice = b - 3 * W_NG - W_NC; }
+    }
+
+    // CTAs of one phase read the same activation tile at the same time: each starts at a different k-chunk so the requests
+    // spread over the tile's L2 slices instead of queueing on one 16 KB region
+    const int kc0 = (slice * 3 + role) % W_KC;
+
+    if (tid == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled operand layout needs a 1024-byte aligned base
+        for (int s = 0; s < W_RING; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        for (int b = 0; b < W_NACC; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], W_EPI_THREADS); }
+        for (int i = 0; i < W_Q; ++i) { mbar_init(&sm.q_full[i], 1); mbar_init(&sm.q_empty[i], 1 + W_EPI_WARPS); }
+        mbar_init(&sm.wfull, 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < W_MAX_MT; i += W_THREADS) sm.dead[i] = 0;
+    if (warp == 1) tmem_alloc(&sm.tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- stationary weights: one TMA burst, overlapped with the prologue below ----
+    if (warp == 0 && lane == 0) {
+        const CUtensorMap *mh, *ml;
+        int kcol = 0;
+        if (role == R_A) { mh = &p.whh0_hi; ml = &p.whh0_lo; }
+        else if (role == R_BI) { mh = &p.w1_hi; ml = &p.w1_lo; }
+        else if (role == R_BH) { mh = &p.w1_hi; ml = &p.w1_lo; kcol = kH; }
+        else if (role == R_C) { mh = &p.wp_hi; ml = &p.wp_lo; }
+        else { mh = &p.wo_hi; ml = &p.wo_lo; }
+        tma_prefetch_desc(mh);
+        tma_prefetch_desc(ml);
+        mbar_expect_tx(&sm.wfull, W_WBYTES);
+        for (int kc = 0; kc < W_KC; ++kc) {  // w_lo directly below w_hi: together one 128-row B operand
+            tma_load_2d(w_hi + kc * 2 * W_WCHUNK, mh, &sm.wfull, kcol + kc * BK, slice * W_SL);
+            tma_load_2d(w_hi + kc * 2 * W_WCHUNK + W_WCHUNK, ml, &sm.wfull, kcol + kc * BK, slice * W_SL);
+        }
+    }
+
+    // ---- prologue: initial LSTM state (fp32 + split bf16, parity 0), control, default results ----
+    const size_t n_state = (size_t)p.Mpad * kH;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < n_state; i += (size_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / kH), j = (int)(i % kH);
+        const int b = row < p.B ? p.perm[row] : -1;
+        const float h0 = (b >= 0 && p.s1) ? p.s1[ws_state_off(p, 0, b) + j] : 0.f;
+        const float h1 = (b >= 0 && p.s1) ? p.s1[ws_state_off(p, 1, b) + j] : 0.f;
+        p.h0f[i] = h0;
+        p.h1f[i] = h1;
+        p.c0[i] = (b >= 0 && p.s2) ? p.s2[ws_state_off(p, 0, b) + j] : 0.f;
+        p.c1[i] = (b >= 0 && p.s2) ? p.s2[ws_state_off(p, 1, b) + j] : 0.f;
+        __nv_bfloat16 hh, hl;
+        split_bf16(h0, hh, hl);
+        p.h0b_hi[i] = hh; p.h0b_lo[i] = hl;
+        split_bf16(h1, hh, hl);
+        p.h1b_hi[i] = hh; p.h1b_lo[i] = hl;
+    }
+    for (int row = blockIdx.x * blockDim.x + tid; row < p.Mpad; row += gridDim.x * blockDim.x) {
+        WCtl c;
+        c.t = 0; c.sym = 0; c.total = 0; c.last = p.blank; c.nsteps = 0; c.failed = 0; c.pad = 0;
+        c.active = (row < p.B && p.lens[p.perm[row]] > 0) ? 1 : 0;
+        p.ctl[row] = c;
+        if (c.active) atomicAdd(&p.tile_active[row / W_BM], 1);
+        if (row < p.B) {
+            p.ntok[p.perm[row]] = 0;
+            if (p.nsteps) p.nsteps[p.perm[row]] = 0;
+        }
+    }
+    __threadfence();
+    fence_proxy_async();
+    grid.sync();
+    // M-tiles with no active stream never start (dead_at = 0); the host zero-initialised every counter
+    for (int mt = blockIdx.x * blockDim.x + tid; mt < p.MT; mt += gridDim.x * blockDim.x)
+        p.dead_at[mt] = __ldcg(p.tile_active + mt) > 0 ? 0x7fffffff : 0;
+    __threadfence();
+    grid.sync();
+
+    const uint32_t tmem_base = sm.tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===================== scheduler + TMA producer =====================
+            const CUtensorMap *a_hi, *a_lo;
+            if (role == R_A || role == R_BI) { a_hi = &p.h0_hi; a_lo = &p.h0_lo; }
+            else if (role == R_BH || role == R_C) { a_hi = &p.h1_hi; a_lo = &p.h1_lo; }
+            else { a_hi = &p.z_hi; a_lo = &p.z_lo; }
+            tma_prefetch_desc(a_hi);
+            tma_prefetch_desc(a_lo);
+            uint32_t u = 0, qn = 0;
+            for (int it = 0;; ++it) {
+                const int par = it & 1;
+                bool any = false;
+                for (int mt = 0; mt < p.MT; ++mt) {
+                    if (sm.dead[mt]) continue;
+                    int st, a_row;
+                    if (role == R_A) {          // h0(it-1): every layer-0 epilogue of the previous step
+                        st = spin_ge_or_dead(p.cnt_a + mt, W_NG * it, p.dead_at + mt, it);
+                        a_row = par * p.Mpad;
+                    } else if (role == R_BI) {  // h0(it)
+                        st = spin_ge_or_dead(p.cnt_a + mt, W_NG * (it + 1), p.dead_at + mt, it);
+                        a_row = (par ^ 1) * p.Mpad;
+                    } else if (role == R_BH) {  // h1(it-1)
+                        st = spin_ge_or_dead(p.cnt_b + mt, W_NG * it, p.dead_at + mt, it);
+                        a_row = par * p.Mpad;
+                    } else if (role == R_C) {   // h1(it)
+                        st = spin_ge_or_dead(p.cnt_b + mt, W_NG * (it + 1), p.dead_at + mt, it);
+                        a_row = (par ^ 1) * p.Mpad;
+                    } else {                    // z(it)
+                        st = spin_ge_or_dead(p.cnt_c + mt, W_NC * (it + 1), p.dead_at + mt, it);
+                        a_row = 0;
+                    }
+                    if (st) { sm.dead[mt] = 1; continue; }
+                    any = true;
+                    WS_TRACE(0);
+                    fence_proxy_async();
+                    {   // publish the unit
+                        const uint32_t slot = qn % W_Q;
+                        mbar_wait_wd(&sm.q_empty[slot], ((qn / W_Q) & 1) ^ 1);
+                        sm.q[slot].mt = mt; sm.q[slot].it = it;
+                        mbar_arrive(&sm.q_full[slot]);
+                        ++qn;
+                    }
+                    for (int ki = 0; ki < W_KC; ++ki) {
+                        const int kc = (kc0 + ki) % W_KC;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const uint32_t s = u % W_RING;
+                            mbar_wait_wd(&sm.empty[s], ((u / W_RING) & 1) ^ 1);
+                            mbar_expect_tx(&sm.full[s], W_UNIT);
+                            tma_load_2d(ring + s * W_UNIT, half ? a_lo : a_hi, &sm.full[s], kc * BK, a_row + mt * W_BM);
+                            ++u;
+                        }
+                    }
+                }
+                if (!any) break;
+            }
+            const uint32_t slot = qn % W_Q;  // exit descriptor
+            mbar_wait_wd(&sm.q_empty[slot], ((qn / W_Q) & 1) ^ 1);
+            sm.q[slot].mt = -1;
+            mbar_arrive(&sm.q_full[slot]);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===================== MMA issuer =====================
+            // descriptors are (smem address >> 4) in the low word plus constant fields: precomputed so the issue loop is a handful
+            // of integer adds per tcgen05.mma (a single thread issuing ~100 of them per unit must not be the bottleneck)
+            constexpr uint32_t idesc_cat = make_idesc_bf16(W_BM, 2 * W_SL), idesc_hi = make_idesc_bf16(W_BM, W_SL);
+            const uint32_t w_lo32 = sdesc_lo(smem_u32(w_hi)), ring_lo32 = sdesc_lo(smem_u32(ring));
+            mbar_wait_wd(&sm.wfull, 0);
+            uint32_t u = 0, qn = 0, tile = 0;
+            for (;;) {
+                const uint32_t slot = qn % W_Q;
+                mbar_wait_wd(&sm.q_full[slot], (qn / W_Q) & 1);
+                const int mt = sm.q[slot].mt, it = sm.q[slot].it;
+                mbar_arrive(&sm.q_empty[slot]);
+                ++qn;
+                if (mt < 0) break;
+                const uint32_t buf = tile % W_NACC, use = tile / W_NACC;
+                mbar_wait_wd(&sm.acc_empty[buf], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + buf * W_ACC_COLS;
+                int kc = kc0;
+#pragma unroll 1
+                for (int ki = 0; ki < W_KC; ++ki) {
+                    const uint32_t wd = w_lo32 + kc * (2 * W_WCHUNK >> 4);
+                    {   // hi unit: a_hi * [w_hi ; w_lo]  (N = 128)
+                        const uint32_t s = u % W_RING;
+                        mbar_wait_wd(&sm.full[s], (u / W_RING) & 1);
+                        if (ki == 0) WS_TRACE(1);
+                        tc_fence_after();
+                        const uint32_t ad = ring_lo32 + s * (W_UNIT >> 4);
+                        umma_bf16_lo(acc, ad, wd, idesc_cat, ki != 0);
+                        umma_bf16_lo(acc, ad + 2, wd + 2, idesc_cat, 1);
+                        umma_bf16_lo(acc, ad + 4, wd + 4, idesc_cat, 1);
+                        umma_bf16_lo(acc, ad + 6, wd + 6, idesc_cat, 1);
+                        umma_commit(&sm.empty[s]);
+                        ++u;
+                    }
+                    {   // lo unit: a_lo * w_hi  (N = 64, accumulator columns 0..63)
+                        const uint32_t s = u % W_RING;
+                        mbar_wait_wd(&sm.full[s], (u / W_RING) & 1);
+                        tc_fence_after();
+                        const uint32_t ad = ring_lo32 + s * (W_UNIT >> 4);
+                        umma_bf16_lo(acc, ad, wd, idesc_hi, 1);
+                        umma_bf16_lo(acc, ad + 2, wd + 2, idesc_hi, 1);
+                        umma_bf16_lo(acc, ad + 4, wd + 4, idesc_hi, 1);
+                        umma_bf16_lo(acc, ad + 6, wd + 6, idesc_hi, 1);
+                        umma_commit(&sm.empty[s]);
+                        ++u;
+                    }
+                    kc = kc + 1 == W_KC ? 0 : kc + 1;
+                }
+                umma_commit(&sm.acc_full[buf]);
+                WS_TRACE(2);
+                ++tile;
+            }
+        }
+    } else {  // ===================== epilogue: 8 warps =====================
+        const int e = warp - 2, q = warp & 3, cgp = e >> 2;  // TMEM lane quarter (must be warp % 4), 32-column group
+        const int etid = tid - 64;
+        const int r_in = q * 32 + lane;
+        const int nb = slice * W_SL + cgp * 32;           // first of this thread's 32 output columns
+        uint32_t qn = 0, tile = 0;
+        for (;;) {
+            const uint32_t slot = qn % W_Q;
+            mbar_wait_wd(&sm.q_full[slot], (qn / W_Q) & 1);
+            const WsDesc d = sm.q[slot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.q_empty[slot]);
+            ++qn;
+            if (d.mt < 0) break;
+            const int mt = d.mt, it = d.it, par = it & 1;
+            const uint32_t buf = tile % W_NACC, use = tile / W_NACC;
+            ++tile;
+            const int row = mt * W_BM + r_in;
+            const uint32_t taddr = tmem_base + buf * W_ACC_COLS + ((uint32_t)(q * 32) << 16) + cgp * 32;
+            uint32_t r[32];
+
+            if (role == R_A) {
+                // the recurrent GEMM ran ahead; the cell update needs the previous step's control update (token, activity)
+                if (it > 0) {
+                    if (etid == 0) spin_ge(p.ctl_done + mt, it);
+                    named_bar_sync(1, W_EPI_THREADS);
+                }
+                if (etid == 0) WS_TRACE(5);
+                const bool live = __ldcg(p.dead_at + mt) > it;  // the M-tile may have ended with the previous step
+                const WCtl c = load_ctl(p.ctl + row);
+                const bool act = live && c.active;
+                float4 ad[8], cold4[2];
+                float *cst = p.c0 + (size_t)row * kH + nb / 4;
+                if (act) {
+                    const float4 *addp = reinterpret_cast<const float4 *>(p.g0p + (size_t)c.last * kG + nb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ad[j] = __ldg(addp + j);
+                    cold4[0] = __ldcg(reinterpret_cast<const float4 *>(cst));
+                    cold4[1] = __ldcg(reinterpret_cast<const float4 *>(cst) + 1);
+                }
+                mbar_wait_wd(&sm.acc_full[buf], use & 1);
+                if (etid == 0) WS_TRACE(3);
+                tc_fence_after();
+                tmem_ld32_sum(taddr, r);
+                tc_fence_before();
+                mbar_arrive(&sm.acc_empty[buf]);
+                if (!live) continue;  // speculative unit of an ended M-tile: drop it (uniform across the CTA)
+                if (act) {
+                    float cold[8] = {cold4[0].x, cold4[0].y, cold4[0].z, cold4[0].w, cold4[1].x, cold4[1].y, cold4[1].z, cold4[1].w};
+                    float hnew[8];
+                    __align__(16) __nv_bfloat16 vh[8], vl[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float gi = fsig(__uint_as_float(r[4 * j + 0]) + ad[j].x), gf = fsig(__uint_as_float(r[4 * j + 1]) + ad[j].y);
+                        const float gg = ftanh(__uint_as_float(r[4 * j + 2]) + ad[j].z), go = fsig(__uint_as_float(r[4 * j + 3]) + ad[j].w);
+                        const float cn = gf * cold[j] + gi * gg;
+                        cold[j] = cn;
+                        hnew[j] = go * ftanh(cn);
+                        split_bf16(hnew[j], vh[j], vl[j]);
+                    }
+                    float *hf = p.h0f + (size_t)row * kH + nb / 4;
+                    const size_t ob = ((size_t)(par ^ 1) * p.Mpad + row) * kH + nb / 4;
+                    reinterpret_cast<float4 *>(cst)[0] = make_float4(cold[0], cold[1], cold[2], cold[3]);
+                    reinterpret_cast<float4 *>(cst)[1] = make_float4(cold[4], cold[5], cold[6], cold[7]);
+                    reinterpret_cast<float4 *>(hf)[0] = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
+                    reinterpret_cast<float4 *>(hf)[1] = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
+                    *reinterpret_cast<uint4 *>(p.h0b_hi + ob) = *reinterpret_cast<uint4 *>(vh);
+                    *reinterpret_cast<uint4 *>(p.h0b_lo + ob) = *reinterpret_cast<uint4 *>(vl);
+                }
+                named_bar_sync(1, W_EPI_THREADS);
+                if (etid == 0) {  // cumulative release of every epilogue thread's stores (ordered by the barrier); the readers use TMA
+                    __threadfence();
+                    fence_proxy_async();
+                    atomicAdd(p.cnt_a + mt, 1);
+                    WS_TRACE(4);
+                }
+            } else if (role == R_BH) {
+                // partial sums of the layer-1 recurrent half, for the layer-1 input CTA of the same slice
+                float4 *dst = reinterpret_cast<float4 *>(p.part + ((((size_t)mt * W_NG + slice) * 2 + cgp) * W_BM + r_in) * 32);
+                mbar_wait_wd(&sm.acc_full[buf], use & 1);
+                if (etid == 0) WS_TRACE(3);
+                tc_fence_after();
+                tmem_ld32_sum(taddr, r);
+                tc_fence_before();
+                mbar_arrive(&sm.acc_empty[buf]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    __stcg(dst + j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                                __uint_as_float(r[4 * j + 3])));
+                named_bar_sync(1, W_EPI_THREADS);
+                if (etid == 0) {
+                    __threadfence();
+                    st_release(p.part_ready + mt * W_NG + slice, it + 1);
+                    WS_TRACE(4);
+                }
+            } else if (role == R_BI) {
+                const WCtl c = load_ctl(p.ctl + row);
+                float4 ad[8], cold4[2], pr[8];
+                float *cst = p.c1 + (size_t)row * kH + nb / 4;
+                if (c.active) {
+                    const float4 *addp = reinterpret_cast<const float4 *>(p.b1p + nb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ad[j] = __ldg(addp + j);
+                    cold4[0] = __ldcg(reinterpret_cast<const float4 *>(cst));
+                    cold4[1] = __ldcg(reinterpret_cast<const float4 *>(cst) + 1);
+                }
+                if (etid == 0) spin_ge(p.part_ready + mt * W_NG + slice, it + 1);
+                named_bar_sync(1, W_EPI_THREADS);
+                if (c.active) {
+                    const float4 *src = reinterpret_cast<const float4 *>(p.part + ((((size_t)mt * W_NG + slice) * 2 + cgp) * W_BM + r_in) * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pr[j] = __ldcg(src + j);
+                }
+                mbar_wait_wd(&sm.acc_full[buf], use & 1);
+                if (etid == 0) WS_TRACE(3);
+                tc_fence_after();
+                tmem_ld32_sum(taddr, r);
+                tc_fence_before();
+                mbar_arrive(&sm.acc_empty[buf]);
+                if (c.active) {
+                    float cold[8] = {cold4[0].x, cold4[0].y, cold4[0].z, cold4[0].w, cold4[1].x, cold4[1].y, cold4[1].z, cold4[1].w};
+                    float hnew[8];
+                    __align__(16) __nv_bfloat16 vh[8], vl[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float gi = fsig(__uint_as_float(r[4 * j + 0]) + pr[j].x + ad[j].x), gf = fsig(__uint_as_float(r[4 * j + 1]) + pr[j].y + ad[j].y);
+                        const float gg = ftanh(__uint_as_float(r[4 * j + 2]) + pr[j].z + ad[j].z), go = fsig(__uint_as_float(r[4 * j + 3]) + pr[j].w + ad[j].w);
+                        const float cn = gf * cold[j] + gi * gg;
+                        cold[j] = cn;
+                        hnew[j] = go * ftanh(cn);
+                        split_bf16(hnew[j], vh[j], vl[j]);
+                    }
+                    float *hf = p.h1f + (size_t)row * kH + nb / 4;
+                    const size_t ob = ((size_t)(par ^ 1) * p.Mpad + row) * kH + nb / 4;
+                    reinterpret_cast<float4 *>(cst)[0] = make_float4(cold[0], cold[1], cold[2], cold[3]);
+                    reinterpret_cast<float4 *>(cst)[1] = make_float4(cold[4], cold[5], cold[6], cold[7]);
+                    reinterpret_cast<float4 *>(hf)[0] = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
+                    reinterpret_cast<float4 *>(hf)[1] = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
+                    *reinterpret_cast<uint4 *>(p.h1b_hi + ob) = *reinterpret_cast<uint4 *>(vh);
+                    *reinterpret_cast<uint4 *>(p.h1b_lo + ob) = *reinterpret_cast<uint4 *>(vl);
+                }
+                named_bar_sync(1, W_EPI_THREADS);
+                if (etid == 0) {
+                    __threadfence();
+                    fence_proxy_async();
+                    atomicAdd(p.cnt_b + mt, 1);
+                    WS_TRACE(4);
+                }
+            } else if (role == R_C) {
+                const WCtl c = load_ctl(p.ctl + row);
+                float4 ev[8];
+                if (c.active) {
+                    const float4 *ep = reinterpret_cast<const float4 *>(p.E + ((size_t)p.perm[row] * p.T + c.t) * kH + nb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ev[j] = __ldg(ep + j);
+                }
+                mbar_wait_wd(&sm.acc_full[buf], use & 1);
+                if (etid == 0) WS_TRACE(3);
+                tc_fence_after();
+                tmem_ld32_sum(taddr, r);
+                tc_fence_before();
+                mbar_arrive(&sm.acc_empty[buf]);
+                if (c.active) {
+                    __nv_bfloat16 *bh = p.zb_hi + (size_t)row * kH + nb, *bl = p.zb_lo + (size_t)row * kH + nb;
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        __align__(16) __nv_bfloat16 vh[8], vl[8];
+                        const float e8[8] = {ev[2 * j8].x, ev[2 * j8].y, ev[2 * j8].z, ev[2 * j8].w,
+                                             ev[2 * j8 + 1].x, ev[2 * j8 + 1].y, ev[2 * j8 + 1].z, ev[2 * j8 + 1].w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float v = __uint_as_float(r[8 * j8 + j]) + e8[j];
+                            split_bf16(p.relu ? fmaxf(v, 0.f) : ftanh(v), vh[j], vl[j]);
+                        }
+                        reinterpret_cast<uint4 *>(bh)[j8] = *reinterpret_cast<uint4 *>(vh);
+                        reinterpret_cast<uint4 *>(bl)[j8] = *reinterpret_cast<uint4 *>(vl);
+                    }
+                }
+                named_bar_sync(1, W_EPI_THREADS);
+                if (etid == 0) {
+                    __threadfence();
+                    fence_proxy_async();
+                    atomicAdd(p.cnt_c + mt, 1);
+                    WS_TRACE(4);
+                }
+            } else {  // R_D: vocabulary slice -> first-max argmax partial (zero_copy.rs:190-232 tie rule) -> control update
+                const WCtl c = load_ctl(p.ctl + row);
+                const int prow = row < p.B ? __ldg(p.perm + row) : 0;
+                const int len = __ldg(p.lens + prow);  // for the control update: fetched ahead of the accumulator wait
+                float4 bo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bo[j] = __ldg(reinterpret_cast<const float4 *>(p.boutp + nb) + j);
+                mbar_wait_wd(&sm.acc_full[buf], use & 1);
+                if (etid == 0) WS_TRACE(3);
+                tc_fence_after();
+                tmem_ld32_sum(taddr, r);
+                tc_fence_before();
+                mbar_arrive(&sm.acc_empty[buf]);
+                if (c.active) {
+                    float best_v = -INFINITY;
+                    int best_i = 0x7fffffff;
+                    const float *bof = reinterpret_cast<const float *>(bo);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = nb + j;
+                        if (n < kV) {
+                            const float v = __uint_as_float(r[j]) + bof[j];
+                            if (v > best_v || best_i == 0x7fffffff) { best_v = v; best_i = n; }
+                        }
+                    }
+                    const size_t po = ((size_t)mt * W_NPART + slice * 2 + cgp) * W_BM + r_in;
+                    __stcg(p.pval + po, best_v);
+                    __stcg(p.pidx + po, best_i);
+                }
+                named_bar_sync(1, W_EPI_THREADS);
+                if (etid == 0) {
+                    __threadfence();
+                    const int old = atomicAdd(p.done_d + mt, 1);
+                    WS_TRACE(4);
+                    sm.flag = (old == W_ND - 1);
+                    sm.act_cnt = 0;
+                }
+                named_bar_sync(1, W_EPI_THREADS);
+                if (!sm.flag) continue;
+                // ---- this CTA finished the M-tile's last vocabulary slice: per-stream control update (one thread per row) ----
+                __threadfence();
+                if (cgp == 0) {
+                    WCtl n = c;
+                    if (n.active) {
+                        float bv = -INFINITY;
+                        int bi = 0x7fffffff;
+                        const size_t po = (size_t)mt * W_NPART * W_BM + r_in;
+                        float pv[W_NPART];
+                        int pi[W_NPART];
+#pragma unroll
+                        for (int qi = 0; qi < W_NPART; ++qi) {  // every load in flight at once
+                            pi[qi] = __ldcg(p.pidx + po + (size_t)qi * W_BM);
+                            pv[qi] = __ldcg(p.pval + po + (size_t)qi * W_BM);
+                        }
+#pragma unroll
+                        for (int qi = 0; qi < W_NPART; ++qi)
+                            if (pi[qi] != 0x7fffffff && (bi == 0x7fffffff || pv[qi] > bv)) { bv = pv[qi]; bi = pi[qi]; }
+                        n.nsteps += 1;                       // state carried unconditionally (decoder_optimized.rs:154)
+                        n.sym += 1;                          // :133
+                        if (bi == p.blank) {                 // :171-173
+                            n.t += 1; n.sym = 0;
+                            if (n.t >= len) n.active = 0;
+                        } else {
+                            p.tokens[(size_t)prow * p.max_total + n.total] = bi;   // :176
+                            n.total += 1;
+                            n.last = bi;
+                            if (n.total >= p.max_total) n.active = 0;                    // :179-188
+                            else if (n.sym >= p.max_sym) {                               // :133-137
+                                n.t += 1; n.sym = 0;
+                                if (n.t >= len) n.active = 0;
+                            }
+                            if (n.active && bi >= kEmbRows) { n.active = 0; n.failed = 1; }  // next step would fail (:148-152)
+                        }
+                        p.ctl[row] = n;
+                        if (n.active) atomicAdd(&sm.act_cnt, 1);
+                    }
+                }
+                named_bar_sync(1, W_EPI_THREADS);
+                const int alive = sm.act_cnt;
+                if (alive == 0) {  // M-tile finished: write its streams' results
+                    for (int rr = etid; rr < W_BM; rr += W_EPI_THREADS) {
+                        const int grow = mt * W_BM + rr;
+                        if (grow < p.B) {
+                            const WCtl f = load_ctl(p.ctl + grow);
+                            const int b = p.perm[grow];
+                            p.ntok[b] = f.failed ? -1 : f.total;
+                            if (p.nsteps) p.nsteps[b] = f.nsteps;
+                            if (f.failed) atomicAdd(p.fail_count, 1);
+                        }
+                    }
+                    if (p.s1 && p.s2) {
+                        for (int i = etid; i < W_BM * kH; i += W_EPI_THREADS) {
+                            const int grow = mt * W_BM + i / kH, j = i % kH;
+                            if (grow < p.B) {
+                                const int b = p.perm[grow];
+                                const size_t src = (size_t)grow * kH + j;
+                                p.s1[ws_state_off(p, 0, b) + j] = __ldcg(p.h0f + src);
+                                p.s1[ws_state_off(p, 1, b) + j] = __ldcg(p.h1f + src);
+                                p.s2[ws_state_off(p, 0, b) + j] = __ldcg(p.c0 + src);
+                                p.s2[ws_state_off(p, 1, b) + j] = __ldcg(p.c1 + src);
+                            }
+                        }
+                    }
+                    __threadfence();
+                    named_bar_sync(1, W_EPI_THREADS);
+                }
+                if (etid == 0) {
+                    p.done_d[mt] = 0;
+                    if (alive == 0) st_release(p.dead_at + mt, it + 1);
+                    __threadfence();
+                    atomicAdd(p.ctl_done + mt, 1);
+                    if (p.trace && mt == 0 && it < W_TRACE_ITS) p.trace[it * 32 + 30] = gtime();
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(sm.tmem_slot, 512);
+}
+
+size_t ws_align(size_t x) { return (x + 1023) & ~(size_t)1023; }
+
+}  // namespace
+
+bool decoder_ws_supported(const Ctx *c) { return c->sm_count >= W_CTAS; }
+
+cudaError_t decoder_ws_prepare(Ctx *c) {
+    TcWeights *w = c->dec->tc;
+    cudaError_t e;
+    if ((e = make_tmap_bf16(&w->s_whh0_hi, w->whh0_hi, kG, kH, kH, W_SL)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&w->s_whh0_lo, w->whh0_lo, kG, kH, kH, W_SL)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&w->s_w1_hi, w->w1_hi, kG, 2 * kH, 2 * kH, W_SL)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&w->s_w1_lo, w->w1_lo, kG, 2 * kH, 2 * kH, W_SL)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&w->s_wp_hi, w->wp_hi, kH, kH, kH, W_SL)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&w->s_wp_lo, w->wp_lo, kH, kH, kH, W_SL)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&w->s_wo_hi, w->wo_hi, W_ND * W_SL, kH, kH, W_SL)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&w->s_wo_lo, w->wo_lo, W_ND * W_SL, kH, kH, W_SL)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(greedy_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
+    w->ws_ready = true;
+    return cudaSuccess;
+}
+
+// E [B*T][640] fp32 (hoisted encoder projection) is produced by the caller (decoder_tc.cu) into `E`.
+cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t *lens_dev, const int *perm_dev,
+                             const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
+                             int32_t *nsteps_dev, char *work, size_t *work_bytes) {
+    DecoderPriv *d = c->dec;
+    TcWeights *w = d->tc;
+    const int MT = (B + W_BM - 1) / W_BM, Mpad = MT * W_BM;
+    const size_t MH = (size_t)Mpad * kH;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += ws_align(bytes); return o; };
+    const size_t oh0h = take(2 * 2 * MH), oh0l = take(2 * 2 * MH), oh1h = take(2 * 2 * MH), oh1l = take(2 * 2 * MH);
+    const size_t ozh = take(2 * MH), ozl = take(2 * MH);
+    const size_t oact_end = off;
+    const size_t oh0f = take(4 * MH), oh1f = take(4 * MH), oc0 = take(4 * MH), oc1 = take(4 * MH);
+    const size_t opart = take(sizeof(float) * (size_t)MT * W_NG * 2 * W_BM * 32);
+    const size_t opv = take(sizeof(float) * (size_t)MT * W_NPART * W_BM), opi = take(sizeof(int) * (size_t)MT * W_NPART * W_BM);
+    const size_t octl = take(sizeof(WCtl) * (size_t)Mpad);
+    const size_t n_cnt = 7 * (size_t)MT + (size_t)MT * W_NG + 4;
+    const size_t ocnt = take(sizeof(int) * n_cnt);
+    const size_t otrace = take(sizeof(long long) * W_TRACE_ITS * 32);
+    if (!work) {  // size query
+        *work_bytes = off;
+        return cudaSuccess;
+    }
+    if (MT > W_MAX_MT || !w || !w->ws_ready) return cudaErrorInvalidValue;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(work + ocnt, 0, sizeof(int) * n_cnt, c->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(work + oh0h, 0, oact_end - oh0h, c->stream)) != cudaSuccess) return e;  // padding rows feed the MMA too
+
+    WsParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.h0b_hi = reinterpret_cast<__nv_bfloat16 *>(work + oh0h); p.h0b_lo = reinterpret_cast<__nv_bfloat16 *>(work + oh0l);
+    p.h1b_hi = reinterpret_cast<__nv_bfloat16 *>(work + oh1h); p.h1b_lo = reinterpret_cast<__nv_bfloat16 *>(work + oh1l);
+    p.zb_hi = reinterpret_cast<__nv_bfloat16 *>(work + ozh); p.zb_lo = reinterpret_cast<__nv_bfloat16 *>(work + ozl);
+    if ((e = make_tmap_bf16(&p.h0_hi, p.h0b_hi, 2 * (uint64_t)Mpad, kH, kH, W_BM)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&p.h0_lo, p.h0b_lo, 2 * (uint64_t)Mpad, kH, kH, W_BM)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&p.h1_hi, p.h1b_hi, 2 * (uint64_t)Mpad, kH, kH, W_BM)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&p.h1_lo, p.h1b_lo, 2 * (uint64_t)Mpad, kH, kH, W_BM)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&p.z_hi, p.zb_hi, (uint64_t)Mpad, kH, kH, W_BM)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&p.z_lo, p.zb_lo, (uint64_t)Mpad, kH, kH, W_BM)) != cudaSuccess) return e;
+    p.whh0_hi = w->s_whh0_hi; p.whh0_lo = w->s_whh0_lo; p.w1_hi = w->s_w1_hi; p.w1_lo = w->s_w1_lo;
+    p.wp_hi = w->s_wp_hi; p.wp_lo = w->s_wp_lo; p.wo_hi = w->s_wo_hi; p.wo_lo = w->s_wo_lo;
+    p.g0p = d->g0p; p.b1p = d->b1p; p.boutp = d->boutp; p.E = E;
+    p.B = B; p.Mpad = Mpad; p.MT = MT; p.T = T > 0 ? T : 1;
+    p.lens = lens_dev; p.slots = slots_dev; p.perm = perm_dev;
+    p.h0f = reinterpret_cast<float *>(work + oh0f); p.h1f = reinterpret_cast<float *>(work + oh1f);
+    p.c0 = reinterpret_cast<float *>(work + oc0); p.c1 = reinterpret_cast<float *>(work + oc1);
+    p.part = reinterpret_cast<float *>(work + opart);
+    p.pval = reinterpret_cast<float *>(work + opv); p.pidx = reinterpret_cast<int *>(work + opi);
+    p.ctl = reinterpret_cast<WCtl *>(work + octl);
+    int *cnt = reinterpret_cast<int *>(work + ocnt);
+    p.tile_active = cnt; p.done_d = cnt + MT; p.cnt_a = cnt + 2 * MT; p.cnt_b = cnt + 3 * MT; p.cnt_c = cnt + 4 * MT;
+    p.ctl_done = cnt + 5 * MT; p.dead_at = cnt + 6 * MT; p.part_ready = cnt + 7 * MT; p.fail_count = cnt + 7 * MT + MT * W_NG;
+    if (slots_dev) { p.s1 = c->slot_s1; p.s2 = c->slot_s2; } else { p.s1 = s1_dev; p.s2 = s2_dev; }
+    p.tokens = tokens_dev; p.ntok = ntok_dev; p.nsteps = nsteps_dev;
+    p.max_sym = c->cfg.max_symbols_per_step; p.max_total = c->cfg.max_total_tokens; p.blank = c->cfg.blank_id;
+    p.relu = c->cfg.joint_activation;
+    d->fail_count_dev = p.fail_count;
+    if (getenv("AMIRA_WS_TRACE")) {
+        p.trace = reinterpret_cast<long long *>(work + otrace);
+        cudaMemsetAsync(p.trace, 0, sizeof(long long) * W_TRACE_ITS * 32, c->stream);
+        d->ws_trace_dev = p.trace;
+    }
+
+    void *params[] = {&p};
+    ProfScope prof(c, PK_GREEDY);
+    e = cudaLaunchCooperativeKernel((const void *)greedy_ws_kernel, dim3(W_CTAS), dim3(W_THREADS), params, W_SMEM, c->stream);
+    c->launches++;
+    return e;
+}
+
+}  // namespace amira
+
+// ---- diagnostics: globaltimer stamps of the last weight-stationary launch (set AMIRA_WS_TRACE=1 before the call) ----
+extern "C" int32_t amira_debug_ws_trace(amira_ctx *ctx, int64_t *out, int32_t n_its) {
+    using namespace amira;
+    if (!ctx || !out || n_its <= 0 || n_its > W_TRACE_ITS) return AMIRA_ERR_INVALID_VALUE;
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!c->dec || !c->dec->ws_trace_dev) return AMIRA_ERR_NOT_READY;
+    cudaSetDevice(c->device);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return AMIRA_ERR_UNKNOWN;
+    return cudaMemcpy(out, c->dec->ws_trace_dev, sizeof(int64_t) * 32 * (size_t)n_its, cudaMemcpyDeviceToHost) == cudaSuccess
+               ? AMIRA_OK : AMIRA_ERR_UNKNOWN;
+}

@@ -60,8 +60,9 @@ typedef struct {
     int32_t max_total_tokens;     /* 200 */
     int32_t blank_id;             /* 1024 */
     int32_t joint_activation;     /* 0 = tanh (north_star), 1 = relu */
-    int32_t decode_engine;        /* 0 = auto (3); 1 = fp32 CUDA-core persistent kernel; tcgen05 split-bf16 persistent
-                                   * kernels: 2 = grid-synchronised phases, 3 = dataflow (per-M-tile dependency counters) */
+    int32_t decode_engine;        /* 0 = auto (4); 1 = fp32 CUDA-core persistent kernel; tcgen05 split-bf16 persistent
+                                   * kernels: 2 = grid-synchronised phases, 3 = dataflow (per-M-tile dependency counters),
+                                   * 4 = weight-stationary dataflow (weights resident in shared memory, one slice per SM) */
     int32_t max_streams;          /* resident stream-state slots for the WebSocket path (default 1024) */
     int32_t reserved;
 } amira_config;
@@ -93,6 +94,10 @@ int32_t amira_ctx_kernel_ms(amira_ctx *ctx, int32_t kernel, double *total_ms, in
  * hoisted encoder projection; host pointers; K % 8 == 0.  Unit test hook for the UMMA descriptor conventions. */
 int32_t amira_debug_tc_gemm(amira_ctx *ctx, const float *A, const float *W, const float *bias, int32_t M, int32_t N,
                             int32_t K, float *C);
+
+/* diagnostics: per-step globaltimer stamps [n_its][32] of M-tile 0 from the last weight-stationary greedy launch made with
+ * the environment variable AMIRA_WS_TRACE set (slot = role * 6 + event; slot 30 = control update done). */
+int32_t amira_debug_ws_trace(amira_ctx *ctx, int64_t *out, int32_t n_its);
 
 /* ---- weights: stand-in for model-repo/decoder_joint/1/model.onnx (absent LFS object) ---- */
 /* flat fp32 blob, order: emb[1025][640]; per layer l=0,1: w_ih[2560][640], w_hh[2560][640], b_ih[2560],
