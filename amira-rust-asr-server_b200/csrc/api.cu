@@ -4,7 +4,9 @@
 // no exception crosses the boundary.  There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -190,6 +192,10 @@ int32_t amira_ctx_create(const amira_config *cfg, amira_ctx **out) {
     if ((e = cudaSetDevice(c->device)) != cudaSuccess) return bail(e, "cudaSetDevice");
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
     c->stream = c->own_stream;
+    if ((e = cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    if ((e = cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    for (cudaEvent_t &ev : c->ev_pool)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     FrontendTables *ht = new FrontendTables();
     build_frontend_tables(ht);
     e = cudaMalloc(&c->tables_dev, sizeof(FrontendTables));
@@ -217,9 +223,15 @@ int32_t amira_ctx_destroy(amira_ctx *c) {
     if (c->w_blob) cudaFree(c->w_blob);
     if (c->slot_s1) cudaFree(c->slot_s1);
     if (c->slot_s2) cudaFree(c->slot_s2);
-    c->fe_meta.release();
-    c->fe_partials.release();
-    c->fe_meta_pin.release();
+    for (int k = 0; k < Ctx::kMaxChunks; ++k) {
+        c->fe_meta[k].release();
+        c->fe_partials[k].release();
+        c->fe_meta_pin[k].release();
+    }
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    for (cudaEvent_t ev : c->ev_pool)
+        if (ev) cudaEventDestroy(ev);
     prof_collect(c);
     for (auto &b : c->stage) b.release();
     for (auto &b : c->pin) b.release();
@@ -332,15 +344,69 @@ static int32_t preprocess_common(amira_ctx *c, const void *wave, bool pcm16, con
     if (t_stride < max_len || t_stride <= 0)
         return fail(c, AMIRA_ERR_INVALID_VALUE, "t_stride smaller than the longest features_len");
     const size_t esz = pcm16 ? sizeof(int16_t) : sizeof(float);
-    const uint8_t *wave_dev = nullptr;
-    CK(stage_in<uint8_t>(c, 0, static_cast<const uint8_t *>(wave), (size_t)total_elems * esz, &wave_dev), "waveform H2D");
-    float *feat_dev = nullptr;
-    bool feat_host = false;
     const size_t feat_count = (size_t)B * kMel * (size_t)t_stride;
-    CK(stage_out<float>(c, 1, features, feat_count, &feat_dev, &feat_host), "features staging");
-    CK(launch_frontend(c, wave_dev, pcm16, starts, lens, B, feat_dev, t_stride), "front-end launch");
-    CK(finish_out<float>(c, features, feat_dev, feat_count, feat_host), "features D2H");
+    const bool wave_host = wave && total_elems > 0 && !is_device_ptr(wave), feat_host = !is_device_ptr(features);
+    const uint8_t *wave_dev = static_cast<const uint8_t *>(wave);
+    float *feat_dev = features;
+    if (wave_host || !wave || total_elems == 0) {
+        CK(c->stage[0].reserve((size_t)total_elems * esz + 16), "waveform staging");
+        wave_dev = c->stage[0].as<uint8_t>();
+    }
+    if (feat_host) {
+        CK(c->stage[1].reserve(feat_count * sizeof(float) + 16), "features staging");
+        feat_dev = c->stage[1].as<float>();
+    }
+    // Host buffers: utterances are independent, so the call is pipelined in chunks of utterances — H2D of chunk k+1, the
+    // kernels of chunk k and the D2H of chunk k-1 run concurrently on three streams.  Device buffers: one chunk, no copies.
+    const int n_chunks = (wave_host || feat_host) ? std::max(1, std::min(Ctx::kMaxChunks, B / 32)) : 1;
+    const bool dbg = std::getenv("AMIRA_DEBUG_TIMELINE") != nullptr;
+    cudaEvent_t dbg_ev[1 + 3 * Ctx::kMaxChunks] = {};
+    if (dbg) {
+        for (auto &ev : dbg_ev) cudaEventCreate(&ev);
+        cudaEventRecord(dbg_ev[0], c->stream);
+    }
+    auto chunk_elem = [&](int b) -> int64_t { return b >= B ? total_elems : starts[b]; };
+    for (int k = 0; k < n_chunks && n_chunks > 1; ++k) {  // every chunk's metadata first (see launch_frontend)
+        const int b0 = (int)((int64_t)B * k / n_chunks), b1 = (int)((int64_t)B * (k + 1) / n_chunks);
+        if (b1 > b0)
+            CK(launch_frontend(c, wave_dev, pcm16, starts + b0, lens + b0, b1 - b0, feat_dev + (size_t)b0 * kMel * t_stride, t_stride, k, 1),
+               "front-end metadata");
+    }
+    for (int k = 0; k < n_chunks; ++k) {
+        const int b0 = (int)((int64_t)B * k / n_chunks), b1 = (int)((int64_t)B * (k + 1) / n_chunks);
+        if (b1 <= b0) continue;
+        if (wave_host) {
+            const int64_t e0 = chunk_elem(b0), e1 = chunk_elem(b1);
+            if (e1 > e0)
+                CK(cudaMemcpyAsync(c->stage[0].as<uint8_t>() + (size_t)e0 * esz, static_cast<const uint8_t *>(wave) + (size_t)e0 * esz,
+                                   (size_t)(e1 - e0) * esz, cudaMemcpyHostToDevice, c->h2d_stream), "waveform H2D");
+            CK(cudaEventRecord(c->ev_pool[2 * k], c->h2d_stream), "event");
+            CK(cudaStreamWaitEvent(c->stream, c->ev_pool[2 * k], 0), "event wait");
+            if (dbg) cudaEventRecord(dbg_ev[1 + 3 * k], c->h2d_stream);
+        }
+        CK(launch_frontend(c, wave_dev, pcm16, starts + b0, lens + b0, b1 - b0, feat_dev + (size_t)b0 * kMel * t_stride, t_stride, k,
+                           n_chunks > 1 ? 2 : 0),
+           "front-end launch");
+        if (feat_host) {
+            CK(cudaEventRecord(c->ev_pool[2 * k + 1], c->stream), "event");
+            CK(cudaStreamWaitEvent(c->d2h_stream, c->ev_pool[2 * k + 1], 0), "event wait");
+            const size_t o = (size_t)b0 * kMel * t_stride, n = (size_t)(b1 - b0) * kMel * t_stride;
+            CK(cudaMemcpyAsync(features + o, feat_dev + o, n * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream), "features D2H");
+            if (dbg) { cudaEventRecord(dbg_ev[2 + 3 * k], c->stream); cudaEventRecord(dbg_ev[3 + 3 * k], c->d2h_stream); }
+        }
+    }
+    if (feat_host) CK(cudaStreamSynchronize(c->d2h_stream), "features D2H sync");
     CK(cudaStreamSynchronize(c->stream), "front-end sync");
+    if (dbg) {
+        for (int k = 0; k < n_chunks && wave_host && feat_host; ++k) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, dbg_ev[0], dbg_ev[1 + 3 * k]);
+            cudaEventElapsedTime(&b, dbg_ev[0], dbg_ev[2 + 3 * k]);
+            cudaEventElapsedTime(&d, dbg_ev[0], dbg_ev[3 + 3 * k]);
+            std::fprintf(stderr, "[fe timeline] chunk %d: H2D done %.2f ms, kernels done %.2f ms, D2H done %.2f ms\n", k, a, b, d);
+        }
+        for (auto &ev : dbg_ev) cudaEventDestroy(ev);
+    }
     return AMIRA_OK;
 }
 
@@ -468,8 +534,13 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
     const int32_t *lens_dev = c->stage[9].as<int32_t>();
     const int32_t *slots_dev = slots_host ? lens_dev + B : nullptr;
 
-    const float *enc_dev;
-    CK(stage_in<float>(c, 0, encoder_outputs, (size_t)B * kEnc * T, &enc_dev), "encoder_outputs H2D");
+    // encoder outputs in host memory are uploaded by the launcher, chunk by chunk, overlapped with their projection
+    const float *enc_dev = encoder_outputs, *enc_host = nullptr;
+    if (encoder_outputs && T > 0 && !is_device_ptr(encoder_outputs)) {
+        CK(c->stage[0].reserve(sizeof(float) * (size_t)B * kEnc * T), "encoder_outputs staging");
+        enc_dev = c->stage[0].as<float>();
+        enc_host = encoder_outputs;
+    }
     const size_t n_state = (size_t)2 * B * kH;
     float *s1_dev = nullptr, *s2_dev = nullptr;
     bool s1_h = false, s2_h = false;
@@ -486,7 +557,7 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
     CK(stage_out<int32_t>(c, 3, tokens, (size_t)B * cap, &tok_dev, &tok_h), "tokens staging");
     CK(stage_out<int32_t>(c, 4, n_tokens, (size_t)B, &nt_dev, &nt_h), "n_tokens staging");
     CK(stage_out<int32_t>(c, 5, n_steps, (size_t)B, &ns_dev, &ns_h), "n_steps staging");
-    CK(launch_greedy_decode(c, enc_dev, B, T, lens_dev, h_lens, slots_dev, s1_dev, s2_dev, tok_dev, nt_dev, ns_dev),
+    CK(launch_greedy_decode(c, enc_dev, enc_host, B, T, lens_dev, h_lens, slots_dev, s1_dev, s2_dev, tok_dev, nt_dev, ns_dev),
        "greedy decode launch");
     CK(finish_out<int32_t>(c, tokens, tok_dev, (size_t)B * cap, tok_h), "tokens D2H");
     CK(finish_out<int32_t>(c, n_tokens, nt_dev, (size_t)B, nt_h), "n_tokens D2H");

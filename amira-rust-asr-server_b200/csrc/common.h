@@ -118,11 +118,17 @@ struct Ctx {
     double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-    // front end
+    // front end; one set of scratch per in-flight chunk of a pipelined (host-buffer) call
+    static constexpr int kMaxChunks = 8;
     FrontendTables *tables_dev = nullptr;
-    DevBuf fe_meta;      // per call: starts[B], lens[B], tile prefix[B+1]
-    DevBuf fe_partials;  // per tile x mel: (mean, M2) in double
-    PinBuf fe_meta_pin;
+    DevBuf fe_meta[kMaxChunks];      // per chunk: starts[B], lens[B], tile prefix[B+1]
+    DevBuf fe_partials[kMaxChunks];  // per tile x mel: (mean, M2) in double
+    PinBuf fe_meta_pin[kMaxChunks];
+
+    // host-buffer calls overlap H2D copies, kernels and D2H copies chunk by chunk: copies run on these two streams,
+    // ordered against `stream` with events from this pool
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_pool[4 * kMaxChunks] = {};
 
     // staging for host-pointer arguments (slot per argument position)
     DevBuf stage[10];
@@ -157,7 +163,7 @@ struct ProfScope {  // RAII: records begin/end events around one launch when pro
 // wave_dev: int16 PCM or float samples; utterance b occupies [starts[b], starts[b]+lens[b]) (element units).
 // features_dev [B][128][t_stride]; frames >= features_len are zero.
 cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const int64_t *starts_host,
-                            const int64_t *lens_host, int B, float *features_dev, int64_t t_stride);
+                            const int64_t *lens_host, int B, float *features_dev, int64_t t_stride, int slot = 0, int phase = 0);
 cudaError_t launch_bytes_to_f32(Ctx *c, const uint8_t *bytes_dev, size_t n_bytes, bool drop_odd, float *out_dev);
 
 // decoder.cu ---------------------------------------------------------------------------------------------------
@@ -165,7 +171,9 @@ cudaError_t decoder_prepare_weights(Ctx *c);  // derived tables from c->w_blob
 void decoder_release(Ctx *c);
 // enc_dev [B][1024][T]; lens_dev int32[B]; slots_dev nullable: when given, states live in c->slot_s1/2 rows
 // slots[b] ([slot][2][640]); otherwise s1/s2 are [2][B][640] in/out (nullable => zero start, result dropped).
-cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, int B, int T, const int32_t *lens_dev,
+// enc_host != nullptr: the encoder outputs still live in host memory; the launcher uploads them into enc_dev chunk by
+// chunk on c->h2d_stream and overlaps the upload with the encoder projection of the chunks already on the device.
+cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, const float *enc_host, int B, int T, const int32_t *lens_dev,
                                  const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev,
                                  int32_t *ntok_dev, int32_t *nsteps_dev);
 const int32_t *decoder_fail_count_dev(Ctx *c);  // failed-stream counter of the last greedy launch
@@ -177,7 +185,7 @@ cudaError_t launch_decoder_joint(Ctx *c, const float *enc_dev, int B, int T, con
 // decoder_tc.cu (tcgen05 paths) --------------------------------------------------------------------------------
 cudaError_t decoder_tc_prepare_weights(Ctx *c);
 void decoder_tc_release(Ctx *c);
-cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, int B, int T, const int32_t *lens_dev,
+cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *enc_host, int B, int T, const int32_t *lens_dev,
                                     const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev,
                                     int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev);
 cudaError_t launch_tc_gemm(Ctx *c, const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_lo, const __nv_bfloat16 *w_hi,

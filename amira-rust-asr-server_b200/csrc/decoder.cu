@@ -618,15 +618,19 @@ cudaError_t decoder_prepare_weights(Ctx *c) {
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, int B, int T, const int32_t *lens_dev,
+cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, const float *enc_host, int B, int T, const int32_t *lens_dev,
                                  const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev,
                                  int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev) {
     // decode_engine: 1 = fp32 CUDA-core persistent kernel (this file); tcgen05 split-bf16 (decoder_tc.cu): 2 = grid-synchronised,
     // 3 = dataflow; 0 = auto (3)
     if (c->cfg.decode_engine != 1)
-        return launch_greedy_decode_tc(c, enc_dev, B, T, lens_dev, lens_host, slots_dev, s1_dev, s2_dev, tokens_dev, ntok_dev,
+        return launch_greedy_decode_tc(c, enc_dev, enc_host, B, T, lens_dev, lens_host, slots_dev, s1_dev, s2_dev, tokens_dev, ntok_dev,
                                        nsteps_dev);
     DecoderPriv *d = c->dec;
+    if (enc_host) {  // fp32 reference engine: plain upload
+        cudaError_t eu = cudaMemcpyAsync(const_cast<float *>(enc_dev), enc_host, sizeof(float) * (size_t)B * kEnc * T, cudaMemcpyHostToDevice, c->stream);
+        if (eu != cudaSuccess) return eu;
+    }
     const BlobLayout L = blob_layout();
     const size_t BH = (size_t)B * kH;
     const int Tq = T > 0 ? T : 1;

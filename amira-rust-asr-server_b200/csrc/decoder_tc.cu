@@ -1091,7 +1091,7 @@ cudaError_t decoder_tc_prepare_weights(Ctx *c) {
 
 static size_t tc_align(size_t x) { return (x + 1023) & ~(size_t)1023; }
 
-cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, int B, int T, const int32_t *lens_dev,
+cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *enc_host, int B, int T, const int32_t *lens_dev,
                                     const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev,
                                     int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev) {
     DecoderPriv *d = c->dec;
@@ -1136,8 +1136,24 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, int B, int T, 
     if (T > 0) {  // hoisted encoder projection on tcgen05: E[(b,t)][:] = W_enc enc[b][:, t] + b_enc + b_pred
         __nv_bfloat16 *eh = reinterpret_cast<__nv_bfloat16 *>(base + oeh), *el = reinterpret_cast<__nv_bfloat16 *>(base + oel);
         ProfScope prof(c, PK_ENC_PROJ);
-        if ((e = launch_split_transpose_enc(c, enc_dev, B, T, lens_dev, eh, el)) != cudaSuccess) return e;
-        if ((e = launch_tc_gemm(c, eh, el, w->we_hi, w->we_lo, d->bjoint, E, kH, B * T, kH, kEnc)) != cudaSuccess) return e;
+        // host-resident encoder outputs: upload chunk k+1 (h2d_stream) while chunk k is split and projected (stream).  At most
+        // three uploads are queued at a time (the host waits on the event of chunk k-3): the copy engine is FIFO across
+        // streams, and a burst of bulk copies would starve the copies of any other context sharing the GPU.
+        const int n_chunks = enc_host ? std::max(1, std::min(2 * Ctx::kMaxChunks, B / 32)) : 1;
+        for (int k = 0; k < n_chunks; ++k) {
+            const int b0 = (int)((long long)B * k / n_chunks), b1 = (int)((long long)B * (k + 1) / n_chunks);
+            if (b1 <= b0) continue;
+            const size_t eo = (size_t)b0 * kEnc * T, ro = (size_t)b0 * T;
+            if (enc_host) {
+                if (k >= 3 && (e = cudaEventSynchronize(c->ev_pool[2 * Ctx::kMaxChunks + k - 3])) != cudaSuccess) return e;
+                if ((e = cudaMemcpyAsync(const_cast<float *>(enc_dev) + eo, enc_host + eo, sizeof(float) * (size_t)(b1 - b0) * kEnc * T,
+                                         cudaMemcpyHostToDevice, c->h2d_stream)) != cudaSuccess) return e;
+                if ((e = cudaEventRecord(c->ev_pool[2 * Ctx::kMaxChunks + k], c->h2d_stream)) != cudaSuccess) return e;
+                if ((e = cudaStreamWaitEvent(c->stream, c->ev_pool[2 * Ctx::kMaxChunks + k], 0)) != cudaSuccess) return e;
+            }
+            if ((e = launch_split_transpose_enc(c, enc_dev + eo, b1 - b0, T, lens_dev + b0, eh + ro * kEnc, el + ro * kEnc)) != cudaSuccess) return e;
+            if ((e = launch_tc_gemm(c, eh + ro * kEnc, el + ro * kEnc, w->we_hi, w->we_lo, d->bjoint, E + ro * kH, kH, (b1 - b0) * T, kH, kEnc)) != cudaSuccess) return e;
+        }
     }
     if (use_ws)
         return launch_greedy_ws(c, E, B, T, lens_dev, reinterpret_cast<int *>(base + operm), slots_dev, s1_dev, s2_dev, tokens_dev,

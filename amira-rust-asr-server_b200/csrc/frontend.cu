@@ -421,14 +421,17 @@ size_t fe_smem_bytes() {
 }  // namespace
 
 cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const int64_t *starts_host,
-                            const int64_t *lens_host, int B, float *features_dev, int64_t t_stride) {
+                            const int64_t *lens_host, int B, float *features_dev, int64_t t_stride, int slot, int phase) {
     if (B <= 0) return cudaSuccess;
+    if (slot < 0 || slot >= Ctx::kMaxChunks) return cudaErrorInvalidValue;
+    DevBuf &fe_meta = c->fe_meta[slot], &fe_partials = c->fe_partials[slot];
+    PinBuf &fe_meta_pin = c->fe_meta_pin[slot];
     // host metadata: starts, lens, tile prefix -> one pinned block, one async copy
     const size_t meta_bytes = sizeof(int64_t) * 2 * (size_t)B + sizeof(int32_t) * ((size_t)B + 1);
     cudaError_t e;
-    if ((e = c->fe_meta_pin.reserve(meta_bytes)) != cudaSuccess) return e;
-    if ((e = c->fe_meta.reserve(meta_bytes)) != cudaSuccess) return e;
-    int64_t *h_starts = c->fe_meta_pin.as<int64_t>();
+    if ((e = fe_meta_pin.reserve(meta_bytes)) != cudaSuccess) return e;
+    if ((e = fe_meta.reserve(meta_bytes)) != cudaSuccess) return e;
+    int64_t *h_starts = fe_meta_pin.as<int64_t>();
     int64_t *h_lens = h_starts + B;
     int32_t *h_pfx = reinterpret_cast<int32_t *>(h_lens + B);
     int64_t tiles = 0;
@@ -441,15 +444,19 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
     }
     h_pfx[B] = (int32_t)tiles;
     if (tiles > 0x7fffffff) return cudaErrorInvalidValue;
-    if ((e = cudaMemcpyAsync(c->fe_meta.p, c->fe_meta_pin.p, meta_bytes, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
+    // phase 1 = metadata upload only, 2 = kernels only (metadata already uploaded for this slot), 0 = both.  Pipelined host
+    // calls upload every chunk's metadata BEFORE queueing the bulk copies: a small copy that becomes runnable later would
+    // wait in the copy engine behind all bulk copies already queued there, and its kernels with it.
+    if (phase != 2 && (e = cudaMemcpyAsync(fe_meta.p, fe_meta_pin.p, meta_bytes, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
         return e;
+    if (phase == 1) return fe_partials.reserve(sizeof(double2) * (size_t)std::max<int64_t>(tiles, 1) * kMel);
     FeMeta meta;
-    meta.starts = c->fe_meta.as<int64_t>();
+    meta.starts = fe_meta.as<int64_t>();
     meta.lens = meta.starts + B;
     meta.tile_pfx = reinterpret_cast<const int32_t *>(meta.lens + B);
     meta.B = B;
     meta.n_tiles = (int)tiles;
-    if ((e = c->fe_partials.reserve(sizeof(double2) * (size_t)std::max<int64_t>(tiles, 1) * kMel)) != cudaSuccess) return e;
+    if ((e = fe_partials.reserve(sizeof(double2) * (size_t)std::max<int64_t>(tiles, 1) * kMel)) != cudaSuccess) return e;
 
     if (tiles > 0) {
         ProfScope prof(c, PK_FE_LOGMEL);
@@ -463,7 +470,7 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
             }
             fe_logmel_kernel<int16_t><<<grid, FE_THREADS, smem, c->stream>>>(
                 static_cast<const int16_t *>(wave_dev), meta, c->tables_dev, features_dev, t_stride,
-                c->fe_partials.as<double2>());
+                fe_partials.as<double2>());
         } else {
             const size_t smem = fe_smem_bytes<float>();
             static bool attr_done = false;
@@ -473,7 +480,7 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
             }
             fe_logmel_kernel<float><<<grid, FE_THREADS, smem, c->stream>>>(
                 static_cast<const float *>(wave_dev), meta, c->tables_dev, features_dev, t_stride,
-                c->fe_partials.as<double2>());
+                fe_partials.as<double2>());
         }
         c->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -481,7 +488,7 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
     const int64_t rows = (int64_t)B * kMel;
     ProfScope prof(c, PK_FE_NORMALIZE);
     fe_normalize_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, c->stream>>>(meta, features_dev, t_stride,
-                                                                            c->fe_partials.as<double2>());
+                                                                            fe_partials.as<double2>());
     c->launches++;
     return cudaGetLastError();
 }
