@@ -1,5 +1,5 @@
 """Builds libamira_b200.so (sm_100a only) with nvcc, in-tree.  No torch, no JIT cache: the .so travels with the repo
-snapshot to the GPU box.  Mirrors what the Rust crate's build.rs does (rust/amira-b200-sys/build.rs)."""
+snapshot to the GPU box.  Mirrors what the Rust crate's build.rs does."""
 from __future__ import annotations
 
 import os

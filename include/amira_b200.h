@@ -4,8 +4,8 @@
  *   (1) the `preprocessor` front end  (i16 PCM -> f32, pre-emphasis, STFT, 128-mel, log, normalise)
  *   (2) the `decoder_joint` RNN-T greedy decode loop (LSTM prediction net, joint, argmax, limits)
  *
- * This header is the single source of truth for every binding (Rust FFI crate in rust/, ctypes in
- * amira_b200/_lib.py, the C++ host in csrc/host_pipeline.*).  It follows the FFI conventions of the reference's
+ * This header is the single source of truth for every binding (Rust FFI binding in INTEGRATION.md, ctypes in
+ * amira-rust-asr-server_b200/_lib.py, the C++ host in csrc/host_pipeline.*).  It follows the FFI conventions of the reference's
  * own CUDA crate (citations relative to the reference root):
  *   - plain `extern "C"`, POD arguments, opaque handles with create/destroy pairs
  *       (src/cuda/mod.rs:371-412, src/cuda/cuda_helper.cu:63-142)
