@@ -86,6 +86,7 @@ struct WsParams {
     float *s1, *s2;
     int *tokens, *ntok, *nsteps;
     int max_sym, max_total, blank, relu;
+    int norot;          // debug: all CTAs walk the k-chunks in the same order
     long long *trace;   // nullable: [W_TRACE_ITS][32] globaltimer stamps of M-tile 0 (debug)
 };
 
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
 
     // CTAs of one phase read the same activation tile at the same time: each starts at a different k-chunk so the requests
     // spread over the tile's L2 slices instead of queueing on one 16 KB region
-    const int kc0 = (slice * 3 + role) % W_KC;
+    const int kc0 = p.norot ? 0 : (slice * 3 + role) % W_KC;
 
     if (tid == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled operand layout needs a 1024-byte aligned base
@@ -367,12 +368,15 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * W_ACC_COLS;
                 int kc = kc0;
+                long long wait_cyc = 0;
 #pragma unroll 1
                 for (int ki = 0; ki < W_KC; ++ki) {
                     const uint32_t wd = w_lo32 + kc * (2 * W_WCHUNK >> 4);
                     {   // hi unit: a_hi * [w_hi ; w_lo]  (N = 128)
                         const uint32_t s = u % W_RING;
+                        const long long tw0 = p.trace ? clock64() : 0;
                         mbar_wait_wd(&sm.full[s], (u / W_RING) & 1);
+                        if (p.trace && ki > 0) wait_cyc += clock64() - tw0;
                         if (ki == 0) WS_TRACE(1);
                         tc_fence_after();
                         const uint32_t ad = ring_lo32 + s * (W_UNIT >> 4);
@@ -385,7 +389,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     }
                     {   // lo unit: a_lo * w_hi  (N = 64, accumulator columns 0..63)
                         const uint32_t s = u % W_RING;
+                        const long long tw0 = p.trace ? clock64() : 0;
                         mbar_wait_wd(&sm.full[s], (u / W_RING) & 1);
+                        if (p.trace) wait_cyc += clock64() - tw0;
                         tc_fence_after();
                         const uint32_t ad = ring_lo32 + s * (W_UNIT >> 4);
                         umma_bf16_lo(acc, ad, wd, idesc_hi, 1);
@@ -399,6 +405,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 }
                 umma_commit(&sm.acc_full[buf]);
                 WS_TRACE(2);
+                if (p.trace && role == R_D && slice == 0 && mt == 0 && it < W_TRACE_ITS) p.trace[it * 32 + 31] = wait_cyc;
                 ++tile;
             }
         }
@@ -788,6 +795,7 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     p.max_sym = c->cfg.max_symbols_per_step; p.max_total = c->cfg.max_total_tokens; p.blank = c->cfg.blank_id;
     p.relu = c->cfg.joint_activation;
     d->fail_count_dev = p.fail_count;
+    p.norot = getenv("AMIRA_WS_NOROT") ? 1 : 0;
     if (getenv("AMIRA_WS_TRACE")) {
         p.trace = reinterpret_cast<long long *>(work + otrace);
         cudaMemsetAsync(p.trace, 0, sizeof(long long) * W_TRACE_ITS * 32, c->stream);

@@ -44,4 +44,4 @@ for lo, hi in ((4, 120), (140, 300), (380, 470)):
             row.append(f"{ev[e]}={np.median(v) / 1e3:7.2f}" if v else f"{ev[e]}=   --  ")
         print(f"  {names[role]:>2}: " + "  ".join(row))
     v = [tr[i, 30] - tr[i - 1, 30] for i in sel]
-    print(f"  ctl done = {np.median(v) / 1e3:7.2f}")
+    print(f"  ctl done = {np.median(v) / 1e3:7.2f};  D-role MMA thread waited on TMA data {np.median([tr[i, 31] for i in sel]) / 1.965e3:.2f} us per unit (after the first chunk)")
