@@ -379,6 +379,12 @@ class Context:
         s2 = np.ascontiguousarray(state.states_2, np.float32)
         self._check(self._L.amira_stream_set_state(self._h, slot, _ptr(s1), _ptr(s2)))
 
+    def stream_decode_raw(self, slots: np.ndarray, enc_ptr: int, T: int, lens: np.ndarray | None, tokens_ptr: int, ntok_ptr: int,
+                          nsteps_ptr: int | None = None):
+        """One tick on device-resident state slots with caller-managed (host or device) buffers."""
+        self._check(self._L.amira_stream_decode(self._h, _ptr(slots), int(slots.size), _ptr(enc_ptr), T, _ptr(lens),
+                                                _ptr(tokens_ptr), _ptr(ntok_ptr), _ptr(nsteps_ptr)))
+
     def stream_decode(self, slots, encoder_outputs: np.ndarray, encoded_lengths=None):
         enc = np.ascontiguousarray(encoder_outputs, dtype=np.float32)
         n, _, T = enc.shape

@@ -516,19 +516,29 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
     CK(c->pin[0].reserve(sizeof(int32_t) * 2 * (size_t)B), "lens pin");
     int32_t *h_lens = c->pin[0].as<int32_t>();
     int32_t *h_slots = h_lens + B;
+    auto unmark = [&](int upto) {  // slot_used == 2 marks "seen in this tick" (duplicate detection in O(B))
+        if (slots_host)
+            for (int q = 0; q < upto; ++q) c->slot_used[(size_t)h_slots[q]] = 1;
+    };
     for (int b = 0; b < B; ++b) {
         const int64_t L = encoded_lengths ? encoded_lengths[b] : T;
-        if (L < 0 || L > T) return fail(c, AMIRA_ERR_INVALID_VALUE, "encoded_lengths out of range");
+        if (L < 0 || L > T) { unmark(b); return fail(c, AMIRA_ERR_INVALID_VALUE, "encoded_lengths out of range"); }
         h_lens[b] = (int32_t)L;
         if (slots_host) {
             const int32_t s = slots_host[b];
-            if (s < 0 || s >= c->cfg.max_streams || !c->slot_used[(size_t)s])
+            if (s < 0 || s >= c->cfg.max_streams || !c->slot_used[(size_t)s]) {
+                unmark(b);
                 return fail(c, AMIRA_ERR_INVALID_VALUE, "stream slot not open");
-            for (int q = 0; q < b; ++q)
-                if (h_slots[q] == s) return fail(c, AMIRA_ERR_INVALID_VALUE, "duplicate stream slot in one tick");
+            }
+            if (c->slot_used[(size_t)s] == 2) {
+                unmark(b);
+                return fail(c, AMIRA_ERR_INVALID_VALUE, "duplicate stream slot in one tick");
+            }
+            c->slot_used[(size_t)s] = 2;
             h_slots[b] = s;
         }
     }
+    unmark(B);
     CK(c->stage[9].reserve(sizeof(int32_t) * 2 * (size_t)B), "lens dev");
     CK(cudaMemcpyAsync(c->stage[9].p, h_lens, sizeof(int32_t) * 2 * (size_t)B, cudaMemcpyHostToDevice, c->stream), "lens H2D");
     const int32_t *lens_dev = c->stage[9].as<int32_t>();

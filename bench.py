@@ -108,6 +108,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this rank to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned host buffer is allocated, so
+    the staging memory of the host-buffer path sits on the GPU's NUMA node (one process per GPU, as a server would)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -167,6 +185,37 @@ def run_reference(args, rank: int):
         "gpu_launches": 0}))
 
 
+# ------------------------------------------------------------------------------------------------ cfg4: streaming tick
+def run_streaming(A, torch, dev, ctx, n_streams: int, ticks: int, warm: int):
+    """BASELINE config 4: n_streams concurrent WebSocket streams, 160 ms chunks (2560 samples -> 17 mel frames -> 3 encoder
+    frames), LSTM state carried in device-resident slots.  One tick = front end of every stream's chunk + one incremental
+    decode of every stream (encoder stubbed by synthetic [n,1024,3]).  Host buffers in and out (PCM, encoder chunk in;
+    features, tokens out), wall clock per tick around the two blocking C-ABI calls."""
+    chunk, T = 2560, 3
+    rng = np.random.default_rng(99)
+    pcm = torch.from_numpy((rng.standard_normal(n_streams * chunk) * 3000).astype(np.int16)).pin_memory()
+    offsets = np.arange(n_streams + 1, dtype=np.int64) * chunk
+    feats = torch.empty((n_streams, 128, 32), dtype=torch.float32).pin_memory()
+    enc = torch.from_numpy((0.5 * rng.standard_normal((n_streams, 1024, T))).astype(np.float32)).pin_memory()
+    tok = torch.zeros((n_streams, ctx.max_total_tokens), dtype=torch.int32).pin_memory()
+    ntok = torch.zeros(n_streams, dtype=torch.int32).pin_memory()
+    flens = np.zeros(n_streams, np.int64)
+    slots = np.array([ctx.stream_open() for _ in range(n_streams)], np.int32)
+    lat = []
+    for i in range(warm + ticks):
+        t0 = time.perf_counter()
+        ctx.preprocess_pcm16_raw(pcm.data_ptr(), offsets, n_streams, feats.data_ptr(), 32, flens)
+        ctx.stream_decode_raw(slots, enc.data_ptr(), T, None, tok.data_ptr(), ntok.data_ptr(), None)
+        if i >= warm:
+            lat.append((time.perf_counter() - t0) * 1e3)
+    for sl in slots:
+        ctx.stream_close(int(sl))
+    lat = np.array(lat)
+    return {"workload": f"cfg4: {n_streams} streams x 160 ms chunks, {ticks} ticks, state in resident slots, host buffers",
+            "p50_chunk_ms": float(np.percentile(lat, 50)), "p99_chunk_ms": float(np.percentile(lat, 99)),
+            "audio_s_per_s": float(n_streams * 0.16 / (np.mean(lat) / 1e3)), "tokens_last_tick": int(ntok.numpy().clip(min=0).sum())}
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def main():
     ap = argparse.ArgumentParser()
@@ -179,6 +228,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=24)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-stream", action="store_true")
+    ap.add_argument("--stream-ticks", type=int, default=60)
     ap.add_argument("--engine", type=int, default=0)
     args = ap.parse_args()
 
@@ -195,6 +246,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: amira_b200 has no CPU path")
+    bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -306,6 +358,10 @@ def main():
         ctx_fe.close()
         del enc_pin, feats_pin
 
+    streaming = None
+    if not args.no_stream and rank == 0:
+        streaming = run_streaming(A, torch, dev, ctx, 1024, args.stream_ticks, 5)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -346,6 +402,8 @@ def main():
                               "frac": fe_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind, "bytes_per_launch": fe_bytes,
                               "avg_launch_ms": fe_avg_ms},
     }
+    if streaming:
+        out["streaming"] = streaming
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu:
