@@ -192,8 +192,8 @@ cudaError_t launch_tc_gemm(Ctx *c, const __nv_bfloat16 *a_hi, const __nv_bfloat1
                            const __nv_bfloat16 *w_lo, const float *bias, float *C, long long ldc, int M, int N, int K);
 cudaError_t launch_split_rows(Ctx *c, const float *x, size_t ldx, __nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t ldo,
                               size_t rows, size_t cols);
-cudaError_t launch_split_transpose_enc(Ctx *c, const float *enc, int B, int T, const int *lens_dev, __nv_bfloat16 *hi,
-                                       __nv_bfloat16 *lo);
+cudaError_t launch_split_transpose_enc(Ctx *c, const float *enc, int B, int T, const int *lens_dev, const int *eoff_dev,
+                                       int row_base, __nv_bfloat16 *hi, __nv_bfloat16 *lo);
 
 
 // decoder_ws.cu (weight-stationary dataflow engine, decode_engine = 4) ------------------------------------------
@@ -201,7 +201,7 @@ bool decoder_ws_supported(const Ctx *c);
 cudaError_t decoder_ws_prepare(Ctx *c);
 // work == nullptr: size query (*work_bytes receives the workspace size).  E [B*T][640] and perm_dev [Mpad] from the caller.
 cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t *lens_dev, const int *perm_dev,
-                             const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
+                             const int *eoff_dev, const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
                              int32_t *nsteps_dev, char *work, size_t *work_bytes);
 
 }  // namespace amira

@@ -65,12 +65,16 @@ __global__ void split_rows_kernel(const float *__restrict__ x, size_t ldx, __nv_
     }
 }
 
-// encoder_outputs [B][1024][T] (t contiguous) -> K-major rows [(b*T + t)][1024] hi/lo bf16, via a 32x32 smem transpose
+// encoder_outputs [B][1024][T] (t contiguous) -> K-major rows [(eoff[b] + t)][1024] hi/lo bf16 (valid frames packed back to
+// back: frames >= lens[b] are never projected), via a 32x32 smem transpose
 __global__ void split_transpose_enc_kernel(const float *__restrict__ enc, int T, const int *__restrict__ lens,
-                                           __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+                                           const int *__restrict__ eoff, int row_base, __nv_bfloat16 *__restrict__ hi,
+                                           __nv_bfloat16 *__restrict__ lo) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
-    if (t0 >= lens[b]) return;
+    const int len = lens[b];
+    if (t0 >= len) return;
+    const size_t r0 = (size_t)(eoff[b] - row_base);
     const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
     const float *src = enc + (size_t)b * kEnc * T;
     for (int j = ty; j < 32; j += 8) {
@@ -80,10 +84,10 @@ __global__ void split_transpose_enc_kernel(const float *__restrict__ enc, int T,
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
         const int t = t0 + j;
-        if (t < T) {
+        if (t < len) {
             __nv_bfloat16 h, l;
             split_bf16(tile[tx][j], h, l);
-            const size_t o = ((size_t)b * T + t) * kEnc + f0 + tx;
+            const size_t o = (r0 + t) * kEnc + f0 + tx;
             hi[o] = h;
             lo[o] = l;
         }
@@ -232,11 +236,11 @@ cudaError_t launch_split_rows(Ctx *c, const float *x, size_t ldx, __nv_bfloat16 
     return cudaGetLastError();
 }
 
-cudaError_t launch_split_transpose_enc(Ctx *c, const float *enc, int B, int T, const int *lens_dev, __nv_bfloat16 *hi,
-                                       __nv_bfloat16 *lo) {
+cudaError_t launch_split_transpose_enc(Ctx *c, const float *enc, int B, int T, const int *lens_dev, const int *eoff_dev,
+                                       int row_base, __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
     if (B <= 0 || T <= 0) return cudaSuccess;
     dim3 grid((T + 31) / 32, kEnc / 32, B), block(32, 8);
-    split_transpose_enc_kernel<<<grid, block, 0, c->stream>>>(enc, T, lens_dev, hi, lo);
+    split_transpose_enc_kernel<<<grid, block, 0, c->stream>>>(enc, T, lens_dev, eoff_dev, row_base, hi, lo);
     c->launches++;
     return cudaGetLastError();
 }
@@ -275,7 +279,7 @@ struct TcDecParams {
     CUtensorMap whh0_hi, whh0_lo, w1_hi, w1_lo, wp_hi, wp_lo, wo_hi, wo_lo;
     const float *g0p, *b1p, *boutp, *E;
     int B, Mpad, MT, T;
-    const int *lens, *slots, *perm;
+    const int *lens, *slots, *perm, *eoff;
     __nv_bfloat16 *h0b_hi, *h0b_lo, *h1b_hi, *h1b_lo, *zb_hi, *zb_lo;
     float *h0f, *h1f, *c0, *c1;
     float *pval;
@@ -436,7 +440,7 @@ __device__ __forceinline__ void run_phase(const TcDecParams &p, unsigned char *s
                     *reinterpret_cast<uint4 *>(bh) = *reinterpret_cast<uint4 *>(vh);
                     *reinterpret_cast<uint4 *>(bl) = *reinterpret_cast<uint4 *>(vl);
                 } else if (PH == PH_C) {
-                    const float *e = p.E + ((size_t)p.perm[row] * p.T + c.t) * kH + nb;
+                    const float *e = p.E + ((size_t)p.eoff[p.perm[row]] + c.t) * kH + nb;
                     __nv_bfloat16 *bh = p.zb_hi + (size_t)row * kH + nb, *bl = p.zb_lo + (size_t)row * kH + nb;
 #pragma unroll
                     for (int j8 = 0; j8 < 4; ++j8) {
@@ -920,7 +924,7 @@ __global__ void __launch_bounds__(D_THREADS, 1) greedy_df_kernel(const __grid_co
                     *reinterpret_cast<uint4 *>(bh) = *reinterpret_cast<uint4 *>(vh);
                     *reinterpret_cast<uint4 *>(bl) = *reinterpret_cast<uint4 *>(vl);
                 } else if (ph == PH_C) {
-                    const float *ep = p.E + ((size_t)p.perm[row] * p.T + c.t) * kH + nb;
+                    const float *ep = p.E + ((size_t)p.eoff[p.perm[row]] + c.t) * kH + nb;
                     __nv_bfloat16 *bh = p.zb_hi + (size_t)row * kH + nb, *bl = p.zb_lo + (size_t)row * kH + nb;
 #pragma unroll
                     for (int j8 = 0; j8 < 4; ++j8) {
@@ -1106,12 +1110,12 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
     auto take = [&](size_t bytes) { size_t o = off; off += tc_align(bytes); return o; };
     const size_t oE = take(sizeof(float) * (size_t)B * Tq * kH);
     const size_t oeh = take(2 * (size_t)B * Tq * kEnc), oel = take(2 * (size_t)B * Tq * kEnc);
-    const size_t operm = take(sizeof(int) * (size_t)Mpad);
+    const size_t operm = take(sizeof(int) * ((size_t)Mpad + (size_t)B + 1));  // perm[Mpad] then eoff[B+1]
     size_t ows = 0, ws_bytes = 0;
     size_t oh0h = 0, oh0l = 0, oh1h = 0, oh1l = 0, ozh = 0, ozl = 0, oh0f = 0, oh1f = 0, oc0 = 0, oc1 = 0, opv = 0, opi = 0, octl = 0, ocnt = 0;
     cudaError_t e;
     if (use_ws) {
-        if ((e = launch_greedy_ws(c, nullptr, B, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &ws_bytes)) != cudaSuccess) return e;
+        if ((e = launch_greedy_ws(c, nullptr, B, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &ws_bytes)) != cudaSuccess) return e;
         ows = take(ws_bytes);
     } else {
         oh0h = take(2 * 2 * MH); oh0l = take(2 * 2 * MH); oh1h = take(2 * 2 * MH); oh1l = take(2 * 2 * MH);
@@ -1125,12 +1129,16 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
     char *base = d->work.as<char>();
 
     // rows sorted by encoded length (descending, stable): active rows stay a prefix, whole M-tiles retire early
-    if ((e = c->pin[1].reserve(sizeof(int) * (size_t)Mpad)) != cudaSuccess) return e;
+    if ((e = c->pin[1].reserve(sizeof(int) * ((size_t)Mpad + (size_t)B + 1))) != cudaSuccess) return e;
     int *h_perm = c->pin[1].as<int>();
+    int *h_eoff = h_perm + Mpad;  // first packed row of each stream's valid frames in E
+    h_eoff[0] = 0;
+    for (int i = 0; i < B; ++i) h_eoff[i + 1] = h_eoff[i] + lens_host[i];
     for (int i = 0; i < B; ++i) h_perm[i] = i;
     std::stable_sort(h_perm, h_perm + B, [&](int a, int b2) { return lens_host[a] > lens_host[b2]; });
     for (int i = B; i < Mpad; ++i) h_perm[i] = 0;
-    if ((e = cudaMemcpyAsync(base + operm, h_perm, sizeof(int) * (size_t)Mpad, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(base + operm, h_perm, sizeof(int) * ((size_t)Mpad + (size_t)B + 1), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return e;
+    const int *eoff_dev = reinterpret_cast<int *>(base + operm) + Mpad;
 
     float *E = reinterpret_cast<float *>(base + oE);
     if (T > 0) {  // hoisted encoder projection on tcgen05: E[(b,t)][:] = W_enc enc[b][:, t] + b_enc + b_pred
@@ -1143,7 +1151,8 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
         for (int k = 0; k < n_chunks; ++k) {
             const int b0 = (int)((long long)B * k / n_chunks), b1 = (int)((long long)B * (k + 1) / n_chunks);
             if (b1 <= b0) continue;
-            const size_t eo = (size_t)b0 * kEnc * T, ro = (size_t)b0 * T;
+            const size_t eo = (size_t)b0 * kEnc * T, ro = (size_t)h_eoff[b0];
+            const int rows = h_eoff[b1] - h_eoff[b0];
             if (enc_host) {
                 if (k >= 3 && (e = cudaEventSynchronize(c->ev_pool[2 * Ctx::kMaxChunks + k - 3])) != cudaSuccess) return e;
                 if ((e = cudaMemcpyAsync(const_cast<float *>(enc_dev) + eo, enc_host + eo, sizeof(float) * (size_t)(b1 - b0) * kEnc * T,
@@ -1151,13 +1160,14 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
                 if ((e = cudaEventRecord(c->ev_pool[2 * Ctx::kMaxChunks + k], c->h2d_stream)) != cudaSuccess) return e;
                 if ((e = cudaStreamWaitEvent(c->stream, c->ev_pool[2 * Ctx::kMaxChunks + k], 0)) != cudaSuccess) return e;
             }
-            if ((e = launch_split_transpose_enc(c, enc_dev + eo, b1 - b0, T, lens_dev + b0, eh + ro * kEnc, el + ro * kEnc)) != cudaSuccess) return e;
-            if ((e = launch_tc_gemm(c, eh + ro * kEnc, el + ro * kEnc, w->we_hi, w->we_lo, d->bjoint, E + ro * kH, kH, (b1 - b0) * T, kH, kEnc)) != cudaSuccess) return e;
+            if ((e = launch_split_transpose_enc(c, enc_dev + eo, b1 - b0, T, lens_dev + b0, eoff_dev + b0, h_eoff[b0], eh + ro * kEnc,
+                                                el + ro * kEnc)) != cudaSuccess) return e;
+            if ((e = launch_tc_gemm(c, eh + ro * kEnc, el + ro * kEnc, w->we_hi, w->we_lo, d->bjoint, E + ro * kH, kH, rows, kH, kEnc)) != cudaSuccess) return e;
         }
     }
     if (use_ws)
-        return launch_greedy_ws(c, E, B, T, lens_dev, reinterpret_cast<int *>(base + operm), slots_dev, s1_dev, s2_dev, tokens_dev,
-                                ntok_dev, nsteps_dev, base + ows, &ws_bytes);
+        return launch_greedy_ws(c, E, B, T, lens_dev, reinterpret_cast<int *>(base + operm), eoff_dev, slots_dev, s1_dev, s2_dev,
+                                tokens_dev, ntok_dev, nsteps_dev, base + ows, &ws_bytes);
 
     if ((e = cudaMemsetAsync(base + ocnt, 0, sizeof(int) * (7 * (size_t)MT + 4), c->stream)) != cudaSuccess) return e;
     // activation buffers start defined (padding rows feed the MMA too)
@@ -1178,7 +1188,7 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
     p.wp_hi = w->m_wp_hi; p.wp_lo = w->m_wp_lo; p.wo_hi = w->m_wo_hi; p.wo_lo = w->m_wo_lo;
     p.g0p = d->g0p; p.b1p = d->b1p; p.boutp = d->boutp; p.E = E;
     p.B = B; p.Mpad = Mpad; p.MT = MT; p.T = Tq;
-    p.lens = lens_dev; p.slots = slots_dev; p.perm = reinterpret_cast<int *>(base + operm);
+    p.lens = lens_dev; p.slots = slots_dev; p.perm = reinterpret_cast<int *>(base + operm); p.eoff = eoff_dev;
     p.h0f = reinterpret_cast<float *>(base + oh0f); p.h1f = reinterpret_cast<float *>(base + oh1f);
     p.c0 = reinterpret_cast<float *>(base + oc0); p.c1 = reinterpret_cast<float *>(base + oc1);
     p.pval = reinterpret_cast<float *>(base + opv); p.pidx = reinterpret_cast<int *>(base + opi);

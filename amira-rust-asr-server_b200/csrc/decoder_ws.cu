@@ -75,7 +75,7 @@ struct WsParams {
     CUtensorMap whh0_hi, whh0_lo, w1_hi, w1_lo, wp_hi, wp_lo, wo_hi, wo_lo;                // weights, box {64, 64}
     const float *g0p, *b1p, *boutp, *E;
     int B, Mpad, MT, T;
-    const int *lens, *slots, *perm;
+    const int *lens, *slots, *perm, *eoff;
     __nv_bfloat16 *h0b_hi, *h0b_lo, *h1b_hi, *h1b_lo, *zb_hi, *zb_lo;
     float *h0f, *h1f, *c0, *c1;
     float *part;        // [MT][40 slices][2 column groups][128 rows][32] fp32: h1(t-1) W_hh1 partial sums
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 const WCtl c = load_ctl(p.ctl + row);
                 float4 ev[8];
                 if (c.active) {
-                    const float4 *ep = reinterpret_cast<const float4 *>(p.E + ((size_t)p.perm[row] * p.T + c.t) * kH + nb);
+                    const float4 *ep = reinterpret_cast<const float4 *>(p.E + ((size_t)p.eoff[p.perm[row]] + c.t) * kH + nb);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) ev[j] = __ldg(ep + j);
                 }
@@ -737,9 +737,10 @@ cudaError_t decoder_ws_prepare(Ctx *c) {
     return cudaSuccess;
 }
 
-// E [B*T][640] fp32 (hoisted encoder projection) is produced by the caller (decoder_tc.cu) into `E`.
+// E [sum of encoded lengths][640] fp32 (hoisted encoder projection, valid frames packed; stream b starts at row eoff[b]) is
+// produced by the caller (decoder_tc.cu).
 cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t *lens_dev, const int *perm_dev,
-                             const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
+                             const int *eoff_dev, const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
                              int32_t *nsteps_dev, char *work, size_t *work_bytes) {
     DecoderPriv *d = c->dec;
     TcWeights *w = d->tc;
@@ -781,7 +782,7 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     p.wp_hi = w->s_wp_hi; p.wp_lo = w->s_wp_lo; p.wo_hi = w->s_wo_hi; p.wo_lo = w->s_wo_lo;
     p.g0p = d->g0p; p.b1p = d->b1p; p.boutp = d->boutp; p.E = E;
     p.B = B; p.Mpad = Mpad; p.MT = MT; p.T = T > 0 ? T : 1;
-    p.lens = lens_dev; p.slots = slots_dev; p.perm = perm_dev;
+    p.lens = lens_dev; p.slots = slots_dev; p.perm = perm_dev; p.eoff = eoff_dev;
     p.h0f = reinterpret_cast<float *>(work + oh0f); p.h1f = reinterpret_cast<float *>(work + oh1f);
     p.c0 = reinterpret_cast<float *>(work + oc0); p.c1 = reinterpret_cast<float *>(work + oc1);
     p.part = reinterpret_cast<float *>(work + opart);

@@ -108,6 +108,9 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+ORIG_AFFINITY = None
+
+
 def bind_to_gpu_numa_node(gpu_index: int):
     """Pin this rank to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned host buffer is allocated, so
     the staging memory of the host-buffer path sits on the GPU's NUMA node (one process per GPU, as a server would)."""
@@ -119,6 +122,8 @@ def bind_to_gpu_numa_node(gpu_index: int):
         mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
         cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1]
         allowed = os.sched_getaffinity(0)
+        global ORIG_AFFINITY
+        ORIG_AFFINITY = set(allowed)
         cpus = [c for c in cpus if c in allowed]
         if cpus:
             os.sched_setaffinity(0, cpus)
@@ -162,7 +167,7 @@ def cpu_reference(pcm, offsets, lens, sample: int, threads: int):
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0)) or 1
     pcm, offsets, lens = make_workload(args.ref_sample, 4567)
     for _ in range(max(args.warmup, 0) and 1):
         cpu_reference(pcm, offsets, lens, min(2, args.ref_sample), threads)
@@ -407,7 +412,9 @@ def main():
     if e2e:
         out["e2e"] = e2e
     if not args.no_cpu:
-        threads = os.cpu_count() or 1
+        if ORIG_AFFINITY:
+            os.sched_setaffinity(0, ORIG_AFFINITY)  # the CPU baseline uses every host core this process may use
+        threads = len(os.sched_getaffinity(0)) or 1
         r = cpu_reference(pcm, offsets, lens, args.cpu_sample, threads)
         out["cpu_baseline"] = {"value": r["value"], "unit": "audio-s/s", "cores": threads, "kind": "port",
                                "sample": f"first {min(args.cpu_sample, B)} utterances of this workload ({r['audio_s']:.0f} audio-s): "
