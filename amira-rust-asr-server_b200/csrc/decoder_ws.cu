@@ -58,7 +58,7 @@ constexpr int W_ACC_COLS = 2 * W_SL;                        // accumulator = [a_
 constexpr int W_NACC = 4;                                   // TMEM accumulators of 128 columns
 constexpr int W_Q = 8;                                      // descriptor queue depth
 constexpr int W_EPI_WARPS = 8, W_EPI_THREADS = W_EPI_WARPS * 32;
-constexpr int W_THREADS = (2 + W_EPI_WARPS) * 32;           // 320: warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int W_THREADS = (4 + W_EPI_WARPS) * 32;           // 384: warp 0 TMA, 1 MMA, 2 scheduler, 3 idle, 4..11 epilogue
 constexpr int W_NPART = 2 * W_ND;                           // argmax partials per row (32 columns each)
 constexpr int W_MAX_MT = 256;
 constexpr long long W_SPIN_LIMIT = 6000000000LL;            // ~3 s of SM clocks
@@ -82,11 +82,13 @@ struct WsParams {
     float *pval;        // [MT][34][128]
     int *pidx;
     WCtl *ctl;
+    int4 *rowinfo;      // [Mpad] {stream index, encoded length, first packed row of E, 0}: one load instead of perm -> lens / eoff chains
     int *tile_active, *done_d, *cnt_a, *cnt_b, *cnt_c, *ctl_done, *dead_at, *part_ready /* [MT][40] */, *fail_count;
     float *s1, *s2;
     int *tokens, *ntok, *nsteps;
     int max_sym, max_total, blank, relu;
     int norot;          // debug: all CTAs walk the k-chunks in the same order
+    int trace_role;     // debug: role whose slice-0 CTA is traced for every M-tile
     long long *trace;   // nullable: [W_TRACE_ITS][32] globaltimer stamps of M-tile 0 (debug)
 };
 
@@ -132,7 +134,10 @@ __device__ __forceinline__ long long gtime() {
 // debug trace: slice 0 of every role stamps its events for M-tile `W_TRACE_MT`
 #define WS_TRACE(ev)                                                                                   \
     do {                                                                                               \
-        if (p.trace && slice == 0 && mt == 0 && it < W_TRACE_ITS) p.trace[it * 32 + role * 6 + (ev)] = gtime(); \
+        if (p.trace && slice == 0 && it < W_TRACE_ITS) {                                               \
+            if (mt == 0) p.trace[it * 32 + role * 6 + (ev)] = gtime();                                 \
+            if (role == p.trace_role && mt < 8) p.trace[W_TRACE_ITS * 32 + (it * 8 + mt) * 8 + (ev)] = gtime(); \
+        }                                                                                              \
     } while (0)
 
 // this thread's 32 accumulator columns: (a_hi w_hi + a_lo w_hi) + (a_hi w_lo), the two halves of the 128-column accumulator
@@ -157,6 +162,12 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -170,9 +181,10 @@ __device__ __forceinline__ void spin_ge(const int *p, int target) {
 // wait until *cnt >= target (returns 0) or the M-tile is known to have ended before iteration `it` (returns 1)
 __device__ __forceinline__ int spin_ge_or_dead(const int *cnt, int target, const int *dead_at, int it) {
     const long long t0 = clock64();
-    for (;;) {
-        if (ld_acquire(dead_at) <= it) return 1;
-        if (ld_acquire(cnt) >= target) return 0;
+    for (;;) {  // both polls in flight together (relaxed), one acquire fence on the way out
+        const int d = ld_relaxed(dead_at), v = ld_relaxed(cnt);
+        if (d <= it) { fence_acq_rel_gpu(); return 1; }
+        if (v >= target) { fence_acq_rel_gpu(); return 0; }
         if (clock64() - t0 > W_SPIN_LIMIT) __trap();
     }
 }
@@ -220,7 +232,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
         if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled operand layout needs a 1024-byte aligned base
         for (int s = 0; s < W_RING; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
         for (int b = 0; b < W_NACC; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], W_EPI_THREADS); }
-        for (int i = 0; i < W_Q; ++i) { mbar_init(&sm.q_full[i], 1); mbar_init(&sm.q_empty[i], 1 + W_EPI_WARPS); }
+        for (int i = 0; i < W_Q; ++i) { mbar_init(&sm.q_full[i], 1); mbar_init(&sm.q_empty[i], 2 + W_EPI_WARPS);  // TMA thread, MMA thread, one lane per epilogue warp }
         mbar_init(&sm.wfull, 1);
         mbar_fence_init();
     }
@@ -270,6 +282,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
         c.t = 0; c.sym = 0; c.total = 0; c.last = p.blank; c.nsteps = 0; c.failed = 0; c.pad = 0;
         c.active = (row < p.B && p.lens[p.perm[row]] > 0) ? 1 : 0;
         p.ctl[row] = c;
+        const int prow_ = row < p.B ? p.perm[row] : 0;
+        p.rowinfo[row] = make_int4(prow_, row < p.B ? p.lens[prow_] : 0, row < p.B ? p.eoff[prow_] : 0, 0);
         if (c.active) atomicAdd(&p.tile_active[row / W_BM], 1);
         if (row < p.B) {
             p.ntok[p.perm[row]] = 0;
@@ -287,59 +301,29 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
 
     const uint32_t tmem_base = sm.tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {  // ===================== scheduler + TMA producer =====================
-            const CUtensorMap *a_hi, *a_lo;
-            if (role == R_A || role == R_BI) { a_hi = &p.h0_hi; a_lo = &p.h0_lo; }
-            else if (role == R_BH || role == R_C) { a_hi = &p.h1_hi; a_lo = &p.h1_lo; }
-            else { a_hi = &p.z_hi; a_lo = &p.z_lo; }
-            tma_prefetch_desc(a_hi);
-            tma_prefetch_desc(a_lo);
-            uint32_t u = 0, qn = 0;
+    if (warp == 2) {
+        if (lane == 0) {  // ===================== scheduler: polls the dependency counters, publishes runnable units =====================
+            // A thread of its own so that the TMA thread never stalls on a global-memory poll: the next unit's loads go out
+            // the moment ring slots free up, and the first-load latency hides behind the tail of the current unit.
+            uint32_t qn = 0;
             for (int it = 0;; ++it) {
-                const int par = it & 1;
                 bool any = false;
                 for (int mt = 0; mt < p.MT; ++mt) {
                     if (sm.dead[mt]) continue;
-                    int st, a_row;
-                    if (role == R_A) {          // h0(it-1): every layer-0 epilogue of the previous step
-                        st = spin_ge_or_dead(p.cnt_a + mt, W_NG * it, p.dead_at + mt, it);
-                        a_row = par * p.Mpad;
-                    } else if (role == R_BI) {  // h0(it)
-                        st = spin_ge_or_dead(p.cnt_a + mt, W_NG * (it + 1), p.dead_at + mt, it);
-                        a_row = (par ^ 1) * p.Mpad;
-                    } else if (role == R_BH) {  // h1(it-1)
-                        st = spin_ge_or_dead(p.cnt_b + mt, W_NG * it, p.dead_at + mt, it);
-                        a_row = par * p.Mpad;
-                    } else if (role == R_C) {   // h1(it)
-                        st = spin_ge_or_dead(p.cnt_b + mt, W_NG * (it + 1), p.dead_at + mt, it);
-                        a_row = (par ^ 1) * p.Mpad;
-                    } else {                    // z(it)
-                        st = spin_ge_or_dead(p.cnt_c + mt, W_NC * (it + 1), p.dead_at + mt, it);
-                        a_row = 0;
-                    }
+                    int st;
+                    if (role == R_A) st = spin_ge_or_dead(p.cnt_a + mt, W_NG * it, p.dead_at + mt, it);              // h0(it-1)
+                    else if (role == R_BI) st = spin_ge_or_dead(p.cnt_a + mt, W_NG * (it + 1), p.dead_at + mt, it);  // h0(it)
+                    else if (role == R_BH) st = spin_ge_or_dead(p.cnt_b + mt, W_NG * it, p.dead_at + mt, it);        // h1(it-1)
+                    else if (role == R_C) st = spin_ge_or_dead(p.cnt_b + mt, W_NG * (it + 1), p.dead_at + mt, it);   // h1(it)
+                    else st = spin_ge_or_dead(p.cnt_c + mt, W_NC * (it + 1), p.dead_at + mt, it);                    // z(it)
                     if (st) { sm.dead[mt] = 1; continue; }
                     any = true;
                     WS_TRACE(0);
-                    fence_proxy_async();
-                    {   // publish the unit
-                        const uint32_t slot = qn % W_Q;
-                        mbar_wait_wd(&sm.q_empty[slot], ((qn / W_Q) & 1) ^ 1);
-                        sm.q[slot].mt = mt; sm.q[slot].it = it;
-                        mbar_arrive(&sm.q_full[slot]);
-                        ++qn;
-                    }
-                    for (int ki = 0; ki < W_KC; ++ki) {
-                        const int kc = (kc0 + ki) % W_KC;
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            const uint32_t s = u % W_RING;
-                            mbar_wait_wd(&sm.empty[s], ((u / W_RING) & 1) ^ 1);
-                            mbar_expect_tx(&sm.full[s], W_UNIT);
-                            tma_load_2d(ring + s * W_UNIT, half ? a_lo : a_hi, &sm.full[s], kc * BK, a_row + mt * W_BM);
-                            ++u;
-                        }
-                    }
+                    const uint32_t slot = qn % W_Q;
+                    mbar_wait_wd(&sm.q_empty[slot], ((qn / W_Q) & 1) ^ 1);
+                    sm.q[slot].mt = mt; sm.q[slot].it = it;
+                    mbar_arrive(&sm.q_full[slot]);
+                    ++qn;
                 }
                 if (!any) break;
             }
@@ -347,6 +331,39 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
             mbar_wait_wd(&sm.q_empty[slot], ((qn / W_Q) & 1) ^ 1);
             sm.q[slot].mt = -1;
             mbar_arrive(&sm.q_full[slot]);
+        }
+    } else if (warp == 0) {
+        if (lane == 0) {  // ===================== TMA producer =====================
+            const CUtensorMap *a_hi, *a_lo;
+            if (role == R_A || role == R_BI) { a_hi = &p.h0_hi; a_lo = &p.h0_lo; }
+            else if (role == R_BH || role == R_C) { a_hi = &p.h1_hi; a_lo = &p.h1_lo; }
+            else { a_hi = &p.z_hi; a_lo = &p.z_lo; }
+            tma_prefetch_desc(a_hi);
+            tma_prefetch_desc(a_lo);
+            uint32_t u = 0, qn = 0;
+            for (;;) {
+                const uint32_t slot = qn % W_Q;
+                mbar_wait_wd(&sm.q_full[slot], (qn / W_Q) & 1);
+                const int mt = sm.q[slot].mt, it = sm.q[slot].it;
+                mbar_arrive(&sm.q_empty[slot]);
+                ++qn;
+                if (mt < 0) break;
+                const int par = it & 1;
+                // activations of step it-1 for the recurrent roles (parity par), of step it for the others (parity par^1)
+                const int a_row = (role == R_D) ? 0 : ((role == R_A || role == R_BH) ? par : (par ^ 1)) * p.Mpad;
+                fence_proxy_async();  // the scheduler's acquire (through the queue barrier) before these async-proxy reads
+                for (int ki = 0; ki < W_KC; ++ki) {
+                    const int kc = (kc0 + ki) % W_KC;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const uint32_t s = u % W_RING;
+                        mbar_wait_wd(&sm.empty[s], ((u / W_RING) & 1) ^ 1);
+                        mbar_expect_tx(&sm.full[s], W_UNIT);
+                        tma_load_2d(ring + s * W_UNIT, half ? a_lo : a_hi, &sm.full[s], kc * BK, a_row + mt * W_BM);
+                        ++u;
+                    }
+                }
+            }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===================== MMA issuer =====================
@@ -409,9 +426,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 ++tile;
             }
         }
-    } else {  // ===================== epilogue: 8 warps =====================
-        const int e = warp - 2, q = warp & 3, cgp = e >> 2;  // TMEM lane quarter (must be warp % 4), 32-column group
-        const int etid = tid - 64;
+    } else if (warp >= 4) {  // ===================== epilogue: 8 warps =====================
+        const int e = warp - 4, q = warp & 3, cgp = e >> 2;  // TMEM lane quarter (must be warp % 4), 32-column group
+        const int etid = tid - 128;
         const int r_in = q * 32 + lane;
         const int nb = slice * W_SL + cgp * 32;           // first of this thread's 32 output columns
         uint32_t qn = 0, tile = 0;
@@ -437,17 +454,17 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     named_bar_sync(1, W_EPI_THREADS);
                 }
                 if (etid == 0) WS_TRACE(5);
+                float4 ad[8], cold4[2];
+                float *cst = p.c0 + (size_t)row * kH + nb / 4;
+                cold4[0] = __ldcg(reinterpret_cast<const float4 *>(cst));  // independent of the control row: same round trip
+                cold4[1] = __ldcg(reinterpret_cast<const float4 *>(cst) + 1);
                 const bool live = __ldcg(p.dead_at + mt) > it;  // the M-tile may have ended with the previous step
                 const WCtl c = load_ctl(p.ctl + row);
                 const bool act = live && c.active;
-                float4 ad[8], cold4[2];
-                float *cst = p.c0 + (size_t)row * kH + nb / 4;
                 if (act) {
                     const float4 *addp = reinterpret_cast<const float4 *>(p.g0p + (size_t)c.last * kG + nb);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) ad[j] = __ldg(addp + j);
-                    cold4[0] = __ldcg(reinterpret_cast<const float4 *>(cst));
-                    cold4[1] = __ldcg(reinterpret_cast<const float4 *>(cst) + 1);
                 }
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
@@ -505,23 +522,25 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     WS_TRACE(4);
                 }
             } else if (role == R_BI) {
-                const WCtl c = load_ctl(p.ctl + row);
-                float4 ad[8], cold4[2], pr[8];
+                // every load that does not depend on another is issued up front (at full occupancy the epilogue pipeline, one
+                // unit at a time, is what bounds a CTA: dependent L2 round trips are its cost): control row + cell state go out
+                // together with the acquire of the recurrent partner's flag, the partial sums right after it
                 float *cst = p.c1 + (size_t)row * kH + nb / 4;
-                if (c.active) {
-                    const float4 *addp = reinterpret_cast<const float4 *>(p.b1p + nb);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) ad[j] = __ldg(addp + j);
-                    cold4[0] = __ldcg(reinterpret_cast<const float4 *>(cst));
-                    cold4[1] = __ldcg(reinterpret_cast<const float4 *>(cst) + 1);
-                }
-                if (etid == 0) spin_ge(p.part_ready + mt * W_NG + slice, it + 1);
-                named_bar_sync(1, W_EPI_THREADS);
-                if (c.active) {
+                const int4 ctl_a = __ldcg(reinterpret_cast<const int4 *>(p.ctl + row)), ctl_b = __ldcg(reinterpret_cast<const int4 *>(p.ctl + row) + 1);
+                float4 ad[8], cold4[2], pr[8];
+                cold4[0] = __ldcg(reinterpret_cast<const float4 *>(cst));
+                cold4[1] = __ldcg(reinterpret_cast<const float4 *>(cst) + 1);
+                spin_ge(p.part_ready + mt * W_NG + slice, it + 1);  // per thread: acquire orders the partial-sum loads below
+                {
                     const float4 *src = reinterpret_cast<const float4 *>(p.part + ((((size_t)mt * W_NG + slice) * 2 + cgp) * W_BM + r_in) * 32);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) pr[j] = __ldcg(src + j);
+                    const float4 *addp = reinterpret_cast<const float4 *>(p.b1p + nb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ad[j] = __ldg(addp + j);
                 }
+                WCtl c;
+                c.t = ctl_a.x; c.sym = ctl_a.y; c.total = ctl_a.z; c.last = ctl_a.w; c.active = ctl_b.x; c.nsteps = ctl_b.y; c.failed = ctl_b.z; c.pad = ctl_b.w;
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
                 tc_fence_after();
@@ -558,10 +577,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     WS_TRACE(4);
                 }
             } else if (role == R_C) {
+                const int4 ri = __ldg(p.rowinfo + row);
                 const WCtl c = load_ctl(p.ctl + row);
                 float4 ev[8];
                 if (c.active) {
-                    const float4 *ep = reinterpret_cast<const float4 *>(p.E + ((size_t)p.eoff[p.perm[row]] + c.t) * kH + nb);
+                    const float4 *ep = reinterpret_cast<const float4 *>(p.E + ((size_t)ri.z + c.t) * kH + nb);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) ev[j] = __ldg(ep + j);
                 }
@@ -595,9 +615,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     WS_TRACE(4);
                 }
             } else {  // R_D: vocabulary slice -> first-max argmax partial (zero_copy.rs:190-232 tie rule) -> control update
+                const int4 ri = __ldg(p.rowinfo + row);  // for the control update: fetched ahead of the accumulator wait
                 const WCtl c = load_ctl(p.ctl + row);
-                const int prow = row < p.B ? __ldg(p.perm + row) : 0;
-                const int len = __ldg(p.lens + prow);  // for the control update: fetched ahead of the accumulator wait
+                const int prow = ri.x, len = ri.y;
                 float4 bo[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) bo[j] = __ldg(reinterpret_cast<const float4 *>(p.boutp + nb) + j);
@@ -755,9 +775,10 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     const size_t opart = take(sizeof(float) * (size_t)MT * W_NG * 2 * W_BM * 32);
     const size_t opv = take(sizeof(float) * (size_t)MT * W_NPART * W_BM), opi = take(sizeof(int) * (size_t)MT * W_NPART * W_BM);
     const size_t octl = take(sizeof(WCtl) * (size_t)Mpad);
+    const size_t ori = take(sizeof(int4) * (size_t)Mpad);
     const size_t n_cnt = 7 * (size_t)MT + (size_t)MT * W_NG + 4;
     const size_t ocnt = take(sizeof(int) * n_cnt);
-    const size_t otrace = take(sizeof(long long) * W_TRACE_ITS * 32);
+    const size_t otrace = take(sizeof(long long) * W_TRACE_ITS * (32 + 64));
     if (!work) {  // size query
         *work_bytes = off;
         return cudaSuccess;
@@ -788,6 +809,7 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     p.part = reinterpret_cast<float *>(work + opart);
     p.pval = reinterpret_cast<float *>(work + opv); p.pidx = reinterpret_cast<int *>(work + opi);
     p.ctl = reinterpret_cast<WCtl *>(work + octl);
+    p.rowinfo = reinterpret_cast<int4 *>(work + ori);
     int *cnt = reinterpret_cast<int *>(work + ocnt);
     p.tile_active = cnt; p.done_d = cnt + MT; p.cnt_a = cnt + 2 * MT; p.cnt_b = cnt + 3 * MT; p.cnt_c = cnt + 4 * MT;
     p.ctl_done = cnt + 5 * MT; p.dead_at = cnt + 6 * MT; p.part_ready = cnt + 7 * MT; p.fail_count = cnt + 7 * MT + MT * W_NG;
@@ -799,7 +821,8 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     p.norot = getenv("AMIRA_WS_NOROT") ? 1 : 0;
     if (getenv("AMIRA_WS_TRACE")) {
         p.trace = reinterpret_cast<long long *>(work + otrace);
-        cudaMemsetAsync(p.trace, 0, sizeof(long long) * W_TRACE_ITS * 32, c->stream);
+        cudaMemsetAsync(p.trace, 0, sizeof(long long) * W_TRACE_ITS * (32 + 64), c->stream);
+        p.trace_role = getenv("AMIRA_WS_TRACE_ROLE") ? atoi(getenv("AMIRA_WS_TRACE_ROLE")) : R_BI;
         d->ws_trace_dev = p.trace;
     }
 
@@ -815,7 +838,7 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
 // ---- diagnostics: globaltimer stamps of the last weight-stationary launch (set AMIRA_WS_TRACE=1 before the call) ----
 extern "C" int32_t amira_debug_ws_trace(amira_ctx *ctx, int64_t *out, int32_t n_its) {
     using namespace amira;
-    if (!ctx || !out || n_its <= 0 || n_its > W_TRACE_ITS) return AMIRA_ERR_INVALID_VALUE;
+    if (!ctx || !out || n_its <= 0 || (n_its > W_TRACE_ITS && n_its != 3 * W_TRACE_ITS)) return AMIRA_ERR_INVALID_VALUE;
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     std::lock_guard<std::mutex> lock(c->mu);
     if (!c->dec || !c->dec->ws_trace_dev) return AMIRA_ERR_NOT_READY;

@@ -31,8 +31,9 @@ __device__ __forceinline__ uint64_t sdesc(uint32_t addr) { return (uint64_t)((ad
 __global__ void __launch_bounds__(128, 1) umma_kernel(int mode, int N, int n_iter, long long *out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bar;
+    __shared__ uint64_t bar2[8];
     __shared__ uint32_t tslot;
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(&bar2[i], 1); mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     for (int i = threadIdx.x; i < 196608 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
     if (threadIdx.x < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tslot)) : "memory");
@@ -61,13 +62,23 @@ __global__ void __launch_bounds__(128, 1) umma_kernel(int mode, int N, int n_ite
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) umma(acc, sdesc(a_lo + kk * 32), sdesc(w + kk * 32), id, 1);
             }
-        } else {
+        } else if (mode == 2) {
             const uint32_t id128 = idesc_bf16(128, 128), id64 = idesc_bf16(128, 64);
             for (int i = 0; i < n_iter; ++i) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) umma(acc, sdesc(a_hi + kk * 32), sdesc(w + kk * 32), id128, 1);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) umma(acc, sdesc(a_lo + kk * 32), sdesc(w + kk * 32), id64, 1);
+            }
+        } else {  // mode 3: fused pattern with a tcgen05.commit after every group of four (as a smem ring would need)
+            const uint32_t id128 = idesc_bf16(128, 128), id64 = idesc_bf16(128, 64);
+            for (int i = 0; i < n_iter; ++i) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma(acc, sdesc(a_hi + kk * 32), sdesc(w + kk * 32), id128, 1);
+                commit(&bar2[(2 * i) & 7]);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma(acc, sdesc(a_lo + kk * 32), sdesc(w + kk * 32), id64, 1);
+                commit(&bar2[(2 * i + 1) & 7]);
             }
         }
         commit(&bar);
@@ -86,7 +97,8 @@ int main() {
     const int n_iter = 2000;
     struct { int mode, N; const char *what; int mmas; double units; } cases[] = {
         {0, 64, "N=64", 4, 0}, {0, 128, "N=128", 4, 0}, {0, 256, "N=256", 4, 0},
-        {1, 64, "split pattern 3 x N=64 per k-step", 12, 0}, {2, 128, "fused pattern N=128 + N=64 per k-step", 8, 0}};
+        {1, 64, "split pattern 3 x N=64 per k-step", 12, 0}, {2, 128, "fused pattern N=128 + N=64 per k-step", 8, 0},
+        {3, 128, "fused pattern + commit per 4 mma", 8, 0}};
     for (auto &c : cases)
         for (int grid : {1, 148}) {
             umma_kernel<<<grid, 128, 196608>>>(c.mode, c.N, n_iter, out);
