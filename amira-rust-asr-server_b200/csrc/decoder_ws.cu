@@ -47,6 +47,8 @@ constexpr int W_NG = kG / W_SL;                             // 40 slices per gat
 constexpr int W_NC = kH / W_SL;                             // 10
 constexpr int W_ND = (kV + W_SL - 1) / W_SL;                // 17
 constexpr int W_CTAS = 3 * W_NG + W_NC + W_ND;              // 147
+constexpr int W_ND2 = W_ND + 1;                             // cluster variant: vocabulary padded to an even slice count
+constexpr int W_CTAS2 = 3 * W_NG + W_NC + W_ND2;            // 148 = every SM of a B200, 74 CTA pairs
 constexpr int W_KC = kH / BK;                               // 10 k-chunks
 constexpr int W_WCHUNK = W_SL * BK * 2;                     // 8 KB: [64 rows][64 k] bf16
 constexpr int W_WBYTES = 2 * W_KC * W_WCHUNK;               // 160 KB: per k-chunk [w_hi rows 0-63 | w_lo rows 64-127]
@@ -59,7 +61,7 @@ constexpr int W_NACC = 4;                                   // TMEM accumulators
 constexpr int W_Q = 8;                                      // descriptor queue depth
 constexpr int W_EPI_WARPS = 8, W_EPI_THREADS = W_EPI_WARPS * 32;
 constexpr int W_THREADS = (4 + W_EPI_WARPS) * 32;           // 384: warp 0 TMA, 1 MMA, 2 scheduler, 3 idle, 4..11 epilogue
-constexpr int W_NPART = 2 * W_ND;                           // argmax partials per row (32 columns each)
+constexpr int W_NPART = 2 * W_ND2;                          // argmax partial slots per row (32 columns each; 2*W_ND used without clusters)
 constexpr int W_MAX_MT = 256;
 constexpr long long W_SPIN_LIMIT = 6000000000LL;            // ~3 s of SM clocks
 constexpr int W_TRACE_ITS = 512;
@@ -71,7 +73,7 @@ struct WCtl {
 };
 
 struct WsParams {
-    CUtensorMap h0_hi, h0_lo, h1_hi, h1_lo, z_hi, z_lo;                                    // activations, box {64, 128}
+    CUtensorMap h0_hi, h0_lo, h1_hi, h1_lo, z_hi, z_lo;   // activations, box {64 k, 128 rows} (64 rows in the cluster variant)
     CUtensorMap whh0_hi, whh0_lo, w1_hi, w1_lo, wp_hi, wp_lo, wo_hi, wo_lo;                // weights, box {64, 64}
     const float *g0p, *b1p, *boutp, *E;
     int B, Mpad, MT, T;
@@ -125,6 +127,34 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo32, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
         "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(64u | (1u << 14) | (2u << 29))
         : "memory");
+}
+// ---- thread-block-cluster helpers (CTA pairs share every activation tile: each CTA loads half, TMA multicast to both) ----
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_cluster_s32(uint32_t cluster_addr, int v) {
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+// arrive on the same mbarrier in every CTA of `mask` once all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ long long gtime() {
     long long t;
@@ -196,6 +226,12 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
         if ((++n & 0xfff) == 0 && clock64() - t0 > W_SPIN_LIMIT) __trap();
     }
 }
+// a queue consumer is done with a descriptor slot: rank 0 owns the queue barriers
+template <int CL>
+__device__ __forceinline__ void q_release(uint64_t *q_empty_local, uint32_t crank) {
+    if (CL == 1 || crank == 0) mbar_arrive(q_empty_local);
+    else mbar_arrive_cluster(map_to_cta(smem_u32(q_empty_local), 0));
+}
 __device__ __forceinline__ WCtl load_ctl(const WCtl *q) {  // L1-bypassing: written by another SM's control update
     const int4 a = __ldcg(reinterpret_cast<const int4 *>(q)), b = __ldcg(reinterpret_cast<const int4 *>(q) + 1);
     WCtl c;
@@ -206,8 +242,14 @@ __device__ __forceinline__ size_t ws_state_off(const WsParams &p, int layer, int
     return p.slots ? ((size_t)p.slots[b] * 2 + layer) * kH : ((size_t)layer * p.B + b) * kH;
 }
 
+// CL = 1: 147 independent CTAs.  CL = 2: 148 CTAs in 74 clusters of two neighbouring slices of one role; the pair shares every
+// activation tile (each CTA loads 64 of the 128 rows, TMA multicast delivers them to both), which halves the L2 read traffic
+// that bounds the kernel while many M-tiles are in flight.  Rank 0's scheduler drives both CTAs in lock step.
+template <int CL>
 __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_constant__ WsParams p) {
     cg::grid_group grid = cg::this_grid();
+    constexpr int ND = CL == 2 ? W_ND2 : W_ND;
+    const uint32_t crank = CL == 2 ? (blockIdx.x & 1) : 0;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *w_hi = smem, *ring = smem + W_WBYTES;  // w_hi: [k-chunk][w_hi 8 KB | w_lo 8 KB]
     WsSmem &sm = *reinterpret_cast<WsSmem *>(smem + W_WBYTES + W_RING * W_UNIT);
@@ -226,13 +268,14 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
 
     // CTAs of one phase read the same activation tile at the same time: each starts at a different k-chunk so the requests
     // spread over the tile's L2 slices instead of queueing on one 16 KB region
-    const int kc0 = p.norot ? 0 : (slice * 3 + role) % W_KC;
+    const int kc0 = p.norot ? 0 : ((slice / CL) * 3 + role) % W_KC;  // one order per cluster: its CTAs share the ring contents
 
     if (tid == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled operand layout needs a 1024-byte aligned base
-        for (int s = 0; s < W_RING; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        for (int s = 0; s < W_RING; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], CL); }  // empty: every CTA's MMA commit
         for (int b = 0; b < W_NACC; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], W_EPI_THREADS); }
-        for (int i = 0; i < W_Q; ++i) { mbar_init(&sm.q_full[i], 1); mbar_init(&sm.q_empty[i], 2 + W_EPI_WARPS);  // TMA thread, MMA thread, one lane per epilogue warp }
+        // queue consumers: TMA thread, MMA thread, one lane per epilogue warp — of every CTA of the cluster (rank 0 owns the queue)
+        for (int i = 0; i < W_Q; ++i) { mbar_init(&sm.q_full[i], 1); mbar_init(&sm.q_empty[i], CL * (2 + W_EPI_WARPS)); }
         mbar_init(&sm.wfull, 1);
         mbar_fence_init();
     }
@@ -241,6 +284,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (CL == 2) cluster_sync_all();  // the peer's barriers exist before any multicast copy or remote arrive targets them
 
     // ---- stationary weights: one TMA burst, overlapped with the prologue below ----
     if (warp == 0 && lane == 0) {
@@ -302,10 +346,22 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
     const uint32_t tmem_base = sm.tmem_slot;
 
     if (warp == 2) {
-        if (lane == 0) {  // ===================== scheduler: polls the dependency counters, publishes runnable units =====================
+        if (lane == 0 && crank == 0) {  // ===================== scheduler: polls the dependency counters, publishes runnable units =====================
             // A thread of its own so that the TMA thread never stalls on a global-memory poll: the next unit's loads go out
             // the moment ring slots free up, and the first-load latency hides behind the tail of the current unit.
             uint32_t qn = 0;
+            auto publish = [&](int mt_, int it_, uint32_t &n) {  // into the queue of every CTA of the cluster
+                const uint32_t slot = n % W_Q;
+                mbar_wait_wd(&sm.q_empty[slot], ((n / W_Q) & 1) ^ 1);
+                sm.q[slot].mt = mt_; sm.q[slot].it = it_;
+                mbar_arrive(&sm.q_full[slot]);
+                if (CL == 2) {
+                    st_cluster_s32(map_to_cta(smem_u32(&sm.q[slot].mt), 1), mt_);
+                    st_cluster_s32(map_to_cta(smem_u32(&sm.q[slot].it), 1), it_);
+                    mbar_arrive_cluster(map_to_cta(smem_u32(&sm.q_full[slot]), 1));  // release.cluster orders the two stores
+                }
+                ++n;
+            };
             for (int it = 0;; ++it) {
                 bool any = false;
                 for (int mt = 0; mt < p.MT; ++mt) {
@@ -319,18 +375,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     if (st) { sm.dead[mt] = 1; continue; }
                     any = true;
                     WS_TRACE(0);
-                    const uint32_t slot = qn % W_Q;
-                    mbar_wait_wd(&sm.q_empty[slot], ((qn / W_Q) & 1) ^ 1);
-                    sm.q[slot].mt = mt; sm.q[slot].it = it;
-                    mbar_arrive(&sm.q_full[slot]);
-                    ++qn;
+                    publish(mt, it, qn);
                 }
                 if (!any) break;
             }
-            const uint32_t slot = qn % W_Q;  // exit descriptor
-            mbar_wait_wd(&sm.q_empty[slot], ((qn / W_Q) & 1) ^ 1);
-            sm.q[slot].mt = -1;
-            mbar_arrive(&sm.q_full[slot]);
+            publish(-1, 0, qn);  // exit descriptor
         }
     } else if (warp == 0) {
         if (lane == 0) {  // ===================== TMA producer =====================
@@ -345,7 +394,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 const uint32_t slot = qn % W_Q;
                 mbar_wait_wd(&sm.q_full[slot], (qn / W_Q) & 1);
                 const int mt = sm.q[slot].mt, it = sm.q[slot].it;
-                mbar_arrive(&sm.q_empty[slot]);
+                q_release<CL>(&sm.q_empty[slot], crank);
                 ++qn;
                 if (mt < 0) break;
                 const int par = it & 1;
@@ -359,7 +408,10 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         const uint32_t s = u % W_RING;
                         mbar_wait_wd(&sm.empty[s], ((u / W_RING) & 1) ^ 1);
                         mbar_expect_tx(&sm.full[s], W_UNIT);
-                        tma_load_2d(ring + s * W_UNIT, half ? a_lo : a_hi, &sm.full[s], kc * BK, a_row + mt * W_BM);
+                        if (CL == 1) tma_load_2d(ring + s * W_UNIT, half ? a_lo : a_hi, &sm.full[s], kc * BK, a_row + mt * W_BM);
+                        else  // this CTA's 64 rows of the tile, delivered to both CTAs (each full barrier sees 2 x 8 KB)
+                            tma_load_2d_mc(ring + s * W_UNIT + crank * (W_UNIT / 2), half ? a_lo : a_hi, &sm.full[s], kc * BK,
+                                           a_row + mt * W_BM + (int)crank * (W_BM / 2), (uint16_t)3);
                         ++u;
                     }
                 }
@@ -377,7 +429,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 const uint32_t slot = qn % W_Q;
                 mbar_wait_wd(&sm.q_full[slot], (qn / W_Q) & 1);
                 const int mt = sm.q[slot].mt, it = sm.q[slot].it;
-                mbar_arrive(&sm.q_empty[slot]);
+                q_release<CL>(&sm.q_empty[slot], crank);
                 ++qn;
                 if (mt < 0) break;
                 const uint32_t buf = tile % W_NACC, use = tile / W_NACC;
@@ -401,7 +453,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         umma_bf16_lo(acc, ad + 2, wd + 2, idesc_cat, 1);
                         umma_bf16_lo(acc, ad + 4, wd + 4, idesc_cat, 1);
                         umma_bf16_lo(acc, ad + 6, wd + 6, idesc_cat, 1);
-                        umma_commit(&sm.empty[s]);
+                        if (CL == 1) umma_commit(&sm.empty[s]); else umma_commit_mc(&sm.empty[s], (uint16_t)3);  // slot free in both CTAs
                         ++u;
                     }
                     {   // lo unit: a_lo * w_hi  (N = 64, accumulator columns 0..63)
@@ -415,7 +467,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         umma_bf16_lo(acc, ad + 2, wd + 2, idesc_hi, 1);
                         umma_bf16_lo(acc, ad + 4, wd + 4, idesc_hi, 1);
                         umma_bf16_lo(acc, ad + 6, wd + 6, idesc_hi, 1);
-                        umma_commit(&sm.empty[s]);
+                        if (CL == 1) umma_commit(&sm.empty[s]); else umma_commit_mc(&sm.empty[s], (uint16_t)3);  // slot free in both CTAs
                         ++u;
                     }
                     kc = kc + 1 == W_KC ? 0 : kc + 1;
@@ -437,7 +489,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
             mbar_wait_wd(&sm.q_full[slot], (qn / W_Q) & 1);
             const WsDesc d = sm.q[slot];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.q_empty[slot]);
+            if (lane == 0) q_release<CL>(&sm.q_empty[slot], crank);
             ++qn;
             if (d.mt < 0) break;
             const int mt = d.mt, it = d.it, par = it & 1;
@@ -620,7 +672,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 const int prow = ri.x, len = ri.y;
                 float4 bo[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) bo[j] = __ldg(reinterpret_cast<const float4 *>(p.boutp + nb) + j);
+                for (int j = 0; j < 8; ++j)  // the padding slice of the cluster variant lies beyond the padded bias vector
+                    bo[j] = nb + 32 <= W_ND * W_SL ? __ldg(reinterpret_cast<const float4 *>(p.boutp + nb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
                 tc_fence_after();
@@ -648,7 +701,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     __threadfence();
                     const int old = atomicAdd(p.done_d + mt, 1);
                     WS_TRACE(4);
-                    sm.flag = (old == W_ND - 1);
+                    sm.flag = (old == ND - 1);
                     sm.act_cnt = 0;
                 }
                 named_bar_sync(1, W_EPI_THREADS);
@@ -664,12 +717,12 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         float pv[W_NPART];
                         int pi[W_NPART];
 #pragma unroll
-                        for (int qi = 0; qi < W_NPART; ++qi) {  // every load in flight at once
+                        for (int qi = 0; qi < 2 * ND; ++qi) {  // every load in flight at once
                             pi[qi] = __ldcg(p.pidx + po + (size_t)qi * W_BM);
                             pv[qi] = __ldcg(p.pval + po + (size_t)qi * W_BM);
                         }
 #pragma unroll
-                        for (int qi = 0; qi < W_NPART; ++qi)
+                        for (int qi = 0; qi < 2 * ND; ++qi)
                             if (pi[qi] != 0x7fffffff && (bi == 0x7fffffff || pv[qi] > bv)) { bv = pv[qi]; bi = pi[qi]; }
                         n.nsteps += 1;                       // state carried unconditionally (decoder_optimized.rs:154)
                         n.sym += 1;                          // :133
@@ -732,6 +785,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 1) tmem_dealloc(sm.tmem_slot, 512);
 }
 
@@ -752,7 +806,28 @@ cudaError_t decoder_ws_prepare(Ctx *c) {
     if ((e = make_tmap_bf16(&w->s_wp_lo, w->wp_lo, kH, kH, kH, W_SL)) != cudaSuccess) return e;
     if ((e = make_tmap_bf16(&w->s_wo_hi, w->wo_hi, W_ND * W_SL, kH, kH, W_SL)) != cudaSuccess) return e;
     if ((e = make_tmap_bf16(&w->s_wo_lo, w->wo_lo, W_ND * W_SL, kH, kH, W_SL)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(greedy_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(greedy_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(greedy_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
+    // cluster variant: all 74 CTA pairs must be co-resident (one pair per TPC)
+    w->ws_cluster = false;
+    // Opt-in (AMIRA_WS_CLUSTER=1): measured on B200 the pair variant halves the kernel's L2 read traffic but is ~8 % slower —
+    // the per-unit cost is the SM's shared-memory port (TMA writes + tcgen05 operand reads), not L2, and the lock step between
+    // the two CTAs adds hand-off latency.  Kept as a validated building block for a cta_group::2 version.
+    if (c->sm_count >= W_CTAS2 && getenv("AMIRA_WS_CLUSTER") && atoi(getenv("AMIRA_WS_CLUSTER")) == 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(W_CTAS2);
+        cfg.blockDim = dim3(W_THREADS);
+        cfg.dynamicSmemBytes = W_SMEM;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, greedy_ws_kernel<2>, &cfg) == cudaSuccess && n_clusters >= W_CTAS2 / 2)
+            w->ws_cluster = true;
+        cudaGetLastError();
+    }
     w->ws_ready = true;
     return cudaSuccess;
 }
@@ -793,12 +868,14 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     p.h0b_hi = reinterpret_cast<__nv_bfloat16 *>(work + oh0h); p.h0b_lo = reinterpret_cast<__nv_bfloat16 *>(work + oh0l);
     p.h1b_hi = reinterpret_cast<__nv_bfloat16 *>(work + oh1h); p.h1b_lo = reinterpret_cast<__nv_bfloat16 *>(work + oh1l);
     p.zb_hi = reinterpret_cast<__nv_bfloat16 *>(work + ozh); p.zb_lo = reinterpret_cast<__nv_bfloat16 *>(work + ozl);
-    if ((e = make_tmap_bf16(&p.h0_hi, p.h0b_hi, 2 * (uint64_t)Mpad, kH, kH, W_BM)) != cudaSuccess) return e;
-    if ((e = make_tmap_bf16(&p.h0_lo, p.h0b_lo, 2 * (uint64_t)Mpad, kH, kH, W_BM)) != cudaSuccess) return e;
-    if ((e = make_tmap_bf16(&p.h1_hi, p.h1b_hi, 2 * (uint64_t)Mpad, kH, kH, W_BM)) != cudaSuccess) return e;
-    if ((e = make_tmap_bf16(&p.h1_lo, p.h1b_lo, 2 * (uint64_t)Mpad, kH, kH, W_BM)) != cudaSuccess) return e;
-    if ((e = make_tmap_bf16(&p.z_hi, p.zb_hi, (uint64_t)Mpad, kH, kH, W_BM)) != cudaSuccess) return e;
-    if ((e = make_tmap_bf16(&p.z_lo, p.zb_lo, (uint64_t)Mpad, kH, kH, W_BM)) != cudaSuccess) return e;
+    const bool cluster = w->ws_cluster;
+    const uint32_t box_rows = cluster ? W_BM / 2 : W_BM;  // the cluster variant loads half a tile per CTA and multicasts it
+    if ((e = make_tmap_bf16(&p.h0_hi, p.h0b_hi, 2 * (uint64_t)Mpad, kH, kH, box_rows)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&p.h0_lo, p.h0b_lo, 2 * (uint64_t)Mpad, kH, kH, box_rows)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&p.h1_hi, p.h1b_hi, 2 * (uint64_t)Mpad, kH, kH, box_rows)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&p.h1_lo, p.h1b_lo, 2 * (uint64_t)Mpad, kH, kH, box_rows)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&p.z_hi, p.zb_hi, (uint64_t)Mpad, kH, kH, box_rows)) != cudaSuccess) return e;
+    if ((e = make_tmap_bf16(&p.z_lo, p.zb_lo, (uint64_t)Mpad, kH, kH, box_rows)) != cudaSuccess) return e;
     p.whh0_hi = w->s_whh0_hi; p.whh0_lo = w->s_whh0_lo; p.w1_hi = w->s_w1_hi; p.w1_lo = w->s_w1_lo;
     p.wp_hi = w->s_wp_hi; p.wp_lo = w->s_wp_lo; p.wo_hi = w->s_wo_hi; p.wo_lo = w->s_wo_lo;
     p.g0p = d->g0p; p.b1p = d->b1p; p.boutp = d->boutp; p.E = E;
@@ -828,7 +905,23 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
 
     void *params[] = {&p};
     ProfScope prof(c, PK_GREEDY);
-    e = cudaLaunchCooperativeKernel((const void *)greedy_ws_kernel, dim3(W_CTAS), dim3(W_THREADS), params, W_SMEM, c->stream);
+    if (cluster) {  // cooperative (grid.sync in the prologue) + clusters of two
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(W_CTAS2);
+        cfg.blockDim = dim3(W_THREADS);
+        cfg.dynamicSmemBytes = W_SMEM;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeCooperative;
+        at[1].val.cooperative = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 2;
+        e = cudaLaunchKernelExC(&cfg, (const void *)greedy_ws_kernel<2>, params);
+    } else {
+        e = cudaLaunchCooperativeKernel((const void *)greedy_ws_kernel<1>, dim3(W_CTAS), dim3(W_THREADS), params, W_SMEM, c->stream);
+    }
     c->launches++;
     return e;
 }

@@ -128,7 +128,8 @@ struct TcWeights {
     CUtensorMap m_whh0_hi, m_whh0_lo, m_w1_hi, m_w1_lo, m_wp_hi, m_wp_lo, m_wo_hi, m_wo_lo;          // box {64 k, 128 rows}
     CUtensorMap s_whh0_hi, s_whh0_lo, s_w1_hi, s_w1_lo, s_wp_hi, s_wp_lo, s_wo_hi, s_wo_lo;          // box {64 k, 64 rows}
     int coop_blocks_per_sm = 0;
-    bool ws_ready = false;  // decoder_ws.cu: kernel attributes set
+    bool ws_ready = false;    // decoder_ws.cu: kernel attributes set
+    bool ws_cluster = false;  // decoder_ws.cu: the 74-CTA-pair cluster variant fits this device
 };
 
 // host: 2-D bf16 row-major [rows][cols] tensor map with box {64 cols, box_rows}, 128-byte swizzle

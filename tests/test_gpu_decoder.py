@@ -15,13 +15,19 @@ NEAR_TIE = 2e-4
 ENGINES = {1: "fp32 persistent kernel", 2: "tcgen05 grid-synchronised", 3: "tcgen05 dataflow", 4: "tcgen05 weight-stationary dataflow (default)"}
 
 
-@pytest.fixture(scope="module", params=[1, 2, 3, 4], ids=["fp32", "tcgen05", "dataflow", "ws"])
+@pytest.fixture(scope="module", params=[1, 2, 3, 4, 40], ids=["fp32", "tcgen05", "dataflow", "ws", "ws-cluster"])
 def ctx(request, amira):
-    """One context per decode engine: every test in this module runs against both."""
-    c = amira.Context(device_id=0, decode_engine=request.param)
-    c.engine = request.param
+    """One context per decode engine: every test in this module runs against each of them.  40 = engine 4 in its CTA-pair
+    (thread-block cluster + TMA multicast) variant (AMIRA_WS_CLUSTER=1 is read when the weights are loaded)."""
+    import os
+    engine = 4 if request.param == 40 else request.param
+    if request.param == 40:
+        os.environ["AMIRA_WS_CLUSTER"] = "1"
+    c = amira.Context(device_id=0, decode_engine=engine)
+    c.engine = engine
     yield c
     c.close()
+    os.environ.pop("AMIRA_WS_CLUSTER", None)
 
 
 @pytest.fixture(scope="module")
