@@ -5,12 +5,12 @@
 //   PreprocessorModel::infer_zero_copy (src/triton/model.rs:71-160)               waveform -> [1,128,T'] features
 // Spec of the (absent, LFS) preprocessor ONNX: SURVEY.md 8(c).
 //
-// Kernel 1 (fe_logmel_kernel, persistent, one warp per frame):
+// Kernel 1 (fe_logmel_kernel, persistent, 32-frame tiles, a half-warp per frame):
 //   global i16/f32 -> smem (128-bit loads) -> pre-emphasis + reflect padding staged in smem (exact: for PCM the
 //   pre-emphasised sample 100*s[n]-97*s[n-1] is an integer < 2^24) -> Hann window -> 512-point real FFT as a
-//   256-point complex FFT: radix-8 in registers + five radix-2 stages over warp shuffles -> |X|^2 ->
-//   banded mel reduction (each lane owns 4 filters) -> log -> smem tile -> coalesced stores of the un-normalised
-//   log-mel tile + per-tile (mean, M2) partials.
+//   256-point complex FFT factored 16 x 16: radix-16 in registers, twiddle, 16x16 transpose through shared memory,
+//   radix-16 in registers; real-input split against the mirrored bin -> |X|^2 -> banded mel reduction (each lane owns
+//   4 filters) -> log -> smem tile -> coalesced stores of the un-normalised log-mel tile + per-tile (mean, M2) partials.
 //   The FFT runs in fp64: an fp32 FFT leaves ~2e-4 max-abs error after normalisation on low mel bins (deep
 //   fades under pre-emphasis), above the 1e-4 contract; B200 has a 1:2 fp64 pipe (DESIGN.md "front end").
 // Kernel 2 (fe_normalize_kernel, one warp per (utterance, mel) row): Chan-merge of the partials in fp64,
@@ -33,6 +33,9 @@ constexpr int SPAN = (TF - 1) * kHop + kNfft;      // 5472 padded samples per ti
 constexpr int RAW_CAP = SPAN + 16;                 // raw samples staged per tile (+ previous sample, alignment slack)
 constexpr int PPAD = 272;                          // power spectrum row (257 bins, index k + (k >> 5))
 constexpr int OUT_LD = TF + 1;
+constexpr int FE_HALVES = 2 * FE_WARPS;            // a half-warp (16 lanes) transforms one frame
+constexpr int TLD = 17;                            // row stride (complex doubles) of the 16x16 transpose buffer
+constexpr int TBUF = 16 * TLD;                     // complex doubles per half-warp exchange buffer (>= 256 for the Z spectrum)
 
 struct FeMeta {
     const int64_t *starts;   // [B] first element of each utterance
@@ -92,6 +95,44 @@ __device__ __forceinline__ void dft8(cplx (&a)[8]) {
     }
 }
 
+
+// ---- 16-point DFT in registers (two radix-4 passes; forward transform, W = exp(-2 pi i / 16)), natural order in/out ----
+__device__ __forceinline__ void radix4(cplx &x0, cplx &x1, cplx &x2, cplx &x3) {
+    const cplx s0 = cadd(x0, x2), d0 = csub(x0, x2), s1 = cadd(x1, x3), d1 = mul_mi(csub(x1, x3));
+    x0 = cadd(s0, s1);
+    x2 = csub(s0, s1);
+    x1 = cadd(d0, d1);
+    x3 = csub(d0, d1);
+}
+__device__ __forceinline__ void dft16(cplx (&a)[16]) {
+    const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, r = 0.70710678118654752440;
+    // pass 1: for each n2, DFT over n1 of a[n2 + 4 n1]  ->  y[n2][k1] stored at a[n2 + 4 k1]
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) radix4(a[n2], a[n2 + 4], a[n2 + 8], a[n2 + 12]);
+    // twiddles W16^(n2 k1)
+    a[1 + 4] = cmul(a[1 + 4], cplx{c1, -s1});    // W^1
+    a[1 + 8] = cplx{r * (a[1 + 8].x + a[1 + 8].y), r * (a[1 + 8].y - a[1 + 8].x)};  // W^2
+    a[1 + 12] = cmul(a[1 + 12], cplx{s1, -c1});  // W^3
+    a[2 + 4] = cplx{r * (a[2 + 4].x + a[2 + 4].y), r * (a[2 + 4].y - a[2 + 4].x)};  // W^2
+    a[2 + 8] = mul_mi(a[2 + 8]);                 // W^4
+    a[2 + 12] = cplx{r * (a[2 + 12].y - a[2 + 12].x), -r * (a[2 + 12].x + a[2 + 12].y)};  // W^6
+    a[3 + 4] = cmul(a[3 + 4], cplx{s1, -c1});    // W^3
+    a[3 + 8] = cplx{r * (a[3 + 8].y - a[3 + 8].x), -r * (a[3 + 8].x + a[3 + 8].y)};      // W^6
+    a[3 + 12] = cmul(a[3 + 12], cplx{-c1, s1});  // W^9
+    // pass 2: for each k1, DFT over n2 of y[n2][k1]  ->  X[k1 + 4 k2] left at a[k2 + 4 k1]
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) radix4(a[4 * k1], a[4 * k1 + 1], a[4 * k1 + 2], a[4 * k1 + 3]);
+    // a[k2 + 4 k1] holds X[k1 + 4 k2]: transpose the 4x4 index grid back to natural order
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j) {
+            const cplx t = a[i + 4 * j];
+            a[i + 4 * j] = a[j + 4 * i];
+            a[j + 4 * i] = t;
+        }
+}
+
 template <typename RawT>
 struct Stage;  // staged (pre-emphasised, reflect-padded) sample type per input type
 template <>
@@ -112,44 +153,42 @@ struct Stage<float> {
 };
 
 template <typename RawT>
-__global__ void __launch_bounds__(FE_THREADS, 3)
+__global__ void __launch_bounds__(FE_THREADS, 2)
 fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables *__restrict__ tab,
                  float *__restrict__ features, int64_t t_stride, double2 *__restrict__ partials) {
     using StT = typename Stage<RawT>::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    StT *ystage = reinterpret_cast<StT *>(smem_raw);                                  // [SPAN]
-    float *outt = reinterpret_cast<float *>(smem_raw + sizeof(StT) * SPAN);           // [128][OUT_LD]
-    float *pw = outt + kMel * OUT_LD;                                                 // [FE_WARPS][PPAD]
-    float *melw = pw + FE_WARPS * PPAD;                                               // [kMelRowsMax][32]
-    RawT *raw = reinterpret_cast<RawT *>(melw + kMelRowsMax * 32);                    // [RAW_CAP]
+    double2 *xbuf = reinterpret_cast<double2 *>(smem_raw);                            // [FE_HALVES][TBUF] transpose / spectrum exchange
+    double2 *tw256 = xbuf + FE_HALVES * TBUF;                                         // [16][16] W256^(m2 k1) at [k1][m2]
+    double2 *tw512 = tw256 + 256;                                                     // [129] exp(-2 pi i k / 512)
+    double2 *winp = tw512 + 130;                                                      // [256] scaled window pairs (w[2m], w[2m+1])
+    StT *ystage = reinterpret_cast<StT *>(winp + 256);                                // [SPAN]
+    float *outt = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ystage) + sizeof(StT) * SPAN);  // [128][OUT_LD]
+    float *pw = outt + kMel * OUT_LD;                                                 // [FE_HALVES][PPAD]
+    float *melw = pw + FE_HALVES * PPAD;                                              // [kMelRowsMax][32]
+    RawT *raw = reinterpret_cast<RawT *>(xbuf);  // [RAW_CAP] raw samples are staged before, the exchange buffers used after, the barrier
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = lane >> 4, hl = lane & 15;  // half-warp and lane within it
 
-    // ---- loop-invariant per-lane constants (registers) ----
-    double win[16];  // window at samples 2*(lane+32j), 2*(lane+32j)+1, scaled
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        win[2 * j] = (double)tab->win[2 * (lane + 32 * j)] * Stage<RawT>::kScale;
-        win[2 * j + 1] = (double)tab->win[2 * (lane + 32 * j) + 1] * Stage<RawT>::kScale;
+    // ---- loop-invariant tables (shared memory) and per-lane constants ----
+    for (int i = tid; i < 256; i += FE_THREADS) {
+        double sn, cs;
+        sincospi(-2.0 * (double)(((i >> 4) * (i & 15)) & 255) / 256.0, &sn, &cs);  // entry [k1][m2] = W256^(m2 k1): lanes read consecutively
+        tw256[i] = make_double2(cs, sn);
+        winp[i] = make_double2((double)tab->win[2 * i] * Stage<RawT>::kScale, (double)tab->win[2 * i + 1] * Stage<RawT>::kScale);
     }
-    cplx tw2[7];  // W256^(lane*k2), k2 = 1..7
-#pragma unroll
-    for (int k2 = 1; k2 < 8; ++k2) tw2[k2 - 1] = twiddle((lane * k2) & 255, 256);
-    cplx tws[4];  // cross-lane DIF stage twiddles (1 on the lower lane of each pair)
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const int h = 16 >> s;
-        tws[s] = (lane & h) ? twiddle((lane & (h - 1)) * (16 / h), 32) : cplx{1.0, 0.0};
+    for (int i = tid; i < 129; i += FE_THREADS) {
+        double sn, cs;
+        sincospi(-2.0 * (double)i / 512.0, &sn, &cs);
+        tw512[i] = make_double2(cs, sn);
     }
-    const int k1 = rev5(lane);                         // this lane ends up holding Z[k2 + 8*k1]
-    const cplx twl = twiddle(8 * k1, 512);             // W512^(8*k1); W512^k = W512^k2 * twl
-    const int src0 = rev5((32 - k1) & 31);             // lane holding Z[8*((32-k1)%32)]
     int mk[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) mk[g] = tab->kstart[lane + 32 * g];
     const int r0 = tab->melRow[0], r1 = tab->melRow[1], r2 = tab->melRow[2], r3 = tab->melRow[3], r4 = tab->melRow[4];
     for (int i = tid; i < kMelRowsMax * 32; i += FE_THREADS) melw[i] = (&tab->melw_t[0][0])[i];
-    float *mypw = pw + warp * PPAD;
+    double2 *myx = xbuf + (warp * 2 + half) * TBUF;
 
     for (int tile = blockIdx.x; tile < meta.n_tiles; tile += gridDim.x) {
         // ---- locate (utterance, first frame) ----
@@ -215,74 +254,77 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
         }
         __syncthreads();
 
-        // ---- one warp per frame ----
-        for (int fl = warp; fl < nf; fl += FE_WARPS) {
-            const StT *fr = ystage + fl * kHop;
-            cplx a[8];
+        // ---- a half-warp per frame, two frames per warp at a time: 512-point real FFT = 256-point complex FFT (z[m] = x[2m] +
+        // i x[2m+1]) as 16 x 16: radix-16 in registers over m1 (m = 16 m1 + lane), twiddle W256^(lane k1), transpose through
+        // shared memory, radix-16 over m2; then the real-input split against the mirrored bin, |X|^2, banded mel, log ----
+        for (int fp = warp; 2 * fp < nf; fp += FE_WARPS) {
+            const int fl = 2 * fp + half;  // frames >= nf transform stale-but-finite staging data; their results are not stored
+            const StT *fr = ystage + min(fl, TF - 1) * kHop;
+            cplx a[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int s = 2 * (lane + 32 * j);
-                a[j].x = (double)fr[s] * win[2 * j];
-                a[j].y = (double)fr[s + 1] * win[2 * j + 1];
+            for (int m1 = 0; m1 < 16; ++m1) {
+                const int m = 16 * m1 + hl;
+                const double2 w = winp[m];
+                a[m1].x = (double)fr[2 * m] * w.x;
+                a[m1].y = (double)fr[2 * m + 1] * w.y;
             }
-            dft8(a);  // A[k2] = sum_j z[32j + lane] W8^(j k2)
+            dft16(a);  // Y[k1] = sum_m1 z[16 m1 + hl] W16^(m1 k1)
 #pragma unroll
-            for (int k2 = 1; k2 < 8; ++k2) a[k2] = cmul(a[k2], tw2[k2 - 1]);
-            // 32-point DIF across lanes; lane l ends with C[rev5(l)]
-#pragma unroll
-            for (int s = 0; s < 5; ++s) {
-                const int h = 16 >> s;
-                const bool upper = lane & h;
-#pragma unroll
-                for (int k2 = 0; k2 < 8; ++k2) {
-                    const cplx o = {shfl_xor_d(a[k2].x, h), shfl_xor_d(a[k2].y, h)};
-                    cplx v = upper ? csub(o, a[k2]) : cadd(o, a[k2]);
-                    if (s < 4) v = cmul(v, tws[s]);
-                    a[k2] = v;
-                }
+            for (int k1 = 1; k1 < 16; ++k1) {
+                const double2 t = tw256[k1 * 16 + hl];
+                a[k1] = cmul(a[k1], cplx{t.x, t.y});
             }
-            // real-FFT post-processing: X[k] = E + W512^k O with E = (Z[k] + conj Z[256-k]) / 2,
-            // O = (Z[k] - conj Z[256-k]) / (2i); this lane owns k = k2 + 8*k1
-            const double c512r[8] = {1.0, 0.99992470183914454, 0.99969881869620422, 0.99932238458834954,
-                                     0.99879545620517241, 0.99811811290014918, 0.99729045667869021,
-                                     0.99631261218277801};
-            const double c512i[8] = {-0.0, -0.012271538285719925, -0.024541228522912288, -0.036807222941358832,
-                                     -0.049067674327418015, -0.061320736302208578, -0.073564563599667426,
-                                     -0.085797312344439894};
 #pragma unroll
-            for (int k2 = 0; k2 < 8; ++k2) {
-                cplx zp;
-                if (k2 == 0) zp = {shfl_d(a[0].x, src0), shfl_d(a[0].y, src0)};
-                else zp = {shfl_xor_d(a[8 - k2].x, 31), shfl_xor_d(a[8 - k2].y, 31)};
-                const cplx z = a[k2];
-                const cplx e = {0.5 * (z.x + zp.x), 0.5 * (z.y - zp.y)};
-                const cplx d = {0.5 * (z.x - zp.x), 0.5 * (z.y + zp.y)};  // (Z[k] - conj Z[N-k]) / 2
-                const cplx o = mul_mi(d);                                 // / i
-                const cplx w = cmul(cplx{c512r[k2], c512i[k2]}, twl);
-                const cplx wo = cmul(w, o);
-                const cplx xk = cadd(e, wo);
-                const int k = k2 + 8 * k1;
-                mypw[k + (k >> 5)] = (float)(xk.x * xk.x + xk.y * xk.y);
-                if (k == 0) {  // Nyquist bin: X[256] = Re Z[0] - Im Z[0]
-                    const double ny = z.x - z.y;
-                    mypw[256 + 8] = (float)(ny * ny);
+            for (int k1 = 0; k1 < 16; ++k1) myx[k1 * TLD + hl] = make_double2(a[k1].x, a[k1].y);
+            __syncwarp();
+#pragma unroll
+            for (int m2 = 0; m2 < 16; ++m2) {
+                const double2 t = myx[hl * TLD + m2];
+                a[m2] = cplx{t.x, t.y};
+            }
+            dft16(a);  // Z[hl + 16 k2] = sum_m2 (...) W16^(m2 k2)
+            __syncwarp();
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) myx[hl + 16 * k2] = make_double2(a[k2].x, a[k2].y);
+            __syncwarp();
+            // X[k] = E + W512^k O, X[256-k] = conj(E - W512^k O) with E = (Z[k] + conj Z[256-k]) / 2, O = (Z[k] - conj Z[256-k]) / (2i)
+            float *mypw = pw + (warp * 2 + half) * PPAD;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const int k = hl + 16 * j;
+                if (k <= 128) {
+                    const double2 z = myx[k], zp = myx[(256 - k) & 255], w = tw512[k];
+                    const double ex = 0.5 * (z.x + zp.x), ey = 0.5 * (z.y - zp.y);
+                    const double dx = 0.5 * (z.x - zp.x), dy = 0.5 * (z.y + zp.y);  // (Z[k] - conj Z[256-k]) / 2
+                    const double ox = dy, oy = -dx;                                  // / i
+                    const double wx = w.x * ox - w.y * oy, wy = w.x * oy + w.y * ox;
+                    const double px = ex + wx, py = ey + wy, qx = ex - wx, qy = ey - wy;
+                    mypw[k + (k >> 5)] = (float)(px * px + py * py);
+                    const int k2m = 256 - k;
+                    if (k != 128) mypw[k2m + (k2m >> 5)] = (float)(qx * qx + qy * qy);
                 }
             }
             __syncwarp();
-            // banded mel reduction: lane owns filters lane + 32 g
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            auto band = [&](int g, int ra, int rb) {
-                for (int r = ra; r < rb; ++r) {
-                    const int k = min(mk[g] + (r - ra), 256);
-                    acc[g] = fmaf(melw[r * 32 + lane], mypw[k + (k >> 5)], acc[g]);
-                }
-            };
-            band(0, r0, r1);
-            band(1, r1, r2);
-            band(2, r2, r3);
-            band(3, r3, r4);
+            // banded mel reduction, both frames in turn with all 32 lanes: lane owns filters lane + 32 g
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+                const int f = 2 * fp + hh;
+                if (f >= nf) break;
+                const float *ppw = pw + (warp * 2 + hh) * PPAD;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                auto band = [&](int g, int ra, int rb) {
+                    for (int r = ra; r < rb; ++r) {
+                        const int k = min(mk[g] + (r - ra), 256);
+                        acc[g] = fmaf(melw[r * 32 + lane], ppw[k + (k >> 5)], acc[g]);
+                    }
+                };
+                band(0, r0, r1);
+                band(1, r1, r2);
+                band(2, r2, r3);
+                band(3, r3, r4);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) outt[(lane + 32 * g) * OUT_LD + fl] = logf(acc[g] + 5.9604644775390625e-08f);
+                for (int g = 0; g < 4; ++g) outt[(lane + 32 * g) * OUT_LD + f] = logf(acc[g] + 5.9604644775390625e-08f);
+            }
             __syncwarp();
         }
         __syncthreads();
@@ -414,8 +456,8 @@ __global__ void bytes_to_f32_kernel(const uint8_t *__restrict__ in, size_t n_byt
 
 template <typename RawT>
 size_t fe_smem_bytes() {
-    return sizeof(typename Stage<RawT>::T) * SPAN + sizeof(float) * (kMel * OUT_LD + FE_WARPS * PPAD + kMelRowsMax * 32) +
-           sizeof(RawT) * RAW_CAP;
+    return sizeof(double2) * (FE_HALVES * TBUF + 256 + 130 + 256) + sizeof(typename Stage<RawT>::T) * SPAN +
+           sizeof(float) * (kMel * OUT_LD + FE_HALVES * PPAD + kMelRowsMax * 32);
 }
 
 }  // namespace
@@ -460,7 +502,7 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
 
     if (tiles > 0) {
         ProfScope prof(c, PK_FE_LOGMEL);
-        const int grid = (int)std::min<int64_t>(tiles, (int64_t)c->sm_count * 3);
+        const int grid = (int)std::min<int64_t>(tiles, (int64_t)c->sm_count * 2);
         if (is_pcm16) {
             const size_t smem = fe_smem_bytes<int16_t>();
             static bool attr_done = false;
