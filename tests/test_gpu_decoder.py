@@ -218,3 +218,47 @@ def test_full_size_batch_256_properties(ctx, amira):
             assert toks[b] == small[b % 8] and steps[b] == ssteps[b % 8]
         if len(toks[b]) < 200:
             assert steps[b] >= lens[b] + len(toks[b]) - 29  # every frame ends with a blank step or the symbol limit
+
+
+def test_pipelined_host_upload_equals_resident_decode(amira):
+    """Encoder outputs in host memory are uploaded chunk by chunk, overlapped with the projection of the chunks already on
+    the device (>= 64 streams => several chunks); the tokens must equal the device-resident decode of the same batch."""
+    import torch
+    rng = np.random.default_rng(21)
+    B, T = 96, 24
+    enc = (0.5 * rng.standard_normal((B, 1024, T))).astype(np.float32)
+    lens = rng.integers(1, T + 1, size=B).astype(np.int64)
+    with amira.Context(device_id=0) as c:
+        c.load_weights(amira.synthetic_weights(3456))
+        toks_h, _, steps_h = c.greedy_decode(enc, lens)
+        enc_d = torch.from_numpy(enc).cuda()
+        tok_d = torch.zeros((B, c.max_total_tokens), dtype=torch.int32, device="cuda")
+        nt_d = torch.zeros(B, dtype=torch.int32, device="cuda")
+        ns_d = torch.zeros(B, dtype=torch.int32, device="cuda")
+        c.greedy_decode_raw(enc_d.data_ptr(), B, T, lens, tok_d.data_ptr(), nt_d.data_ptr(), ns_d.data_ptr())
+        torch.cuda.synchronize()
+        nt, tk, ns = nt_d.cpu().numpy(), tok_d.cpu().numpy(), ns_d.cpu().numpy()
+        for b in range(B):
+            assert toks_h[b] == tk[b, :nt[b]].tolist(), b
+            assert steps_h[b] == ns[b]
+
+
+def test_streaming_tick_1024_slots(amira):
+    """BASELINE config 4 shape: 1024 resident stream slots, T = 3 encoder frames per tick; two ticks through the slots equal
+    one decode with caller-carried state."""
+    rng = np.random.default_rng(31)
+    n, T = 1024, 3
+    enc = (0.5 * rng.standard_normal((2, n, 1024, T))).astype(np.float32)
+    with amira.Context(device_id=0) as c:
+        c.load_weights(amira.synthetic_weights(3456))
+        slots = [c.stream_open() for _ in range(n)]
+        assert len(set(slots)) == n
+        st = amira.DecoderState.new(n)
+        for tick in range(2):
+            got, _ = c.stream_decode(slots, enc[tick])
+            ref, st, _ = c.greedy_decode(enc[tick], [T] * n, state=st)
+            assert got == ref
+        with pytest.raises(amira.AmiraError):
+            c.stream_decode([slots[0], slots[0]], enc[0, :2])  # duplicate slot in one tick
+        for s in slots:
+            c.stream_close(s)

@@ -114,3 +114,21 @@ def test_golden_fixture(ctx):
     feats, lens = ctx.preprocess_pcm16(g["pcm"], [0, g["pcm"].size])
     assert int(lens[0]) == int(g["features_len"])
     assert np.abs(feats[0, :, :int(lens[0])] - g["features"]).max() <= TOL
+
+
+def test_pipelined_host_path_equals_resident_path(ctx, amira):
+    """Host buffers take the chunked H2D / kernel / D2H pipeline (>= 64 utterances => several chunks); device buffers take
+    the single-launch path.  Both must produce bit-identical features (utterances are independent)."""
+    import torch
+    rng = np.random.default_rng(11)
+    pcms = [synth_pcm(float(rng.uniform(0.3, 1.2)), 300 + i) for i in range(96)]
+    pcm, offs = _pack(pcms)
+    t_stride = 128
+    host, lens_h = ctx.preprocess_pcm16(pcm, offs, t_stride=t_stride)
+    pcm_d = torch.from_numpy(pcm).cuda()
+    out_d = torch.empty((len(pcms), 128, t_stride), dtype=torch.float32, device="cuda")
+    lens_d = np.zeros(len(pcms), np.int64)
+    ctx.preprocess_pcm16_raw(pcm_d.data_ptr(), offs, len(pcms), out_d.data_ptr(), t_stride, lens_d)
+    torch.cuda.synchronize()
+    assert lens_h.tolist() == lens_d.tolist()
+    assert np.array_equal(host, out_d.cpu().numpy())
