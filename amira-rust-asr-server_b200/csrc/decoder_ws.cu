@@ -621,10 +621,13 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     *reinterpret_cast<uint4 *>(p.h1b_hi + ob) = *reinterpret_cast<uint4 *>(vh);
                     *reinterpret_cast<uint4 *>(p.h1b_lo + ob) = *reinterpret_cast<uint4 *>(vl);
                 }
+                if (etid == 0) WS_TRACE(5);
                 named_bar_sync(1, W_EPI_THREADS);
                 if (etid == 0) {
+                    WS_TRACE(6);
                     __threadfence();
                     fence_proxy_async();
+                    WS_TRACE(7);
                     atomicAdd(p.cnt_b + mt, 1);
                     WS_TRACE(4);
                 }
