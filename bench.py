@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 F_STEP = 15_244_800      # flop per (stream, decode step): 2 LSTM layers + pred proj + vocab proj
 F_FRAME = 1_310_720      # flop per (stream, encoder frame): hoisted encoder projection
 BYTES_PER_AUDIO_S = 83_200  # front end, i16 in + f32 [128, T'] out
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this command's default workload
+# (profiles/r1c_ncu_full_raw.csv); reported as roofline.traffic only for that workload
+NCU_DRAM_BYTES = {"greedy": 657_217_024, "fe_logmel": 1_552_202_240}
 ENGINE_NAMES = {0: ("greedy_ws_kernel", "tcgen05 split-bf16 weight-stationary dataflow kernel"),
                 1: ("greedy_persistent_kernel", "fp32 persistent cooperative kernel"),
                 2: ("greedy_tc_kernel", "tcgen05 split-bf16 grid-synchronised kernel"),
@@ -373,6 +376,7 @@ def main():
         return
 
     hbm_peak, tf_peak, peak_kind = peaks()
+    default_workload = B == 1024 and args.engine in (0, 4) and world == 1
     # dominant kernel = the persistent decode kernel (tensor-pipe roofline)
     dec_ms, dec_n = kms["greedy"]
     flops = float(nsteps.sum()) * F_STEP
@@ -401,10 +405,10 @@ def main():
         "gpu_launches": int(launches),
         "kernel_ms_per_step": share,
         "roofline": {"kernel": ENGINE_NAMES[args.engine][0], "bound": "tensor", "achieved": ach_tf, "peak": tf_peak,
-                     "unit": "TFLOP/s", "frac": ach_tf / tf_peak, "traffic": None, "peak_kind": f"bf16 sustained, {peak_kind}",
+                     "unit": "TFLOP/s", "frac": ach_tf / tf_peak, "traffic": NCU_DRAM_BYTES["greedy"] if default_workload else None, "peak_kind": f"bf16 sustained, {peak_kind}",
                      "flops_per_launch": flops, "avg_launch_ms": dec_avg_ms},
         "roofline_frontend": {"kernel": "fe_logmel_kernel", "bound": "hbm", "achieved": fe_gbs, "peak": hbm_peak, "unit": "GB/s",
-                              "frac": fe_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind, "bytes_per_launch": fe_bytes,
+                              "frac": fe_gbs / hbm_peak, "traffic": NCU_DRAM_BYTES["fe_logmel"] if default_workload else None, "peak_kind": peak_kind, "bytes_per_launch": fe_bytes,
                               "avg_launch_ms": fe_avg_ms},
     }
     if streaming:
