@@ -17,8 +17,8 @@ from __future__ import annotations
 from ._lib import (AMIRA_N_PARAMS, BLANK_ID, ENC_DIM, MAX_SYMBOLS_PER_STEP, MAX_TOTAL_TOKENS, N_MELS, STATE_SIZE,
                    VOCAB_SIZE, AmiraError, Context, DecoderState, EXPORTS, device_count, features_len, lib_path,
                    load_library, random_weights, synthetic_weights, blob_views)
-from .pipeline import B200AsrPipeline, Transcription, Vocabulary, shard_utterances
+from .pipeline import B200AsrPipeline, Batcher, Transcription, Vocabulary, shard_utterances
 
 __all__ = ["AMIRA_N_PARAMS", "BLANK_ID", "ENC_DIM", "MAX_SYMBOLS_PER_STEP", "MAX_TOTAL_TOKENS", "N_MELS", "STATE_SIZE",
            "VOCAB_SIZE", "AmiraError", "Context", "DecoderState", "EXPORTS", "device_count", "features_len", "lib_path",
-           "load_library", "random_weights", "synthetic_weights", "blob_views", "B200AsrPipeline", "Transcription", "Vocabulary", "shard_utterances"]
+           "load_library", "random_weights", "synthetic_weights", "blob_views", "B200AsrPipeline", "Batcher", "Transcription", "Vocabulary", "shard_utterances"]

@@ -28,7 +28,8 @@ EXPORTS = ["amira_device_count", "amira_config_default", "amira_ctx_create", "am
            "amira_stream_decode", "amira_pipeline_create", "amira_pipeline_destroy", "amira_pipeline_process_batch",
            "amira_pipeline_process_stream_chunk", "amira_pipeline_process_batch_samples",
            "amira_pipeline_process_stream_samples", "amira_pipeline_last_error", "amira_vocab_decode",
-           "amira_shard_utterances"]
+           "amira_shard_utterances", "amira_batcher_create", "amira_batcher_destroy", "amira_batcher_process_batch",
+           "amira_batcher_stats", "amira_ctx_max_total_tokens"]
 
 
 class AmiraError(RuntimeError):
@@ -70,6 +71,7 @@ def load_library():
     L.amira_ctx_set_stream.argtypes = [vp, vp]
     L.amira_ctx_synchronize.argtypes = [vp]
     L.amira_ctx_launch_count.argtypes = [vp, C.POINTER(i64)]
+    L.amira_ctx_max_total_tokens.argtypes = [vp, C.POINTER(i32)]
     L.amira_ctx_profile.argtypes = [vp, i32]
     L.amira_ctx_kernel_ms.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(i64)]
     L.amira_debug_tc_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]

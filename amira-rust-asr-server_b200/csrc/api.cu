@@ -263,6 +263,12 @@ int32_t amira_ctx_launch_count(amira_ctx *c, int64_t *count) {
     return AMIRA_OK;
 }
 
+int32_t amira_ctx_max_total_tokens(amira_ctx *c, int32_t *value) {
+    if (!c || !value) return AMIRA_ERR_INVALID_VALUE;
+    *value = c->cfg.max_total_tokens;
+    return AMIRA_OK;
+}
+
 int32_t amira_ctx_profile(amira_ctx *c, int32_t enable) {
     API_BEGIN(c)
     CK(cudaStreamSynchronize(c->stream), "profile sync");

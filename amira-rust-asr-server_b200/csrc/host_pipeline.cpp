@@ -1,10 +1,15 @@
 // host_pipeline.cpp — C++ host side above the C ABI: the mirror of the reference's Rust `AsrPipeline` trait
 // (src/asr/pipeline.rs:20-67) and of TritonAsrPipeline::process_audio_zero_copy (src/asr/pipeline.rs:269-380),
 // with `preprocessor` and `decoder_joint` served by the GPU library instead of Triton.  Rust is not available in
-// this build environment; rust/amira-b200-sys carries the equivalent crate as source.
+// this build environment; INTEGRATION.md carries the equivalent Rust binding as source.
 // Also: Vocabulary (src/asr/types.rs:77-155) and the host-side utterance sharder for multi-GPU.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
+#include <thread>
 #include <cstring>
 #include <fstream>
 #include <mutex>
@@ -273,6 +278,240 @@ int32_t amira_shard_utterances(const int64_t *costs, int32_t n, int32_t n_shards
     } catch (...) {
         return AMIRA_ERR_OUT_OF_MEMORY;
     }
+    return AMIRA_OK;
+}
+
+}  // extern "C"
+
+
+// =================================================================================================================
+// Request micro-batcher.  The reference is strictly B = 1 per request (src/triton/model.rs:84,298,590)
+// and bounds concurrency with semaphores (src/server/state.rs:47-61, 10 streams / 50 batches); the GPU path wants the
+// opposite: concurrent `process_batch` calls coalesced into ONE front-end launch and ONE persistent decode launch.
+// amira_batcher_process_batch is a blocking, thread-safe drop-in for AsrPipeline::process_batch: callers park on a
+// condition variable while a worker thread drains the queue every `max_wait_us` (or as soon as `max_batch` requests
+// wait), runs the batch and hands each caller its own Transcription.  Results are identical to the one-by-one calls:
+// utterances are independent in every kernel.
+namespace {
+
+struct BatchReq {
+    const uint8_t *bytes = nullptr;
+    size_t n_bytes = 0;
+    amira_transcription *out = nullptr;
+    int32_t *tokens = nullptr;
+    int32_t tokens_cap = 0;
+    char *text = nullptr;
+    size_t text_cap = 0;
+    int32_t rc = 0;
+    bool done = false;
+    std::string err;
+};
+
+}  // namespace
+
+struct amira_batcher {
+    amira_pipeline *p = nullptr;
+    int max_batch = 64;
+    int max_wait_us = 200;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<BatchReq *> queue;
+    bool stop = false;
+    std::thread worker;
+    std::atomic<int64_t> n_requests{0}, n_batches{0};
+    // worker-owned scratch
+    std::vector<int16_t> pcm;
+    std::vector<int64_t> offsets, flens, elens;
+    std::vector<float> features, one_feat, enc;
+    std::vector<int32_t> tokens, ntok;
+};
+
+namespace {
+
+void finish_req(amira_batcher *b, BatchReq *r, int32_t rc, const std::string &err) {
+    r->rc = rc;
+    r->err = err;
+    std::lock_guard<std::mutex> lock(b->mu);
+    r->done = true;
+    b->cv_done.notify_all();
+}
+
+// one coalesced batch: fused front end over all requests, the injected encoder per utterance, one greedy decode
+void run_batch(amira_batcher *b, std::vector<BatchReq *> &reqs) {
+    amira_pipeline *p = b->p;
+    std::lock_guard<std::mutex> plock(p->mu);  // the pipeline's context calls are serialised like single requests
+    const int B = (int)reqs.size();
+    auto fail_all = [&](int32_t rc, const std::string &m) {
+        for (BatchReq *r : reqs) finish_req(b, r, rc, m);
+    };
+    try {
+        b->offsets.assign((size_t)B + 1, 0);
+        for (int i = 0; i < B; ++i) b->offsets[(size_t)i + 1] = b->offsets[(size_t)i] + (int64_t)(reqs[(size_t)i]->n_bytes / 2);
+        b->pcm.resize((size_t)std::max<int64_t>(b->offsets[(size_t)B], 1));
+        int64_t max_flen = 1;
+        for (int i = 0; i < B; ++i) {
+            std::memcpy(b->pcm.data() + b->offsets[(size_t)i], reqs[(size_t)i]->bytes, reqs[(size_t)i]->n_bytes);
+            int64_t fl = 0;
+            amira_features_len((int64_t)(reqs[(size_t)i]->n_bytes / 2), &fl);
+            max_flen = std::max(max_flen, fl);
+        }
+        const int64_t t_stride = (max_flen + 3) / 4 * 4;
+        b->features.resize((size_t)B * AMIRA_N_MELS * (size_t)t_stride);
+        b->flens.assign((size_t)B, 0);
+        int32_t rc = amira_preprocess_pcm16(p->ctx, b->pcm.data(), b->offsets.data(), B, b->features.data(), t_stride, b->flens.data());
+        if (rc) return fail_all(rc, amira_last_error(p->ctx));
+        // encoder (out of scope, injected): per utterance, contract [1][128][features_len] -> [1][1024][encoded_len]
+        if (!p->encoder) return fail_all(AMIRA_ERR_NOT_READY, "no encoder callback installed");
+        b->elens.assign((size_t)B, 0);
+        std::vector<std::vector<float>> enc_out((size_t)B);
+        int64_t T = 0;
+        for (int i = 0; i < B; ++i) {
+            const int64_t fl = b->flens[(size_t)i];
+            b->one_feat.resize((size_t)AMIRA_N_MELS * (size_t)std::max<int64_t>(fl, 1));
+            for (int m = 0; m < AMIRA_N_MELS; ++m)
+                std::memcpy(b->one_feat.data() + (size_t)m * (size_t)fl,
+                            b->features.data() + ((size_t)i * AMIRA_N_MELS + (size_t)m) * (size_t)t_stride, sizeof(float) * (size_t)fl);
+            const float *e = nullptr;
+            int64_t el = 0;
+            if (p->encoder(p->encoder_user, b->one_feat.data(), fl, &e, &el) != 0 || el < 0 || (el > 0 && !e)) {
+                finish_req(b, reqs[(size_t)i], AMIRA_ERR_UNKNOWN, "encoder callback failed");
+                reqs[(size_t)i] = nullptr;  // this request is out; the rest of the batch goes on
+                continue;
+            }
+            enc_out[(size_t)i].assign(e, e + (size_t)AMIRA_ENC_DIM * (size_t)el);  // the callback's buffer is only valid until its next call
+            b->elens[(size_t)i] = el;
+            T = std::max(T, el);
+        }
+        const int cap = AMIRA_MAX_TOTAL_TOKENS * 8;
+        b->tokens.assign((size_t)B * (size_t)cap, 0);
+        b->ntok.assign((size_t)B, 0);
+        if (T > 0) {
+            b->enc.assign((size_t)B * AMIRA_ENC_DIM * (size_t)T, 0.f);
+            for (int i = 0; i < B; ++i) {
+                const int64_t el = b->elens[(size_t)i];
+                for (int f = 0; f < AMIRA_ENC_DIM && el > 0; ++f)  // [1024][el] -> [1024][T]
+                    std::memcpy(b->enc.data() + ((size_t)i * AMIRA_ENC_DIM + (size_t)f) * (size_t)T,
+                                enc_out[(size_t)i].data() + (size_t)f * (size_t)el, sizeof(float) * (size_t)el);
+            }
+            // the decode entry writes max_total_tokens ids per stream: use the context's own capacity as the row stride
+            rc = amira_greedy_decode(p->ctx, b->enc.data(), B, (int32_t)T, b->elens.data(), nullptr, nullptr, b->tokens.data(),
+                                     b->ntok.data(), nullptr);
+            if (rc && rc != AMIRA_ERR_DECODE_STEP) return fail_all(rc, amira_last_error(p->ctx));
+        }
+        int32_t row_cap = AMIRA_MAX_TOTAL_TOKENS;
+        amira_ctx_max_total_tokens(p->ctx, &row_cap);
+        for (int i = 0; i < B; ++i) {
+            BatchReq *r = reqs[(size_t)i];
+            if (!r) continue;
+            const int32_t n = b->ntok[(size_t)i];
+            if (n < 0) {  // this stream's argmax left the embedding table ("Decode step failed", decoder_optimized.rs:148-152)
+                finish_req(b, r, AMIRA_ERR_DECODE_STEP, "Decode step failed");
+                continue;
+            }
+            const int32_t *tk = b->tokens.data() + (size_t)i * (size_t)row_cap;
+            r->out->audio_length_samples = (int64_t)(r->n_bytes / 2);
+            r->out->features_length = b->flens[(size_t)i];
+            r->out->encoded_length = b->elens[(size_t)i];
+            r->out->n_tokens = n;
+            if (r->tokens) std::memcpy(r->tokens, tk, sizeof(int32_t) * (size_t)std::min(n, r->tokens_cap));
+            const std::string s = p->vocab.decode(tk, n);
+            r->out->text_len = (int32_t)s.size();
+            if (r->text && r->text_cap) {
+                const size_t m = std::min(s.size(), r->text_cap - 1);
+                std::memcpy(r->text, s.data(), m);
+                r->text[m] = '\0';
+            }
+            finish_req(b, r, AMIRA_OK, "");
+        }
+    } catch (const std::bad_alloc &) {
+        for (BatchReq *r : reqs)
+            if (r && !r->done) finish_req(b, r, AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed");
+    } catch (...) {
+        for (BatchReq *r : reqs)
+            if (r && !r->done) finish_req(b, r, AMIRA_ERR_UNKNOWN, "unexpected exception");
+    }
+}
+
+void batcher_loop(amira_batcher *b) {
+    std::unique_lock<std::mutex> lock(b->mu);
+    for (;;) {
+        b->cv_work.wait(lock, [&] { return b->stop || !b->queue.empty(); });
+        if (b->stop && b->queue.empty()) return;
+        // coalescing window: wait for more requests, up to max_wait_us after the first one or until the batch is full
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(b->max_wait_us);
+        b->cv_work.wait_until(lock, deadline, [&] { return b->stop || (int)b->queue.size() >= b->max_batch; });
+        std::vector<BatchReq *> reqs;
+        while (!b->queue.empty() && (int)reqs.size() < b->max_batch) {
+            reqs.push_back(b->queue.front());
+            b->queue.pop_front();
+        }
+        lock.unlock();
+        b->n_batches.fetch_add(1);
+        run_batch(b, reqs);
+        lock.lock();
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t amira_batcher_create(amira_pipeline *p, int32_t max_batch, int32_t max_wait_us, amira_batcher **out) {
+    if (!p || !out || max_batch <= 0 || max_wait_us < 0) return pfail(p, AMIRA_ERR_INVALID_VALUE, "amira_batcher_create: bad arguments");
+    *out = nullptr;
+    if (!p->ctx) return pfail(p, AMIRA_ERR_NO_DEVICE, "pipeline was created without a GPU context");
+    try {
+        amira_batcher *b = new amira_batcher();
+        b->p = p;
+        b->max_batch = max_batch;
+        b->max_wait_us = max_wait_us;
+        b->worker = std::thread(batcher_loop, b);
+        *out = b;
+    } catch (...) {
+        return pfail(p, AMIRA_ERR_OUT_OF_MEMORY, "cannot start the batcher thread");
+    }
+    return AMIRA_OK;
+}
+
+int32_t amira_batcher_destroy(amira_batcher *b) {
+    if (!b) return AMIRA_OK;
+    {
+        std::lock_guard<std::mutex> lock(b->mu);
+        b->stop = true;
+    }
+    b->cv_work.notify_all();
+    if (b->worker.joinable()) b->worker.join();
+    delete b;
+    return AMIRA_OK;
+}
+
+int32_t amira_batcher_process_batch(amira_batcher *b, const uint8_t *audio_bytes, size_t n_bytes, amira_transcription *out,
+                                    int32_t *tokens, int32_t tokens_cap, char *text, size_t text_cap) {
+    if (!b || !out) return AMIRA_ERR_INVALID_VALUE;
+    std::memset(out, 0, sizeof(*out));
+    if (text && text_cap) text[0] = '\0';
+    if (!audio_bytes || n_bytes == 0 || (n_bytes & 1))  // empty / odd-length requests take the single-request path and its rules
+        return amira_pipeline_process_batch(b->p, audio_bytes, n_bytes, out, tokens, tokens_cap, text, text_cap);
+    BatchReq r;
+    r.bytes = audio_bytes; r.n_bytes = n_bytes; r.out = out; r.tokens = tokens; r.tokens_cap = tokens_cap; r.text = text; r.text_cap = text_cap;
+    b->n_requests.fetch_add(1);
+    std::unique_lock<std::mutex> lock(b->mu);
+    if (b->stop) return AMIRA_ERR_NOT_READY;
+    b->queue.push_back(&r);
+    b->cv_work.notify_all();
+    b->cv_done.wait(lock, [&] { return r.done; });
+    lock.unlock();
+    if (r.rc) {
+        std::lock_guard<std::mutex> plock(b->p->mu);
+        b->p->err = r.err;
+    }
+    return r.rc;
+}
+
+int32_t amira_batcher_stats(amira_batcher *b, int64_t *n_requests, int64_t *n_batches) {
+    if (!b) return AMIRA_ERR_INVALID_VALUE;
+    if (n_requests) *n_requests = b->n_requests.load();
+    if (n_batches) *n_batches = b->n_batches.load();
     return AMIRA_OK;
 }
 

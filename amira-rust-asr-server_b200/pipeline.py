@@ -45,6 +45,10 @@ def _bind(L):
     L.amira_pipeline_process_stream_samples.argtypes = [vp, vp, C.c_size_t, vp, vp] + tail
     L.amira_vocab_decode.argtypes = [vp, vp, i32, vp, C.c_size_t, C.POINTER(i32)]
     L.amira_shard_utterances.argtypes = [vp, i32, i32, vp]
+    L.amira_batcher_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    L.amira_batcher_destroy.argtypes = [vp]
+    L.amira_batcher_process_batch.argtypes = [vp, vp, C.c_size_t] + tail
+    L.amira_batcher_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L._pipeline_bound = True
 
 
@@ -150,6 +154,43 @@ class B200AsrPipeline:
         if rc:
             raise AmiraError(rc, (self._L.amira_pipeline_last_error(self._h) or b"").decode())
         return text.value.decode("utf-8", "replace")
+
+
+class Batcher:
+    """Request micro-batcher above a B200AsrPipeline (csrc/host_pipeline.cpp): concurrent process_batch calls from many
+    threads are coalesced into one front-end launch and one decode launch; each caller gets its own Transcription."""
+
+    def __init__(self, pipeline: B200AsrPipeline, max_batch: int = 64, max_wait_us: int = 200):
+        self._p = pipeline
+        self._L = pipeline._L
+        self._h = C.c_void_p()
+        rc = self._L.amira_batcher_create(pipeline._h, max_batch, max_wait_us, C.byref(self._h))
+        if rc:
+            raise AmiraError(rc, (self._L.amira_pipeline_last_error(pipeline._h) or b"").decode())
+
+    def process_batch(self, audio_bytes: bytes) -> Transcription:
+        t, toks, text = self._p._bufs()
+        b = np.frombuffer(bytes(audio_bytes), dtype=np.uint8)
+        rc = self._L.amira_batcher_process_batch(self._h, b.ctypes.data if b.size else None, b.size, C.byref(t),
+                                                 toks.ctypes.data, toks.size, text, len(text))
+        return self._p._finish(rc, t, toks, text)
+
+    def stats(self) -> tuple[int, int]:
+        """(requests that went through the queue, launches they were coalesced into)"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._L.amira_batcher_stats(self._h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.amira_batcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Vocabulary:

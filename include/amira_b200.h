@@ -194,6 +194,19 @@ int32_t amira_pipeline_process_stream_samples(amira_pipeline *p, const float *sa
  * returns the full length in *text_len (may exceed text_cap - 1: output truncated). */
 int32_t amira_vocab_decode(amira_pipeline *p, const int32_t *tokens, int32_t n_tokens, char *text, size_t text_cap,
                            int32_t *text_len);
+/* Request micro-batcher: the reference is B = 1 per request behind semaphores (src/server/state.rs:47-61);
+ * this coalesces concurrent AsrPipeline::process_batch calls into one front-end launch + one persistent decode launch.
+ * amira_batcher_process_batch is blocking and thread-safe; results equal the one-by-one amira_pipeline_process_batch calls.
+ * max_wait_us: coalescing window after the first queued request; max_batch: requests per launch. */
+typedef struct amira_batcher amira_batcher;
+int32_t amira_batcher_create(amira_pipeline *p, int32_t max_batch, int32_t max_wait_us, amira_batcher **out);
+int32_t amira_batcher_destroy(amira_batcher *b);
+int32_t amira_batcher_process_batch(amira_batcher *b, const uint8_t *audio_bytes, size_t n_bytes, amira_transcription *out,
+                                    int32_t *tokens, int32_t tokens_cap, char *text, size_t text_cap);
+int32_t amira_batcher_stats(amira_batcher *b, int64_t *n_requests, int64_t *n_batches);
+/* configured max_total_tokens of a context (row stride of the tokens output of the decode entries) */
+int32_t amira_ctx_max_total_tokens(amira_ctx *ctx, int32_t *value);
+
 /* Multi-GPU: utterances are independent — longest-processing-time assignment of n utterances with
  * costs[i] (e.g. samples) to n_shards GPUs; shard_of[i] receives the shard index.  No collective follows. */
 int32_t amira_shard_utterances(const int64_t *costs, int32_t n, int32_t n_shards, int32_t *shard_of);

@@ -1,0 +1,129 @@
+"""GPU tests of the host pipeline above the C ABI: the C++ mirror of the reference's `AsrPipeline` trait
+(src/asr/pipeline.rs:20-67, process_audio_zero_copy :269-380) and the request micro-batcher.  The encoder model is out
+of scope and injected; here it is a fixed numpy function so that every path sees the same encoder."""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import synth_pcm
+
+pytestmark = pytest.mark.gpu
+NEAR_TIE = 2e-4
+VOCAB = "/tmp/amira_test_vocab.txt"
+
+
+def _write_vocab():
+    with open(VOCAB, "w", encoding="utf-8") as f:
+        for i in range(1024):
+            f.write(("▁w%d %d\n" if i % 3 == 0 else "p%d %d\n") % (i, i))
+        f.write("<blk> 1024\n")
+
+
+_rng = np.random.default_rng(123)
+_W = (_rng.standard_normal((1024, 128)) / np.sqrt(128)).astype(np.float32)
+
+
+def stub_encoder(feats: np.ndarray) -> np.ndarray:
+    """[128, L] -> [1024, T], T = the 8x subsampled length of the real encoder (L <- (L-1)//2+1 three times)."""
+    L = feats.shape[1]
+    T = L
+    for _ in range(3):
+        T = (T - 1) // 2 + 1 if T > 0 else 0
+    if T == 0:
+        return np.zeros((1024, 0), np.float32)
+    pooled = np.stack([feats[:, 8 * t:8 * t + 8].mean(axis=1) for t in range(T)], axis=1)
+    return np.ascontiguousarray(0.5 * np.tanh(_W @ pooled), dtype=np.float32)
+
+
+@pytest.fixture(scope="module")
+def pipe(amira):
+    _write_vocab()
+    ctx = amira.Context(device_id=0)
+    ctx.load_weights(amira.synthetic_weights(3456))
+    p = amira.B200AsrPipeline(ctx, VOCAB, stub_encoder)
+    yield p, ctx
+    p.close()
+    ctx.close()
+
+
+def test_process_batch_equals_the_composed_primitives_and_the_oracle(pipe, amira, oracle):
+    p, ctx = pipe
+    model = oracle.Model(blob=amira.synthetic_weights(3456))
+    vocab = oracle.Vocabulary.load_from_file(VOCAB)
+    for i, secs in enumerate((2.0, 0.6, 3.3)):
+        pcm = synth_pcm(secs, 40 + i)
+        tr = p.process_batch(pcm.tobytes())
+        # same thing through the library's own primitives
+        feats, lens = ctx.preprocess_pcm16(pcm, [0, pcm.size])
+        enc = stub_encoder(feats[0, :, :int(lens[0])])
+        toks, _, _ = ctx.greedy_decode(enc[None], [enc.shape[1]])
+        assert tr.tokens == toks[0]
+        assert (tr.audio_length_samples, tr.features_length, tr.encoded_length) == (pcm.size, int(lens[0]), enc.shape[1])
+        assert tr.text == vocab.decode_tokens(tr.tokens) == p.decode_tokens(tr.tokens)
+        # and through the CPU oracle end to end (features differ by <= 1e-4, so only near-ties may flip a token)
+        ref_f, L = oracle.preprocess(pcm.astype(np.float32) / 32768.0, "f64")
+        ref_enc = stub_encoder(ref_f[:, :L])
+        r = oracle.greedy_decode(ref_enc, ref_enc.shape[1], model)
+        assert r.tokens == tr.tokens or r.margins.min() < 50 * NEAR_TIE
+
+
+def test_stream_chunks_carry_the_lstm_state(pipe, amira):
+    p, ctx = pipe
+    pcm = synth_pcm(1.92, 77)
+    st = amira.DecoderState.new(1)
+    toks_stream = []
+    for c in range(4):  # four 480 ms chunks; token history is per call, the state is carried (pipeline.rs:384-401)
+        chunk = pcm[c * 7680:(c + 1) * 7680]
+        tr = p.process_stream_chunk(chunk.tobytes(), st)
+        feats, lens = ctx.preprocess_pcm16(chunk, [0, chunk.size])
+        enc = stub_encoder(feats[0, :, :int(lens[0])])
+        if c == 0:
+            ref_state = amira.DecoderState.new(1)
+        ref_toks, ref_state, _ = ctx.greedy_decode(enc[None], [enc.shape[1]], state=ref_state)
+        assert tr.tokens == ref_toks[0]
+        toks_stream += tr.tokens
+    assert np.array_equal(st.states_1, ref_state.states_1) and np.array_equal(st.states_2, ref_state.states_2)
+    assert np.abs(st.states_1).max() > 0
+
+
+def test_odd_length_and_empty_requests(pipe):
+    p, _ = pipe
+    pcm = synth_pcm(0.5, 9)
+    odd = pcm.tobytes() + b"\x05"  # trailing byte: bytes_to_f32_optimized rule (performance_opts.rs:26-30)
+    tr = p.process_batch(odd)
+    assert tr.audio_length_samples == pcm.size + 1
+    tr0 = p.process_batch(b"")
+    assert tr0.tokens == [] and tr0.text == ""
+
+
+def test_micro_batcher_equals_one_by_one(pipe, amira):
+    """Concurrent process_batch calls are coalesced into few launches; every caller gets exactly the one-by-one result."""
+    p, ctx = pipe
+    utts = [synth_pcm(float(0.4 + 0.13 * i), 500 + i).tobytes() for i in range(24)]
+    want = [p.process_batch(u) for u in utts]
+    batcher = amira.Batcher(p, max_batch=16, max_wait_us=20000)
+    got = [None] * len(utts)
+    errs = []
+
+    def work(i):
+        try:
+            got[i] = batcher.process_batch(utts[i])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(len(utts))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs
+    for g, w in zip(got, want):
+        assert g.tokens == w.tokens and g.text == w.text
+        assert (g.audio_length_samples, g.features_length, g.encoded_length) == (w.audio_length_samples, w.features_length, w.encoded_length)
+    n_req, n_batches = batcher.stats()
+    assert n_req == len(utts) and n_batches < len(utts)
+    # empty request through the batcher takes the single-request path
+    assert batcher.process_batch(b"").tokens == []
+    batcher.close()
