@@ -8,7 +8,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libamira_b200.so")
+_SO = os.path.join(_HERE, os.environ.get("AMIRA_B200_LIB", "libamira_b200.so"))  # the override exists for A/B timing of builds
 
 VOCAB_SIZE, BLANK_ID, STATE_SIZE, ENC_DIM, N_MELS = 1030, 1024, 640, 1024, 128
 MAX_SYMBOLS_PER_STEP, MAX_TOTAL_TOKENS = 30, 200  # src/constants.rs:135-136

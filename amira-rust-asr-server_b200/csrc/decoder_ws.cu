@@ -81,11 +81,10 @@ struct WsParams {
     __nv_bfloat16 *h0b_hi, *h0b_lo, *h1b_hi, *h1b_lo, *zb_hi, *zb_lo;
     float *h0f, *h1f, *c0, *c1;
     float *part;        // [MT][40 slices][2 column groups][128 rows][32] fp32: h1(t-1) W_hh1 partial sums
-    float *pval;        // [MT][34][128]
-    int *pidx;
+    unsigned long long *amax;  // [2 step parities][Mpad] packed (orderable logit << 32 | ~column): atomicMax = first-max argmax
     WCtl *ctl;
     int4 *rowinfo;      // [Mpad] {stream index, encoded length, first packed row of E, 0}: one load instead of perm -> lens / eoff chains
-    int *tile_active, *done_d, *cnt_a, *cnt_b, *cnt_c, *ctl_done, *dead_at, *part_ready /* [MT][40] */, *fail_count;
+    int *tile_active, *cnt_d, *cnt_a, *cnt_b, *cnt_c, *dead_at, *part_ready /* [MT][40] */, *fail_count;
     float *s1, *s2;
     int *tokens, *ntok, *nsteps;
     int max_sym, max_total, blank, relu;
@@ -100,7 +99,7 @@ struct WsDesc {
 struct WsSmem {
     uint64_t full[W_RING], empty[W_RING], acc_full[W_NACC], acc_empty[W_NACC], q_full[W_Q], q_empty[W_Q], wfull;
     uint32_t tmem_slot;
-    int flag, act_cnt;
+    int act2[2];  // live-stream count of the unit in the layer-0 epilogue (alternating slots)
     WsDesc q[W_Q];
     unsigned char dead[W_MAX_MT];
 };
@@ -280,6 +279,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
         mbar_fence_init();
     }
     for (int i = tid; i < W_MAX_MT; i += W_THREADS) sm.dead[i] = 0;
+    if (tid == 0) { sm.act2[0] = 0; sm.act2[1] = 0; }
     if (warp == 1) tmem_alloc(&sm.tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
@@ -325,7 +325,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
         WCtl c;
         c.t = 0; c.sym = 0; c.total = 0; c.last = p.blank; c.nsteps = 0; c.failed = 0; c.pad = 0;
         c.active = (row < p.B && p.lens[p.perm[row]] > 0) ? 1 : 0;
-        p.ctl[row] = c;
+        p.ctl[row] = c;  // the control rows are double-buffered by step parity (see the layer-0 epilogue)
+        p.ctl[p.Mpad + row] = c;
         const int prow_ = row < p.B ? p.perm[row] : 0;
         p.rowinfo[row] = make_int4(prow_, row < p.B ? p.lens[prow_] : 0, row < p.B ? p.eoff[prow_] : 0, 0);
         if (c.active) atomicAdd(&p.tile_active[row / W_BM], 1);
@@ -500,23 +501,90 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
             uint32_t r[32];
 
             if (role == R_A) {
-                // the recurrent GEMM ran ahead; the cell update needs the previous step's control update (token, activity)
+                // The recurrent GEMM ran ahead.  This epilogue first applies the control flow of the previous step
+                // (decoder_optimized.rs:133-188) to its 128 streams: the vocabulary CTAs left each stream's first-max argmax as
+                // one packed 64-bit key (atomicMax), so every layer-0 CTA derives the same control rows redundantly from one
+                // 8-byte load per stream and no separate control phase sits on the critical path.  Slice 0 publishes the rows
+                // (double-buffered by step parity: other layer-0 CTAs may still be reading the previous ones), the tokens and,
+                // when no stream of the M-tile is left, the results and the end marker.
+                float4 ad[8], cold4[2];
+                float *cst = p.c0 + (size_t)row * kH + nb / 4;
+                cold4[0] = __ldcg(reinterpret_cast<const float4 *>(cst));  // loads that do not depend on the previous step's
+                cold4[1] = __ldcg(reinterpret_cast<const float4 *>(cst) + 1);  // vocabulary phase go out before the wait on it
+                const int4 ri = __ldg(p.rowinfo + row);
+                WCtl c = load_ctl(p.ctl + (size_t)((it & 1) ^ 1) * p.Mpad + row);  // state after the update of step it-2
                 if (it > 0) {
-                    if (etid == 0) spin_ge(p.ctl_done + mt, it);
+                    if (etid == 0) spin_ge(p.cnt_d + mt, ND * it);  // every vocabulary slice of step it-1 has merged its argmax
                     named_bar_sync(1, W_EPI_THREADS);
                 }
                 if (etid == 0) WS_TRACE(5);
-                float4 ad[8], cold4[2];
-                float *cst = p.c0 + (size_t)row * kH + nb / 4;
-                cold4[0] = __ldcg(reinterpret_cast<const float4 *>(cst));  // independent of the control row: same round trip
-                cold4[1] = __ldcg(reinterpret_cast<const float4 *>(cst) + 1);
-                const bool live = __ldcg(p.dead_at + mt) > it;  // the M-tile may have ended with the previous step
-                const WCtl c = load_ctl(p.ctl + row);
-                const bool act = live && c.active;
-                if (act) {
+                int &act_cnt = sm.act2[tile & 1];  // `tile` was advanced above: consecutive units alternate slots
+                if (it > 0 && c.active) {
+                    const unsigned long long key = __ldcg(p.amax + (size_t)((it - 1) & 1) * p.Mpad + row);
+                    const int bi = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+                    const int len = ri.y;
+                    c.nsteps += 1;                       // state carried unconditionally (decoder_optimized.rs:154)
+                    c.sym += 1;                          // :133
+                    if (bi == p.blank) {                 // :171-173
+                        c.t += 1; c.sym = 0;
+                        if (c.t >= len) c.active = 0;
+                    } else {
+                        if (slice == 0 && cgp == 0) p.tokens[(size_t)ri.x * p.max_total + c.total] = bi;   // :176
+                        c.total += 1;
+                        c.last = bi;
+                        if (c.total >= p.max_total) c.active = 0;                    // :179-188
+                        else if (c.sym >= p.max_sym) {                               // :133-137
+                            c.t += 1; c.sym = 0;
+                            if (c.t >= len) c.active = 0;
+                        }
+                        if (c.active && bi >= kEmbRows) { c.active = 0; c.failed = 1; }  // next step would fail (:148-152)
+                    }
+                }
+                if (slice == 0 && cgp == 0) {  // the control rows of step `it`, for every other role's epilogue
+                    int4 *dstc = reinterpret_cast<int4 *>(p.ctl + (size_t)(it & 1) * p.Mpad + row);
+                    __stcg(dstc, make_int4(c.t, c.sym, c.total, c.last));
+                    __stcg(dstc + 1, make_int4(c.active, c.nsteps, c.failed, 0));
+                }
+                if (cgp == 0 && c.active) atomicAdd(&act_cnt, 1);
+                const bool act = c.active;
+                if (act) {  // the token-dependent gather overlaps the barrier below
                     const float4 *addp = reinterpret_cast<const float4 *>(p.g0p + (size_t)c.last * kG + nb);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) ad[j] = __ldg(addp + j);
+                }
+                named_bar_sync(1, W_EPI_THREADS);
+                const bool live = act_cnt > 0;  // identical in every layer-0 CTA
+                if (etid == 0) sm.act2[(tile & 1) ^ 1] = 0;  // the next unit's slot: nobody touches it before that unit's barrier
+                if (etid == 0 && slice == 0 && p.trace && mt == 0 && it > 0 && it - 1 < W_TRACE_ITS) p.trace[(it - 1) * 32 + 30] = gtime();
+                if (!live && slice == 0) {  // the M-tile is finished: its streams' results, then the end marker
+                    for (int rr = etid; rr < W_BM; rr += W_EPI_THREADS) {
+                        const int grow = mt * W_BM + rr;
+                        if (grow < p.B) {
+                            const WCtl f = load_ctl(p.ctl + (size_t)(it & 1) * p.Mpad + grow);
+                            const int b = __ldg(p.rowinfo + grow).x;
+                            p.ntok[b] = f.failed ? -1 : f.total;
+                            if (p.nsteps) p.nsteps[b] = f.nsteps;
+                            if (f.failed) atomicAdd(p.fail_count, 1);
+                        }
+                    }
+                    if (p.s1 && p.s2) {
+                        for (int i = etid; i < W_BM * kH; i += W_EPI_THREADS) {
+                            const int grow = mt * W_BM + i / kH, j = i % kH;
+                            if (grow < p.B) {
+                                const int b = __ldg(p.rowinfo + grow).x;
+                                const size_t src = (size_t)grow * kH + j;
+                                p.s1[ws_state_off(p, 0, b) + j] = __ldcg(p.h0f + src);
+                                p.s1[ws_state_off(p, 1, b) + j] = __ldcg(p.h1f + src);
+                                p.s2[ws_state_off(p, 0, b) + j] = __ldcg(p.c0 + src);
+                                p.s2[ws_state_off(p, 1, b) + j] = __ldcg(p.c1 + src);
+                            }
+                        }
+                    }
+                    named_bar_sync(1, W_EPI_THREADS);
+                    if (etid == 0) {
+                        __threadfence();
+                        st_release(p.dead_at + mt, it);  // iteration `it` of this M-tile does not exist
+                    }
                 }
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
@@ -578,7 +646,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 // unit at a time, is what bounds a CTA: dependent L2 round trips are its cost): control row + cell state go out
                 // together with the acquire of the recurrent partner's flag, the partial sums right after it
                 float *cst = p.c1 + (size_t)row * kH + nb / 4;
-                const int4 ctl_a = __ldcg(reinterpret_cast<const int4 *>(p.ctl + row)), ctl_b = __ldcg(reinterpret_cast<const int4 *>(p.ctl + row) + 1);
+                const WCtl *crow = p.ctl + (size_t)(it & 1) * p.Mpad + row;  // control rows of step `it` (published by layer-0 slice 0)
+                const int4 ctl_a = __ldcg(reinterpret_cast<const int4 *>(crow)), ctl_b = __ldcg(reinterpret_cast<const int4 *>(crow) + 1);
+                // every layer-0 epilogue of this step has consumed the argmax keys of step it-1 (that is what released this unit):
+                // clear them for the vocabulary phase of step it+1, which reuses the buffer
+                if (slice == 0 && cgp == 0) __stcg(p.amax + (size_t)((it + 1) & 1) * p.Mpad + row, 0ull);
                 float4 ad[8], cold4[2], pr[8];
                 cold4[0] = __ldcg(reinterpret_cast<const float4 *>(cst));
                 cold4[1] = __ldcg(reinterpret_cast<const float4 *>(cst) + 1);
@@ -633,7 +705,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 }
             } else if (role == R_C) {
                 const int4 ri = __ldg(p.rowinfo + row);
-                const WCtl c = load_ctl(p.ctl + row);
+                const WCtl c = load_ctl(p.ctl + (size_t)(it & 1) * p.Mpad + row);
                 float4 ev[8];
                 if (c.active) {
                     const float4 *ep = reinterpret_cast<const float4 *>(p.E + ((size_t)ri.z + c.t) * kH + nb);
@@ -670,9 +742,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     WS_TRACE(4);
                 }
             } else {  // R_D: vocabulary slice -> first-max argmax partial (zero_copy.rs:190-232 tie rule) -> control update
-                const int4 ri = __ldg(p.rowinfo + row);  // for the control update: fetched ahead of the accumulator wait
-                const WCtl c = load_ctl(p.ctl + row);
-                const int prow = ri.x, len = ri.y;
+                const WCtl c = load_ctl(p.ctl + (size_t)(it & 1) * p.Mpad + row);
                 float4 bo[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)  // the padding slice of the cluster variant lies beyond the padded bias vector
@@ -695,93 +765,19 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                             if (v > best_v || best_i == 0x7fffffff) { best_v = v; best_i = n; }
                         }
                     }
-                    const size_t po = ((size_t)mt * W_NPART + slice * 2 + cgp) * W_BM + r_in;
-                    __stcg(p.pval + po, best_v);
-                    __stcg(p.pidx + po, best_i);
+                    if (best_i != 0x7fffffff) {
+                        // order-preserving map of the float, then ~column: the maximum key is the largest logit and, among equal
+                        // logits, the smallest column — the strict-'>' first-max rule of zero_copy.rs:190-232
+                        const unsigned fb = __float_as_uint(best_v);
+                        const unsigned ord = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+                        atomicMax(p.amax + (size_t)(it & 1) * p.Mpad + row, ((unsigned long long)ord << 32) | (0xFFFFFFFFu - (unsigned)best_i));
+                    }
                 }
                 named_bar_sync(1, W_EPI_THREADS);
-                if (etid == 0) {
+                if (etid == 0) {  // the layer-0 epilogues of the next step read the merged argmax and apply the control flow
                     __threadfence();
-                    const int old = atomicAdd(p.done_d + mt, 1);
+                    atomicAdd(p.cnt_d + mt, 1);
                     WS_TRACE(4);
-                    sm.flag = (old == ND - 1);
-                    sm.act_cnt = 0;
-                }
-                named_bar_sync(1, W_EPI_THREADS);
-                if (!sm.flag) continue;
-                // ---- this CTA finished the M-tile's last vocabulary slice: per-stream control update (one thread per row) ----
-                __threadfence();
-                if (cgp == 0) {
-                    WCtl n = c;
-                    if (n.active) {
-                        float bv = -INFINITY;
-                        int bi = 0x7fffffff;
-                        const size_t po = (size_t)mt * W_NPART * W_BM + r_in;
-                        float pv[W_NPART];
-                        int pi[W_NPART];
-#pragma unroll
-                        for (int qi = 0; qi < 2 * ND; ++qi) {  // every load in flight at once
-                            pi[qi] = __ldcg(p.pidx + po + (size_t)qi * W_BM);
-                            pv[qi] = __ldcg(p.pval + po + (size_t)qi * W_BM);
-                        }
-#pragma unroll
-                        for (int qi = 0; qi < 2 * ND; ++qi)
-                            if (pi[qi] != 0x7fffffff && (bi == 0x7fffffff || pv[qi] > bv)) { bv = pv[qi]; bi = pi[qi]; }
-                        n.nsteps += 1;                       // state carried unconditionally (decoder_optimized.rs:154)
-                        n.sym += 1;                          // :133
-                        if (bi == p.blank) {                 // :171-173
-                            n.t += 1; n.sym = 0;
-                            if (n.t >= len) n.active = 0;
-                        } else {
-                            p.tokens[(size_t)prow * p.max_total + n.total] = bi;   // :176
-                            n.total += 1;
-                            n.last = bi;
-                            if (n.total >= p.max_total) n.active = 0;                    // :179-188
-                            else if (n.sym >= p.max_sym) {                               // :133-137
-                                n.t += 1; n.sym = 0;
-                                if (n.t >= len) n.active = 0;
-                            }
-                            if (n.active && bi >= kEmbRows) { n.active = 0; n.failed = 1; }  // next step would fail (:148-152)
-                        }
-                        p.ctl[row] = n;
-                        if (n.active) atomicAdd(&sm.act_cnt, 1);
-                    }
-                }
-                named_bar_sync(1, W_EPI_THREADS);
-                const int alive = sm.act_cnt;
-                if (alive == 0) {  // M-tile finished: write its streams' results
-                    for (int rr = etid; rr < W_BM; rr += W_EPI_THREADS) {
-                        const int grow = mt * W_BM + rr;
-                        if (grow < p.B) {
-                            const WCtl f = load_ctl(p.ctl + grow);
-                            const int b = p.perm[grow];
-                            p.ntok[b] = f.failed ? -1 : f.total;
-                            if (p.nsteps) p.nsteps[b] = f.nsteps;
-                            if (f.failed) atomicAdd(p.fail_count, 1);
-                        }
-                    }
-                    if (p.s1 && p.s2) {
-                        for (int i = etid; i < W_BM * kH; i += W_EPI_THREADS) {
-                            const int grow = mt * W_BM + i / kH, j = i % kH;
-                            if (grow < p.B) {
-                                const int b = p.perm[grow];
-                                const size_t src = (size_t)grow * kH + j;
-                                p.s1[ws_state_off(p, 0, b) + j] = __ldcg(p.h0f + src);
-                                p.s1[ws_state_off(p, 1, b) + j] = __ldcg(p.h1f + src);
-                                p.s2[ws_state_off(p, 0, b) + j] = __ldcg(p.c0 + src);
-                                p.s2[ws_state_off(p, 1, b) + j] = __ldcg(p.c1 + src);
-                            }
-                        }
-                    }
-                    __threadfence();
-                    named_bar_sync(1, W_EPI_THREADS);
-                }
-                if (etid == 0) {
-                    p.done_d[mt] = 0;
-                    if (alive == 0) st_release(p.dead_at + mt, it + 1);
-                    __threadfence();
-                    atomicAdd(p.ctl_done + mt, 1);
-                    if (p.trace && mt == 0 && it < W_TRACE_ITS) p.trace[it * 32 + 30] = gtime();
                 }
             }
         }
@@ -851,8 +847,8 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     const size_t oact_end = off;
     const size_t oh0f = take(4 * MH), oh1f = take(4 * MH), oc0 = take(4 * MH), oc1 = take(4 * MH);
     const size_t opart = take(sizeof(float) * (size_t)MT * W_NG * 2 * W_BM * 32);
-    const size_t opv = take(sizeof(float) * (size_t)MT * W_NPART * W_BM), opi = take(sizeof(int) * (size_t)MT * W_NPART * W_BM);
-    const size_t octl = take(sizeof(WCtl) * (size_t)Mpad);
+    const size_t oamax = take(sizeof(unsigned long long) * 2 * (size_t)Mpad);
+    const size_t octl = take(sizeof(WCtl) * 2 * (size_t)Mpad);  // double-buffered by step parity
     const size_t ori = take(sizeof(int4) * (size_t)Mpad);
     const size_t n_cnt = 7 * (size_t)MT + (size_t)MT * W_NG + 4;
     const size_t ocnt = take(sizeof(int) * n_cnt);
@@ -864,6 +860,7 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     if (MT > W_MAX_MT || !w || !w->ws_ready) return cudaErrorInvalidValue;
     cudaError_t e;
     if ((e = cudaMemsetAsync(work + ocnt, 0, sizeof(int) * n_cnt, c->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(work + oamax, 0, sizeof(unsigned long long) * 2 * (size_t)Mpad, c->stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(work + oh0h, 0, oact_end - oh0h, c->stream)) != cudaSuccess) return e;  // padding rows feed the MMA too
 
     WsParams p;
@@ -887,12 +884,12 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     p.h0f = reinterpret_cast<float *>(work + oh0f); p.h1f = reinterpret_cast<float *>(work + oh1f);
     p.c0 = reinterpret_cast<float *>(work + oc0); p.c1 = reinterpret_cast<float *>(work + oc1);
     p.part = reinterpret_cast<float *>(work + opart);
-    p.pval = reinterpret_cast<float *>(work + opv); p.pidx = reinterpret_cast<int *>(work + opi);
+    p.amax = reinterpret_cast<unsigned long long *>(work + oamax);
     p.ctl = reinterpret_cast<WCtl *>(work + octl);
     p.rowinfo = reinterpret_cast<int4 *>(work + ori);
     int *cnt = reinterpret_cast<int *>(work + ocnt);
-    p.tile_active = cnt; p.done_d = cnt + MT; p.cnt_a = cnt + 2 * MT; p.cnt_b = cnt + 3 * MT; p.cnt_c = cnt + 4 * MT;
-    p.ctl_done = cnt + 5 * MT; p.dead_at = cnt + 6 * MT; p.part_ready = cnt + 7 * MT; p.fail_count = cnt + 7 * MT + MT * W_NG;
+    p.tile_active = cnt; p.cnt_d = cnt + MT; p.cnt_a = cnt + 2 * MT; p.cnt_b = cnt + 3 * MT; p.cnt_c = cnt + 4 * MT;
+    p.dead_at = cnt + 6 * MT; p.part_ready = cnt + 7 * MT; p.fail_count = cnt + 7 * MT + MT * W_NG;
     if (slots_dev) { p.s1 = c->slot_s1; p.s2 = c->slot_s2; } else { p.s1 = s1_dev; p.s2 = s2_dev; }
     p.tokens = tokens_dev; p.ntok = ntok_dev; p.nsteps = nsteps_dev;
     p.max_sym = c->cfg.max_symbols_per_step; p.max_total = c->cfg.max_total_tokens; p.blank = c->cfg.blank_id;
