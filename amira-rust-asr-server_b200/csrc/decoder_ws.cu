@@ -209,11 +209,12 @@ __device__ __forceinline__ void spin_ge(const int *p, int target) {
     }
 }
 // wait until *cnt >= target (returns 0) or the M-tile is known to have ended before iteration `it` (returns 1)
-__device__ __forceinline__ int spin_ge_or_dead_acq(const int *cnt, int target, const int *dead_at, int it) {
+__device__ __forceinline__ int spin_ge_or_dead_acq(const int *cnt, int target, const int *dead_at, int it, int lazy_dead) {
     const long long t0 = clock64();
-    for (;;) {
-        if (ld_acquire(dead_at) <= it) return 1;
-        if (ld_acquire(cnt) >= target) return 0;
+    if (ld_acquire(dead_at) <= it) return 1;
+    for (uint32_t n = 0;; ++n) {  // the end-of-tile marker is a rare event: with lazy_dead it is polled every 4th miss only, which
+        if (ld_acquire(cnt) >= target) return 0;  // halves the poll period (one L2 round trip) and the detection delay with it
+        if ((!lazy_dead || (n & 3) == 3) && ld_acquire(dead_at) <= it) return 1;
         if (clock64() - t0 > W_SPIN_LIMIT) __trap();
     }
 }
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     if (p.variant & 1) {
                         const int *cp = (role == R_A || role == R_BI) ? p.cnt_a + mt : (role == R_D ? p.cnt_c + mt : p.cnt_b + mt);
                         const int tg = (role == R_A ? W_NG * it : (role == R_BI ? W_NG * (it + 1) : (role == R_BH ? W_NG * it : (role == R_C ? W_NG * (it + 1) : W_NC * (it + 1)))));
-                        st = spin_ge_or_dead_acq(cp, tg, p.dead_at + mt, it);
+                        st = spin_ge_or_dead_acq(cp, tg, p.dead_at + mt, it, p.variant & 8);
                     } else
                     if (role == R_A) st = spin_ge_or_dead(p.cnt_a + mt, W_NG * it, p.dead_at + mt, it);              // h0(it-1)
                     else if (role == R_BI) st = spin_ge_or_dead(p.cnt_a + mt, W_NG * (it + 1), p.dead_at + mt, it);  // h0(it)

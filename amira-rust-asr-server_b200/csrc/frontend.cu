@@ -31,7 +31,7 @@ constexpr int FE_THREADS = 128;                    // 4 warps, 8 frames each
 constexpr int FE_WARPS = FE_THREADS / 32;
 constexpr int SPAN = (TF - 1) * kHop + kNfft;      // 5472 padded samples per tile
 constexpr int RAW_CAP = SPAN + 16;                 // raw samples staged per tile (+ previous sample, alignment slack)
-constexpr int PPAD = 272;                          // power spectrum row (257 bins, index k + (k >> 5))
+constexpr int PPAD = 320;                          // power spectrum row: 257 bins + zero padding read by the padded filter rows
 constexpr int OUT_LD = TF + 1;
 constexpr int FE_HALVES = 2 * FE_WARPS;            // a half-warp (16 lanes) transforms one frame
 constexpr int TLD = 17;                            // row stride (complex doubles) of the 16x16 transpose buffer
@@ -188,6 +188,7 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
     for (int g = 0; g < 4; ++g) mk[g] = tab->kstart[lane + 32 * g];
     const int r0 = tab->melRow[0], r1 = tab->melRow[1], r2 = tab->melRow[2], r3 = tab->melRow[3], r4 = tab->melRow[4];
     for (int i = tid; i < kMelRowsMax * 32; i += FE_THREADS) melw[i] = (&tab->melw_t[0][0])[i];
+    for (int i = tid; i < FE_HALVES * PPAD; i += FE_THREADS) pw[i] = 0.f;  // the padding beyond bin 256 stays zero
     double2 *myx = xbuf + (warp * 2 + half) * TBUF;
 
     for (int tile = blockIdx.x; tile < meta.n_tiles; tile += gridDim.x) {
@@ -236,8 +237,14 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
         // ---- pre-emphasis (y[0] = x[0]; y[i] = x[i] - 0.97 x[i-1]) + reflect padding ----
         const bool interior = fits && i0 >= 1 && i0 + span <= n;
         if (interior) {
-            for (int p = tid; p < span; p += FE_THREADS)  // raw[q] = x[i0 - 1 + q]
-                ystage[p] = Stage<RawT>::make(raw[p + 1], raw[p], false);
+            // raw[q] = x[i0 - 1 + q]; two consecutive samples per thread and step (one staged pair store), unrolled for ILP:
+            // this loop is pure shared-memory latency otherwise (it showed up with a quarter of the kernel's stall samples)
+#pragma unroll 4
+            for (int p = 2 * tid; p < span; p += 2 * FE_THREADS) {
+                const RawT x0 = raw[p], x1 = raw[p + 1], x2 = raw[p + 2];
+                ystage[p] = Stage<RawT>::make(x1, x0, false);
+                if (p + 1 < span) ystage[p + 1] = Stage<RawT>::make(x2, x1, false);
+            }
         } else {
             for (int p = tid; p < span; p += FE_THREADS) {
                 const int64_t r = reflect_index(i0 + p, n);
@@ -299,9 +306,8 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
                     const double ox = dy, oy = -dx;                                  // / i
                     const double wx = w.x * ox - w.y * oy, wy = w.x * oy + w.y * ox;
                     const double px = ex + wx, py = ey + wy, qx = ex - wx, qy = ey - wy;
-                    mypw[k + (k >> 5)] = (float)(px * px + py * py);
-                    const int k2m = 256 - k;
-                    if (k != 128) mypw[k2m + (k2m >> 5)] = (float)(qx * qx + qy * qy);
+                    mypw[k] = (float)(px * px + py * py);
+                    if (k != 128) mypw[256 - k] = (float)(qx * qx + qy * qy);
                 }
             }
             __syncwarp();
@@ -312,11 +318,11 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
                 if (f >= nf) break;
                 const float *ppw = pw + (warp * 2 + hh) * PPAD;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                auto band = [&](int g, int ra, int rb) {
-                    for (int r = ra; r < rb; ++r) {
-                        const int k = min(mk[g] + (r - ra), 256);
-                        acc[g] = fmaf(melw[r * 32 + lane], ppw[k + (k >> 5)], acc[g]);
-                    }
+                auto band = [&](int g, int ra, int rb) {  // rows past a filter's support carry zero weights and read the zero padding
+                    const float *pk = ppw + mk[g];
+                    const float *wk = melw + ra * 32 + lane;
+#pragma unroll 4
+                    for (int r = 0; r < rb - ra; ++r) acc[g] = fmaf(wk[r * 32], pk[r], acc[g]);
                 };
                 band(0, r0, r1);
                 band(1, r1, r2);
