@@ -214,13 +214,25 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
         if (g_hi > n) { g_hi = n; g_lo = min(g_lo, n - (kNfft / 2 + 2)); }
         if (g_lo < 0) g_lo = 0;
         const bool fits = (g_hi - g_lo) <= RAW_CAP;  // false only for pathological tiny signals with long reflections
-        if (fits) {
+        constexpr int PER = 16 / sizeof(RawT);
+        // common case: the tile lies well inside its utterance — copy the 16-byte aligned image of x[i0-1 ..] (one 128-bit load and
+        // one 128-bit shared store per thread and step; raw[q + delta] = x[i0 - 1 + q])
+        const bool fast = fits && i0 >= 1 + PER && i0 + span + PER <= n;
+        int delta = 0;
+        if (fast) {
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(x + (i0 - 1));
+            delta = (int)((ga & 15) / sizeof(RawT));
+            const int4 *src = reinterpret_cast<const int4 *>(ga & ~(uintptr_t)15);
+            const int nvec = (span + 1 + delta + PER - 1) / PER;  // <= RAW_CAP / PER
+            int4 *dst = reinterpret_cast<int4 *>(raw);
+#pragma unroll 4
+            for (int v = tid; v < nvec; v += FE_THREADS) dst[v] = __ldg(src + v);
+        } else if (fits) {
             const int cnt = (int)(g_hi - g_lo);
             // 128-bit path over the 16-byte aligned interior, scalar head/tail
             const uintptr_t a0 = reinterpret_cast<uintptr_t>(x + g_lo);
             int head = (int)(((16 - (a0 & 15)) & 15) / sizeof(RawT));
             if (head > cnt) head = cnt;
-            constexpr int PER = 16 / sizeof(RawT);
             const int nvec = (cnt - head) / PER;
             for (int i = tid; i < head; i += FE_THREADS) raw[i] = x[g_lo + i];
             const int4 *src = reinterpret_cast<const int4 *>(x + g_lo + head);
@@ -237,11 +249,12 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
         // ---- pre-emphasis (y[0] = x[0]; y[i] = x[i] - 0.97 x[i-1]) + reflect padding ----
         const bool interior = fits && i0 >= 1 && i0 + span <= n;
         if (interior) {
-            // raw[q] = x[i0 - 1 + q]; two consecutive samples per thread and step (one staged pair store), unrolled for ILP:
+            // rq[q] = x[i0 - 1 + q]; two consecutive samples per thread and step (one staged pair store), unrolled for ILP:
             // this loop is pure shared-memory latency otherwise (it showed up with a quarter of the kernel's stall samples)
+            const RawT *rq = raw + delta;
 #pragma unroll 4
             for (int p = 2 * tid; p < span; p += 2 * FE_THREADS) {
-                const RawT x0 = raw[p], x1 = raw[p + 1], x2 = raw[p + 2];
+                const RawT x0 = rq[p], x1 = rq[p + 1], x2 = rq[p + 2];
                 ystage[p] = Stage<RawT>::make(x1, x0, false);
                 if (p + 1 < span) ystage[p + 1] = Stage<RawT>::make(x2, x1, false);
             }
