@@ -52,8 +52,14 @@ constexpr int W_CTAS2 = 3 * W_NG + W_NC + W_ND2;            // 148 = every SM of
 constexpr int W_KC = kH / BK;                               // 10 k-chunks
 constexpr int W_WCHUNK = W_SL * BK * 2;                     // 8 KB: [64 rows][64 k] bf16
 constexpr int W_WBYTES = 2 * W_KC * W_WCHUNK;               // 160 KB: per k-chunk [w_hi rows 0-63 | w_lo rows 64-127]
-constexpr int W_UNIT = W_BM * BK * 2;                       // 16 KB: [128 rows][64 k] bf16
+constexpr int W_UNIT = W_BM * BK * 2;                       // 16 KB: [128 rows][64 k] bf16 — also exactly one fused weight k-chunk
 constexpr int W_RING = 4;
+// Weight k-chunks kept resident (of 10).  With W_RES < 10 the other chunks' 16 KB stream through the ring with the
+// activations and every chunk given up adds 16 KB of ring.  Measured (A/B on one GPU): W_RES = 7 (112 KB ring) is 3.7 %
+// SLOWER than 10 (64 KB ring) — the unit is bound by the shared-memory port (TMA writes + operand reads), not by the bytes
+// in flight, so the extra 15 % of bytes per unit costs more than the deeper ring hides.
+constexpr int W_RES = 10;
+constexpr int W_RING_MAX = W_RING + W_KC;
 constexpr int W_CTRL = 2048;
 constexpr int W_SMEM = W_WBYTES + W_RING * W_UNIT + W_CTRL;  // 231424 of the 232448-byte per-CTA maximum
 constexpr int W_ACC_COLS = 2 * W_SL;                        // accumulator = [a_hi w_hi + a_lo w_hi | a_hi w_lo], summed in the epilogue
@@ -98,7 +104,7 @@ struct WsDesc {
     int mt, it;
 };
 struct WsSmem {
-    uint64_t full[W_RING], empty[W_RING], acc_full[W_NACC], acc_empty[W_NACC], q_full[W_Q], q_empty[W_Q], wfull;
+    uint64_t full[W_RING_MAX], empty[W_RING_MAX], acc_full[W_NACC], acc_empty[W_NACC], q_full[W_Q], q_empty[W_Q], wfull;
     uint32_t tmem_slot;
     int act2[2];  // live-stream count of the unit in the layer-0 epilogue (alternating slots)
     WsDesc q[W_Q];
@@ -260,7 +266,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
     constexpr int ND = CL == 2 ? W_ND2 : W_ND;
     const uint32_t crank = CL == 2 ? (blockIdx.x & 1) : 0;
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *w_hi = smem, *ring = smem + W_WBYTES;  // w_hi: [k-chunk][w_hi 8 KB | w_lo 8 KB]
+    constexpr int RES = CL == 1 ? W_RES : W_KC;        // resident weight k-chunks (the CTA-pair variant shares its ring: all resident)
+    constexpr int NRING = W_RING + (W_KC - RES);       // ring slots of 16 KB; RES + NRING = 14 slots = 224 KB either way
+    unsigned char *w_hi = smem, *ring = smem + RES * 2 * W_WCHUNK;  // w_hi: [resident k-chunk][w_hi 8 KB | w_lo 8 KB]
     WsSmem &sm = *reinterpret_cast<WsSmem *>(smem + W_WBYTES + W_RING * W_UNIT);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
 
     if (tid == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled operand layout needs a 1024-byte aligned base
-        for (int s = 0; s < W_RING; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], CL); }  // empty: every CTA's MMA commit
+        for (int s = 0; s < NRING; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], CL); }  // empty: every CTA's MMA commit
         for (int b = 0; b < W_NACC; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], W_EPI_THREADS); }
         // queue consumers: TMA thread, MMA thread, one lane per epilogue warp — of every CTA of the cluster (rank 0 owns the queue)
         for (int i = 0; i < W_Q; ++i) { mbar_init(&sm.q_full[i], 1); mbar_init(&sm.q_empty[i], CL * (2 + W_EPI_WARPS)); }
@@ -307,8 +315,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
         else { mh = &p.wo_hi; ml = &p.wo_lo; }
         tma_prefetch_desc(mh);
         tma_prefetch_desc(ml);
-        mbar_expect_tx(&sm.wfull, W_WBYTES);
-        for (int kc = 0; kc < W_KC; ++kc) {  // w_lo directly below w_hi: together one 128-row B operand
+        mbar_expect_tx(&sm.wfull, RES * 2 * W_WCHUNK);
+        for (int kc = 0; kc < RES; ++kc) {  // w_lo directly below w_hi: together one 128-row B operand
             tma_load_2d(w_hi + kc * 2 * W_WCHUNK, mh, &sm.wfull, kcol + kc * BK, slice * W_SL);
             tma_load_2d(w_hi + kc * 2 * W_WCHUNK + W_WCHUNK, ml, &sm.wfull, kcol + kc * BK, slice * W_SL);
         }
@@ -405,6 +413,13 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
             else { a_hi = &p.z_hi; a_lo = &p.z_lo; }
             tma_prefetch_desc(a_hi);
             tma_prefetch_desc(a_lo);
+            const CUtensorMap *wmh, *wml;  // this slice's weights, for the k-chunks that are not resident
+            int wcol = 0;
+            if (role == R_A) { wmh = &p.whh0_hi; wml = &p.whh0_lo; }
+            else if (role == R_BI) { wmh = &p.w1_hi; wml = &p.w1_lo; }
+            else if (role == R_BH) { wmh = &p.w1_hi; wml = &p.w1_lo; wcol = kH; }
+            else if (role == R_C) { wmh = &p.wp_hi; wml = &p.wp_lo; }
+            else { wmh = &p.wo_hi; wml = &p.wo_lo; }
             uint32_t u = 0, qn = 0;
             for (;;) {
                 const uint32_t slot = qn % W_Q;
@@ -419,10 +434,18 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 fence_proxy_async();  // the scheduler's acquire (through the queue barrier) before these async-proxy reads
                 for (int ki = 0; ki < W_KC; ++ki) {
                     const int kc = (kc0 + ki) % W_KC;
+                    if (kc >= RES) {  // this chunk's weights travel with the activations: one slot, [w_hi ; w_lo] like the resident ones
+                        const uint32_t s = u % NRING;
+                        mbar_wait_wd(&sm.empty[s], ((u / NRING) & 1) ^ 1);
+                        mbar_expect_tx(&sm.full[s], W_UNIT);
+                        tma_load_2d(ring + s * W_UNIT, wmh, &sm.full[s], wcol + kc * BK, slice * W_SL);
+                        tma_load_2d(ring + s * W_UNIT + W_WCHUNK, wml, &sm.full[s], wcol + kc * BK, slice * W_SL);
+                        ++u;
+                    }
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        const uint32_t s = u % W_RING;
-                        mbar_wait_wd(&sm.empty[s], ((u / W_RING) & 1) ^ 1);
+                        const uint32_t s = u % NRING;
+                        mbar_wait_wd(&sm.empty[s], ((u / NRING) & 1) ^ 1);
                         mbar_expect_tx(&sm.full[s], W_UNIT);
                         if (CL == 1) tma_load_2d(ring + s * W_UNIT, half ? a_lo : a_hi, &sm.full[s], kc * BK, a_row + mt * W_BM);
                         else  // this CTA's 64 rows of the tile, delivered to both CTAs (each full barrier sees 2 x 8 KB)
@@ -456,11 +479,18 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 long long wait_cyc = 0;
 #pragma unroll 1
                 for (int ki = 0; ki < W_KC; ++ki) {
-                    const uint32_t wd = w_lo32 + kc * (2 * W_WCHUNK >> 4);
+                    uint32_t wd = w_lo32 + kc * (2 * W_WCHUNK >> 4);
+                    uint32_t ws = 0xffffffffu;  // ring slot of a streamed weight chunk
+                    if (kc >= RES) {
+                        ws = u % NRING;
+                        mbar_wait_wd(&sm.full[ws], (u / NRING) & 1);
+                        wd = ring_lo32 + ws * (W_UNIT >> 4);
+                        ++u;
+                    }
                     {   // hi unit: a_hi * [w_hi ; w_lo]  (N = 128)
-                        const uint32_t s = u % W_RING;
+                        const uint32_t s = u % NRING;
                         const long long tw0 = p.trace ? clock64() : 0;
-                        mbar_wait_wd(&sm.full[s], (u / W_RING) & 1);
+                        mbar_wait_wd(&sm.full[s], (u / NRING) & 1);
                         if (p.trace && ki > 0) wait_cyc += clock64() - tw0;
                         if (ki == 0) WS_TRACE(1);
                         tc_fence_after();
@@ -473,9 +503,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         ++u;
                     }
                     {   // lo unit: a_lo * w_hi  (N = 64, accumulator columns 0..63)
-                        const uint32_t s = u % W_RING;
+                        const uint32_t s = u % NRING;
                         const long long tw0 = p.trace ? clock64() : 0;
-                        mbar_wait_wd(&sm.full[s], (u / W_RING) & 1);
+                        mbar_wait_wd(&sm.full[s], (u / NRING) & 1);
                         if (p.trace) wait_cyc += clock64() - tw0;
                         tc_fence_after();
                         const uint32_t ad = ring_lo32 + s * (W_UNIT >> 4);
@@ -484,6 +514,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         umma_bf16_lo(acc, ad + 4, wd + 4, idesc_hi, 1);
                         umma_bf16_lo(acc, ad + 6, wd + 6, idesc_hi, 1);
                         if (CL == 1) umma_commit(&sm.empty[s]); else umma_commit_mc(&sm.empty[s], (uint16_t)3);  // slot free in both CTAs
+                        if (ws != 0xffffffffu) umma_commit(&sm.empty[ws]);  // both products of the chunk have read the streamed weights
                         ++u;
                     }
                     kc = kc + 1 == W_KC ? 0 : kc + 1;
