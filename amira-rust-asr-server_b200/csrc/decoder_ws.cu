@@ -81,6 +81,7 @@ struct WCtl {
 struct WsParams {
     CUtensorMap h0_hi, h0_lo, h1_hi, h1_lo, z_hi, z_lo;   // activations, box {64 k, 128 rows} (64 rows in the cluster variant)
     CUtensorMap whh0_hi, whh0_lo, w1_hi, w1_lo, wp_hi, wp_lo, wo_hi, wo_lo;                // weights, box {64, 64}
+    const __nv_bfloat16 *g_whh0_hi, *g_whh0_lo, *g_w1_hi, *g_w1_lo, *g_wp_hi, *g_wp_lo, *g_wo_hi, *g_wo_lo;  // TS variant: weights -> TMEM
     const float *g0p, *b1p, *boutp, *E;
     int B, Mpad, MT, T;
     const int *lens, *slots, *perm, *eoff;
@@ -111,6 +112,7 @@ struct WsSmem {
     unsigned char dead[W_MAX_MT];
 };
 static_assert(sizeof(WsSmem) <= W_CTRL, "control block exceeds its reservation");
+static_assert(10 * W_UNIT + W_BM * (W_BM + 1) * 4 + (int)sizeof(WsSmem) <= W_SMEM, "TS layout exceeds the shared-memory budget");
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -161,6 +163,26 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                  "h"(mask)
                  : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]^T: the A operand (row m in TMEM lane m, k-pair j in 32-bit column j) is read from tensor
+// memory, so only B costs shared-memory bandwidth (measured 64 clk per M=128 N=128 K=16 instruction, scripts/bench_umma.cu)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo32, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(64u | (1u << 14) | (2u << 29))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
 }
 __device__ __forceinline__ long long gtime() {
     long long t;
@@ -260,16 +282,27 @@ __device__ __forceinline__ size_t ws_state_off(const WsParams &p, int layer, int
 // CL = 1: 147 independent CTAs.  CL = 2: 148 CTAs in 74 clusters of two neighbouring slices of one role; the pair shares every
 // activation tile (each CTA loads 64 of the 128 rows, TMA multicast delivers them to both), which halves the L2 read traffic
 // that bounds the kernel while many M-tiles are in flight.  Rank 0's scheduler drives both CTAs in lock step.
-template <int CL>
+// TS = true ("tensor-memory-stationary"): the slice's [w_hi ; w_lo] lives in 320 columns of TENSOR memory as the A operand
+// (M = 128 rows: 64 hi + 64 lo), the activation tile is the B operand (N = 128 streams) and the accumulator comes out transposed
+// (feature parts along the lanes, streams along the columns).  Shared memory then holds no weights at all: the TMA ring grows
+// from 4 to 9 slots, the tcgen05 operand reads drop from 14 KB to 8 KB per k-step (the shared-memory port is what bounds a
+// unit), and the epilogue transposes the accumulator through a 66 KB shared tile back to the stream-per-thread layout.
+template <int CL, bool TS>
 __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_constant__ WsParams p) {
     cg::grid_group grid = cg::this_grid();
+    static_assert(!(TS && CL != 1), "the tensor-memory-stationary variant is single-CTA");
     constexpr int ND = CL == 2 ? W_ND2 : W_ND;
+    constexpr int NACC = TS ? 1 : W_NACC;              // TS: one 128-column accumulator behind the 320 weight columns
+    constexpr uint32_t ACC_COL0 = TS ? 320 : 0;
+    constexpr int T_LD = W_BM + 1;                     // TS: row stride (floats) of the transposition tile
     const uint32_t crank = CL == 2 ? (blockIdx.x & 1) : 0;
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr int RES = CL == 1 ? W_RES : W_KC;        // resident weight k-chunks (the CTA-pair variant shares its ring: all resident)
-    constexpr int NRING = W_RING + (W_KC - RES);       // ring slots of 16 KB; RES + NRING = 14 slots = 224 KB either way
+    constexpr int RES = TS ? 0 : (CL == 1 ? W_RES : W_KC);  // weight k-chunks resident in SHARED memory (CTA pairs share the ring: all)
+    constexpr int NRING = TS ? 10 : W_RING + (W_KC - RES);  // ring slots of 16 KB; RES + NRING = 14 slots = 224 KB unless TS
     unsigned char *w_hi = smem, *ring = smem + RES * 2 * W_WCHUNK;  // w_hi: [resident k-chunk][w_hi 8 KB | w_lo 8 KB]
-    WsSmem &sm = *reinterpret_cast<WsSmem *>(smem + W_WBYTES + W_RING * W_UNIT);
+    float *ttile = reinterpret_cast<float *>(smem + 10 * W_UNIT);  // TS: [128 feature parts][T_LD] accumulator transposition tile
+    // control block: behind the 224 KB of weights + ring, or (TS) behind the 160 KB ring and the 64.5 KB transposition tile
+    WsSmem &sm = *reinterpret_cast<WsSmem *>(smem + (TS ? 10 * W_UNIT + W_BM * T_LD * 4 : W_WBYTES + W_RING * W_UNIT));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // role and slice of this CTA
@@ -290,7 +323,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
     if (tid == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled operand layout needs a 1024-byte aligned base
         for (int s = 0; s < NRING; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], CL); }  // empty: every CTA's MMA commit
-        for (int b = 0; b < W_NACC; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], W_EPI_THREADS); }
+        for (int b = 0; b < NACC; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], W_EPI_THREADS); }
         // queue consumers: TMA thread, MMA thread, one lane per epilogue warp — of every CTA of the cluster (rank 0 owns the queue)
         for (int i = 0; i < W_Q; ++i) { mbar_init(&sm.q_full[i], 1); mbar_init(&sm.q_empty[i], CL * (2 + W_EPI_WARPS)); }
         mbar_init(&sm.wfull, 1);
@@ -305,7 +338,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
     if (CL == 2) cluster_sync_all();  // the peer's barriers exist before any multicast copy or remote arrive targets them
 
     // ---- stationary weights: one TMA burst, overlapped with the prologue below ----
-    if (warp == 0 && lane == 0) {
+    if (!TS && warp == 0 && lane == 0) {
         const CUtensorMap *mh, *ml;
         int kcol = 0;
         if (role == R_A) { mh = &p.whh0_hi; ml = &p.whh0_lo; }
@@ -320,6 +353,30 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
             tma_load_2d(w_hi + kc * 2 * W_WCHUNK, mh, &sm.wfull, kcol + kc * BK, slice * W_SL);
             tma_load_2d(w_hi + kc * 2 * W_WCHUNK + W_WCHUNK, ml, &sm.wfull, kcol + kc * BK, slice * W_SL);
         }
+    }
+
+    if (TS && warp >= 4) {  // weights -> tensor memory: TMEM lane L = A row (L < 64: w_hi of feature L, else w_lo of feature L - 64)
+        const int q_ = warp & 3, ch = (warp - 4) >> 2, L = q_ * 32 + lane, part = L >> 6, j = L & 63;
+        const __nv_bfloat16 *gh, *gl;
+        int ldw = kH, kcol = 0;
+        if (role == R_A) { gh = p.g_whh0_hi; gl = p.g_whh0_lo; }
+        else if (role == R_BI) { gh = p.g_w1_hi; gl = p.g_w1_lo; ldw = 2 * kH; }
+        else if (role == R_BH) { gh = p.g_w1_hi; gl = p.g_w1_lo; ldw = 2 * kH; kcol = kH; }
+        else if (role == R_C) { gh = p.g_wp_hi; gl = p.g_wp_lo; }
+        else { gh = p.g_wo_hi; gl = p.g_wo_lo; }
+        const uint4 *src = reinterpret_cast<const uint4 *>((part ? gl : gh) + (size_t)(slice * W_SL + j) * ldw + kcol + ch * (kH / 2));
+#pragma unroll 1
+        for (int blk = 0; blk < 5; ++blk) {  // 5 x 32 columns = 320 bf16 = this thread's half of the row
+            uint32_t v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 t4 = __ldg(src + blk * 8 + i);
+                v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+            }
+            tmem_st32(sm.tmem_slot + ((uint32_t)(q_ * 32) << 16) + ch * (kH / 4) + blk * 32, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
     }
 
     // ---- prologue: initial LSTM state (fp32 + split bf16, parity 0), control, default results ----
@@ -434,7 +491,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 fence_proxy_async();  // the scheduler's acquire (through the queue barrier) before these async-proxy reads
                 for (int ki = 0; ki < W_KC; ++ki) {
                     const int kc = (kc0 + ki) % W_KC;
-                    if (kc >= RES) {  // this chunk's weights travel with the activations: one slot, [w_hi ; w_lo] like the resident ones
+                    if (!TS && kc >= RES) {  // this chunk's weights travel with the activations: one slot, [w_hi ; w_lo] like the resident ones
                         const uint32_t s = u % NRING;
                         mbar_wait_wd(&sm.empty[s], ((u / NRING) & 1) ^ 1);
                         mbar_expect_tx(&sm.full[s], W_UNIT);
@@ -462,7 +519,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
             // of integer adds per tcgen05.mma (a single thread issuing ~100 of them per unit must not be the bottleneck)
             constexpr uint32_t idesc_cat = make_idesc_bf16(W_BM, 2 * W_SL), idesc_hi = make_idesc_bf16(W_BM, W_SL);
             const uint32_t w_lo32 = sdesc_lo(smem_u32(w_hi)), ring_lo32 = sdesc_lo(smem_u32(ring));
-            mbar_wait_wd(&sm.wfull, 0);
+            if (!TS) mbar_wait_wd(&sm.wfull, 0);
             uint32_t u = 0, qn = 0, tile = 0;
             for (;;) {
                 const uint32_t slot = qn % W_Q;
@@ -471,12 +528,40 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 q_release<CL>(&sm.q_empty[slot], crank);
                 ++qn;
                 if (mt < 0) break;
-                const uint32_t buf = tile % W_NACC, use = tile / W_NACC;
+                const uint32_t buf = tile % NACC, use = tile / NACC;
                 mbar_wait_wd(&sm.acc_empty[buf], (use & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + buf * W_ACC_COLS;
+                const uint32_t acc = tmem_base + ACC_COL0 + buf * W_ACC_COLS;
                 int kc = kc0;
                 long long wait_cyc = 0;
+                if (TS) {
+                    // A = the slice's [w_hi ; w_lo] in tensor memory (32 columns per k-chunk), B = activation tile (N = 128 streams):
+                    // two instructions per k-step, a_hi then a_lo, both against all 128 weight rows (w_lo x a_lo is a free 2^-18 term).
+                    // One thread issues all of it, and a lone thread retires an instruction only every few cycles: measured
+                    // (scripts/bench_pipe.cu) ~150 instructions of bookkeeping per ring slot made the ISSUE loop, not the tensor pipe
+                    // or shared memory, the limit of a unit.  Hence: 20 slots per unit on a 10-slot ring, so slot index and barrier
+                    // parity are compile-time constants of the fully unrolled loop; descriptors are one add; no watchdog here.
+                    static_assert(!TS || NRING == 10, "slot / parity constants below assume two ring revolutions per unit");
+                    constexpr uint32_t idesc_t = make_idesc_bf16(W_BM, W_BM);
+#pragma unroll
+                    for (int ki = 0; ki < W_KC; ++ki) {
+                        const uint32_t wa = tmem_base + kc * 32;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const int j = 2 * ki + half, s = j % 10;
+                            mbar_wait(&sm.full[s], (uint32_t)(j / 10));
+                            if (j == 0) WS_TRACE(1);
+                            const uint32_t bd = ring_lo32 + s * (W_UNIT >> 4);
+                            umma_bf16_ts(acc, wa, bd, idesc_t, j != 0);
+                            umma_bf16_ts(acc, wa + 8, bd + 2, idesc_t, 1);
+                            umma_bf16_ts(acc, wa + 16, bd + 4, idesc_t, 1);
+                            umma_bf16_ts(acc, wa + 24, bd + 6, idesc_t, 1);
+                            umma_commit(&sm.empty[s]);
+                        }
+                        kc = kc + 1 == W_KC ? 0 : kc + 1;
+                    }
+                    u += 2 * W_KC;
+                } else {
 #pragma unroll 1
                 for (int ki = 0; ki < W_KC; ++ki) {
                     uint32_t wd = w_lo32 + kc * (2 * W_WCHUNK >> 4);
@@ -493,7 +578,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         mbar_wait_wd(&sm.full[s], (u / NRING) & 1);
                         if (p.trace && ki > 0) wait_cyc += clock64() - tw0;
                         if (ki == 0) WS_TRACE(1);
-                        tc_fence_after();
+                        if (p.variant & 16) tc_fence_after();
                         const uint32_t ad = ring_lo32 + s * (W_UNIT >> 4);
                         umma_bf16_lo(acc, ad, wd, idesc_cat, ki != 0);
                         umma_bf16_lo(acc, ad + 2, wd + 2, idesc_cat, 1);
@@ -507,7 +592,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         const long long tw0 = p.trace ? clock64() : 0;
                         mbar_wait_wd(&sm.full[s], (u / NRING) & 1);
                         if (p.trace) wait_cyc += clock64() - tw0;
-                        tc_fence_after();
+                        if (p.variant & 16) tc_fence_after();
                         const uint32_t ad = ring_lo32 + s * (W_UNIT >> 4);
                         umma_bf16_lo(acc, ad, wd, idesc_hi, 1);
                         umma_bf16_lo(acc, ad + 2, wd + 2, idesc_hi, 1);
@@ -518,6 +603,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         ++u;
                     }
                     kc = kc + 1 == W_KC ? 0 : kc + 1;
+                }
                 }
                 umma_commit(&sm.acc_full[buf]);
                 WS_TRACE(2);
@@ -530,6 +616,32 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
         const int etid = tid - 128;
         const int r_in = q * 32 + lane;
         const int nb = slice * W_SL + cgp * 32;           // first of this thread's 32 output columns
+        // this thread's 32 pre-activations (stream r_in, features nb .. nb+31) out of the accumulator, which is then handed back
+        auto load_acc = [&](uint32_t taddr, uint32_t buf, uint32_t (&r)[32]) {
+            if (!TS) {
+                tmem_ld32_sum(taddr, r);
+                tc_fence_before();
+                mbar_arrive(&sm.acc_empty[buf]);
+            } else {
+                // transposed accumulator: this thread first drains TMEM lane r_in (a feature part) for 64 of the 128 streams into the
+                // shared tile, then — after the barrier — gathers its stream's column: hi-part row + lo-part row of each feature
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    tmem_ld32(taddr + h * 32, r);
+                    tmem_ld_wait();
+                    float *dstt = ttile + r_in * T_LD + cgp * 64 + h * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dstt[j] = __uint_as_float(r[j]);
+                }
+                tc_fence_before();
+                mbar_arrive(&sm.acc_empty[buf]);
+                named_bar_sync(2, W_EPI_THREADS);
+                const float *srct = ttile + (cgp * 32) * T_LD + r_in;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(srct[j * T_LD] + srct[(W_SL + j) * T_LD]);
+                named_bar_sync(2, W_EPI_THREADS);  // the tile is free for the next unit
+            }
+        };
         uint32_t qn = 0, tile = 0;
         for (;;) {
             const uint32_t slot = qn % W_Q;
@@ -540,10 +652,10 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
             ++qn;
             if (d.mt < 0) break;
             const int mt = d.mt, it = d.it, par = it & 1;
-            const uint32_t buf = tile % W_NACC, use = tile / W_NACC;
+            const uint32_t buf = tile % NACC, use = tile / NACC;
             ++tile;
             const int row = mt * W_BM + r_in;
-            const uint32_t taddr = tmem_base + buf * W_ACC_COLS + ((uint32_t)(q * 32) << 16) + cgp * 32;
+            const uint32_t taddr = tmem_base + ACC_COL0 + buf * W_ACC_COLS + ((uint32_t)(q * 32) << 16) + cgp * (TS ? 64 : 32);
             uint32_t r[32];
 
             if (role == R_A) {
@@ -638,9 +750,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
                 tc_fence_after();
-                tmem_ld32_sum(taddr, r);
-                tc_fence_before();
-                mbar_arrive(&sm.acc_empty[buf]);
+                load_acc(taddr, buf, r);
                 if (!live) continue;  // speculative unit of an ended M-tile: drop it (uniform across the CTA)
                 if (act) {
                     float cold[8] = {cold4[0].x, cold4[0].y, cold4[0].z, cold4[0].w, cold4[1].x, cold4[1].y, cold4[1].z, cold4[1].w};
@@ -678,9 +788,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
                 tc_fence_after();
-                tmem_ld32_sum(taddr, r);
-                tc_fence_before();
-                mbar_arrive(&sm.acc_empty[buf]);
+                load_acc(taddr, buf, r);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     __stcg(dst + j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
@@ -718,9 +826,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
                 tc_fence_after();
-                tmem_ld32_sum(taddr, r);
-                tc_fence_before();
-                mbar_arrive(&sm.acc_empty[buf]);
+                load_acc(taddr, buf, r);
                 if (c.active) {
                     float cold[8] = {cold4[0].x, cold4[0].y, cold4[0].z, cold4[0].w, cold4[1].x, cold4[1].y, cold4[1].z, cold4[1].w};
                     float hnew[8];
@@ -764,9 +870,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
                 tc_fence_after();
-                tmem_ld32_sum(taddr, r);
-                tc_fence_before();
-                mbar_arrive(&sm.acc_empty[buf]);
+                load_acc(taddr, buf, r);
                 if (c.active) {
                     __nv_bfloat16 *bh = p.zb_hi + (size_t)row * kH + nb, *bl = p.zb_lo + (size_t)row * kH + nb;
 #pragma unroll
@@ -800,9 +904,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
                 tc_fence_after();
-                tmem_ld32_sum(taddr, r);
-                tc_fence_before();
-                mbar_arrive(&sm.acc_empty[buf]);
+                load_acc(taddr, buf, r);
                 if (c.active) {
                     float best_v = -INFINITY;
                     int best_i = 0x7fffffff;
@@ -855,8 +957,9 @@ cudaError_t decoder_ws_prepare(Ctx *c) {
     if ((e = make_tmap_bf16(&w->s_wp_lo, w->wp_lo, kH, kH, kH, W_SL)) != cudaSuccess) return e;
     if ((e = make_tmap_bf16(&w->s_wo_hi, w->wo_hi, W_ND * W_SL, kH, kH, W_SL)) != cudaSuccess) return e;
     if ((e = make_tmap_bf16(&w->s_wo_lo, w->wo_lo, W_ND * W_SL, kH, kH, W_SL)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(greedy_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(greedy_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(greedy_ws_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(greedy_ws_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(greedy_ws_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
     // cluster variant: all 74 CTA pairs must be co-resident (one pair per TPC)
     w->ws_cluster = false;
     // Opt-in (AMIRA_WS_CLUSTER=1): measured on B200 the pair variant halves the kernel's L2 read traffic but is ~8 % slower —
@@ -873,7 +976,7 @@ cudaError_t decoder_ws_prepare(Ctx *c) {
         cfg.attrs = at;
         cfg.numAttrs = 1;
         int n_clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&n_clusters, greedy_ws_kernel<2>, &cfg) == cudaSuccess && n_clusters >= W_CTAS2 / 2)
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, greedy_ws_kernel<2, false>, &cfg) == cudaSuccess && n_clusters >= W_CTAS2 / 2)
             w->ws_cluster = true;
         cudaGetLastError();
     }
@@ -929,6 +1032,8 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     p.whh0_hi = w->s_whh0_hi; p.whh0_lo = w->s_whh0_lo; p.w1_hi = w->s_w1_hi; p.w1_lo = w->s_w1_lo;
     p.wp_hi = w->s_wp_hi; p.wp_lo = w->s_wp_lo; p.wo_hi = w->s_wo_hi; p.wo_lo = w->s_wo_lo;
     p.g0p = d->g0p; p.b1p = d->b1p; p.boutp = d->boutp; p.E = E;
+    p.g_whh0_hi = w->whh0_hi; p.g_whh0_lo = w->whh0_lo; p.g_w1_hi = w->w1_hi; p.g_w1_lo = w->w1_lo;
+    p.g_wp_hi = w->wp_hi; p.g_wp_lo = w->wp_lo; p.g_wo_hi = w->wo_hi; p.g_wo_lo = w->wo_lo;
     p.B = B; p.Mpad = Mpad; p.MT = MT; p.T = T > 0 ? T : 1;
     p.lens = lens_dev; p.slots = slots_dev; p.perm = perm_dev; p.eoff = eoff_dev;
     p.h0f = reinterpret_cast<float *>(work + oh0f); p.h1f = reinterpret_cast<float *>(work + oh1f);
@@ -969,9 +1074,12 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
         at[1].val.cooperative = 1;
         cfg.attrs = at;
         cfg.numAttrs = 2;
-        e = cudaLaunchKernelExC(&cfg, (const void *)greedy_ws_kernel<2>, params);
+        e = cudaLaunchKernelExC(&cfg, (const void *)greedy_ws_kernel<2, false>, params);
     } else {
-        e = cudaLaunchCooperativeKernel((const void *)greedy_ws_kernel<1>, dim3(W_CTAS), dim3(W_THREADS), params, W_SMEM, c->stream);
+        // default: weights in tensor memory (TS); AMIRA_WS_TS=0 selects the shared-memory-stationary variant
+        const bool ts = !(getenv("AMIRA_WS_TS") && atoi(getenv("AMIRA_WS_TS")) == 0);
+        e = cudaLaunchCooperativeKernel(ts ? (const void *)greedy_ws_kernel<1, true> : (const void *)greedy_ws_kernel<1, false>, dim3(W_CTAS),
+                                        dim3(W_THREADS), params, W_SMEM, c->stream);
     }
     c->launches++;
     return e;

@@ -70,6 +70,27 @@ __global__ void __launch_bounds__(128, 1) umma_kernel(int mode, int N, int n_ite
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) umma(acc, sdesc(a_lo + kk * 32), sdesc(w + kk * 32), id64, 1);
             }
+        } else if (mode >= 5) {  // A in TMEM, N = 128; mode 5: B walks 9 different 16 KB tiles; 6: A walks 10 k-chunks; 7: both
+            const uint32_t id = idesc_bf16(128, 128);
+            for (int i = 0; i < n_iter; ++i) {
+                const uint32_t bt = (mode == 5 || mode == 7) ? a_hi + (i % 9) * 16384 : w;
+                const uint32_t at = acc + 128 + ((mode == 6 || mode == 7) ? (i % 10) * 32 : 0);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t bd = sdesc(bt + kk * 32);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(acc),
+                                 "r"(at + kk * 8), "l"(bd), "r"(id), "r"(1u) : "memory");
+                }
+            }
+        } else if (mode == 4) {  // A operand in tensor memory (columns 256..), B from shared memory, N columns
+            const uint32_t id = idesc_bf16(128, N);
+            for (int i = 0; i < n_iter; ++i)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t bd = sdesc(w + kk * 32);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(acc),
+                                 "r"(acc + 256 + kk * 8), "l"(bd), "r"(id), "r"(1u) : "memory");
+                }
         } else {  // mode 3: fused pattern with a tcgen05.commit after every group of four (as a smem ring would need)
             const uint32_t id128 = idesc_bf16(128, 128), id64 = idesc_bf16(128, 64);
             for (int i = 0; i < n_iter; ++i) {
@@ -98,7 +119,9 @@ int main() {
     struct { int mode, N; const char *what; int mmas; double units; } cases[] = {
         {0, 64, "N=64", 4, 0}, {0, 128, "N=128", 4, 0}, {0, 256, "N=256", 4, 0},
         {1, 64, "split pattern 3 x N=64 per k-step", 12, 0}, {2, 128, "fused pattern N=128 + N=64 per k-step", 8, 0},
-        {3, 128, "fused pattern + commit per 4 mma", 8, 0}};
+        {3, 128, "fused pattern + commit per 4 mma", 8, 0}, {4, 64, "A in TMEM, N=64", 4, 0}, {4, 128, "A in TMEM, N=128", 4, 0},
+        {4, 256, "A in TMEM, N=256", 4, 0}, {5, 128, "A in TMEM fixed, B walks 9 tiles", 4, 0}, {6, 128, "A in TMEM walks 10 chunks, B fixed", 4, 0},
+        {7, 128, "A in TMEM walks, B walks", 4, 0}};
     for (auto &c : cases)
         for (int grid : {1, 148}) {
             umma_kernel<<<grid, 128, 196608>>>(c.mode, c.N, n_iter, out);
