@@ -617,29 +617,37 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
         const int r_in = q * 32 + lane;
         const int nb = slice * W_SL + cgp * 32;           // first of this thread's 32 output columns
         // this thread's 32 pre-activations (stream r_in, features nb .. nb+31) out of the accumulator, which is then handed back
+        // TS, step 1: drain this thread's TMEM lane (a feature part) for 64 of the 128 streams into the shared transposition tile and
+        // hand the accumulator back to the MMA thread (the tile is the second buffer that lets the next unit's MMAs run meanwhile)
+        auto drain_acc = [&](uint32_t taddr, uint32_t buf, uint32_t (&r)[32]) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                tmem_ld32(taddr + h * 32, r);
+                tmem_ld_wait();
+                float *dstt = ttile + r_in * T_LD + cgp * 64 + h * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dstt[j] = __uint_as_float(r[j]);
+            }
+            tc_fence_before();
+            mbar_arrive(&sm.acc_empty[buf]);
+            named_bar_sync(2, W_EPI_THREADS);
+        };
+        // TS, step 2: gather this thread's stream column — hi-part row + lo-part row of each of its 32 features
+        auto gather_acc = [&](uint32_t (&r)[32]) {
+            const float *srct = ttile + (cgp * 32) * T_LD + r_in;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(srct[j * T_LD] + srct[(W_SL + j) * T_LD]);
+            named_bar_sync(2, W_EPI_THREADS);  // the tile is free for the next unit
+        };
+        // this thread's 32 pre-activations (stream r_in, features nb .. nb+31) out of the accumulator, which is then handed back
         auto load_acc = [&](uint32_t taddr, uint32_t buf, uint32_t (&r)[32]) {
             if (!TS) {
                 tmem_ld32_sum(taddr, r);
                 tc_fence_before();
                 mbar_arrive(&sm.acc_empty[buf]);
             } else {
-                // transposed accumulator: this thread first drains TMEM lane r_in (a feature part) for 64 of the 128 streams into the
-                // shared tile, then — after the barrier — gathers its stream's column: hi-part row + lo-part row of each feature
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    tmem_ld32(taddr + h * 32, r);
-                    tmem_ld_wait();
-                    float *dstt = ttile + r_in * T_LD + cgp * 64 + h * 32;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) dstt[j] = __uint_as_float(r[j]);
-                }
-                tc_fence_before();
-                mbar_arrive(&sm.acc_empty[buf]);
-                named_bar_sync(2, W_EPI_THREADS);
-                const float *srct = ttile + (cgp * 32) * T_LD + r_in;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(srct[j * T_LD] + srct[(W_SL + j) * T_LD]);
-                named_bar_sync(2, W_EPI_THREADS);  // the tile is free for the next unit
+                drain_acc(taddr, buf, r);
+                gather_acc(r);
             }
         };
         uint32_t qn = 0, tile = 0;
@@ -665,6 +673,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 // 8-byte load per stream and no separate control phase sits on the critical path.  Slice 0 publishes the rows
                 // (double-buffered by step parity: other layer-0 CTAs may still be reading the previous ones), the tokens and,
                 // when no stream of the M-tile is left, the results and the end marker.
+                if (TS) {  // the recurrent GEMM ran ahead: park its result in the shared tile now, so the NEXT unit's GEMM can run
+                    mbar_wait_wd(&sm.acc_full[buf], use & 1);  // while this epilogue waits for the previous step's vocabulary phase
+                    tc_fence_after();
+                    drain_acc(taddr, buf, r);
+                }
                 float4 ad[8], cold4[2];
                 float *cst = p.c0 + (size_t)row * kH + nb / 4;
                 cold4[0] = __ldcg(reinterpret_cast<const float4 *>(cst));  // loads that do not depend on the previous step's
@@ -747,10 +760,15 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         st_release(p.dead_at + mt, it);  // iteration `it` of this M-tile does not exist
                     }
                 }
-                mbar_wait_wd(&sm.acc_full[buf], use & 1);
-                if (etid == 0) WS_TRACE(3);
-                tc_fence_after();
-                load_acc(taddr, buf, r);
+                if (TS) {
+                    if (etid == 0) WS_TRACE(3);
+                    gather_acc(r);  // drained into the shared tile at the top of this unit
+                } else {
+                    mbar_wait_wd(&sm.acc_full[buf], use & 1);
+                    if (etid == 0) WS_TRACE(3);
+                    tc_fence_after();
+                    load_acc(taddr, buf, r);
+                }
                 if (!live) continue;  // speculative unit of an ended M-tile: drop it (uniform across the CTA)
                 if (act) {
                     float cold[8] = {cold4[0].x, cold4[0].y, cold4[0].z, cold4[0].w, cold4[1].x, cold4[1].y, cold4[1].z, cold4[1].w};
