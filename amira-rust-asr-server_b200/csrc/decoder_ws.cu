@@ -64,7 +64,7 @@ constexpr int W_CTRL = 2048;
 constexpr int W_SMEM = W_WBYTES + W_RING * W_UNIT + W_CTRL;  // 231424 of the 232448-byte per-CTA maximum
 constexpr int W_ACC_COLS = 2 * W_SL;                        // accumulator = [a_hi w_hi + a_lo w_hi | a_hi w_lo], summed in the epilogue
 constexpr int W_NACC = 4;                                   // TMEM accumulators of 128 columns
-constexpr int W_Q = 8;                                      // descriptor queue depth
+constexpr int W_Q = 4;                                      // descriptor queue depth (= signal slots: bounds the epilogue's run-ahead)
 constexpr int W_EPI_WARPS = 8, W_EPI_THREADS = W_EPI_WARPS * 32;
 constexpr int W_THREADS = (4 + W_EPI_WARPS) * 32;           // 384: warp 0 TMA, 1 MMA, 2 scheduler, 3 idle, 4..11 epilogue
 constexpr int W_NPART = 2 * W_ND2;                          // argmax partial slots per row (32 columns each; 2*W_ND used without clusters)
@@ -108,6 +108,8 @@ struct WsSmem {
     uint64_t full[W_RING_MAX], empty[W_RING_MAX], acc_full[W_NACC], acc_empty[W_NACC], q_full[W_Q], q_empty[W_Q], wfull;
     uint32_t tmem_slot;
     int act2[2];  // live-stream count of the unit in the layer-0 epilogue (alternating slots)
+    uint64_t sig_full[W_Q];  // TS: all epilogue threads have issued the unit's stores -> the signal thread fences and publishes
+    int sig_skip[W_Q];       // TS: the unit has nothing to publish (layer-0 unit of an M-tile that just ended)
     WsDesc q[W_Q];
     unsigned char dead[W_MAX_MT];
 };
@@ -325,7 +327,12 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
         for (int s = 0; s < NRING; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], CL); }  // empty: every CTA's MMA commit
         for (int b = 0; b < NACC; ++b) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], W_EPI_THREADS); }
         // queue consumers: TMA thread, MMA thread, one lane per epilogue warp — of every CTA of the cluster (rank 0 owns the queue)
-        for (int i = 0; i < W_Q; ++i) { mbar_init(&sm.q_full[i], 1); mbar_init(&sm.q_empty[i], CL * (2 + W_EPI_WARPS)); }
+        for (int i = 0; i < W_Q; ++i) {
+            mbar_init(&sm.q_full[i], 1);
+            mbar_init(&sm.q_empty[i], CL * (2 + W_EPI_WARPS) + (TS ? 1 : 0));  // + the signal thread
+            mbar_init(&sm.sig_full[i], W_EPI_THREADS);
+            sm.sig_skip[i] = 0;
+        }
         mbar_init(&sm.wfull, 1);
         mbar_fence_init();
     }
@@ -611,6 +618,34 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 ++tile;
             }
         }
+    } else if (TS && warp == 3) {
+        if (lane == 0) {  // ===================== signal thread (TS) =====================
+            // Publishing a unit costs a gpu-scope fence that waits for the CTA's stores to be acknowledged (1 us idle, 3 us under
+            // load).  The epilogue threads only ARRIVE on a shared-memory barrier once their stores are issued and go on to the next
+            // unit; this thread waits for the 256 arrivals, fences (cumulative over the stores it observed through the barrier) and
+            // bumps the dependency counter.  The descriptor slot is released last, so the epilogue is never more than W_Q units ahead.
+            uint32_t qn = 0;
+            for (;;) {
+                const uint32_t slot = qn % W_Q;
+                mbar_wait_wd(&sm.q_full[slot], (qn / W_Q) & 1);
+                const int mt = sm.q[slot].mt, it = sm.q[slot].it;
+                if (mt < 0) { q_release<CL>(&sm.q_empty[slot], crank); break; }
+                mbar_wait_wd(&sm.sig_full[slot], (qn / W_Q) & 1);
+                const int skip = sm.sig_skip[slot];
+                sm.sig_skip[slot] = 0;
+                if (!skip) {
+                    __threadfence();
+                    if (role == R_A) { fence_proxy_async(); atomicAdd(p.cnt_a + mt, 1); }
+                    else if (role == R_BI) { fence_proxy_async(); atomicAdd(p.cnt_b + mt, 1); }
+                    else if (role == R_BH) st_release(p.part_ready + mt * W_NG + slice, it + 1);
+                    else if (role == R_C) { fence_proxy_async(); atomicAdd(p.cnt_c + mt, 1); }
+                    else atomicAdd(p.cnt_d + mt, 1);
+                    WS_TRACE(4);
+                }
+                q_release<CL>(&sm.q_empty[slot], crank);
+                ++qn;
+            }
+        }
     } else if (warp >= 4) {  // ===================== epilogue: 8 warps =====================
         const int e = warp - 4, q = warp & 3, cgp = e >> 2;  // TMEM lane quarter (must be warp % 4), 32-column group
         const int etid = tid - 128;
@@ -769,7 +804,13 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     tc_fence_after();
                     load_acc(taddr, buf, r);
                 }
-                if (!live) continue;  // speculative unit of an ended M-tile: drop it (uniform across the CTA)
+                if (!live) {  // speculative unit of an ended M-tile: drop it (uniform across the CTA)
+                    if (TS) {
+                        if (etid == 0) sm.sig_skip[(tile - 1) % W_Q] = 1;
+                        mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);
+                    }
+                    continue;
+                }
                 if (act) {
                     float cold[8] = {cold4[0].x, cold4[0].y, cold4[0].z, cold4[0].w, cold4[1].x, cold4[1].y, cold4[1].z, cold4[1].w};
                     float hnew[8];
@@ -792,13 +833,18 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     *reinterpret_cast<uint4 *>(p.h0b_hi + ob) = *reinterpret_cast<uint4 *>(vh);
                     *reinterpret_cast<uint4 *>(p.h0b_lo + ob) = *reinterpret_cast<uint4 *>(vl);
                 }
-                named_bar_sync(1, W_EPI_THREADS);
-                if (etid == 0) {  // cumulative release of every epilogue thread's stores (ordered by the barrier); the readers use TMA.
-                    // (One release per thread instead — no barrier — was measured 3x slower: 10 k atomics per M-tile step on one word.)
-                    __threadfence();
-                    fence_proxy_async();
-                    atomicAdd(p.cnt_a + mt, 1);
-                    WS_TRACE(4);
+                if (TS) {  // the unit's stores are issued: the signal thread fences and publishes them; this thread moves on
+                    if (etid == 0) WS_TRACE(5);
+                    mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);
+                } else {
+                    named_bar_sync(1, W_EPI_THREADS);
+                    if (etid == 0) {  // cumulative release of every epilogue thread's stores (ordered by the barrier); the readers use TMA.
+                        // (One release per thread instead — no barrier — was measured 3x slower: 10 k atomics per M-tile step on one word.)
+                        __threadfence();
+                        fence_proxy_async();
+                        atomicAdd(p.cnt_a + mt, 1);
+                        WS_TRACE(4);
+                    }
                 }
             } else if (role == R_BH) {
                 // partial sums of the layer-1 recurrent half, for the layer-1 input CTA of the same slice
@@ -811,11 +857,16 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 for (int j = 0; j < 8; ++j)
                     __stcg(dst + j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                                 __uint_as_float(r[4 * j + 3])));
-                named_bar_sync(1, W_EPI_THREADS);
-                if (etid == 0) {
-                    __threadfence();
-                    st_release(p.part_ready + mt * W_NG + slice, it + 1);
-                    WS_TRACE(4);
+                if (TS) {  // the unit's stores are issued: the signal thread fences and publishes them; this thread moves on
+                    if (etid == 0) WS_TRACE(5);
+                    mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);
+                } else {
+                    named_bar_sync(1, W_EPI_THREADS);
+                    if (etid == 0) {
+                        __threadfence();
+                        st_release(p.part_ready + mt * W_NG + slice, it + 1);
+                        WS_TRACE(4);
+                    }
                 }
             } else if (role == R_BI) {
                 // every load that does not depend on another is issued up front (at full occupancy the epilogue pipeline, one
@@ -867,14 +918,18 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     *reinterpret_cast<uint4 *>(p.h1b_hi + ob) = *reinterpret_cast<uint4 *>(vh);
                     *reinterpret_cast<uint4 *>(p.h1b_lo + ob) = *reinterpret_cast<uint4 *>(vl);
                 }
-                if (etid == 0) WS_TRACE(5);
-                named_bar_sync(1, W_EPI_THREADS);
-                if (etid == 0) {  // cumulative release of every epilogue thread's stores (ordered by the barrier); the readers use TMA.
-                    // (One release per thread instead — no barrier — was measured 3x slower: 10 k atomics per M-tile step on one word.)
-                    __threadfence();
-                    fence_proxy_async();
-                    atomicAdd(p.cnt_b + mt, 1);
-                    WS_TRACE(4);
+                if (TS) {  // the unit's stores are issued: the signal thread fences and publishes them; this thread moves on
+                    if (etid == 0) WS_TRACE(5);
+                    mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);
+                } else {
+                        named_bar_sync(1, W_EPI_THREADS);
+                    if (etid == 0) {  // cumulative release of every epilogue thread's stores (ordered by the barrier); the readers use TMA.
+                        // (One release per thread instead — no barrier — was measured 3x slower: 10 k atomics per M-tile step on one word.)
+                        __threadfence();
+                        fence_proxy_async();
+                        atomicAdd(p.cnt_b + mt, 1);
+                        WS_TRACE(4);
+                    }
                 }
             } else if (role == R_C) {
                 const int4 ri = __ldg(p.rowinfo + row);
@@ -905,13 +960,18 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         reinterpret_cast<uint4 *>(bl)[j8] = *reinterpret_cast<uint4 *>(vl);
                     }
                 }
-                named_bar_sync(1, W_EPI_THREADS);
-                if (etid == 0) {  // cumulative release of every epilogue thread's stores (ordered by the barrier); the readers use TMA.
-                    // (One release per thread instead — no barrier — was measured 3x slower: 10 k atomics per M-tile step on one word.)
-                    __threadfence();
-                    fence_proxy_async();
-                    atomicAdd(p.cnt_c + mt, 1);
-                    WS_TRACE(4);
+                if (TS) {  // the unit's stores are issued: the signal thread fences and publishes them; this thread moves on
+                    if (etid == 0) WS_TRACE(5);
+                    mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);
+                } else {
+                    named_bar_sync(1, W_EPI_THREADS);
+                    if (etid == 0) {  // cumulative release of every epilogue thread's stores (ordered by the barrier); the readers use TMA.
+                        // (One release per thread instead — no barrier — was measured 3x slower: 10 k atomics per M-tile step on one word.)
+                        __threadfence();
+                        fence_proxy_async();
+                        atomicAdd(p.cnt_c + mt, 1);
+                        WS_TRACE(4);
+                    }
                 }
             } else {  // R_D: vocabulary slice -> first-max argmax partial (zero_copy.rs:190-232 tie rule) -> control update
                 const WCtl c = load_ctl(p.ctl + (size_t)(it & 1) * p.Mpad + row);
@@ -943,11 +1003,16 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         atomicMax(p.amax + (size_t)(it & 1) * p.Mpad + row, ((unsigned long long)ord << 32) | (0xFFFFFFFFu - (unsigned)best_i));
                     }
                 }
-                named_bar_sync(1, W_EPI_THREADS);
-                if (etid == 0) {  // the layer-0 epilogues of the next step read the merged argmax and apply the control flow
-                    __threadfence();
-                    atomicAdd(p.cnt_d + mt, 1);
-                    WS_TRACE(4);
+                if (TS) {  // the unit's stores are issued: the signal thread fences and publishes them; this thread moves on
+                    if (etid == 0) WS_TRACE(5);
+                    mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);
+                } else {
+                    named_bar_sync(1, W_EPI_THREADS);
+                    if (etid == 0) {  // the layer-0 epilogues of the next step read the merged argmax and apply the control flow
+                        __threadfence();
+                        atomicAdd(p.cnt_d + mt, 1);
+                        WS_TRACE(4);
+                    }
                 }
             }
         }
