@@ -29,7 +29,8 @@ EXPORTS = ["amira_device_count", "amira_config_default", "amira_ctx_create", "am
            "amira_pipeline_process_stream_chunk", "amira_pipeline_process_batch_samples",
            "amira_pipeline_process_stream_samples", "amira_pipeline_last_error", "amira_vocab_decode",
            "amira_shard_utterances", "amira_batcher_create", "amira_batcher_destroy", "amira_batcher_process_batch",
-           "amira_batcher_stats", "amira_ctx_max_total_tokens"]
+           "amira_batcher_stats", "amira_ctx_max_total_tokens", "amira_preprocess_pcm16_packed",
+           "amira_greedy_decode_packed"]
 
 
 class AmiraError(RuntimeError):
@@ -82,6 +83,8 @@ def load_library():
     L.amira_features_len.argtypes = [i64, C.POINTER(i64)]
     L.amira_preprocess_pcm16.argtypes = [vp, vp, vp, i32, vp, i64, vp]
     L.amira_preprocess_f32.argtypes = [vp, vp, i64, vp, i32, vp, i64, vp]
+    L.amira_preprocess_pcm16_packed.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    L.amira_greedy_decode_packed.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.amira_bytes_to_f32.argtypes = [vp, vp, C.c_size_t, i32, vp, C.POINTER(C.c_size_t)]
     L.amira_decoder_joint.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.amira_greedy_decode.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
@@ -297,6 +300,51 @@ class Context:
         feats = np.empty((B, N_MELS, t_stride), dtype=np.float32)
         self._check(self._L.amira_preprocess_pcm16(self._h, _ptr(pcm), _ptr(offsets), B, _ptr(feats), t_stride, _ptr(lens)))
         return feats, lens
+
+    def preprocess_pcm16_packed(self, pcm: np.ndarray, offsets):
+        """Ragged form of preprocess_pcm16: returns a list of B dense [128, features_len_b] arrays (views into one packed
+        buffer) and features_lens — the per-request tensors the reference gives its encoder (src/triton/model.rs:126-141)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        B = offsets.size - 1
+        lens = np.zeros(B, dtype=np.int64)
+        foff = np.zeros(B + 1, dtype=np.int64)
+        for b in range(B):
+            foff[b + 1] = foff[b] + N_MELS * features_len(int(offsets[b + 1] - offsets[b]))
+        feats = np.empty(max(int(foff[B]), 1), dtype=np.float32)
+        self._check(self._L.amira_preprocess_pcm16_packed(self._h, _ptr(pcm), _ptr(offsets), B, _ptr(feats), _ptr(foff), _ptr(lens)))
+        return [feats[foff[b]:foff[b + 1]].reshape(N_MELS, -1) for b in range(B)], lens
+
+    def preprocess_pcm16_packed_raw(self, pcm_ptr: int, offsets: np.ndarray, B: int, features_ptr: int, feat_offsets: np.ndarray,
+                                    lens_out: np.ndarray):
+        self._check(self._L.amira_preprocess_pcm16_packed(self._h, _ptr(pcm_ptr), _ptr(offsets), B, _ptr(features_ptr),
+                                                          _ptr(feat_offsets), _ptr(lens_out)))
+
+    def greedy_decode_packed_raw(self, enc_ptr: int, enc_offsets: np.ndarray, B: int, lens: np.ndarray, tokens_ptr: int, ntok_ptr: int,
+                                 nsteps_ptr: int | None = None, s1_ptr: int | None = None, s2_ptr: int | None = None):
+        self._check(self._L.amira_greedy_decode_packed(self._h, _ptr(enc_ptr), _ptr(enc_offsets), B, _ptr(lens), _ptr(s1_ptr),
+                                                       _ptr(s2_ptr), _ptr(tokens_ptr), _ptr(ntok_ptr), _ptr(nsteps_ptr)))
+
+    def greedy_decode_packed(self, encoder_outputs: list, state: DecoderState | None = None, allow_failed: bool = False):
+        """Ragged form of greedy_decode: encoder_outputs is a list of B arrays [1024, T_b] (the per-request encoder tensors of
+        src/triton/model.rs:298-420); only valid frames are uploaded.  Same return value as greedy_decode."""
+        B = len(encoder_outputs)
+        lens = np.array([int(e.shape[-1]) for e in encoder_outputs], dtype=np.int64)
+        eoff = np.zeros(B + 1, dtype=np.int64)
+        eoff[1:] = np.cumsum(lens * ENC_DIM)
+        enc = np.empty(max(int(eoff[B]), 1), dtype=np.float32)
+        for b, e in enumerate(encoder_outputs):
+            enc[eoff[b]:eoff[b + 1]] = np.ascontiguousarray(e, dtype=np.float32).reshape(-1)
+        st = DecoderState.new(B) if state is None else DecoderState(
+            np.ascontiguousarray(state.states_1, np.float32).copy(), np.ascontiguousarray(state.states_2, np.float32).copy())
+        toks = np.zeros((B, self.max_total_tokens), dtype=np.int32)
+        ntok = np.zeros(B, dtype=np.int32)
+        nsteps = np.zeros(B, dtype=np.int32)
+        rc = self._L.amira_greedy_decode_packed(self._h, _ptr(enc), _ptr(eoff), B, _ptr(lens), _ptr(st.states_1), _ptr(st.states_2),
+                                                _ptr(toks), _ptr(ntok), _ptr(nsteps))
+        if rc and not (allow_failed and rc == 6):
+            self._check(rc)
+        return [toks[b, :max(int(ntok[b]), 0)].tolist() if ntok[b] >= 0 else None for b in range(B)], st, nsteps
 
     def preprocessor(self, waveforms: np.ndarray, waveforms_lens, t_stride: int | None = None):
         """Triton contract form (model-repo/preprocessor/config.pbtxt): waveforms [B,N] f32, waveforms_lens [B] i64

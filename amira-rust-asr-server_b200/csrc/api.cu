@@ -339,7 +339,8 @@ int32_t amira_features_len(int64_t n_samples, int64_t *features_len) {
 
 static int32_t preprocess_common(amira_ctx *c, const void *wave, bool pcm16, const int64_t *starts, const int64_t *lens,
                                  int64_t total_elems, int32_t B, float *features, int64_t t_stride,
-                                 int64_t *features_lens) {
+                                 int64_t *features_lens, const int64_t *feat_offsets = nullptr) {
+    // feat_offsets != nullptr: packed output — utterance b is a [128][features_len_b] block at features + feat_offsets[b]
     int64_t max_len = 0;
     for (int b = 0; b < B; ++b) {
         if (lens[b] < 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "negative waveform length");
@@ -347,10 +348,20 @@ static int32_t preprocess_common(amira_ctx *c, const void *wave, bool pcm16, con
         if (features_lens) features_lens[b] = L;
         max_len = L > max_len ? L : max_len;
     }
-    if (t_stride < max_len || t_stride <= 0)
+    if (feat_offsets) {
+        t_stride = 0;
+        if (feat_offsets[0] < 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "feat_offsets must be non-negative");
+        for (int b = 0; b < B; ++b) {
+            const int64_t L = lens[b] <= 0 ? 0 : lens[b] / kHop + 1;
+            if (feat_offsets[b + 1] - feat_offsets[b] < (int64_t)kMel * L)
+                return fail(c, AMIRA_ERR_INVALID_VALUE, "feat_offsets: block smaller than 128 x features_len");
+        }
+    } else if (t_stride < max_len || t_stride <= 0) {
         return fail(c, AMIRA_ERR_INVALID_VALUE, "t_stride smaller than the longest features_len");
+    }
     const size_t esz = pcm16 ? sizeof(int16_t) : sizeof(float);
-    const size_t feat_count = (size_t)B * kMel * (size_t)t_stride;
+    const size_t feat_count = feat_offsets ? (size_t)feat_offsets[B] : (size_t)B * kMel * (size_t)t_stride;
+    auto feat_elem = [&](int b) -> size_t { return feat_offsets ? (size_t)feat_offsets[b] : (size_t)b * kMel * (size_t)t_stride; };
     const bool wave_host = wave && total_elems > 0 && !is_device_ptr(wave), feat_host = !is_device_ptr(features);
     const uint8_t *wave_dev = static_cast<const uint8_t *>(wave);
     float *feat_dev = features;
@@ -375,7 +386,8 @@ static int32_t preprocess_common(amira_ctx *c, const void *wave, bool pcm16, con
     for (int k = 0; k < n_chunks && n_chunks > 1; ++k) {  // every chunk's metadata first (see launch_frontend)
         const int b0 = (int)((int64_t)B * k / n_chunks), b1 = (int)((int64_t)B * (k + 1) / n_chunks);
         if (b1 > b0)
-            CK(launch_frontend(c, wave_dev, pcm16, starts + b0, lens + b0, b1 - b0, feat_dev + (size_t)b0 * kMel * t_stride, t_stride, k, 1),
+            CK(launch_frontend(c, wave_dev, pcm16, starts + b0, lens + b0, b1 - b0, feat_offsets ? feat_dev : feat_dev + feat_elem(b0), t_stride,
+                               k, 1, feat_offsets ? feat_offsets + b0 : nullptr),
                "front-end metadata");
     }
     for (int k = 0; k < n_chunks; ++k) {
@@ -390,14 +402,14 @@ static int32_t preprocess_common(amira_ctx *c, const void *wave, bool pcm16, con
             CK(cudaStreamWaitEvent(c->stream, c->ev_pool[2 * k], 0), "event wait");
             if (dbg) cudaEventRecord(dbg_ev[1 + 3 * k], c->h2d_stream);
         }
-        CK(launch_frontend(c, wave_dev, pcm16, starts + b0, lens + b0, b1 - b0, feat_dev + (size_t)b0 * kMel * t_stride, t_stride, k,
-                           n_chunks > 1 ? 2 : 0),
+        CK(launch_frontend(c, wave_dev, pcm16, starts + b0, lens + b0, b1 - b0, feat_offsets ? feat_dev : feat_dev + feat_elem(b0), t_stride, k,
+                           n_chunks > 1 ? 2 : 0, feat_offsets ? feat_offsets + b0 : nullptr),
            "front-end launch");
         if (feat_host) {
             CK(cudaEventRecord(c->ev_pool[2 * k + 1], c->stream), "event");
             CK(cudaStreamWaitEvent(c->d2h_stream, c->ev_pool[2 * k + 1], 0), "event wait");
-            const size_t o = (size_t)b0 * kMel * t_stride, n = (size_t)(b1 - b0) * kMel * t_stride;
-            CK(cudaMemcpyAsync(features + o, feat_dev + o, n * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream), "features D2H");
+            const size_t o = feat_elem(b0), n = (b1 >= B ? feat_count : feat_elem(b1)) - o;
+            if (n > 0) CK(cudaMemcpyAsync(features + o, feat_dev + o, n * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream), "features D2H");
             if (dbg) { cudaEventRecord(dbg_ev[2 + 3 * k], c->stream); cudaEventRecord(dbg_ev[3 + 3 * k], c->d2h_stream); }
         }
     }
@@ -428,6 +440,21 @@ int32_t amira_preprocess_pcm16(amira_ctx *c, const int16_t *pcm, const int64_t *
         if (lens[b] < 0 || offsets[b] < 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "offsets must be non-decreasing");
     }
     return preprocess_common(c, pcm, true, offsets, lens.data(), offsets[B], B, features, t_stride, features_lens);
+    API_END(c)
+}
+
+int32_t amira_preprocess_pcm16_packed(amira_ctx *c, const int16_t *pcm, const int64_t *offsets, int32_t B, float *features,
+                                      const int64_t *feat_offsets, int64_t *features_lens) {
+    API_BEGIN(c)
+    if (B < 0 || !offsets || !features || !feat_offsets || (B > 0 && !pcm && offsets[B] > 0))
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_preprocess_pcm16_packed: bad arguments");
+    if (B == 0) return AMIRA_OK;
+    std::vector<int64_t> lens((size_t)B);
+    for (int b = 0; b < B; ++b) {
+        lens[b] = offsets[b + 1] - offsets[b];
+        if (lens[b] < 0 || offsets[b] < 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "offsets must be non-decreasing");
+    }
+    return preprocess_common(c, pcm, true, offsets, lens.data(), offsets[B], B, features, 0, features_lens, feat_offsets);
     API_END(c)
 }
 
@@ -512,7 +539,8 @@ int32_t amira_decoder_joint(amira_ctx *c, const float *encoder_outputs, int32_t 
 // ---------------------------------------------------------------------------------------------- greedy decode
 static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t B, int32_t T,
                              const int64_t *encoded_lengths, const int32_t *slots_host, float *states_1, float *states_2,
-                             int32_t *tokens, int32_t *n_tokens, int32_t *n_steps) {
+                             int32_t *tokens, int32_t *n_tokens, int32_t *n_steps, const int64_t *enc_offsets = nullptr) {
+    // enc_offsets != nullptr: packed encoder outputs — stream b is a [1024][encoded_lengths[b]] block at encoder_outputs + enc_offsets[b]
     if (!c->has_weights) return fail(c, AMIRA_ERR_NO_WEIGHTS, "greedy decode: no weights loaded");
     if (B < 0 || T < 0 || !tokens || !n_tokens || (B > 0 && T > 0 && !encoder_outputs))
         return fail(c, AMIRA_ERR_INVALID_VALUE, "greedy decode: bad arguments");
@@ -545,6 +573,13 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
         }
     }
     unmark(B);
+    if (enc_offsets) {
+        if (c->cfg.decode_engine == 1) return fail(c, AMIRA_ERR_INVALID_VALUE, "packed encoder outputs need a tcgen05 decode engine");
+        if (enc_offsets[0] < 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "enc_offsets must be non-negative");
+        for (int b = 0; b < B; ++b)
+            if (enc_offsets[b + 1] - enc_offsets[b] < (int64_t)kEnc * h_lens[b])
+                return fail(c, AMIRA_ERR_INVALID_VALUE, "enc_offsets: block smaller than 1024 x encoded_length");
+    }
     CK(c->stage[9].reserve(sizeof(int32_t) * 2 * (size_t)B), "lens dev");
     CK(cudaMemcpyAsync(c->stage[9].p, h_lens, sizeof(int32_t) * 2 * (size_t)B, cudaMemcpyHostToDevice, c->stream), "lens H2D");
     const int32_t *lens_dev = c->stage[9].as<int32_t>();
@@ -553,7 +588,7 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
     // encoder outputs in host memory are uploaded by the launcher, chunk by chunk, overlapped with their projection
     const float *enc_dev = encoder_outputs, *enc_host = nullptr;
     if (encoder_outputs && T > 0 && !is_device_ptr(encoder_outputs)) {
-        CK(c->stage[0].reserve(sizeof(float) * (size_t)B * kEnc * T), "encoder_outputs staging");
+        CK(c->stage[0].reserve(sizeof(float) * (enc_offsets ? (size_t)enc_offsets[B] : (size_t)B * kEnc * T) + 16), "encoder_outputs staging");
         enc_dev = c->stage[0].as<float>();
         enc_host = encoder_outputs;
     }
@@ -573,7 +608,7 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
     CK(stage_out<int32_t>(c, 3, tokens, (size_t)B * cap, &tok_dev, &tok_h), "tokens staging");
     CK(stage_out<int32_t>(c, 4, n_tokens, (size_t)B, &nt_dev, &nt_h), "n_tokens staging");
     CK(stage_out<int32_t>(c, 5, n_steps, (size_t)B, &ns_dev, &ns_h), "n_steps staging");
-    CK(launch_greedy_decode(c, enc_dev, enc_host, B, T, lens_dev, h_lens, slots_dev, s1_dev, s2_dev, tok_dev, nt_dev, ns_dev),
+    CK(launch_greedy_decode(c, enc_dev, enc_host, B, T, lens_dev, h_lens, slots_dev, s1_dev, s2_dev, tok_dev, nt_dev, ns_dev, enc_offsets),
        "greedy decode launch");
     CK(finish_out<int32_t>(c, tokens, tok_dev, (size_t)B * cap, tok_h), "tokens D2H");
     CK(finish_out<int32_t>(c, n_tokens, nt_dev, (size_t)B, nt_h), "n_tokens D2H");
@@ -594,6 +629,22 @@ int32_t amira_greedy_decode(amira_ctx *c, const float *encoder_outputs, int32_t 
                             int32_t *n_tokens, int32_t *n_steps) {
     API_BEGIN(c)
     return greedy_common(c, encoder_outputs, B, T, encoded_lengths, nullptr, states_1, states_2, tokens, n_tokens, n_steps);
+    API_END(c)
+}
+
+int32_t amira_greedy_decode_packed(amira_ctx *c, const float *encoder_outputs, const int64_t *enc_offsets, int32_t B,
+                                   const int64_t *encoded_lengths, float *states_1, float *states_2, int32_t *tokens,
+                                   int32_t *n_tokens, int32_t *n_steps) {
+    API_BEGIN(c)
+    if (B < 0 || (B > 0 && (!enc_offsets || !encoded_lengths)))
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_greedy_decode_packed: bad arguments");
+    int64_t T = 0;
+    for (int b = 0; b < B; ++b) {
+        if (encoded_lengths[b] < 0 || encoded_lengths[b] > 0x7fffffff) return fail(c, AMIRA_ERR_INVALID_VALUE, "encoded_lengths out of range");
+        T = encoded_lengths[b] > T ? encoded_lengths[b] : T;
+    }
+    return greedy_common(c, encoder_outputs, B, (int32_t)T, encoded_lengths, nullptr, states_1, states_2, tokens, n_tokens, n_steps,
+                         enc_offsets);
     API_END(c)
 }
 

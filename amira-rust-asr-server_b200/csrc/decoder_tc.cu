@@ -66,20 +66,22 @@ __global__ void split_rows_kernel(const float *__restrict__ x, size_t ldx, __nv_
 }
 
 // encoder_outputs [B][1024][T] (t contiguous) -> K-major rows [(eoff[b] + t)][1024] hi/lo bf16 (valid frames packed back to
-// back: frames >= lens[b] are never projected), via a 32x32 smem transpose
+// back: frames >= lens[b] are never projected), via a 32x32 smem transpose.  Packed input (src_off != nullptr): stream b is
+// a [1024][lens[b]] block at enc + src_off[b].
 __global__ void split_transpose_enc_kernel(const float *__restrict__ enc, int T, const int *__restrict__ lens,
-                                           const int *__restrict__ eoff, int row_base, __nv_bfloat16 *__restrict__ hi,
-                                           __nv_bfloat16 *__restrict__ lo) {
+                                           const int *__restrict__ eoff, const long long *__restrict__ src_off, int row_base,
+                                           __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
     const int len = lens[b];
     if (t0 >= len) return;
     const size_t r0 = (size_t)(eoff[b] - row_base);
     const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-    const float *src = enc + (size_t)b * kEnc * T;
+    const float *src = src_off ? enc + src_off[b] : enc + (size_t)b * kEnc * T;
+    const int ld = src_off ? len : T;
     for (int j = ty; j < 32; j += 8) {
         const int t = t0 + tx;
-        tile[j][tx] = t < T ? src[(size_t)(f0 + j) * T + t] : 0.f;
+        tile[j][tx] = t < ld ? src[(size_t)(f0 + j) * ld + t] : 0.f;
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
@@ -237,10 +239,10 @@ cudaError_t launch_split_rows(Ctx *c, const float *x, size_t ldx, __nv_bfloat16 
 }
 
 cudaError_t launch_split_transpose_enc(Ctx *c, const float *enc, int B, int T, const int *lens_dev, const int *eoff_dev,
-                                       int row_base, __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
+                                       int row_base, __nv_bfloat16 *hi, __nv_bfloat16 *lo, const long long *src_off_dev) {
     if (B <= 0 || T <= 0) return cudaSuccess;
     dim3 grid((T + 31) / 32, kEnc / 32, B), block(32, 8);
-    split_transpose_enc_kernel<<<grid, block, 0, c->stream>>>(enc, T, lens_dev, eoff_dev, row_base, hi, lo);
+    split_transpose_enc_kernel<<<grid, block, 0, c->stream>>>(enc, T, lens_dev, eoff_dev, src_off_dev, row_base, hi, lo);
     c->launches++;
     return cudaGetLastError();
 }
@@ -1097,7 +1099,8 @@ static size_t tc_align(size_t x) { return (x + 1023) & ~(size_t)1023; }
 
 cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *enc_host, int B, int T, const int32_t *lens_dev,
                                     const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev,
-                                    int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev) {
+                                    int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev, const int64_t *enc_off_host) {
+    // enc_off_host != nullptr: packed encoder outputs — stream b is a [1024][lens[b]] block at enc + enc_off_host[b]
     DecoderPriv *d = c->dec;
     TcWeights *w = d->tc;
     const int Tq = T > 0 ? T : 1;
@@ -1110,7 +1113,9 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
     auto take = [&](size_t bytes) { size_t o = off; off += tc_align(bytes); return o; };
     const size_t oE = take(sizeof(float) * (size_t)B * Tq * kH);
     const size_t oeh = take(2 * (size_t)B * Tq * kEnc), oel = take(2 * (size_t)B * Tq * kEnc);
-    const size_t operm = take(sizeof(int) * ((size_t)Mpad + (size_t)B + 1));  // perm[Mpad] then eoff[B+1]
+    const size_t meta_bytes = sizeof(long long) * ((size_t)B + 1) + sizeof(int) * ((size_t)Mpad + (size_t)B + 1);
+    const size_t ometa = take(meta_bytes);  // src_off[B+1] (packed input), perm[Mpad], eoff[B+1]
+    const size_t operm = ometa + sizeof(long long) * ((size_t)B + 1);
     size_t ows = 0, ws_bytes = 0;
     size_t oh0h = 0, oh0l = 0, oh1h = 0, oh1l = 0, ozh = 0, ozl = 0, oh0f = 0, oh1f = 0, oc0 = 0, oc1 = 0, opv = 0, opi = 0, octl = 0, ocnt = 0;
     cudaError_t e;
@@ -1129,15 +1134,18 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
     char *base = d->work.as<char>();
 
     // rows sorted by encoded length (descending, stable): active rows stay a prefix, whole M-tiles retire early
-    if ((e = c->pin[1].reserve(sizeof(int) * ((size_t)Mpad + (size_t)B + 1))) != cudaSuccess) return e;
-    int *h_perm = c->pin[1].as<int>();
+    if ((e = c->pin[1].reserve(meta_bytes)) != cudaSuccess) return e;
+    long long *h_soff = c->pin[1].as<long long>();
+    for (int i = 0; i <= B; ++i) h_soff[i] = enc_off_host ? (long long)enc_off_host[i] : 0;
+    int *h_perm = reinterpret_cast<int *>(h_soff + B + 1);
     int *h_eoff = h_perm + Mpad;  // first packed row of each stream's valid frames in E
     h_eoff[0] = 0;
     for (int i = 0; i < B; ++i) h_eoff[i + 1] = h_eoff[i] + lens_host[i];
     for (int i = 0; i < B; ++i) h_perm[i] = i;
     std::stable_sort(h_perm, h_perm + B, [&](int a, int b2) { return lens_host[a] > lens_host[b2]; });
     for (int i = B; i < Mpad; ++i) h_perm[i] = 0;
-    if ((e = cudaMemcpyAsync(base + operm, h_perm, sizeof(int) * ((size_t)Mpad + (size_t)B + 1), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(base + ometa, h_soff, meta_bytes, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return e;
+    const long long *soff_dev = enc_off_host ? reinterpret_cast<const long long *>(base + ometa) : nullptr;
     const int *eoff_dev = reinterpret_cast<int *>(base + operm) + Mpad;
 
     float *E = reinterpret_cast<float *>(base + oE);
@@ -1151,17 +1159,18 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
         for (int k = 0; k < n_chunks; ++k) {
             const int b0 = (int)((long long)B * k / n_chunks), b1 = (int)((long long)B * (k + 1) / n_chunks);
             if (b1 <= b0) continue;
-            const size_t eo = (size_t)b0 * kEnc * T, ro = (size_t)h_eoff[b0];
+            const size_t eo = enc_off_host ? (size_t)enc_off_host[b0] : (size_t)b0 * kEnc * T, ro = (size_t)h_eoff[b0];
+            const size_t en = (enc_off_host ? (size_t)enc_off_host[b1] : (size_t)b1 * kEnc * T) - eo;
             const int rows = h_eoff[b1] - h_eoff[b0];
             if (enc_host) {
                 if (k >= 3 && (e = cudaEventSynchronize(c->ev_pool[2 * Ctx::kMaxChunks + k - 3])) != cudaSuccess) return e;
-                if ((e = cudaMemcpyAsync(const_cast<float *>(enc_dev) + eo, enc_host + eo, sizeof(float) * (size_t)(b1 - b0) * kEnc * T,
-                                         cudaMemcpyHostToDevice, c->h2d_stream)) != cudaSuccess) return e;
+                if (en > 0 && (e = cudaMemcpyAsync(const_cast<float *>(enc_dev) + eo, enc_host + eo, sizeof(float) * en, cudaMemcpyHostToDevice,
+                                                   c->h2d_stream)) != cudaSuccess) return e;
                 if ((e = cudaEventRecord(c->ev_pool[2 * Ctx::kMaxChunks + k], c->h2d_stream)) != cudaSuccess) return e;
                 if ((e = cudaStreamWaitEvent(c->stream, c->ev_pool[2 * Ctx::kMaxChunks + k], 0)) != cudaSuccess) return e;
             }
-            if ((e = launch_split_transpose_enc(c, enc_dev + eo, b1 - b0, T, lens_dev + b0, eoff_dev + b0, h_eoff[b0], eh + ro * kEnc,
-                                                el + ro * kEnc)) != cudaSuccess) return e;
+            if ((e = launch_split_transpose_enc(c, enc_off_host ? enc_dev : enc_dev + eo, b1 - b0, T, lens_dev + b0, eoff_dev + b0, h_eoff[b0],
+                                                eh + ro * kEnc, el + ro * kEnc, soff_dev ? soff_dev + b0 : nullptr)) != cudaSuccess) return e;
             if ((e = launch_tc_gemm(c, eh + ro * kEnc, el + ro * kEnc, w->we_hi, w->we_lo, d->bjoint, E + ro * kH, kH, rows, kH, kEnc)) != cudaSuccess) return e;
         }
     }

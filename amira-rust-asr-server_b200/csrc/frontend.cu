@@ -41,6 +41,7 @@ struct FeMeta {
     const int64_t *starts;   // [B] first element of each utterance
     const int64_t *lens;     // [B] samples
     const int32_t *tile_pfx; // [B+1] prefix sum of tiles per utterance
+    const int64_t *foff;     // [B] first element of each utterance's [128][ld] feature block
     int B;
     int n_tiles;
 };
@@ -361,9 +362,11 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
             }
             partials[(size_t)tile * kMel + m] = make_double2(mean, m2);
         }
-        float *dst = features + (size_t)b * kMel * t_stride + f0;
+        // row stride: t_stride (padded layout) or, packed (t_stride == 0), the utterance's own frame count
+        const int64_t ld = t_stride > 0 ? t_stride : n / kHop + 1;
+        float *dst = features + meta.foff[b] + f0;
         for (int m = warp; m < kMel; m += FE_WARPS)
-            if (lane < nf) dst[(size_t)m * t_stride + lane] = outt[m * OUT_LD + lane];
+            if (lane < nf) dst[(size_t)m * ld + lane] = outt[m * OUT_LD + lane];
     }
 }
 
@@ -376,7 +379,8 @@ fe_normalize_kernel(FeMeta meta, float *__restrict__ features, int64_t t_stride,
     const int b = (int)(row / kMel), m = (int)(row % kMel);
     const int64_t n = meta.lens[b];
     const int64_t L = n <= 0 ? 0 : n / kHop + 1;
-    float *p = features + row * t_stride;
+    const int64_t ld = t_stride > 0 ? t_stride : L;  // packed layout (t_stride == 0): rows are exactly L long
+    float *p = features + meta.foff[b] + (int64_t)m * ld;
     // Chan et al. pairwise merge of (count, mean, M2)
     double cn = 0.0, cmean = 0.0, cm2 = 0.0;
     auto merge = [&](double n2, double mean2, double m22) {
@@ -412,10 +416,10 @@ fe_normalize_kernel(FeMeta meta, float *__restrict__ features, int64_t t_stride,
     const double sd = L > 1 ? sqrt(cm2 / (double)(L - 1)) : 0.0;
     const float mu = (float)cmean;
     const float inv = (float)(1.0 / (sd + 1e-5));
-    const bool vec = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (t_stride % 4 == 0);
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0);
     if (vec) {
         float4 *p4 = reinterpret_cast<float4 *>(p);
-        const int64_t n4 = t_stride / 4;
+        const int64_t n4 = ld / 4;
         for (int64_t i = lane; i < n4; i += 32) {
             const int64_t t = i * 4;
             float4 v;
@@ -434,7 +438,7 @@ fe_normalize_kernel(FeMeta meta, float *__restrict__ features, int64_t t_stride,
             p4[i] = v;
         }
     } else {
-        for (int64_t t = lane; t < t_stride; t += 32) p[t] = t < L ? (p[t] - mu) * inv : 0.f;
+        for (int64_t t = lane; t < ld; t += 32) p[t] = t < L ? (p[t] - mu) * inv : 0.f;
     }
 }
 
@@ -482,23 +486,26 @@ size_t fe_smem_bytes() {
 }  // namespace
 
 cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const int64_t *starts_host,
-                            const int64_t *lens_host, int B, float *features_dev, int64_t t_stride, int slot, int phase) {
+                            const int64_t *lens_host, int B, float *features_dev, int64_t t_stride, int slot, int phase,
+                            const int64_t *foff_host) {
     if (B <= 0) return cudaSuccess;
     if (slot < 0 || slot >= Ctx::kMaxChunks) return cudaErrorInvalidValue;
     DevBuf &fe_meta = c->fe_meta[slot], &fe_partials = c->fe_partials[slot];
     PinBuf &fe_meta_pin = c->fe_meta_pin[slot];
     // host metadata: starts, lens, tile prefix -> one pinned block, one async copy
-    const size_t meta_bytes = sizeof(int64_t) * 2 * (size_t)B + sizeof(int32_t) * ((size_t)B + 1);
+    const size_t meta_bytes = sizeof(int64_t) * 3 * (size_t)B + sizeof(int32_t) * ((size_t)B + 1);
     cudaError_t e;
     if ((e = fe_meta_pin.reserve(meta_bytes)) != cudaSuccess) return e;
     if ((e = fe_meta.reserve(meta_bytes)) != cudaSuccess) return e;
     int64_t *h_starts = fe_meta_pin.as<int64_t>();
     int64_t *h_lens = h_starts + B;
-    int32_t *h_pfx = reinterpret_cast<int32_t *>(h_lens + B);
+    int64_t *h_foff = h_lens + B;
+    int32_t *h_pfx = reinterpret_cast<int32_t *>(h_foff + B);
     int64_t tiles = 0;
     for (int b = 0; b < B; ++b) {
         h_starts[b] = starts_host[b];
         h_lens[b] = lens_host[b];
+        h_foff[b] = foff_host ? foff_host[b] : (int64_t)b * kMel * t_stride;
         h_pfx[b] = (int32_t)tiles;
         const int64_t L = lens_host[b] <= 0 ? 0 : lens_host[b] / kHop + 1;
         tiles += (L + TF - 1) / TF;
@@ -514,7 +521,8 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
     FeMeta meta;
     meta.starts = fe_meta.as<int64_t>();
     meta.lens = meta.starts + B;
-    meta.tile_pfx = reinterpret_cast<const int32_t *>(meta.lens + B);
+    meta.foff = meta.lens + B;
+    meta.tile_pfx = reinterpret_cast<const int32_t *>(meta.foff + B);
     meta.B = B;
     meta.n_tiles = (int)tiles;
     if ((e = fe_partials.reserve(sizeof(double2) * (size_t)std::max<int64_t>(tiles, 1) * kMel)) != cudaSuccess) return e;

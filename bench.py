@@ -237,6 +237,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
+    ap.add_argument("--e2e-layout", choices=["packed", "padded"], default="packed",
+                    help="host buffers of the e2e leg: ragged per-utterance blocks (default) or batch tensors padded to the longest")
     ap.add_argument("--stream-ticks", type=int, default=60)
     ap.add_argument("--engine", type=int, default=0)
     args = ap.parse_args()
@@ -336,9 +338,22 @@ def main():
     # ---- e2e: same calls, pinned host buffers in and out ----
     e2e = None
     if not args.no_e2e:
-        enc_pin = torch.empty((B, 1024, T), dtype=torch.float32).pin_memory()
-        enc_pin.copy_(enc_dev)
-        feats_pin = torch.empty((B, 128, t_stride), dtype=torch.float32).pin_memory()
+        packed = args.e2e_layout == "packed"
+        if packed:
+            # ragged per-utterance blocks, as the reference holds them per request (features [1][128][L_b], encoder outputs
+            # [1][1024][T_b]): nothing is padded to the longest utterance of the batch, only valid frames cross PCIe
+            eoff = np.zeros(B + 1, np.int64)
+            eoff[1:] = np.cumsum(1024 * elens)
+            foff = np.zeros(B + 1, np.int64)
+            foff[1:] = np.cumsum(128 * flens)
+            enc_pin = torch.empty(int(eoff[-1]), dtype=torch.float32).pin_memory()
+            for b in range(B):
+                enc_pin[int(eoff[b]):int(eoff[b + 1])].copy_(enc_dev[b, :, :int(elens[b])].reshape(-1))
+            feats_pin = torch.empty(int(foff[-1]), dtype=torch.float32).pin_memory()
+        else:
+            enc_pin = torch.empty((B, 1024, T), dtype=torch.float32).pin_memory()
+            enc_pin.copy_(enc_dev)
+            feats_pin = torch.empty((B, 128, t_stride), dtype=torch.float32).pin_memory()
         tok_pin = torch.zeros((B, ctx.max_total_tokens), dtype=torch.int32).pin_memory()
         ntok_pin = torch.zeros(B, dtype=torch.int32).pin_memory()
         torch.cuda.synchronize()
@@ -350,16 +365,23 @@ def main():
         ctx_fe = A.Context(device_id=local_rank, decode_engine=args.engine)
 
         def step_host():
-            th = threading.Thread(target=ctx_fe.preprocess_pcm16_raw,
-                                  args=(pcm_pin.data_ptr(), offsets, B, feats_pin.data_ptr(), t_stride, flens_out))
+            if packed:
+                th = threading.Thread(target=ctx_fe.preprocess_pcm16_packed_raw,
+                                      args=(pcm_pin.data_ptr(), offsets, B, feats_pin.data_ptr(), foff, flens_out))
+            else:
+                th = threading.Thread(target=ctx_fe.preprocess_pcm16_raw,
+                                      args=(pcm_pin.data_ptr(), offsets, B, feats_pin.data_ptr(), t_stride, flens_out))
             th.start()
-            ctx.greedy_decode_raw(enc_pin.data_ptr(), B, T, elens, tok_pin.data_ptr(), ntok_pin.data_ptr(), None)
+            if packed:
+                ctx.greedy_decode_packed_raw(enc_pin.data_ptr(), eoff, B, elens, tok_pin.data_ptr(), ntok_pin.data_ptr(), None)
+            else:
+                ctx.greedy_decode_raw(enc_pin.data_ptr(), B, T, elens, tok_pin.data_ptr(), ntok_pin.data_ptr(), None)
             th.join()
 
         step_host()
         ms_e2e = timed(step_host, args.steps) / args.steps
         assert np.array_equal(ntok_pin.numpy().astype(np.int64), ntok), "host-buffer path disagrees with the resident path"
-        e2e = {"value": total_audio / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
+        e2e = {"value": total_audio / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e, "layout": args.e2e_layout,
                "h2d_bytes_per_step": int(pcm.nbytes + enc_pin.numel() * 4 + offsets.nbytes + elens.nbytes),
                "d2h_bytes_per_step": int(feats_pin.numel() * 4 + tok_pin.numel() * 4 + ntok_pin.numel() * 4)}
         launches_e2e = ctx_fe.launch_count()

@@ -116,6 +116,12 @@ int32_t amira_features_len(int64_t n_samples, int64_t *features_len);
  * frames >= features_lens[b] are zero.  t_stride >= max features_len. */
 int32_t amira_preprocess_pcm16(amira_ctx *ctx, const int16_t *pcm, const int64_t *offsets, int32_t B,
                                float *features, int64_t t_stride, int64_t *features_lens);
+/* Same, ragged output: utterance b's features are a dense [128][features_lens[b]] block at features + feat_offsets[b]
+ * (element offsets, int64[B+1], host, non-decreasing, block >= 128 * features_len) — the shape the reference hands its
+ * encoder per request (features [1][128][T_b], src/triton/model.rs:126-141) without padding every utterance of a batch
+ * to the longest one; only valid frames cross PCIe.  Elements of a block beyond 128 * features_len are unspecified. */
+int32_t amira_preprocess_pcm16_packed(amira_ctx *ctx, const int16_t *pcm, const int64_t *offsets, int32_t B,
+                                      float *features, const int64_t *feat_offsets, int64_t *features_lens);
 /* Triton contract form (model-repo/preprocessor/config.pbtxt:4-28): waveforms [B][n_stride] fp32 (host or
  * device), waveforms_lens [B] int64 (host) -> features [B][128][t_stride], features_lens [B] (host). */
 int32_t amira_preprocess_f32(amira_ctx *ctx, const float *waveforms, int64_t n_stride, const int64_t *waveforms_lens,
@@ -143,6 +149,13 @@ int32_t amira_decoder_joint(amira_ctx *ctx, const float *encoder_outputs, int32_
 int32_t amira_greedy_decode(amira_ctx *ctx, const float *encoder_outputs, int32_t B, int32_t T,
                             const int64_t *encoded_lengths, float *states_1, float *states_2, int32_t *tokens,
                             int32_t *n_tokens, int32_t *n_steps);
+/* Same, ragged input: stream b's encoder output is a dense [1024][encoded_lengths[b]] block at
+ * encoder_outputs + enc_offsets[b] (element offsets, int64[B+1], host) — the per-request tensor of
+ * EncoderModel::infer (src/triton/model.rs:298-420, outputs [1][1024][T_b]) as it is, instead of a batch padded to
+ * the longest stream.  decode_engine 0/2/3/4. */
+int32_t amira_greedy_decode_packed(amira_ctx *ctx, const float *encoder_outputs, const int64_t *enc_offsets, int32_t B,
+                                   const int64_t *encoded_lengths, float *states_1, float *states_2, int32_t *tokens,
+                                   int32_t *n_tokens, int32_t *n_steps);
 
 /* ---- WebSocket path: device-resident per-stream LSTM state (replaces the DecoderState carried by
  * IncrementalAsr, src/asr/incremental.rs:45-51,101-105, and process_stream_* in src/asr/pipeline.rs:384-431) */

@@ -243,6 +243,46 @@ def test_pipelined_host_upload_equals_resident_decode(amira):
             assert steps_h[b] == ns[b]
 
 
+def test_packed_encoder_outputs_equal_padded(ctx, amira):
+    """amira_greedy_decode_packed: ragged per-stream [1024][T_b] blocks (the reference's per-request encoder tensors) give
+    the tokens, steps and final states of the padded [B][1024][T] batch — host pipeline (96 streams => several upload
+    chunks) and device-resident, including a zero-length stream."""
+    import torch
+    rng = np.random.default_rng(22)
+    B, T = 96, 24
+    enc = (0.5 * rng.standard_normal((B, 1024, T))).astype(np.float32)
+    lens = rng.integers(1, T + 1, size=B).astype(np.int64)
+    lens[5] = 0
+    ctx.load_weights(amira.synthetic_weights(3456))
+    toks, st, steps = ctx.greedy_decode(enc, lens)
+    ragged = [np.ascontiguousarray(enc[b, :, :int(lens[b])]) for b in range(B)]
+    if ctx.engine == 1:
+        with pytest.raises(amira.AmiraError):
+            ctx.greedy_decode_packed(ragged)
+        return
+    toks_k, st_k, steps_k = ctx.greedy_decode_packed(ragged)
+    assert toks_k == toks and steps_k.tolist() == steps.tolist()
+    assert np.array_equal(st_k.states_1, st.states_1) and np.array_equal(st_k.states_2, st.states_2)
+    # device-resident packed buffer with gaps between blocks
+    eoff = np.zeros(B + 1, np.int64)
+    eoff[0] = 3
+    for b in range(B):
+        eoff[b + 1] = eoff[b] + 1024 * int(lens[b]) + (b % 5)
+    flat = np.zeros(int(eoff[-1]), np.float32)
+    for b in range(B):
+        flat[eoff[b]:eoff[b] + 1024 * int(lens[b])] = ragged[b].reshape(-1)
+    enc_d = torch.from_numpy(flat).cuda()
+    tok_d = torch.zeros((B, ctx.max_total_tokens), dtype=torch.int32, device="cuda")
+    nt_d = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ns_d = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ctx.greedy_decode_packed_raw(enc_d.data_ptr(), eoff, B, lens, tok_d.data_ptr(), nt_d.data_ptr(), ns_d.data_ptr())
+    torch.cuda.synchronize()
+    nt, tk, ns = nt_d.cpu().numpy(), tok_d.cpu().numpy(), ns_d.cpu().numpy()
+    for b in range(B):
+        assert toks[b] == tk[b, :nt[b]].tolist(), b
+        assert steps[b] == ns[b]
+
+
 def test_streaming_tick_1024_slots(amira):
     """BASELINE config 4 shape: 1024 resident stream slots, T = 3 encoder frames per tick; two ticks through the slots equal
     one decode with caller-carried state."""

@@ -132,3 +132,40 @@ def test_pipelined_host_path_equals_resident_path(ctx, amira):
     torch.cuda.synchronize()
     assert lens_h.tolist() == lens_d.tolist()
     assert np.array_equal(host, out_d.cpu().numpy())
+
+
+def test_packed_output_equals_padded_output(ctx, amira):
+    """amira_preprocess_pcm16_packed: ragged [128][features_len_b] blocks (no padding to the longest utterance) must be
+    bit-identical to the padded layout — through the chunked host pipeline (96 utterances), through device pointers,
+    with an empty utterance, a one-frame utterance and a non-zero first offset."""
+    import torch
+    rng = np.random.default_rng(12)
+    pcms = [synth_pcm(float(rng.uniform(0.2, 1.5)), 500 + i) for i in range(96)]
+    pcms[3] = np.zeros(0, np.int16)
+    pcms[7] = synth_pcm(0.005, 1)  # 80 samples -> one frame
+    pcm, offs = _pack(pcms)
+    padded, lens_p = ctx.preprocess_pcm16(pcm, offs, t_stride=160)
+    blocks, lens_k = ctx.preprocess_pcm16_packed(pcm, offs)
+    assert lens_p.tolist() == lens_k.tolist()
+    for b in range(len(pcms)):
+        assert blocks[b].shape == (128, int(lens_p[b]))
+        assert np.array_equal(blocks[b], padded[b, :, :int(lens_p[b])]), b
+    # device pointers, blocks with gaps and a non-zero first offset
+    foff = np.zeros(len(pcms) + 1, np.int64)
+    foff[0] = 5
+    for b in range(len(pcms)):
+        foff[b + 1] = foff[b] + 128 * int(lens_p[b]) + (b % 3)
+    pcm_d = torch.from_numpy(pcm).cuda()
+    out_d = torch.zeros(int(foff[-1]), dtype=torch.float32, device="cuda")
+    lens_d = np.zeros(len(pcms), np.int64)
+    ctx.preprocess_pcm16_packed_raw(pcm_d.data_ptr(), offs, len(pcms), out_d.data_ptr(), foff, lens_d)
+    torch.cuda.synchronize()
+    out = out_d.cpu().numpy()
+    for b in range(len(pcms)):
+        L = int(lens_p[b])
+        assert np.array_equal(out[foff[b]:foff[b] + 128 * L].reshape(128, L), padded[b, :, :L]), b
+    # a block that is too small is refused
+    bad = foff.copy()
+    bad[1:] -= 64
+    with pytest.raises(amira.AmiraError):
+        ctx.preprocess_pcm16_packed_raw(pcm_d.data_ptr(), offs, len(pcms), out_d.data_ptr(), bad, lens_d)
