@@ -237,6 +237,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
+    ap.add_argument("--e2e-inflight", type=int, default=2, help="steps in flight in the e2e leg (each on its own contexts)")
     ap.add_argument("--e2e-layout", choices=["packed", "padded"], default="packed",
                     help="host buffers of the e2e leg: ragged per-utterance blocks (default) or batch tensors padded to the longest")
     ap.add_argument("--stream-ticks", type=int, default=60)
@@ -349,44 +350,71 @@ def main():
             enc_pin = torch.empty(int(eoff[-1]), dtype=torch.float32).pin_memory()
             for b in range(B):
                 enc_pin[int(eoff[b]):int(eoff[b + 1])].copy_(enc_dev[b, :, :int(elens[b])].reshape(-1))
-            feats_pin = torch.empty(int(foff[-1]), dtype=torch.float32).pin_memory()
+            feat_shape = (int(foff[-1]),)
         else:
             enc_pin = torch.empty((B, 1024, T), dtype=torch.float32).pin_memory()
             enc_pin.copy_(enc_dev)
-            feats_pin = torch.empty((B, 128, t_stride), dtype=torch.float32).pin_memory()
-        tok_pin = torch.zeros((B, ctx.max_total_tokens), dtype=torch.int32).pin_memory()
-        ntok_pin = torch.zeros(B, dtype=torch.int32).pin_memory()
+            feat_shape = (B, 128, t_stride)
         torch.cuda.synchronize()
 
-        # the two stages of a step share no data in this benchmark (the encoder between them is out of scope and its
-        # outputs are synthetic), so the host drives them as the server would drive two requests: two contexts on the
-        # same GPU, one blocking C-ABI call each from its own thread; inside each call the library pipelines H2D copies,
-        # kernels and D2H copies chunk by chunk.
-        ctx_fe = A.Context(device_id=local_rank, decode_engine=args.engine)
+        # The two stages of a step share no data in this benchmark (the encoder between them is out of scope and its
+        # outputs are synthetic), so the host drives them as the server would drive two requests: one blocking C-ABI call
+        # each from its own thread, on two contexts of the same GPU; inside each call the library pipelines H2D copies,
+        # kernels and D2H copies chunk by chunk.  `--e2e-inflight` steps are in flight at a time (default 2, each with its
+        # own pair of contexts and its own output buffers), as a server keeps several batches in flight: the upload of one
+        # step then overlaps the decode kernel of the other.  Every step still uploads all of its inputs and reads back
+        # all of its results inside the timed region.
+        n_fl = max(1, args.e2e_inflight)
+        workers = []
+        for w in range(n_fl):
+            cd = ctx if w == 0 else A.Context(device_id=local_rank, decode_engine=args.engine)
+            if w > 0:
+                cd.load_weights(A.synthetic_weights(3456))
+            workers.append({"dec": cd, "fe": A.Context(device_id=local_rank, decode_engine=args.engine),
+                            "feats": torch.empty(feat_shape, dtype=torch.float32).pin_memory(),
+                            "tok": torch.zeros((B, ctx.max_total_tokens), dtype=torch.int32).pin_memory(),
+                            "ntok": torch.zeros(B, dtype=torch.int32).pin_memory(), "flens": np.zeros(B, np.int64)})
 
-        def step_host():
+        def step_host(w):
+            k = workers[w]
             if packed:
-                th = threading.Thread(target=ctx_fe.preprocess_pcm16_packed_raw,
-                                      args=(pcm_pin.data_ptr(), offsets, B, feats_pin.data_ptr(), foff, flens_out))
+                th = threading.Thread(target=k["fe"].preprocess_pcm16_packed_raw,
+                                      args=(pcm_pin.data_ptr(), offsets, B, k["feats"].data_ptr(), foff, k["flens"]))
             else:
-                th = threading.Thread(target=ctx_fe.preprocess_pcm16_raw,
-                                      args=(pcm_pin.data_ptr(), offsets, B, feats_pin.data_ptr(), t_stride, flens_out))
+                th = threading.Thread(target=k["fe"].preprocess_pcm16_raw,
+                                      args=(pcm_pin.data_ptr(), offsets, B, k["feats"].data_ptr(), t_stride, k["flens"]))
             th.start()
             if packed:
-                ctx.greedy_decode_packed_raw(enc_pin.data_ptr(), eoff, B, elens, tok_pin.data_ptr(), ntok_pin.data_ptr(), None)
+                k["dec"].greedy_decode_packed_raw(enc_pin.data_ptr(), eoff, B, elens, k["tok"].data_ptr(), k["ntok"].data_ptr(), None)
             else:
-                ctx.greedy_decode_raw(enc_pin.data_ptr(), B, T, elens, tok_pin.data_ptr(), ntok_pin.data_ptr(), None)
+                k["dec"].greedy_decode_raw(enc_pin.data_ptr(), B, T, elens, k["tok"].data_ptr(), k["ntok"].data_ptr(), None)
             th.join()
 
-        step_host()
-        ms_e2e = timed(step_host, args.steps) / args.steps
-        assert np.array_equal(ntok_pin.numpy().astype(np.int64), ntok), "host-buffer path disagrees with the resident path"
+        def run_steps(steps):  # steps are dealt round-robin to the in-flight workers
+            def loop(w):
+                for _ in range(w, steps, n_fl):
+                    step_host(w)
+            ths = [threading.Thread(target=loop, args=(w,)) for w in range(1, n_fl)]
+            for th in ths:
+                th.start()
+            loop(0)
+            for th in ths:
+                th.join()
+
+        run_steps(n_fl)
+        ms_e2e = timed(lambda: run_steps(args.steps), 1) / args.steps
+        for k in workers:
+            assert np.array_equal(k["ntok"].numpy().astype(np.int64), ntok), "host-buffer path disagrees with the resident path"
         e2e = {"value": total_audio / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e, "layout": args.e2e_layout,
+               "steps_in_flight": n_fl,
                "h2d_bytes_per_step": int(pcm.nbytes + enc_pin.numel() * 4 + offsets.nbytes + elens.nbytes),
-               "d2h_bytes_per_step": int(feats_pin.numel() * 4 + tok_pin.numel() * 4 + ntok_pin.numel() * 4)}
-        launches_e2e = ctx_fe.launch_count()
-        ctx_fe.close()
-        del enc_pin, feats_pin
+               "d2h_bytes_per_step": int(workers[0]["feats"].numel() * 4 + workers[0]["tok"].numel() * 4 + B * 4)}
+        launches_e2e = workers[0]["fe"].launch_count()
+        for w, k in enumerate(workers):
+            k["fe"].close()
+            if w > 0:
+                k["dec"].close()
+        del enc_pin, workers
 
     streaming = None
     if not args.no_stream and rank == 0:
