@@ -765,7 +765,22 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 const bool live = act_cnt > 0;  // identical in every layer-0 CTA
                 if (etid == 0) sm.act2[(tile & 1) ^ 1] = 0;  // the next unit's slot: nobody touches it before that unit's barrier
                 if (etid == 0 && slice == 0 && p.trace && mt == 0 && it > 0 && it - 1 < W_TRACE_ITS) p.trace[(it - 1) * 32 + 30] = gtime();
-                if (!live && slice == 0) {  // the M-tile is finished: its streams' results, then the end marker
+                if (!live && p.s1 && p.s2) {
+                    // the M-tile is finished and every layer's state is final (the vocabulary phase of the last step was
+                    // released by all of them): each layer-0 CTA hands back its 16 hidden features of the four state arrays
+                    for (int i = etid; i < W_BM * (W_SL / 4); i += W_EPI_THREADS) {
+                        const int grow = mt * W_BM + i / (W_SL / 4), j = slice * (W_SL / 4) + i % (W_SL / 4);
+                        if (grow < p.B) {
+                            const int b = __ldg(p.rowinfo + grow).x;
+                            const size_t src = (size_t)grow * kH + j;
+                            p.s1[ws_state_off(p, 0, b) + j] = __ldcg(p.h0f + src);
+                            p.s1[ws_state_off(p, 1, b) + j] = __ldcg(p.h1f + src);
+                            p.s2[ws_state_off(p, 0, b) + j] = __ldcg(p.c0 + src);
+                            p.s2[ws_state_off(p, 1, b) + j] = __ldcg(p.c1 + src);
+                        }
+                    }
+                }
+                if (!live && slice == 0) {  // its streams' results, then the end marker
                     for (int rr = etid; rr < W_BM; rr += W_EPI_THREADS) {
                         const int grow = mt * W_BM + rr;
                         if (grow < p.B) {
@@ -774,19 +789,6 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                             p.ntok[b] = f.failed ? -1 : f.total;
                             if (p.nsteps) p.nsteps[b] = f.nsteps;
                             if (f.failed) atomicAdd(p.fail_count, 1);
-                        }
-                    }
-                    if (p.s1 && p.s2) {
-                        for (int i = etid; i < W_BM * kH; i += W_EPI_THREADS) {
-                            const int grow = mt * W_BM + i / kH, j = i % kH;
-                            if (grow < p.B) {
-                                const int b = __ldg(p.rowinfo + grow).x;
-                                const size_t src = (size_t)grow * kH + j;
-                                p.s1[ws_state_off(p, 0, b) + j] = __ldcg(p.h0f + src);
-                                p.s1[ws_state_off(p, 1, b) + j] = __ldcg(p.h1f + src);
-                                p.s2[ws_state_off(p, 0, b) + j] = __ldcg(p.c0 + src);
-                                p.s2[ws_state_off(p, 1, b) + j] = __ldcg(p.c1 + src);
-                            }
                         }
                     }
                     named_bar_sync(1, W_EPI_THREADS);
