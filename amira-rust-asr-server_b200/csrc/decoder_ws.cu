@@ -941,6 +941,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     const float4 *ep = reinterpret_cast<const float4 *>(p.E + ((size_t)ri.z + c.t) * kH + nb);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) ev[j] = __ldg(ep + j);
+                    // E is streamed from HBM exactly once per (stream, frame): pull the next frame's 128 bytes into L2 now so
+                    // that the load above finds them there when the stream advances (this load sits on the step chain)
+                    if (c.t + 1 < ri.y) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep + kH / 4));
                 }
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
