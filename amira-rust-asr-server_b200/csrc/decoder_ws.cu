@@ -685,6 +685,27 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 gather_acc(r);
             }
         };
+        // the same, summed in place into the 32 addends the caller already holds (bias / gathered row / partial sums): holding
+        // accumulator and addends as separate arrays costs 64 registers at the 168-register cap and spilled on the step chain
+        auto gather_add = [&](float *pre) {
+            const float *srct = ttile + (cgp * 32) * T_LD + r_in;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pre[j] = (srct[j * T_LD] + srct[(W_SL + j) * T_LD]) + pre[j];
+            named_bar_sync(2, W_EPI_THREADS);  // the tile is free for the next unit
+        };
+        auto load_acc_add = [&](uint32_t taddr, uint32_t buf, float *pre) {
+            uint32_t r[32];
+            if (!TS) {
+                tmem_ld32_sum(taddr, r);
+                tc_fence_before();
+                mbar_arrive(&sm.acc_empty[buf]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) pre[j] = __uint_as_float(r[j]) + pre[j];
+            } else {
+                drain_acc(taddr, buf, r);
+                gather_add(pre);
+            }
+        };
         uint32_t qn = 0, tile = 0;
         for (;;) {
             const uint32_t slot = qn % W_Q;
@@ -797,14 +818,19 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         st_release(p.dead_at + mt, it);  // iteration `it` of this M-tile does not exist
                     }
                 }
+                // pre-activations = accumulator + G0[token] row, summed in place in the gathered row's registers (holding both
+                // as separate arrays spilled 24 registers to local memory on this on-chain epilogue)
+                float *pre = reinterpret_cast<float *>(ad);
                 if (TS) {
                     if (etid == 0) WS_TRACE(3);
-                    gather_acc(r);  // drained into the shared tile at the top of this unit
+                    gather_add(pre);  // drained into the shared tile at the top of this unit
                 } else {
                     mbar_wait_wd(&sm.acc_full[buf], use & 1);
                     if (etid == 0) WS_TRACE(3);
                     tc_fence_after();
                     load_acc(taddr, buf, r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) pre[j] = __uint_as_float(r[j]) + pre[j];
                 }
                 if (!live) {  // speculative unit of an ended M-tile: drop it (uniform across the CTA)
                     if (TS) {
@@ -819,8 +845,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     __align__(16) __nv_bfloat16 vh[8], vl[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float gi = fsig(__uint_as_float(r[4 * j + 0]) + ad[j].x), gf = fsig(__uint_as_float(r[4 * j + 1]) + ad[j].y);
-                        const float gg = ftanh(__uint_as_float(r[4 * j + 2]) + ad[j].z), go = fsig(__uint_as_float(r[4 * j + 3]) + ad[j].w);
+                        const float gi = fsig(pre[4 * j + 0]), gf = fsig(pre[4 * j + 1]);
+                        const float gg = ftanh(pre[4 * j + 2]), go = fsig(pre[4 * j + 3]);
                         const float cn = gf * cold[j] + gi * gg;
                         cold[j] = cn;
                         hnew[j] = go * ftanh(cn);
@@ -897,15 +923,15 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
                 tc_fence_after();
-                load_acc(taddr, buf, r);
+                load_acc_add(taddr, buf, reinterpret_cast<float *>(pr));  // (accumulator + recurrent partial sums) ...
                 if (c.active) {
                     float cold[8] = {cold4[0].x, cold4[0].y, cold4[0].z, cold4[0].w, cold4[1].x, cold4[1].y, cold4[1].z, cold4[1].w};
                     float hnew[8];
                     __align__(16) __nv_bfloat16 vh[8], vl[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float gi = fsig(__uint_as_float(r[4 * j + 0]) + pr[j].x + ad[j].x), gf = fsig(__uint_as_float(r[4 * j + 1]) + pr[j].y + ad[j].y);
-                        const float gg = ftanh(__uint_as_float(r[4 * j + 2]) + pr[j].z + ad[j].z), go = fsig(__uint_as_float(r[4 * j + 3]) + pr[j].w + ad[j].w);
+                    for (int j = 0; j < 8; ++j) {  // ... + bias
+                        const float gi = fsig(pr[j].x + ad[j].x), gf = fsig(pr[j].y + ad[j].y);
+                        const float gg = ftanh(pr[j].z + ad[j].z), go = fsig(pr[j].w + ad[j].w);
                         const float cn = gf * cold[j] + gi * gg;
                         cold[j] = cn;
                         hnew[j] = go * ftanh(cn);
@@ -936,7 +962,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
             } else if (role == R_C) {
                 const int4 ri = __ldg(p.rowinfo + row);
                 const WCtl c = load_ctl(p.ctl + (size_t)(it & 1) * p.Mpad + row);
-                float4 ev[8];
+                float4 ev[8] = {};
                 if (c.active) {
                     const float4 *ep = reinterpret_cast<const float4 *>(p.E + ((size_t)ri.z + c.t) * kH + nb);
 #pragma unroll
@@ -948,7 +974,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
                 tc_fence_after();
-                load_acc(taddr, buf, r);
+                load_acc_add(taddr, buf, reinterpret_cast<float *>(ev));
                 if (c.active) {
                     __nv_bfloat16 *bh = p.zb_hi + (size_t)row * kH + nb, *bl = p.zb_lo + (size_t)row * kH + nb;
 #pragma unroll
@@ -958,7 +984,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                                              ev[2 * j8 + 1].x, ev[2 * j8 + 1].y, ev[2 * j8 + 1].z, ev[2 * j8 + 1].w};
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float v = __uint_as_float(r[8 * j8 + j]) + e8[j];
+                            const float v = e8[j];
                             split_bf16(p.relu ? fmaxf(v, 0.f) : ftanh(v), vh[j], vl[j]);
                         }
                         reinterpret_cast<uint4 *>(bh)[j8] = *reinterpret_cast<uint4 *>(vh);
@@ -987,7 +1013,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 mbar_wait_wd(&sm.acc_full[buf], use & 1);
                 if (etid == 0) WS_TRACE(3);
                 tc_fence_after();
-                load_acc(taddr, buf, r);
+                load_acc_add(taddr, buf, reinterpret_cast<float *>(bo));
                 if (c.active) {
                     float best_v = -INFINITY;
                     int best_i = 0x7fffffff;
@@ -996,7 +1022,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     for (int j = 0; j < 32; ++j) {
                         const int n = nb + j;
                         if (n < kV) {
-                            const float v = __uint_as_float(r[j]) + bof[j];
+                            const float v = bof[j];
                             if (v > best_v || best_i == 0x7fffffff) { best_v = v; best_i = n; }
                         }
                     }
