@@ -199,6 +199,10 @@ __device__ __forceinline__ long long gtime() {
             if (role == p.trace_role && mt < 8) p.trace[W_TRACE_ITS * 32 + (it * 8 + mt) * 8 + (ev)] = gtime(); \
         }                                                                                              \
     } while (0)
+// AMIRA_WS_VARIANT bit 7: events 1, 2, 6, 7 of the per-tile trace are stamped by the epilogue (unit popped, head loads back,
+// accumulator gathered, arithmetic done) instead of by the MMA thread
+#define WS_TRACE_MMA(ev) do { if (!(p.variant & 128)) WS_TRACE(ev); } while (0)
+#define WS_TRACE_EPI(ev) do { if ((p.variant & 128) && etid == 0) WS_TRACE(ev); } while (0)
 
 // this thread's 32 accumulator columns: (a_hi w_hi + a_lo w_hi) + (a_hi w_lo), the two halves of the 128-column accumulator
 __device__ __forceinline__ void tmem_ld32_sum(uint32_t taddr, uint32_t (&r)[32]) {
@@ -557,7 +561,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         for (int half = 0; half < 2; ++half) {
                             const int j = 2 * ki + half, s = j % 10;
                             mbar_wait(&sm.full[s], (uint32_t)(j / 10));
-                            if (j == 0) WS_TRACE(1);
+                            if (j == 0) WS_TRACE_MMA(1);
                             const uint32_t bd = ring_lo32 + s * (W_UNIT >> 4);
                             umma_bf16_ts(acc, wa, bd, idesc_t, j != 0);
                             umma_bf16_ts(acc, wa + 8, bd + 2, idesc_t, 1);
@@ -584,7 +588,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         const long long tw0 = p.trace ? clock64() : 0;
                         mbar_wait_wd(&sm.full[s], (u / NRING) & 1);
                         if (p.trace && ki > 0) wait_cyc += clock64() - tw0;
-                        if (ki == 0) WS_TRACE(1);
+                        if (ki == 0) WS_TRACE_MMA(1);
                         if (p.variant & 16) tc_fence_after();
                         const uint32_t ad = ring_lo32 + s * (W_UNIT >> 4);
                         umma_bf16_lo(acc, ad, wd, idesc_cat, ki != 0);
@@ -613,7 +617,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 }
                 }
                 umma_commit(&sm.acc_full[buf]);
-                WS_TRACE(2);
+                WS_TRACE_MMA(2);
                 if (p.trace && role == R_D && slice == 0 && mt == 0 && it < W_TRACE_ITS) p.trace[it * 32 + 31] = wait_cyc;
                 ++tile;
             }
@@ -907,9 +911,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 // clear them for the vocabulary phase of step it+1, which reuses the buffer
                 if (slice == 0 && cgp == 0) __stcg(p.amax + (size_t)((it + 1) & 1) * p.Mpad + row, 0ull);
                 float4 ad[8], cold4[2], pr[8];
+                WS_TRACE_EPI(1);
                 cold4[0] = __ldcg(reinterpret_cast<const float4 *>(cst));
                 cold4[1] = __ldcg(reinterpret_cast<const float4 *>(cst) + 1);
                 spin_ge(p.part_ready + mt * W_NG + slice, it + 1);  // per thread: acquire orders the partial-sum loads below
+                WS_TRACE_EPI(2);
                 {
                     const float4 *src = reinterpret_cast<const float4 *>(p.part + ((((size_t)mt * W_NG + slice) * 2 + cgp) * W_BM + r_in) * 32);
 #pragma unroll
@@ -924,6 +930,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 if (etid == 0) WS_TRACE(3);
                 tc_fence_after();
                 load_acc_add(taddr, buf, reinterpret_cast<float *>(pr));  // (accumulator + recurrent partial sums) ...
+                WS_TRACE_EPI(6);
                 if (c.active) {
                     float cold[8] = {cold4[0].x, cold4[0].y, cold4[0].z, cold4[0].w, cold4[1].x, cold4[1].y, cold4[1].z, cold4[1].w};
                     float hnew[8];
