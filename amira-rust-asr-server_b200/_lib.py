@@ -30,7 +30,11 @@ EXPORTS = ["amira_device_count", "amira_config_default", "amira_ctx_create", "am
            "amira_pipeline_process_stream_samples", "amira_pipeline_last_error", "amira_vocab_decode",
            "amira_shard_utterances", "amira_batcher_create", "amira_batcher_destroy", "amira_batcher_process_batch",
            "amira_batcher_stats", "amira_ctx_max_total_tokens", "amira_preprocess_pcm16_packed",
-           "amira_greedy_decode_packed"]
+           "amira_greedy_decode_packed", "amira_preprocess_f32_packed", "amira_weave_transcript_segs", "amira_best_alignment",
+           "amira_is_overlap_silence", "amira_mean_amplitude", "amira_window_sequence", "amira_stream_group_create",
+           "amira_stream_group_destroy", "amira_stream_group_last_error", "amira_stream_group_clear",
+           "amira_stream_group_process_chunks", "amira_stream_group_transcript", "amira_stream_group_tokens",
+           "amira_stream_group_audio_length", "amira_stream_group_process_batch", "amira_stream_group_stats"]
 
 
 class AmiraError(RuntimeError):
@@ -85,6 +89,23 @@ def load_library():
     L.amira_preprocess_f32.argtypes = [vp, vp, i64, vp, i32, vp, i64, vp]
     L.amira_preprocess_pcm16_packed.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     L.amira_greedy_decode_packed.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.amira_preprocess_f32_packed.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    L.amira_weave_transcript_segs.argtypes = [C.c_char_p, C.c_char_p, C.c_float, C.c_float, vp, C.c_size_t, C.POINTER(i32)]
+    L.amira_best_alignment.argtypes = [C.c_char_p, C.c_char_p, C.c_float, C.POINTER(i32), C.POINTER(C.c_float)]
+    L.amira_is_overlap_silence.argtypes = [vp, C.c_size_t, C.c_float, C.POINTER(i32)]
+    L.amira_mean_amplitude.argtypes = [vp, C.c_size_t, C.POINTER(C.c_float)]
+    L.amira_window_sequence.argtypes = [i64, i64, i64, i64, vp, vp, i32, C.POINTER(i32)]
+    L.amira_stream_group_create.argtypes = [vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(vp)]
+    L.amira_stream_group_destroy.argtypes = [vp]
+    L.amira_stream_group_last_error.argtypes = [vp]
+    L.amira_stream_group_last_error.restype = C.c_char_p
+    L.amira_stream_group_clear.argtypes = [vp, i32]
+    L.amira_stream_group_process_chunks.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.amira_stream_group_transcript.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(i32)]
+    L.amira_stream_group_tokens.argtypes = [vp, i32, vp, i32, C.POINTER(i32)]
+    L.amira_stream_group_audio_length.argtypes = [vp, i32, C.POINTER(C.c_float)]
+    L.amira_stream_group_process_batch.argtypes = [vp, i32, vp, C.c_size_t, vp, vp, i32, vp, C.c_size_t]
+    L.amira_stream_group_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.amira_bytes_to_f32.argtypes = [vp, vp, C.c_size_t, i32, vp, C.POINTER(C.c_size_t)]
     L.amira_decoder_joint.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.amira_greedy_decode.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
@@ -95,7 +116,7 @@ def load_library():
     L.amira_stream_decode.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)  # AttributeError here = header/.so drift
-        if name not in ("amira_last_error", "amira_pipeline_last_error"):
+        if name not in ("amira_last_error", "amira_pipeline_last_error", "amira_stream_group_last_error"):
             fn.restype = i32
     _lib = L
     return L

@@ -474,6 +474,21 @@ int32_t amira_preprocess_f32(amira_ctx *c, const float *waveforms, int64_t n_str
     API_END(c)
 }
 
+int32_t amira_preprocess_f32_packed(amira_ctx *c, const float *waveforms, const int64_t *wave_offsets, int32_t B, float *features,
+                                    const int64_t *feat_offsets, int64_t *features_lens) {
+    API_BEGIN(c)
+    if (B < 0 || !wave_offsets || !features || !feat_offsets || (B > 0 && !waveforms && wave_offsets[B] > 0))
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_preprocess_f32_packed: bad arguments");
+    if (B == 0) return AMIRA_OK;
+    std::vector<int64_t> lens((size_t)B);
+    for (int b = 0; b < B; ++b) {
+        lens[b] = wave_offsets[b + 1] - wave_offsets[b];
+        if (lens[b] < 0 || wave_offsets[b] < 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "wave_offsets must be non-decreasing");
+    }
+    return preprocess_common(c, waveforms, false, wave_offsets, lens.data(), wave_offsets[B], B, features, 0, features_lens, feat_offsets);
+    API_END(c)
+}
+
 int32_t amira_bytes_to_f32(amira_ctx *c, const uint8_t *bytes, size_t n_bytes, int32_t drop_odd, float *out,
                            size_t *n_out) {
     API_BEGIN(c)

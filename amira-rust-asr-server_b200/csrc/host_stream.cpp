@@ -1,0 +1,647 @@
+// host_stream.cpp — the streaming orchestrator above the pipeline: C++ mirror of the reference's
+// IncrementalAsr (src/asr/incremental.rs:35-298), OverlappingAudioBuffer / window_sequence (src/asr/audio.rs:72-293),
+// transcript weaving (src/asr/weaving.rs:16-280) and overlap-silence detection (src/asr/weaving.rs:285-313).
+//
+// The reference runs one IncrementalAsr per WebSocket and one Triton round trip per window per decode step.  Here a
+// *stream group* holds many sessions and `amira_stream_group_process_chunks` advances all of them by one chunk: window k of
+// every session goes through ONE batched front-end launch, the injected encoder, and ONE persistent decode launch (each
+// session's LSTM state carried from its window k-1), then each session weaves its transcript on the host.  Sessions are
+// independent, so the result per session equals the reference's one-at-a-time processing.
+//
+// Rust semantics kept literally: str::len() is bytes while chars() are Unicode scalars; all float arithmetic is f32;
+// usize arithmetic wraps as in a release build (window_sequence's short-last-window branch, audio.rs:112-115).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "host_common.h"
+
+namespace {
+
+using u32s = std::u32string;
+
+// ---- UTF-8 <-> scalar values (Rust strings are valid UTF-8; malformed bytes decode as one char each) ----
+u32s decode_utf8(const char *s) {
+    u32s out;
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(s ? s : "");
+    while (*p) {
+        uint32_t c = *p;
+        int extra = c >= 0xF0 ? 3 : c >= 0xE0 ? 2 : c >= 0xC0 ? 1 : 0;
+        bool ok = c < 0x80 || (c >= 0xC2 && c <= 0xF4);
+        for (int k = 1; k <= extra && ok; ++k) ok = (p[k] & 0xC0) == 0x80;
+        if (!ok || extra == 0) { out.push_back(c); ++p; continue; }
+        uint32_t v = c & (0x3F >> extra);
+        for (int k = 1; k <= extra; ++k) v = (v << 6) | (p[k] & 0x3F);
+        out.push_back(v);
+        p += extra + 1;
+    }
+    return out;
+}
+size_t cp_bytes(char32_t c) { return c < 0x80 ? 1 : c < 0x800 ? 2 : c < 0x10000 ? 3 : 4; }
+size_t blen(const char32_t *s, size_t n) {  // str::len(): bytes
+    size_t b = 0;
+    for (size_t i = 0; i < n; ++i) b += cp_bytes(s[i]);
+    return b;
+}
+std::string encode_utf8(const u32s &s) {
+    std::string out;
+    for (char32_t c : s) {
+        if (c < 0x80) out += (char)c;
+        else if (c < 0x800) { out += (char)(0xC0 | (c >> 6)); out += (char)(0x80 | (c & 0x3F)); }
+        else if (c < 0x10000) { out += (char)(0xE0 | (c >> 12)); out += (char)(0x80 | ((c >> 6) & 0x3F)); out += (char)(0x80 | (c & 0x3F)); }
+        else { out += (char)(0xF0 | (c >> 18)); out += (char)(0x80 | ((c >> 12) & 0x3F)); out += (char)(0x80 | ((c >> 6) & 0x3F)); out += (char)(0x80 | (c & 0x3F)); }
+    }
+    return out;
+}
+struct View {  // a &str: chars [p, p + n)
+    const char32_t *p;
+    size_t n;
+    size_t bytes() const { return blen(p, n); }
+    bool eq(const View &o) const { return n == o.n && std::equal(p, p + n, o.p); }
+};
+size_t f32_as_usize(float x) {  // Rust `as usize`: truncating, saturating, NaN -> 0
+    if (!(x > 0.0f)) return 0;
+    if (x >= 18446744073709551616.0f) return SIZE_MAX;
+    return (size_t)x;
+}
+
+// ---- weaving.rs ----
+constexpr float kExpectedSilenceRatio = 2.0f, kMaxAlignDist = 0.6f, kAlpha = 0.1f;  // src/asr/types.rs:16-20
+
+size_t levenshtein_distance(View a, View b) {  // weaving.rs:16-65 (empty-string shortcuts return BYTE lengths)
+    if (a.eq(b)) return 0;
+    if (a.n == 0) return b.bytes();
+    if (b.n == 0) return a.bytes();
+    std::vector<size_t> prev(b.n + 1), cur(b.n + 1);
+    for (size_t j = 0; j <= b.n; ++j) prev[j] = j;
+    for (size_t i = 1; i <= a.n; ++i) {
+        cur[0] = i;
+        for (size_t j = 1; j <= b.n; ++j) {
+            const size_t cost = a.p[i - 1] == b.p[j - 1] ? 0 : 1;
+            cur[j] = std::min(prev[j] + 1, std::min(cur[j - 1] + 1, prev[j - 1] + cost));
+        }
+        std::swap(prev, cur);
+    }
+    return prev[b.n];
+}
+float word_distance(View a, View b) {  // weaving.rs:71-86
+    if (a.eq(b)) return 0.0f;
+    const size_t al = a.bytes(), bl = b.bytes();
+    if (al == 0 && bl == 0) return 0.0f;
+    const float d = (float)levenshtein_distance(a, b);
+    return 2.0f * d / (float)(al + bl);
+}
+float overlap_prior(View first, View second, size_t overlap, float percent_time) {  // weaving.rs:92-104
+    const float mu = ((float)first.bytes() * 3.0f + (float)second.bytes() * 2.0f) * percent_time / 5.0f;
+    const float sigma = mu / 2.0f;
+    const float diff = ((float)overlap - mu) / sigma;
+    const float exponent = -0.5f * diff * diff;
+    const float normalization = sigma * std::sqrt(2.0f * 3.14159265358979323846f);
+    return std::exp(exponent) / normalization;
+}
+float dist_score(float dist) { return 1.0f / (dist + kAlpha) - 1.0f / (1.0f + kAlpha); }  // weaving.rs:109-111
+// `first.char_indices().nth_back(count.saturating_sub(overlap))` -> &first[idx..] (weaving.rs:122-128, 154-160)
+View first_end(View first, size_t overlap) {
+    const size_t n = first.n, k = n > overlap ? n - overlap : 0;
+    if (k >= n) return first;
+    const size_t i = n - 1 - k;
+    return {first.p + i, n - i};
+}
+// `second.char_indices().nth(overlap.saturating_sub(1))` -> &second[..idx]; out of range -> whole string
+View second_start(View second, size_t overlap) {
+    const size_t k = overlap > 0 ? overlap - 1 : 0;
+    return k < second.n ? View{second.p, k} : second;
+}
+float align_score(View first, View second, size_t overlap, float percent_time) {  // weaving.rs:117-142
+    if (first.bytes() < overlap || second.bytes() < overlap) return 0.0f;
+    const float dist = word_distance(first_end(first, overlap), second_start(second, overlap));
+    if (dist > kMaxAlignDist) return 0.0f;
+    return overlap_prior(first, second, overlap, percent_time) * dist_score(dist);
+}
+float trim_align_score(View first, View second, size_t overlap) {  // weaving.rs:148-174
+    if (first.n == 0 || second.n == 0 || overlap == 0) return 0.0f;
+    const float dist = word_distance(first_end(first, overlap), second_start(second, overlap));
+    if (dist > kMaxAlignDist) return 0.0f;
+    return (1.0f - dist) * std::sqrt((float)overlap);
+}
+void best_alignment(View first, View second, float percent_time, size_t *best_overlap, float *best_score) {  // weaving.rs:180-203
+    *best_overlap = 0;
+    *best_score = 0.0f;
+    if (first.n == 0 || second.n == 0) return;
+    const size_t max_overlap = std::min(first.n, f32_as_usize((float)second.n * 1.25f));
+    for (size_t overlap = 1; overlap <= max_overlap; ++overlap) {
+        const float score = align_score(first, second, overlap, percent_time);
+        if (score > *best_score) { *best_score = score; *best_overlap = overlap; }
+    }
+}
+u32s weave_transcript_segs(const u32s &a, const u32s &b, float percent_time_overlap, float min_alignment_score) {  // weaving.rs:209-280
+    const View first{a.data(), a.size()}, second{b.data(), b.size()};
+    size_t overlap;
+    float a_score;
+    best_alignment(first, second, percent_time_overlap, &overlap, &a_score);
+    if (overlap == 0 || a_score < min_alignment_score) return a + U" " + b;
+    float best_score = 0.0f;
+    size_t trim0 = 0, trim1 = 0;
+    const size_t n1 = a.size(), n2 = b.size();
+    for (size_t idx = 0; idx <= overlap; ++idx) {
+        size_t left_start = idx >= overlap ? 0 : (n1 > overlap - idx ? n1 - (overlap - idx) : 0);
+        if (left_start >= n1) left_start = 0;  // nth() == None -> byte index 0
+        const View left{first.p + left_start, n1 - left_start};
+        for (size_t idx2 = 0; idx2 <= overlap; ++idx2) {
+            const View right{second.p, std::min(overlap, n2)};
+            const size_t adjusted = overlap * 2 > idx + idx2 ? overlap * 2 - (idx + idx2) : 0;
+            const float score = trim_align_score(left, right, adjusted);
+            if (score > best_score) { best_score = score; trim0 = idx; trim1 = idx2; }
+        }
+    }
+    size_t first_keep;
+    if (trim0 >= overlap) first_keep = n1;
+    else first_keep = std::min(n1 > overlap - trim0 ? n1 - (overlap - trim0) : 0, n1);
+    const size_t second_trim = trim1 < n2 ? trim1 : 0;
+    return a.substr(0, first_keep) + b.substr(second_trim);
+}
+bool is_overlap_silence(const float *audio, size_t n, float mean_amplitude) {  // weaving.rs:285-313
+    if (n == 0) return true;
+    const size_t w = std::min<size_t>(800, n);
+    float max_energy = 0.0f;
+    for (size_t i = 0; i + w <= n; ++i) {
+        float sum = 0.0f;  // per-window sums in index order, as `iter().sum()` adds them
+        for (size_t k = 0; k < w; ++k) sum += audio[i + k] * audio[i + k];
+        const float avg = sum / (float)w;
+        if (avg > max_energy) max_energy = avg;  // f32::max ignores NaN
+    }
+    return std::sqrt(max_energy) < mean_amplitude / kExpectedSilenceRatio;
+}
+
+// ---- audio.rs ----
+float mean_amplitude_of(const float *s, size_t n) {  // performance_opts.rs:35-60: one accumulator, index order
+    if (n == 0) return 0.0f;
+    float sum = 0.0f;
+    for (size_t i = 0; i < n; ++i) sum += std::fabs(s[i]);
+    return sum / (float)n;
+}
+struct Window { size_t src_start, src_end, tgt_start, tgt_end; float overlap; };
+std::vector<Window> window_sequence(size_t total_len, size_t window_size, size_t leading, size_t trailing) {  // audio.rs:98-132
+    std::vector<Window> out;
+    size_t consumed = 0;
+    while (consumed < total_len) {
+        const size_t start = consumed, end = std::min(total_len, consumed + window_size);
+        const size_t offset = std::min(leading, consumed);
+        size_t overlap = trailing + leading;
+        if (end < total_len) {
+            consumed = end - leading - trailing;
+        } else {
+            consumed = end;
+            if (end - start < window_size) {
+                const size_t new_start = end - window_size;  // std::cmp::max(0, ..) on usize: wraps when end < window_size,
+                overlap += start - new_start;                // and wraps back here (release-build arithmetic)
+            }
+        }
+        out.push_back({start, end, start + offset, end, (float)overlap / (float)window_size});
+        if (out.size() > (1u << 20)) break;  // degenerate parameters (window <= contexts) would never advance
+    }
+    return out;
+}
+struct OverlappingAudioBuffer {  // audio.rs:134-293
+    std::vector<float> buffer;
+    size_t length = 0, capacity = 0, leading = 0, trailing = 0, chunk = 0;
+    float mean_amplitude = 0.0f;
+    void init(size_t cap, float chunk_size, float leading_context, float trailing_context) {
+        buffer.assign(cap, 0.0f);
+        capacity = cap;
+        chunk = f32_as_usize(chunk_size * 16000.0f);
+        leading = f32_as_usize(leading_context * 16000.0f);
+        trailing = f32_as_usize(trailing_context * 16000.0f);
+    }
+    void add_samples(const float *s, size_t n) {
+        if (length + n > capacity) {
+            const size_t keep = std::min(leading, length), start = length - keep;
+            if (keep > 0) std::memmove(buffer.data(), buffer.data() + start, sizeof(float) * keep);
+            length = keep;
+        }
+        const size_t s0 = length, e0 = s0 + n;
+        if (e0 <= capacity) {
+            if (n) std::memcpy(buffer.data() + s0, s, sizeof(float) * n);
+            length = e0;
+            const float amp = mean_amplitude_of(s, n);
+            mean_amplitude = mean_amplitude == 0.0f ? amp : 0.7f * mean_amplitude + 0.3f * amp;
+        } else {  // truncation; the mean amplitude is not updated (audio.rs:236-241)
+            const size_t avail = capacity - s0;
+            if (avail) std::memcpy(buffer.data() + s0, s, sizeof(float) * avail);
+            length = capacity;
+        }
+    }
+    std::vector<Window> overlapping_windows() const { return window_sequence(length, chunk + leading + trailing, leading, trailing); }
+    void clear() { length = 0; mean_amplitude = 0.0f; }
+};
+
+size_t sample_index_to_logit_index(size_t idx) { return f32_as_usize(((float)idx * 299.0f) / 96000.0f); }  // incremental.rs:27-29
+constexpr float kMinAlignmentScore = 0.01f;  // incremental.rs:19
+
+// ---- one IncrementalAsr (incremental.rs:35-61) ----
+struct Session {
+    OverlappingAudioBuffer audio;
+    std::vector<int32_t> token_ids;   // AccumulatedPredictions (types.rs:185-212)
+    u32s transcript;
+    float acc_mean_amplitude = 0.0f;
+    std::vector<float> s1, s2;        // DecoderState [2][1][640] (types.rs:159-183)
+    float chunk_size = 2.0f;
+    void reset_state() { s1.assign(2 * AMIRA_STATE_SIZE, 0.0f); s2.assign(2 * AMIRA_STATE_SIZE, 0.0f); }
+    void clear() {  // incremental.rs:99-103
+        audio.clear();
+        token_ids.clear();
+        transcript.clear();
+        acc_mean_amplitude = 0.0f;
+        reset_state();
+    }
+};
+
+struct Job {  // one process_stream_samples call of one session
+    Session *s;
+    size_t src_start, src_end, tgt_start, tgt_end;
+    float overlap;
+    bool first;  // the "no tokens yet" branch (incremental.rs:139-150): whole window, result replaces the accumulated state
+    std::vector<int32_t> tokens;
+    std::string text;
+    int64_t flen = 0, elen = 0;
+    int32_t rc = AMIRA_OK;
+};
+
+}  // namespace
+
+struct amira_stream_group {
+    amira_pipeline *p = nullptr;
+    std::vector<std::unique_ptr<Session>> sessions;
+    std::mutex mu;
+    std::string err;
+    int64_t n_pipeline_calls = 0, n_rounds = 0;
+    // batch scratch
+    std::vector<float> wave, features, enc, s1, s2;
+    std::vector<int64_t> woff, foff, eoff, flens, elens;
+    std::vector<int32_t> tokens, ntok;
+};
+
+namespace {
+
+int32_t gfail(amira_stream_group *g, int32_t code, const std::string &m) {
+    if (g) g->err = m;
+    return code;
+}
+
+// One round: job k of every session that has one — process_stream_samples (src/asr/pipeline.rs:416-443 -> :269-380) for all
+// of them at once.  Per-job failures land in job.rc; a failure of a batched call fails every job of the round.
+void run_round(amira_stream_group *g, std::vector<Job *> &jobs) {
+    amira_pipeline *p = g->p;
+    std::lock_guard<std::mutex> plock(p->mu);
+    const int B = (int)jobs.size();
+    auto fail_all = [&](int32_t rc) { for (Job *j : jobs) j->rc = rc; g->err = amira_last_error(p->ctx); };
+    g->n_rounds++;
+    g->n_pipeline_calls += B;
+    // preprocessor, ragged in and out
+    g->woff.assign((size_t)B + 1, 0);
+    g->foff.assign((size_t)B + 1, 0);
+    for (int i = 0; i < B; ++i) {
+        const int64_t n = (int64_t)(jobs[(size_t)i]->src_end - jobs[(size_t)i]->src_start);
+        int64_t fl = 0;
+        amira_features_len(n, &fl);
+        g->woff[(size_t)i + 1] = g->woff[(size_t)i] + n;
+        g->foff[(size_t)i + 1] = g->foff[(size_t)i] + (int64_t)AMIRA_N_MELS * fl;
+    }
+    g->wave.resize((size_t)std::max<int64_t>(g->woff[(size_t)B], 1));
+    for (int i = 0; i < B; ++i) {
+        const Job *j = jobs[(size_t)i];
+        std::memcpy(g->wave.data() + g->woff[(size_t)i], j->s->audio.buffer.data() + j->src_start, sizeof(float) * (j->src_end - j->src_start));
+    }
+    g->features.resize((size_t)std::max<int64_t>(g->foff[(size_t)B], 1));
+    g->flens.assign((size_t)B, 0);
+    int32_t rc = amira_preprocess_f32_packed(p->ctx, g->wave.data(), g->woff.data(), B, g->features.data(), g->foff.data(), g->flens.data());
+    if (rc) return fail_all(rc);
+    // encoder (out of scope, injected): per request [1][128][features_len] -> [1][1024][encoded_len]
+    g->eoff.assign((size_t)B + 1, 0);
+    g->elens.assign((size_t)B, 0);
+    g->enc.clear();
+    for (int i = 0; i < B; ++i) {
+        Job *j = jobs[(size_t)i];
+        j->flen = g->flens[(size_t)i];
+        const float *e = nullptr;
+        int64_t el = 0;
+        if (!p->encoder || p->encoder(p->encoder_user, g->features.data() + g->foff[(size_t)i], j->flen, &e, &el) != 0 || el < 0 || (el > 0 && !e)) {
+            j->rc = p->encoder ? AMIRA_ERR_UNKNOWN : AMIRA_ERR_NOT_READY;
+            el = 0;
+        }
+        if (el > 0) g->enc.insert(g->enc.end(), e, e + (size_t)AMIRA_ENC_DIM * (size_t)el);  // the callback's buffer lives until its next call
+        g->elens[(size_t)i] = el;
+        j->elen = el;
+        g->eoff[(size_t)i + 1] = g->eoff[(size_t)i] + (int64_t)AMIRA_ENC_DIM * el;
+    }
+    // greedy decode with each session's carried state ([2][B][640] in and out)
+    int32_t cap = AMIRA_MAX_TOTAL_TOKENS;
+    amira_ctx_max_total_tokens(p->ctx, &cap);
+    const size_t H = AMIRA_STATE_SIZE;
+    g->s1.resize(2 * (size_t)B * H);
+    g->s2.resize(2 * (size_t)B * H);
+    for (int i = 0; i < B; ++i)
+        for (int l = 0; l < 2; ++l) {
+            std::memcpy(g->s1.data() + ((size_t)l * B + i) * H, jobs[(size_t)i]->s->s1.data() + (size_t)l * H, sizeof(float) * H);
+            std::memcpy(g->s2.data() + ((size_t)l * B + i) * H, jobs[(size_t)i]->s->s2.data() + (size_t)l * H, sizeof(float) * H);
+        }
+    g->tokens.assign((size_t)B * (size_t)cap, 0);
+    g->ntok.assign((size_t)B, 0);
+    if (g->eoff[(size_t)B] > 0) {
+        rc = amira_greedy_decode_packed(p->ctx, g->enc.data(), g->eoff.data(), B, g->elens.data(), g->s1.data(), g->s2.data(),
+                                        g->tokens.data(), g->ntok.data(), nullptr);
+        if (rc && rc != AMIRA_ERR_DECODE_STEP) return fail_all(rc);
+    }
+    for (int i = 0; i < B; ++i) {
+        Job *j = jobs[(size_t)i];
+        if (j->rc) continue;
+        if (g->ntok[(size_t)i] < 0) { j->rc = AMIRA_ERR_DECODE_STEP; continue; }  // "Decode step failed" (decoder_optimized.rs:148-152)
+        if (j->elen > 0)  // a request without encoder frames never reaches the decoder: its state is untouched
+            for (int l = 0; l < 2; ++l) {
+                std::memcpy(j->s->s1.data() + (size_t)l * H, g->s1.data() + ((size_t)l * B + i) * H, sizeof(float) * H);
+                std::memcpy(j->s->s2.data() + (size_t)l * H, g->s2.data() + ((size_t)l * B + i) * H, sizeof(float) * H);
+            }
+        const int32_t *tk = g->tokens.data() + (size_t)i * (size_t)cap;
+        j->tokens.assign(tk, tk + g->ntok[(size_t)i]);
+        j->text = p->vocab.decode(tk, g->ntok[(size_t)i]);
+    }
+}
+
+// IncrementalAsr::accumulate_transcription (incremental.rs:181-258)
+void accumulate(Session &s, const Job &j) {
+    const u32s segment = decode_utf8(j.text.c_str());
+    if (s.transcript.empty()) {
+        s.transcript = segment;
+        s.token_ids = j.tokens;
+        return;
+    }
+    const size_t chunk = f32_as_usize(j.overlap * s.chunk_size * 16000.0f);
+    bool silence = false;
+    if (chunk > 0) {
+        const size_t len = s.audio.length, start = len > chunk ? len - chunk : 0;
+        silence = is_overlap_silence(s.audio.buffer.data() + start, len - start, s.acc_mean_amplitude);
+    }
+    if (silence) {
+        s.transcript += U' ';
+        s.transcript += segment;
+    } else {
+        s.transcript = weave_transcript_segs(s.transcript, segment, j.overlap, kMinAlignmentScore);
+    }
+    const size_t ls = sample_index_to_logit_index(j.tgt_start), le = sample_index_to_logit_index(j.tgt_end);
+    if (s.token_ids.size() < le) s.token_ids.resize(le, 0);
+    const size_t n_copy = std::min(j.tokens.size(), le - ls);
+    if (n_copy > 0 && ls < s.token_ids.size()) {
+        const size_t end = std::min(ls + n_copy, s.token_ids.size());
+        std::copy(j.tokens.begin(), j.tokens.begin() + (end - ls), s.token_ids.begin() + ls);
+    }
+}
+
+// process_buffered_audio (incremental.rs:135-170) of several sessions, advanced in lock step: round k = window k of each
+int32_t process_buffered(amira_stream_group *g, const std::vector<Session *> &active, std::vector<int32_t> &rcs) {
+    std::vector<std::vector<Job>> jobs(active.size());
+    size_t rounds = 0;
+    for (size_t i = 0; i < active.size(); ++i) {
+        Session &s = *active[i];
+        if (s.token_ids.empty()) {
+            Job j{};
+            j.s = &s; j.src_start = 0; j.src_end = s.audio.length; j.tgt_start = 0; j.tgt_end = s.audio.length; j.overlap = 0.f; j.first = true;
+            jobs[i].push_back(std::move(j));
+        } else {
+            for (const Window &w : s.audio.overlapping_windows()) {
+                Job j{};
+                j.s = &s; j.src_start = w.src_start; j.src_end = std::min(w.src_end, s.audio.length);
+                j.tgt_start = w.tgt_start; j.tgt_end = w.tgt_end; j.overlap = w.overlap; j.first = false;
+                jobs[i].push_back(std::move(j));
+            }
+        }
+        rounds = std::max(rounds, jobs[i].size());
+    }
+    for (size_t k = 0; k < rounds; ++k) {
+        std::vector<Job *> round;
+        std::vector<size_t> owner;
+        for (size_t i = 0; i < active.size(); ++i)
+            if (k < jobs[i].size() && rcs[i] == AMIRA_OK) { round.push_back(&jobs[i][k]); owner.push_back(i); }  // `?`: a failed session stops
+        if (round.empty()) continue;
+        run_round(g, round);
+        for (size_t r = 0; r < round.size(); ++r) {
+            Job &j = *round[r];
+            Session &s = *j.s;
+            if (j.rc) { rcs[owner[r]] = j.rc; continue; }
+            if (j.first) { s.token_ids = j.tokens; s.transcript = decode_utf8(j.text.c_str()); }
+            else accumulate(s, j);
+        }
+    }
+    return AMIRA_OK;
+}
+
+void copy_text(const std::string &s, char *text, size_t cap, int32_t *len) {
+    if (len) *len = (int32_t)s.size();
+    if (text && cap) {
+        const size_t m = std::min(s.size(), cap - 1);
+        std::memcpy(text, s.data(), m);
+        text[m] = '\0';
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t amira_weave_transcript_segs(const char *first_seg, const char *second_seg, float percent_time_overlap, float min_alignment_score,
+                                    char *out, size_t out_cap, int32_t *out_len) {
+    if (!first_seg || !second_seg) return AMIRA_ERR_INVALID_VALUE;
+    copy_text(encode_utf8(weave_transcript_segs(decode_utf8(first_seg), decode_utf8(second_seg), percent_time_overlap, min_alignment_score)),
+              out, out_cap, out_len);
+    return AMIRA_OK;
+}
+
+int32_t amira_best_alignment(const char *first, const char *second, float percent_time_overlap, int32_t *overlap, float *score) {
+    if (!first || !second || !overlap || !score) return AMIRA_ERR_INVALID_VALUE;
+    const u32s a = decode_utf8(first), b = decode_utf8(second);
+    size_t o;
+    best_alignment({a.data(), a.size()}, {b.data(), b.size()}, percent_time_overlap, &o, score);
+    *overlap = (int32_t)o;
+    return AMIRA_OK;
+}
+
+int32_t amira_is_overlap_silence(const float *overlap_audio, size_t n, float mean_amplitude, int32_t *silent) {
+    if (!silent || (n && !overlap_audio)) return AMIRA_ERR_INVALID_VALUE;
+    *silent = is_overlap_silence(overlap_audio, n, mean_amplitude) ? 1 : 0;
+    return AMIRA_OK;
+}
+
+int32_t amira_mean_amplitude(const float *samples, size_t n, float *mean) {
+    if (!mean || (n && !samples)) return AMIRA_ERR_INVALID_VALUE;
+    *mean = mean_amplitude_of(samples, n);
+    return AMIRA_OK;
+}
+
+int32_t amira_window_sequence(int64_t total_len, int64_t window_size, int64_t leading_context, int64_t trailing_context, int64_t *slices,
+                              float *overlap_ratio, int32_t cap, int32_t *n_windows) {
+    if (total_len < 0 || window_size <= 0 || leading_context < 0 || trailing_context < 0 || !n_windows ||
+        window_size <= leading_context + trailing_context)
+        return AMIRA_ERR_INVALID_VALUE;
+    const std::vector<Window> w = window_sequence((size_t)total_len, (size_t)window_size, (size_t)leading_context, (size_t)trailing_context);
+    *n_windows = (int32_t)w.size();
+    for (int32_t i = 0; i < *n_windows && i < cap; ++i) {
+        if (slices) {
+            slices[4 * i + 0] = (int64_t)w[(size_t)i].src_start; slices[4 * i + 1] = (int64_t)w[(size_t)i].src_end;
+            slices[4 * i + 2] = (int64_t)w[(size_t)i].tgt_start; slices[4 * i + 3] = (int64_t)w[(size_t)i].tgt_end;
+        }
+        if (overlap_ratio) overlap_ratio[i] = w[(size_t)i].overlap;
+    }
+    return AMIRA_OK;
+}
+
+int32_t amira_stream_group_create(amira_pipeline *p, int32_t n_streams, float chunk_size, float leading_context, float trailing_context,
+                                  float buffer_capacity, amira_stream_group **out) {
+    if (!p || !out || n_streams <= 0 || !(chunk_size > 0.f) || leading_context < 0.f || trailing_context < 0.f || !(buffer_capacity > 0.f) ||
+        f32_as_usize(chunk_size * 16000.0f) == 0)  // a zero-sample chunk would never advance window_sequence
+        return AMIRA_ERR_INVALID_VALUE;
+    auto *g = new (std::nothrow) amira_stream_group();
+    if (!g) return AMIRA_ERR_OUT_OF_MEMORY;
+    g->p = p;
+    try {
+        for (int32_t i = 0; i < n_streams; ++i) {
+            std::unique_ptr<Session> s(new Session());
+            s->audio.init(f32_as_usize(buffer_capacity * 16000.0f), chunk_size, leading_context, trailing_context);  // incremental.rs:80-90
+            s->chunk_size = chunk_size;
+            s->reset_state();
+            g->sessions.push_back(std::move(s));
+        }
+    } catch (const std::bad_alloc &) {
+        delete g;
+        return AMIRA_ERR_OUT_OF_MEMORY;
+    }
+    *out = g;
+    return AMIRA_OK;
+}
+
+int32_t amira_stream_group_destroy(amira_stream_group *g) {
+    delete g;
+    return AMIRA_OK;
+}
+
+const char *amira_stream_group_last_error(amira_stream_group *g) { return g ? g->err.c_str() : "null stream group"; }
+
+int32_t amira_stream_group_clear(amira_stream_group *g, int32_t stream) {
+    if (!g || stream < 0 || (size_t)stream >= g->sessions.size()) return AMIRA_ERR_INVALID_VALUE;
+    std::lock_guard<std::mutex> lock(g->mu);
+    g->sessions[(size_t)stream]->clear();
+    return AMIRA_OK;
+}
+
+// IncrementalAsr::process_chunk (incremental.rs:111-129) for n distinct streams at once
+int32_t amira_stream_group_process_chunks(amira_stream_group *g, int32_t n, const int32_t *streams, const uint8_t *const *audio_bytes,
+                                          const size_t *n_bytes, int32_t *status) {
+    if (!g) return AMIRA_ERR_INVALID_VALUE;
+    std::lock_guard<std::mutex> lock(g->mu);
+    if (n < 0 || (n > 0 && (!streams || !audio_bytes || !n_bytes))) return gfail(g, AMIRA_ERR_INVALID_VALUE, "process_chunks: bad arguments");
+    if (!g->p->ctx) return gfail(g, AMIRA_ERR_NO_DEVICE, "pipeline was created without a GPU context");
+    try {
+        std::vector<char> seen(g->sessions.size(), 0);
+        for (int32_t i = 0; i < n; ++i) {
+            if (streams[i] < 0 || (size_t)streams[i] >= g->sessions.size() || seen[(size_t)streams[i]])
+                return gfail(g, AMIRA_ERR_INVALID_VALUE, "process_chunks: stream id out of range or repeated");
+            seen[(size_t)streams[i]] = 1;
+            if (n_bytes[i] && !audio_bytes[i]) return gfail(g, AMIRA_ERR_INVALID_VALUE, "process_chunks: null audio");
+        }
+        std::vector<Session *> active;
+        std::vector<int32_t> idx;
+        std::vector<float> samples;
+        for (int32_t i = 0; i < n; ++i) {
+            Session &s = *g->sessions[(size_t)streams[i]];
+            const size_t ns = n_bytes[i] / 2;  // bytes_to_f32_samples (audio.rs:18-26): an odd trailing byte is dropped
+            samples.resize(ns);
+            for (size_t k = 0; k < ns; ++k) {
+                const int16_t v = (int16_t)((uint16_t)audio_bytes[i][2 * k] | ((uint16_t)audio_bytes[i][2 * k + 1] << 8));
+                samples[k] = (float)v / 32768.0f;
+            }
+            s.audio.add_samples(samples.data(), ns);
+            s.acc_mean_amplitude = s.audio.mean_amplitude;
+            if (status) status[i] = AMIRA_OK;
+            if (s.audio.length != 0) { active.push_back(&s); idx.push_back(i); }
+        }
+        std::vector<int32_t> rcs(active.size(), AMIRA_OK);
+        process_buffered(g, active, rcs);
+        int32_t worst = AMIRA_OK;
+        for (size_t a = 0; a < active.size(); ++a) {
+            if (status) status[idx[a]] = rcs[a];
+            if (rcs[a] && !worst) worst = rcs[a];
+        }
+        return worst;
+    } catch (const std::bad_alloc &) {
+        return gfail(g, AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+}
+
+int32_t amira_stream_group_transcript(amira_stream_group *g, int32_t stream, char *text, size_t text_cap, int32_t *text_len) {
+    if (!g || stream < 0 || (size_t)stream >= g->sessions.size()) return AMIRA_ERR_INVALID_VALUE;
+    std::lock_guard<std::mutex> lock(g->mu);
+    copy_text(encode_utf8(g->sessions[(size_t)stream]->transcript), text, text_cap, text_len);
+    return AMIRA_OK;
+}
+
+int32_t amira_stream_group_tokens(amira_stream_group *g, int32_t stream, int32_t *tokens, int32_t tokens_cap, int32_t *n_tokens) {
+    if (!g || stream < 0 || (size_t)stream >= g->sessions.size() || !n_tokens) return AMIRA_ERR_INVALID_VALUE;
+    std::lock_guard<std::mutex> lock(g->mu);
+    const std::vector<int32_t> &t = g->sessions[(size_t)stream]->token_ids;
+    *n_tokens = (int32_t)t.size();
+    if (tokens && tokens_cap > 0) std::memcpy(tokens, t.data(), sizeof(int32_t) * std::min<size_t>(t.size(), (size_t)tokens_cap));
+    return AMIRA_OK;
+}
+
+int32_t amira_stream_group_audio_length(amira_stream_group *g, int32_t stream, float *seconds) {  // incremental.rs:295-297
+    if (!g || stream < 0 || (size_t)stream >= g->sessions.size() || !seconds) return AMIRA_ERR_INVALID_VALUE;
+    std::lock_guard<std::mutex> lock(g->mu);
+    *seconds = (float)g->sessions[(size_t)stream]->audio.length / 16000.0f;
+    return AMIRA_OK;
+}
+
+// IncrementalAsr::process_batch (incremental.rs:267-292)
+int32_t amira_stream_group_process_batch(amira_stream_group *g, int32_t stream, const uint8_t *audio_bytes, size_t n_bytes,
+                                         amira_transcription *out, int32_t *tokens, int32_t tokens_cap, char *text, size_t text_cap) {
+    if (!g || stream < 0 || (size_t)stream >= g->sessions.size() || !out || (n_bytes && !audio_bytes)) return AMIRA_ERR_INVALID_VALUE;
+    std::lock_guard<std::mutex> lock(g->mu);
+    Session &s = *g->sessions[(size_t)stream];
+    s.clear();
+    const size_t ns = n_bytes / 2;
+    if ((float)ns / 16000.0f <= s.chunk_size) {
+        const int32_t rc = amira_pipeline_process_batch(g->p, audio_bytes, n_bytes, out, tokens, tokens_cap, text, text_cap);
+        if (rc) g->err = amira_pipeline_last_error(g->p);
+        return rc;
+    }
+    try {
+        std::vector<float> samples(ns);
+        for (size_t k = 0; k < ns; ++k) {
+            const int16_t v = (int16_t)((uint16_t)audio_bytes[2 * k] | ((uint16_t)audio_bytes[2 * k + 1] << 8));
+            samples[k] = (float)v / 32768.0f;
+        }
+        s.audio.add_samples(samples.data(), ns);
+        std::vector<Session *> active{&s};
+        std::vector<int32_t> rcs(1, AMIRA_OK);
+        process_buffered(g, active, rcs);
+        if (rcs[0]) return rcs[0];
+        std::memset(out, 0, sizeof(*out));
+        out->audio_length_samples = (int64_t)ns;  // features_length / encoded_length stay 0 (incremental.rs:288-289)
+        out->n_tokens = (int32_t)s.token_ids.size();
+        if (tokens && tokens_cap > 0) std::memcpy(tokens, s.token_ids.data(), sizeof(int32_t) * std::min<size_t>(s.token_ids.size(), (size_t)tokens_cap));
+        copy_text(encode_utf8(s.transcript), text, text_cap, &out->text_len);
+        return AMIRA_OK;
+    } catch (const std::bad_alloc &) {
+        return gfail(g, AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+}
+
+int32_t amira_stream_group_stats(amira_stream_group *g, int64_t *n_pipeline_calls, int64_t *n_rounds) {
+    if (!g) return AMIRA_ERR_INVALID_VALUE;
+    std::lock_guard<std::mutex> lock(g->mu);
+    if (n_pipeline_calls) *n_pipeline_calls = g->n_pipeline_calls;
+    if (n_rounds) *n_rounds = g->n_rounds;
+    return AMIRA_OK;
+}
+
+}  // extern "C"

@@ -126,6 +126,10 @@ int32_t amira_preprocess_pcm16_packed(amira_ctx *ctx, const int16_t *pcm, const 
  * device), waveforms_lens [B] int64 (host) -> features [B][128][t_stride], features_lens [B] (host). */
 int32_t amira_preprocess_f32(amira_ctx *ctx, const float *waveforms, int64_t n_stride, const int64_t *waveforms_lens,
                              int32_t B, float *features, int64_t t_stride, int64_t *features_lens);
+/* Ragged form of the float entry: utterance b = waveforms[wave_offsets[b]..wave_offsets[b+1]) (the f32 windows of the
+ * streaming path, src/asr/incremental.rs:139-160), features as in amira_preprocess_pcm16_packed. */
+int32_t amira_preprocess_f32_packed(amira_ctx *ctx, const float *waveforms, const int64_t *wave_offsets, int32_t B,
+                                    float *features, const int64_t *feat_offsets, int64_t *features_lens);
 /* replaces performance_opts::audio::bytes_to_f32_optimized (src/performance_opts.rs:14-31), including the
  * odd-trailing-byte rule; drop_odd != 0 gives bytes_to_f32_samples (src/asr/audio.rs:18-26) /
  * simd::bytes_to_f32_optimized (src/asr/simd.rs:222-248).  bytes, out: host or device. */
@@ -217,6 +221,41 @@ int32_t amira_batcher_destroy(amira_batcher *b);
 int32_t amira_batcher_process_batch(amira_batcher *b, const uint8_t *audio_bytes, size_t n_bytes, amira_transcription *out,
                                     int32_t *tokens, int32_t tokens_cap, char *text, size_t text_cap);
 int32_t amira_batcher_stats(amira_batcher *b, int64_t *n_requests, int64_t *n_batches);
+/* ---- streaming orchestrator: the caller of the WebSocket path ----
+ * Pure host functions, literal restatements (Rust byte/char and f32 semantics kept):
+ * weave_transcript_segs / best_alignment (src/asr/weaving.rs:180-280), is_overlap_silence (src/asr/weaving.rs:285-313),
+ * mean_amplitude_optimized (src/performance_opts.rs:35-60), window_sequence (src/asr/audio.rs:72-132; slices[i] =
+ * {source start, source end, target start, target end}; window_size must exceed leading + trailing). */
+int32_t amira_weave_transcript_segs(const char *first_seg, const char *second_seg, float percent_time_overlap,
+                                    float min_alignment_score, char *out, size_t out_cap, int32_t *out_len);
+int32_t amira_best_alignment(const char *first, const char *second, float percent_time_overlap, int32_t *overlap, float *score);
+int32_t amira_is_overlap_silence(const float *overlap_audio, size_t n, float mean_amplitude, int32_t *silent);
+int32_t amira_mean_amplitude(const float *samples, size_t n, float *mean);
+int32_t amira_window_sequence(int64_t total_len, int64_t window_size, int64_t leading_context, int64_t trailing_context,
+                              int64_t *slices, float *overlap_ratio, int32_t cap, int32_t *n_windows);
+/* A stream group = n_streams IncrementalAsr objects (src/asr/incremental.rs:35-298; OverlappingAudioBuffer
+ * src/asr/audio.rs:134-293) over one pipeline.  The reference creates one per WebSocket with chunk 2.0 s, leading 1.0 s,
+ * trailing 0.5 s, capacity 10 s (src/server/stream.rs:106-119) and runs every window through its own Triton round
+ * trips; amira_stream_group_process_chunks is IncrementalAsr::process_chunk for n distinct streams at once: window k of
+ * every stream goes through one front-end launch, the injected encoder and one decode launch.  Per stream the result
+ * equals the one-at-a-time reference flow.  status[i] (nullable) receives each stream's own code; the return value is
+ * the first non-zero one. */
+typedef struct amira_stream_group amira_stream_group;
+int32_t amira_stream_group_create(amira_pipeline *p, int32_t n_streams, float chunk_size, float leading_context,
+                                  float trailing_context, float buffer_capacity, amira_stream_group **out);
+int32_t amira_stream_group_destroy(amira_stream_group *g);
+const char *amira_stream_group_last_error(amira_stream_group *g);
+int32_t amira_stream_group_clear(amira_stream_group *g, int32_t stream);                 /* IncrementalAsr::clear */
+int32_t amira_stream_group_process_chunks(amira_stream_group *g, int32_t n, const int32_t *streams,
+                                          const uint8_t *const *audio_bytes, const size_t *n_bytes, int32_t *status);
+int32_t amira_stream_group_transcript(amira_stream_group *g, int32_t stream, char *text, size_t text_cap, int32_t *text_len);
+int32_t amira_stream_group_tokens(amira_stream_group *g, int32_t stream, int32_t *tokens, int32_t tokens_cap, int32_t *n_tokens);
+int32_t amira_stream_group_audio_length(amira_stream_group *g, int32_t stream, float *seconds);
+/* IncrementalAsr::process_batch (src/asr/incremental.rs:267-292) on one stream of the group */
+int32_t amira_stream_group_process_batch(amira_stream_group *g, int32_t stream, const uint8_t *audio_bytes, size_t n_bytes,
+                                         amira_transcription *out, int32_t *tokens, int32_t tokens_cap, char *text,
+                                         size_t text_cap);
+int32_t amira_stream_group_stats(amira_stream_group *g, int64_t *n_pipeline_calls, int64_t *n_rounds);
 /* configured max_total_tokens of a context (row stride of the tokens output of the decode entries) */
 int32_t amira_ctx_max_total_tokens(amira_ctx *ctx, int32_t *value);
 
