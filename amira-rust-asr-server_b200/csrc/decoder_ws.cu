@@ -96,6 +96,7 @@ struct WsParams {
     int *tokens, *ntok, *nsteps;
     int max_sym, max_total, blank, relu;
     int norot;          // debug: all CTAs walk the k-chunks in the same order
+    int nrows;          // stream rows a unit loads and multiplies (TS form: 32 / 64 when a single M-tile holds that few streams, else 128)
     int variant;        // debug: AMIRA_WS_VARIANT bit mask of experimental code paths (A/B timing)
     int trace_role;     // debug: role whose slice-0 CTA is traced for every M-tile
     long long *trace;   // nullable: [W_TRACE_ITS][32] globaltimer stamps of M-tile 0 (debug)
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     for (int half = 0; half < 2; ++half) {
                         const uint32_t s = u % NRING;
                         mbar_wait_wd(&sm.empty[s], ((u / NRING) & 1) ^ 1);
-                        mbar_expect_tx(&sm.full[s], W_UNIT);
+                        mbar_expect_tx(&sm.full[s], TS ? (uint32_t)p.nrows * (BK * 2) : (uint32_t)W_UNIT);
                         if (CL == 1) tma_load_2d(ring + s * W_UNIT, half ? a_lo : a_hi, &sm.full[s], kc * BK, a_row + mt * W_BM);
                         else  // this CTA's 64 rows of the tile, delivered to both CTAs (each full barrier sees 2 x 8 KB)
                             tma_load_2d_mc(ring + s * W_UNIT + crank * (W_UNIT / 2), half ? a_lo : a_hi, &sm.full[s], kc * BK,
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     // or shared memory, the limit of a unit.  Hence: 20 slots per unit on a 10-slot ring, so slot index and barrier
                     // parity are compile-time constants of the fully unrolled loop; descriptors are one add; no watchdog here.
                     static_assert(!TS || NRING == 10, "slot / parity constants below assume two ring revolutions per unit");
-                    constexpr uint32_t idesc_t = make_idesc_bf16(W_BM, W_BM);
+                    const uint32_t idesc_t = make_idesc_bf16(W_BM, p.nrows);  // M = 128 weight rows (hi | lo), N = stream rows
 #pragma unroll
                     for (int ki = 0; ki < W_KC; ++ki) {
                         const uint32_t wa = tmem_base + kc * 32;
@@ -1143,7 +1144,11 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     p.h1b_hi = reinterpret_cast<__nv_bfloat16 *>(work + oh1h); p.h1b_lo = reinterpret_cast<__nv_bfloat16 *>(work + oh1l);
     p.zb_hi = reinterpret_cast<__nv_bfloat16 *>(work + ozh); p.zb_lo = reinterpret_cast<__nv_bfloat16 *>(work + ozl);
     const bool cluster = w->ws_cluster;
-    const uint32_t box_rows = cluster ? W_BM / 2 : W_BM;  // the cluster variant loads half a tile per CTA and multicasts it
+    // TS form, one M-tile with few streams (the reference's B = 1 request, small micro-batches): a unit loads and multiplies only
+    // the first 32 / 64 rows of the tile — the activation ingest (327 KB per unit at 128 rows) is what a chain phase waits for
+    const bool use_ts_form = !cluster && !(getenv("AMIRA_WS_TS") && atoi(getenv("AMIRA_WS_TS")) == 0);
+    p.nrows = (use_ts_form && MT == 1 && !getenv("AMIRA_WS_FULLROWS")) ? (B <= 32 ? 32 : B <= 64 ? 64 : W_BM) : W_BM;
+    const uint32_t box_rows = cluster ? W_BM / 2 : (uint32_t)p.nrows;  // the cluster variant loads half a tile per CTA and multicasts it
     if ((e = make_tmap_bf16(&p.h0_hi, p.h0b_hi, 2 * (uint64_t)Mpad, kH, kH, box_rows)) != cudaSuccess) return e;
     if ((e = make_tmap_bf16(&p.h0_lo, p.h0b_lo, 2 * (uint64_t)Mpad, kH, kH, box_rows)) != cudaSuccess) return e;
     if ((e = make_tmap_bf16(&p.h1_hi, p.h1b_hi, 2 * (uint64_t)Mpad, kH, kH, box_rows)) != cudaSuccess) return e;
