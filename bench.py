@@ -228,7 +228,7 @@ def run_streaming(A, torch, dev, ctx, n_streams: int, ticks: int, warm: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--utterances", type=int, default=1024, help="utterances per GPU per step")

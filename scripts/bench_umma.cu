@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128, 1) umma_kernel(int mode, int N, int n_ite
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) umma(acc, sdesc(a_lo + kk * 32), sdesc(w + kk * 32), id64, 1);
             }
-        } else if (mode >= 5) {  // A in TMEM, N = 128; mode 5: B walks 9 different 16 KB tiles; 6: A walks 10 k-chunks; 7: both
+        } else if (mode >= 5 && mode <= 7) {  // A in TMEM, N = 128; mode 5: B walks 9 different 16 KB tiles; 6: A walks 10 k-chunks; 7: both
             const uint32_t id = idesc_bf16(128, 128);
             for (int i = 0; i < n_iter; ++i) {
                 const uint32_t bt = (mode == 5 || mode == 7) ? a_hi + (i % 9) * 16384 : w;
@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(128, 1) umma_kernel(int mode, int N, int n_ite
                                  "r"(at + kk * 8), "l"(bd), "r"(id), "r"(1u) : "memory");
                 }
             }
-        } else if (mode == 4) {  // A operand in tensor memory (columns 256..), B from shared memory, N columns
-            const uint32_t id = idesc_bf16(128, N);
+        } else if (mode == 4 || mode == 8) {  // A operand in tensor memory (columns 256..), B from shared memory, N columns; mode 8: M = 64
+            const uint32_t id = idesc_bf16(mode == 8 ? 64 : 128, N);
             for (int i = 0; i < n_iter; ++i)
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
@@ -121,7 +121,7 @@ int main() {
         {1, 64, "split pattern 3 x N=64 per k-step", 12, 0}, {2, 128, "fused pattern N=128 + N=64 per k-step", 8, 0},
         {3, 128, "fused pattern + commit per 4 mma", 8, 0}, {4, 64, "A in TMEM, N=64", 4, 0}, {4, 128, "A in TMEM, N=128", 4, 0},
         {4, 256, "A in TMEM, N=256", 4, 0}, {5, 128, "A in TMEM fixed, B walks 9 tiles", 4, 0}, {6, 128, "A in TMEM walks 10 chunks, B fixed", 4, 0},
-        {7, 128, "A in TMEM walks, B walks", 4, 0}};
+        {7, 128, "A in TMEM walks, B walks", 4, 0}, {8, 128, "A in TMEM, M=64, N=128", 4, 0}, {8, 64, "A in TMEM, M=64, N=64", 4, 0}, {8, 32, "A in TMEM, M=64, N=32", 4, 0}, {4, 32, "A in TMEM, M=128, N=32", 4, 0}};
     for (auto &c : cases)
         for (int grid : {1, 148}) {
             umma_kernel<<<grid, 128, 196608>>>(c.mode, c.N, n_iter, out);

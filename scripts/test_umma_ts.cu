@@ -12,7 +12,10 @@
 #include <vector>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
-constexpr int M = 128, N = 128, K = 64;
+#ifndef MM
+#define MM 128
+#endif
+constexpr int M = MM, N = 128, K = 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(128, 1) probe(const __nv_bfloat16 *A, const __
     {
         const int m = warp * 32 + lane;
         uint32_t r[32];
-        for (int j = 0; j < K / 2; ++j) r[j] = *reinterpret_cast<const uint32_t *>(A + (size_t)m * K + 2 * j);
+        for (int j = 0; j < K / 2; ++j) r[j] = m < M ? *reinterpret_cast<const uint32_t *>(A + (size_t)m * K + 2 * j) : 0u;
         asm volatile(
             "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
             "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(a_tmem + ((uint32_t)(warp * 32) << 16)),
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(128, 1) probe(const __nv_bfloat16 *A, const __
                 : "r"(d_tmem + ((uint32_t)(warp * 32) << 16) + c0)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            for (int j = 0; j < 32; ++j) D[(size_t)m * N + c0 + j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) if (m < M) D[(size_t)m * N + c0 + j] = __uint_as_float(r[j]);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -19,8 +19,8 @@ for _ in range(2):
 torch.cuda.synchronize()
 tr = ctx.debug_ws_trace(1536).astype(np.float64).reshape(-1)
 t1 = tr[:512 * 32].reshape(512, 32); t2 = tr[512 * 32:].reshape(512, 8, 8)
-ev = ["dep seen", "1st TMA", "MMAs issued", "acc seen", "signalled", "t0 stores issued", "barrier passed", "fence done"]
-for it in (100, 420, 440):
+ev = ["dep seen", "1st TMA", "MMAs issued", "acc seen", "signalled", "stores issued", "all arrived", "fence done"]
+for it in (100, 420, 440, 441):
     base = t2[it, 0, 0]
     print(f"step {it}: (us relative to tile 0 dep seen); previous ctl of tile 0 at {(t1[it - 1, 30] - base) / 1e3:.2f}")
     for mt in range(8):
