@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 sm.sig_skip[slot] = 0;
                 if (!skip) {
                     if (!(p.variant & 128)) WS_TRACE(6);  // every epilogue thread has arrived
-                    __threadfence();
+                    __threadfence();  // (fence.acq_rel.gpu instead was measured identical)
                     if (!(p.variant & 128)) WS_TRACE(7);  // their stores are visible device-wide
                     if (role == R_A) { fence_proxy_async(); atomicAdd(p.cnt_a + mt, 1); }
                     else if (role == R_BI) { fence_proxy_async(); atomicAdd(p.cnt_b + mt, 1); }
