@@ -254,8 +254,8 @@ struct amira_batcher {
     std::atomic<int64_t> n_requests{0}, n_batches{0};
     // worker-owned scratch
     std::vector<int16_t> pcm;
-    std::vector<int64_t> offsets, flens, elens;
-    std::vector<float> features, one_feat, enc;
+    std::vector<int64_t> offsets, foff, eoff, flens, elens;
+    std::vector<float> features, enc;
     std::vector<int32_t> tokens, ntok;
 };
 
@@ -281,58 +281,45 @@ void run_batch(amira_batcher *b, std::vector<BatchReq *> &reqs) {
         b->offsets.assign((size_t)B + 1, 0);
         for (int i = 0; i < B; ++i) b->offsets[(size_t)i + 1] = b->offsets[(size_t)i] + (int64_t)(reqs[(size_t)i]->n_bytes / 2);
         b->pcm.resize((size_t)std::max<int64_t>(b->offsets[(size_t)B], 1));
-        int64_t max_flen = 1;
+        // ragged layouts end to end: request i's features are the dense [128][features_len_i] block the reference hands its
+        // encoder (src/triton/model.rs:126-141), its encoder output the [1024][encoded_len_i] block it gets back
+        b->foff.assign((size_t)B + 1, 0);
         for (int i = 0; i < B; ++i) {
             std::memcpy(b->pcm.data() + b->offsets[(size_t)i], reqs[(size_t)i]->bytes, reqs[(size_t)i]->n_bytes);
             int64_t fl = 0;
             amira_features_len((int64_t)(reqs[(size_t)i]->n_bytes / 2), &fl);
-            max_flen = std::max(max_flen, fl);
+            b->foff[(size_t)i + 1] = b->foff[(size_t)i] + (int64_t)AMIRA_N_MELS * fl;
         }
-        const int64_t t_stride = (max_flen + 3) / 4 * 4;
-        b->features.resize((size_t)B * AMIRA_N_MELS * (size_t)t_stride);
+        b->features.resize((size_t)std::max<int64_t>(b->foff[(size_t)B], 1));
         b->flens.assign((size_t)B, 0);
-        int32_t rc = amira_preprocess_pcm16(p->ctx, b->pcm.data(), b->offsets.data(), B, b->features.data(), t_stride, b->flens.data());
+        int32_t rc = amira_preprocess_pcm16_packed(p->ctx, b->pcm.data(), b->offsets.data(), B, b->features.data(), b->foff.data(), b->flens.data());
         if (rc) return fail_all(rc, amira_last_error(p->ctx));
         // encoder (out of scope, injected): per utterance, contract [1][128][features_len] -> [1][1024][encoded_len]
         if (!p->encoder) return fail_all(AMIRA_ERR_NOT_READY, "no encoder callback installed");
         b->elens.assign((size_t)B, 0);
-        std::vector<std::vector<float>> enc_out((size_t)B);
-        int64_t T = 0;
+        b->eoff.assign((size_t)B + 1, 0);
+        b->enc.clear();
         for (int i = 0; i < B; ++i) {
-            const int64_t fl = b->flens[(size_t)i];
-            b->one_feat.resize((size_t)AMIRA_N_MELS * (size_t)std::max<int64_t>(fl, 1));
-            for (int m = 0; m < AMIRA_N_MELS; ++m)
-                std::memcpy(b->one_feat.data() + (size_t)m * (size_t)fl,
-                            b->features.data() + ((size_t)i * AMIRA_N_MELS + (size_t)m) * (size_t)t_stride, sizeof(float) * (size_t)fl);
             const float *e = nullptr;
             int64_t el = 0;
-            if (p->encoder(p->encoder_user, b->one_feat.data(), fl, &e, &el) != 0 || el < 0 || (el > 0 && !e)) {
+            if (p->encoder(p->encoder_user, b->features.data() + b->foff[(size_t)i], b->flens[(size_t)i], &e, &el) != 0 || el < 0 || (el > 0 && !e)) {
                 finish_req(b, reqs[(size_t)i], AMIRA_ERR_UNKNOWN, "encoder callback failed");
                 reqs[(size_t)i] = nullptr;  // this request is out; the rest of the batch goes on
-                continue;
+                el = 0;
             }
-            enc_out[(size_t)i].assign(e, e + (size_t)AMIRA_ENC_DIM * (size_t)el);  // the callback's buffer is only valid until its next call
+            if (el > 0) b->enc.insert(b->enc.end(), e, e + (size_t)AMIRA_ENC_DIM * (size_t)el);  // the callback's buffer is only valid until its next call
             b->elens[(size_t)i] = el;
-            T = std::max(T, el);
+            b->eoff[(size_t)i + 1] = b->eoff[(size_t)i] + (int64_t)AMIRA_ENC_DIM * el;
         }
-        const int cap = AMIRA_MAX_TOTAL_TOKENS * 8;
-        b->tokens.assign((size_t)B * (size_t)cap, 0);
+        int32_t row_cap = AMIRA_MAX_TOTAL_TOKENS;  // the decode entry writes max_total_tokens ids per stream
+        amira_ctx_max_total_tokens(p->ctx, &row_cap);
+        b->tokens.assign((size_t)B * (size_t)row_cap, 0);
         b->ntok.assign((size_t)B, 0);
-        if (T > 0) {
-            b->enc.assign((size_t)B * AMIRA_ENC_DIM * (size_t)T, 0.f);
-            for (int i = 0; i < B; ++i) {
-                const int64_t el = b->elens[(size_t)i];
-                for (int f = 0; f < AMIRA_ENC_DIM && el > 0; ++f)  // [1024][el] -> [1024][T]
-                    std::memcpy(b->enc.data() + ((size_t)i * AMIRA_ENC_DIM + (size_t)f) * (size_t)T,
-                                enc_out[(size_t)i].data() + (size_t)f * (size_t)el, sizeof(float) * (size_t)el);
-            }
-            // the decode entry writes max_total_tokens ids per stream: use the context's own capacity as the row stride
-            rc = amira_greedy_decode(p->ctx, b->enc.data(), B, (int32_t)T, b->elens.data(), nullptr, nullptr, b->tokens.data(),
-                                     b->ntok.data(), nullptr);
+        if (b->eoff[(size_t)B] > 0) {
+            rc = amira_greedy_decode_packed(p->ctx, b->enc.data(), b->eoff.data(), B, b->elens.data(), nullptr, nullptr, b->tokens.data(),
+                                            b->ntok.data(), nullptr);
             if (rc && rc != AMIRA_ERR_DECODE_STEP) return fail_all(rc, amira_last_error(p->ctx));
         }
-        int32_t row_cap = AMIRA_MAX_TOTAL_TOKENS;
-        amira_ctx_max_total_tokens(p->ctx, &row_cap);
         for (int i = 0; i < B; ++i) {
             BatchReq *r = reqs[(size_t)i];
             if (!r) continue;
