@@ -66,32 +66,38 @@ __global__ void split_rows_kernel(const float *__restrict__ x, size_t ldx, __nv_
 }
 
 // encoder_outputs [B][1024][T] (t contiguous) -> K-major rows [(eoff[b] + t)][1024] hi/lo bf16 (valid frames packed back to
-// back: frames >= lens[b] are never projected), via a 32x32 smem transpose.  Packed input (src_off != nullptr): stream b is
+// back: frames >= lens[b] are never projected), via a 128x32 smem transpose.  Packed input (src_off != nullptr): stream b is
 // a [1024][lens[b]] block at enc + src_off[b].
-__global__ void split_transpose_enc_kernel(const float *__restrict__ enc, int T, const int *__restrict__ lens,
-                                           const int *__restrict__ eoff, const long long *__restrict__ src_off, int row_base,
-                                           __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z, t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+__global__ void __launch_bounds__(256)
+split_transpose_enc_kernel(const float *__restrict__ enc, int T, const int *__restrict__ lens, const int *__restrict__ eoff,
+                           const long long *__restrict__ src_off, int row_base, __nv_bfloat16 *__restrict__ hi,
+                           __nv_bfloat16 *__restrict__ lo) {
+    // tile = 128 features x 32 frames: 128-byte reads along t, 128-byte writes (64 bf16 pairs) along f
+    __shared__ float tile[128][33];
+    const int b = blockIdx.z, t0 = blockIdx.x * 32, f0 = blockIdx.y * 128;
     const int len = lens[b];
     if (t0 >= len) return;
     const size_t r0 = (size_t)(eoff[b] - row_base);
-    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float *src = src_off ? enc + src_off[b] : enc + (size_t)b * kEnc * T;
     const int ld = src_off ? len : T;
-    for (int j = ty; j < 32; j += 8) {
-        const int t = t0 + tx;
-        tile[j][tx] = t < ld ? src[(size_t)(f0 + j) * ld + t] : 0.f;
-    }
+    const bool in = t0 + lane < ld;
+#pragma unroll
+    for (int r = warp; r < 128; r += 8) tile[r][lane] = in ? __ldg(src + (size_t)(f0 + r) * ld + t0 + lane) : 0.f;
     __syncthreads();
-    for (int j = ty; j < 32; j += 8) {
-        const int t = t0 + j;
-        if (t < len) {
-            __nv_bfloat16 h, l;
-            split_bf16(tile[tx][j], h, l);
-            const size_t o = (r0 + t) * kEnc + f0 + tx;
-            hi[o] = h;
-            lo[o] = l;
+#pragma unroll
+    for (int tt = warp; tt < 32; tt += 8) {
+        const int t = t0 + tt;
+        if (t >= len) continue;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int f = 64 * g + 2 * lane;
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(tile[f][tt], h0, l0);
+            split_bf16(tile[f + 1][tt], h1, l1);
+            const size_t o = (r0 + t) * kEnc + f0 + f;
+            *reinterpret_cast<__nv_bfloat162 *>(hi + o) = __halves2bfloat162(h0, h1);
+            *reinterpret_cast<__nv_bfloat162 *>(lo + o) = __halves2bfloat162(l0, l1);
         }
     }
 }
@@ -241,7 +247,7 @@ cudaError_t launch_split_rows(Ctx *c, const float *x, size_t ldx, __nv_bfloat16 
 cudaError_t launch_split_transpose_enc(Ctx *c, const float *enc, int B, int T, const int *lens_dev, const int *eoff_dev,
                                        int row_base, __nv_bfloat16 *hi, __nv_bfloat16 *lo, const long long *src_off_dev) {
     if (B <= 0 || T <= 0) return cudaSuccess;
-    dim3 grid((T + 31) / 32, kEnc / 32, B), block(32, 8);
+    dim3 grid((T + 31) / 32, kEnc / 128, B), block(256);
     split_transpose_enc_kernel<<<grid, block, 0, c->stream>>>(enc, T, lens_dev, eoff_dev, src_off_dev, row_base, hi, lo);
     c->launches++;
     return cudaGetLastError();
