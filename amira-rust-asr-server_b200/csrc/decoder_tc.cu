@@ -116,31 +116,38 @@ struct TcGemmParams {
     int M, N, K;
 };
 
+// Persistent: CTA i walks output tiles i, i + grid, ... (n fastest, so the n-tiles of one m-tile run side by side and share the A
+// tile in L2); two 128-column accumulators in tensor memory, so the epilogue of tile j overlaps the main loop of tile j + 1.
 __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + G_STAGES * G_STAGE_BYTES);
     uint64_t *empty = full + G_STAGES;
-    uint64_t *acc_full = empty + G_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+    uint64_t *acc_full = empty + G_STAGES;   // [2]
+    uint64_t *acc_empty = acc_full + 2;      // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * G_BM, n0 = blockIdx.x * G_BN;
     const int nk = (p.K + BK - 1) / BK;
+    const int tiles_n = (p.N + G_BN - 1) / G_BN, tiles_m = (p.M + G_BM - 1) / G_BM;
+    const int n_tiles = tiles_n * tiles_m;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < G_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(acc_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+        }
         mbar_fence_init();
         tma_prefetch_desc(&p.a_hi);
         tma_prefetch_desc(&p.a_lo);
         tma_prefetch_desc(&p.w_hi);
         tma_prefetch_desc(&p.w_lo);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, G_BN);
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * G_BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -148,61 +155,82 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % G_STAGES;
-                mbar_wait(&empty[s], ((kc / G_STAGES) & 1) ^ 1);
-                unsigned char *st = smem + s * G_STAGE_BYTES;
-                mbar_expect_tx(&full[s], G_STAGE_BYTES);
-                tma_load_2d(st + 0 * G_TILE_BYTES, &p.a_hi, &full[s], kc * BK, m0);
-                tma_load_2d(st + 1 * G_TILE_BYTES, &p.a_lo, &full[s], kc * BK, m0);
-                tma_load_2d(st + 2 * G_TILE_BYTES, &p.w_hi, &full[s], kc * BK, n0);
-                tma_load_2d(st + 3 * G_TILE_BYTES, &p.w_lo, &full[s], kc * BK, n0);
+            uint32_t g = 0;  // k-chunks issued so far, across tiles: ring stage and phase
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * G_BM, n0 = (tile % tiles_n) * G_BN;
+                for (int kc = 0; kc < nk; ++kc, ++g) {
+                    const uint32_t s = g % G_STAGES;
+                    mbar_wait(&empty[s], ((g / G_STAGES) & 1) ^ 1);
+                    unsigned char *st = smem + s * G_STAGE_BYTES;
+                    mbar_expect_tx(&full[s], G_STAGE_BYTES);
+                    tma_load_2d(st + 0 * G_TILE_BYTES, &p.a_hi, &full[s], kc * BK, m0);
+                    tma_load_2d(st + 1 * G_TILE_BYTES, &p.a_lo, &full[s], kc * BK, m0);
+                    tma_load_2d(st + 2 * G_TILE_BYTES, &p.w_hi, &full[s], kc * BK, n0);
+                    tma_load_2d(st + 3 * G_TILE_BYTES, &p.w_lo, &full[s], kc * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ===== MMA issuer =====
             constexpr uint32_t idesc = make_idesc_bf16(G_BM, G_BN);
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % G_STAGES;
-                mbar_wait(&full[s], (kc / G_STAGES) & 1);
+            uint32_t g = 0, t = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+                const uint32_t buf = t & 1;
+                mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator (free at first use)
                 tc_fence_after();
-                const uint32_t st = smem_u32(smem + s * G_STAGE_BYTES);
+                const uint32_t acc = tmem_acc + buf * G_BN;
+                for (int kc = 0; kc < nk; ++kc, ++g) {
+                    const uint32_t s = g % G_STAGES;
+                    mbar_wait(&full[s], (g / G_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + s * G_STAGE_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                    const uint32_t off = kk * UMMA_K * 2;  // bytes along the 128-byte swizzle row
-                    const uint64_t ah = make_sdesc_sw128(st + 0 * G_TILE_BYTES + off), al = make_sdesc_sw128(st + 1 * G_TILE_BYTES + off);
-                    const uint64_t wh = make_sdesc_sw128(st + 2 * G_TILE_BYTES + off), wl = make_sdesc_sw128(st + 3 * G_TILE_BYTES + off);
-                    umma_bf16(tmem_acc, al, wh, idesc, (kc | kk) != 0);
-                    umma_bf16(tmem_acc, ah, wl, idesc, 1);
-                    umma_bf16(tmem_acc, ah, wh, idesc, 1);
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                        const uint32_t off = kk * UMMA_K * 2;  // bytes along the 128-byte swizzle row
+                        const uint64_t ah = make_sdesc_sw128(st + 0 * G_TILE_BYTES + off), al = make_sdesc_sw128(st + 1 * G_TILE_BYTES + off);
+                        const uint64_t wh = make_sdesc_sw128(st + 2 * G_TILE_BYTES + off), wl = make_sdesc_sw128(st + 3 * G_TILE_BYTES + off);
+                        umma_bf16(acc, al, wh, idesc, (kc | kk) != 0);
+                        umma_bf16(acc, ah, wl, idesc, 1);
+                        umma_bf16(acc, ah, wh, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);
                 }
-                umma_commit(&empty[s]);
+                umma_commit(&acc_full[buf]);
             }
-            umma_commit(acc_full);
         }
     } else {  // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int row = m0 + q * 32 + lane;
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            const int m0 = (tile / tiles_n) * G_BM, n0 = (tile % tiles_n) * G_BN;
+            const uint32_t buf = t & 1;
+            mbar_wait(&acc_full[buf], (t >> 1) & 1);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-        for (int c = 0; c < G_BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c * 32, r);
-            tmem_ld_wait();
-            if (row < p.M) {
-                float *dst = p.C + (size_t)row * p.ldc + n0 + c * 32;
+            for (int c = 0; c < G_BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_acc + buf * G_BN + ((uint32_t)(q * 32) << 16) + c * 32, r);
+                tmem_ld_wait();
+                if (c == G_BN / 32 - 1) {  // the accumulator is in registers: hand it back before the stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                if (row < p.M) {
+                    float *dst = p.C + (size_t)row * p.ldc + n0 + c * 32;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c * 32 + j;
-                    if (n < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n] : 0.f);
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + c * 32 + j;
+                        if (n < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n] : 0.f);
+                    }
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_acc, G_BN);
+    if (warp == 1) tmem_dealloc(tmem_acc, 2 * G_BN);
 }
 
 }  // namespace
@@ -228,7 +256,8 @@ cudaError_t launch_tc_gemm(Ctx *c, const __nv_bfloat16 *a_hi, const __nv_bfloat1
         if ((e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM)) != cudaSuccess) return e;
         attr_done = true;
     }
-    dim3 grid((N + G_BN - 1) / G_BN, (M + G_BM - 1) / G_BM);
+    const long long n_tiles = (long long)((N + G_BN - 1) / G_BN) * ((M + G_BM - 1) / G_BM);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(n_tiles, c->sm_count));
     tc_gemm_kernel<<<grid, G_THREADS, G_SMEM, c->stream>>>(p);
     c->launches++;
     return cudaGetLastError();
