@@ -201,6 +201,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     } else {  // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
         uint32_t t = 0;
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                            (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
             const int m0 = (tile / tiles_n) * G_BM, n0 = (tile % tiles_n) * G_BN;
             const uint32_t buf = t & 1;
@@ -219,10 +221,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
                 }
                 if (row < p.M) {
                     float *dst = p.C + (size_t)row * p.ldc + n0 + c * 32;
+                    const int nb = n0 + c * 32;
+                    if (vec_ok && nb + 32 <= p.N) {  // 128-bit stores: a thread owns 128 contiguous bytes of its row
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = n0 + c * 32 + j;
-                        if (n < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n] : 0.f);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4 *>(p.bias + nb + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            *reinterpret_cast<float4 *>(dst + j) = make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
+                                                                               __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = nb + j;
+                            if (n < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? p.bias[n] : 0.f);
+                        }
                     }
                 }
             }
