@@ -420,22 +420,32 @@ fe_normalize_kernel(FeMeta meta, float *__restrict__ features, int64_t t_stride,
     if (vec) {
         float4 *p4 = reinterpret_cast<float4 *>(p);
         const int64_t n4 = ld / 4;
-        for (int64_t i = lane; i < n4; i += 32) {
-            const int64_t t = i * 4;
-            float4 v;
-            if (t + 3 < L) {
-                v = p4[i];
-                v.x = (v.x - mu) * inv; v.y = (v.y - mu) * inv; v.z = (v.z - mu) * inv; v.w = (v.w - mu) * inv;
-            } else if (t >= L) {
-                v = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                v = p4[i];
-                v.x = (v.x - mu) * inv;
-                v.y = t + 1 < L ? (v.y - mu) * inv : 0.f;
-                v.z = t + 2 < L ? (v.z - mu) * inv : 0.f;
-                v.w = 0.f;
+        // four independent 128-bit loads in flight per lane before the first store (the row is read and written through
+        // the same pointer, so the compiler keeps load -> store order; batching restores the memory-level parallelism)
+        for (int64_t i0 = lane; i0 < n4; i0 += 128) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + 32 * u;
+                v[u] = (i < n4 && i * 4 < L) ? p4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            p4[i] = v;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + 32 * u, t = i * 4;
+                if (i >= n4) continue;
+                float4 w = v[u];
+                if (t + 3 < L) {
+                    w.x = (w.x - mu) * inv; w.y = (w.y - mu) * inv; w.z = (w.z - mu) * inv; w.w = (w.w - mu) * inv;
+                } else if (t >= L) {
+                    w = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    w.x = (w.x - mu) * inv;
+                    w.y = t + 1 < L ? (w.y - mu) * inv : 0.f;
+                    w.z = t + 2 < L ? (w.z - mu) * inv : 0.f;
+                    w.w = 0.f;
+                }
+                p4[i] = w;
+            }
         }
     } else {
         for (int64_t t = lane; t < ld; t += 32) p[t] = t < L ? (p[t] - mu) * inv : 0.f;
