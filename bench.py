@@ -32,8 +32,8 @@ F_STEP = 15_244_800      # flop per (stream, decode step): 2 LSTM layers + pred 
 F_FRAME = 1_310_720      # flop per (stream, encoder frame): hoisted encoder projection
 BYTES_PER_AUDIO_S = 83_200  # front end, i16 in + f32 [128, T'] out
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this command's default workload
-# (profiles/r1d_ncu_full_raw.csv); reported as roofline.traffic only for that workload
-NCU_DRAM_BYTES = {"greedy": 656_050_944, "fe_logmel": 1_549_484_032}
+# (profiles/r1e_ncu_full_raw.csv); reported as roofline.traffic only for that workload
+NCU_DRAM_BYTES = {"greedy": 649_378_816, "fe_logmel": 1_551_730_688}
 ENGINE_NAMES = {0: ("greedy_ws_kernel", "tcgen05 split-bf16 weight-stationary dataflow kernel"),
                 1: ("greedy_persistent_kernel", "fp32 persistent cooperative kernel"),
                 2: ("greedy_tc_kernel", "tcgen05 split-bf16 grid-synchronised kernel"),
