@@ -105,6 +105,8 @@ struct Ctx {
     amira_config cfg{};
     int device = 0;
     int sm_count = 0;
+    // cudaFuncSetAttribute is per device: remembered per context, not per process (one process may hold contexts on several GPUs)
+    bool attr_fe_i16 = false, attr_fe_f32 = false, attr_gemm = false;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;  // stream in use (own or caller-provided)
     std::mutex mu;

@@ -263,10 +263,9 @@ cudaError_t launch_tc_gemm(Ctx *c, const __nv_bfloat16 *a_hi, const __nv_bfloat1
     p.M = M;
     p.N = N;
     p.K = K;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!c->attr_gemm) {
         if ((e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM)) != cudaSuccess) return e;
-        attr_done = true;
+        c->attr_gemm = true;
     }
     const long long n_tiles = (long long)((N + G_BN - 1) / G_BN) * ((M + G_BM - 1) / G_BM);
     const int grid = (int)std::max<long long>(1, std::min<long long>(n_tiles, c->sm_count));

@@ -542,20 +542,18 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
         const int grid = (int)std::min<int64_t>(tiles, (int64_t)c->sm_count * 2);
         if (is_pcm16) {
             const size_t smem = fe_smem_bytes<int16_t>();
-            static bool attr_done = false;
-            if (!attr_done) {
-                cudaFuncSetAttribute(fe_logmel_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_done = true;
+            if (!c->attr_fe_i16) {
+                if ((e = cudaFuncSetAttribute(fe_logmel_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+                c->attr_fe_i16 = true;
             }
             fe_logmel_kernel<int16_t><<<grid, FE_THREADS, smem, c->stream>>>(
                 static_cast<const int16_t *>(wave_dev), meta, c->tables_dev, features_dev, t_stride,
                 fe_partials.as<double2>());
         } else {
             const size_t smem = fe_smem_bytes<float>();
-            static bool attr_done = false;
-            if (!attr_done) {
-                cudaFuncSetAttribute(fe_logmel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_done = true;
+            if (!c->attr_fe_f32) {
+                if ((e = cudaFuncSetAttribute(fe_logmel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+                c->attr_fe_f32 = true;
             }
             fe_logmel_kernel<float><<<grid, FE_THREADS, smem, c->stream>>>(
                 static_cast<const float *>(wave_dev), meta, c->tables_dev, features_dev, t_stride,

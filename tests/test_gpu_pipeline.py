@@ -127,3 +127,25 @@ def test_micro_batcher_equals_one_by_one(pipe, amira):
     # empty request through the batcher takes the single-request path
     assert batcher.process_batch(b"").tokens == []
     batcher.close()
+
+
+def test_two_gpus_in_one_process(amira):
+    """One process, one context per GPU: per-device kernel attributes, tables and weights — both devices
+    must give the results of device 0.  Skipped on single-GPU boxes."""
+    if amira.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(5)
+    pcms = [synth_pcm(float(rng.uniform(0.5, 2.0)), 700 + i) for i in range(40)]
+    offs = np.zeros(len(pcms) + 1, np.int64)
+    offs[1:] = np.cumsum([p.size for p in pcms])
+    pcm = np.concatenate(pcms)
+    enc = (0.5 * rng.standard_normal((40, 1024, 20))).astype(np.float32)
+    outs = []
+    for dev in (1, 0):  # device 1 first: nothing may depend on device 0 having been initialised
+        with amira.Context(device_id=dev) as c:
+            c.load_weights(amira.synthetic_weights(3456))
+            feats, lens = c.preprocess_pcm16(pcm, offs)
+            toks, st, steps = c.greedy_decode(enc)
+            outs.append((feats, lens, toks, st.states_1, steps))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] == outs[1][2] and np.array_equal(outs[0][3], outs[1][3]) and np.array_equal(outs[0][4], outs[1][4])
