@@ -15,19 +15,23 @@ NEAR_TIE = 2e-4
 ENGINES = {1: "fp32 persistent kernel", 2: "tcgen05 grid-synchronised", 3: "tcgen05 dataflow", 4: "tcgen05 weight-stationary dataflow (default)"}
 
 
-@pytest.fixture(scope="module", params=[1, 2, 3, 4, 40], ids=["fp32", "tcgen05", "dataflow", "ws", "ws-cluster"])
+@pytest.fixture(scope="module", params=[1, 2, 3, 4, 40, 41], ids=["fp32", "tcgen05", "dataflow", "ws", "ws-cluster", "ws-smem"])
 def ctx(request, amira):
     """One context per decode engine: every test in this module runs against each of them.  40 = engine 4 in its CTA-pair
-    (thread-block cluster + TMA multicast) variant (AMIRA_WS_CLUSTER=1 is read when the weights are loaded)."""
+    (thread-block cluster + TMA multicast) variant (AMIRA_WS_CLUSTER=1 is read when the weights are loaded); 41 = engine 4
+    with the weights in shared memory instead of tensor memory (AMIRA_WS_TS=0, read at every launch)."""
     import os
-    engine = 4 if request.param == 40 else request.param
+    engine = 4 if request.param in (40, 41) else request.param
     if request.param == 40:
         os.environ["AMIRA_WS_CLUSTER"] = "1"
+    if request.param == 41:
+        os.environ["AMIRA_WS_TS"] = "0"
     c = amira.Context(device_id=0, decode_engine=engine)
     c.engine = engine
     yield c
     c.close()
     os.environ.pop("AMIRA_WS_CLUSTER", None)
+    os.environ.pop("AMIRA_WS_TS", None)
 
 
 @pytest.fixture(scope="module")
