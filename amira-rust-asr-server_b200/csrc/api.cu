@@ -194,8 +194,9 @@ int32_t amira_ctx_create(const amira_config *cfg, amira_ctx **out) {
     c->stream = c->own_stream;
     if ((e = cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
     if ((e = cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
-    for (cudaEvent_t &ev : c->ev_pool)
-        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+    for (cudaEvent_t &ev : c->ev_pool)  // blocking sync: a host thread throttled on one of these yields its core
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) return bail(e, "event");
+    if ((e = cudaEventCreateWithFlags(&c->ev_block, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) return bail(e, "event");
     FrontendTables *ht = new FrontendTables();
     build_frontend_tables(ht);
     e = cudaMalloc(&c->tables_dev, sizeof(FrontendTables));
@@ -232,6 +233,7 @@ int32_t amira_ctx_destroy(amira_ctx *c) {
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     for (cudaEvent_t ev : c->ev_pool)
         if (ev) cudaEventDestroy(ev);
+    if (c->ev_block) cudaEventDestroy(c->ev_block);
     prof_collect(c);
     for (auto &b : c->stage) b.release();
     for (auto &b : c->pin) b.release();
@@ -330,6 +332,15 @@ int32_t amira_ctx_load_weights_file(amira_ctx *c, const char *path) {
     return amira_ctx_load_weights(c, blob.data(), blob.size());
 }
 
+// End-of-call wait.  Batch-sized calls take tens of milliseconds of GPU time: the host thread sleeps on a blocking-sync event
+// (a server runs many such threads on few cores; spinning ones starve the threads that feed the copy engines).  Small calls
+// (single requests, streaming ticks) keep the spinning wait and its microsecond wake-up.
+static cudaError_t wait_stream(Ctx *c, cudaStream_t s, bool blocking) {
+    if (!blocking) return cudaStreamSynchronize(s);
+    cudaError_t e = cudaEventRecord(c->ev_block, s);
+    return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
+}
+
 // ---------------------------------------------------------------------------------------------- front end
 int32_t amira_features_len(int64_t n_samples, int64_t *features_len) {
     if (!features_len) return AMIRA_ERR_INVALID_VALUE;
@@ -413,8 +424,8 @@ static int32_t preprocess_common(amira_ctx *c, const void *wave, bool pcm16, con
             if (dbg) { cudaEventRecord(dbg_ev[2 + 3 * k], c->stream); cudaEventRecord(dbg_ev[3 + 3 * k], c->d2h_stream); }
         }
     }
-    if (feat_host) CK(cudaStreamSynchronize(c->d2h_stream), "features D2H sync");
-    CK(cudaStreamSynchronize(c->stream), "front-end sync");
+    if (feat_host) CK(wait_stream(c, c->d2h_stream, B >= 64), "features D2H sync");
+    CK(wait_stream(c, c->stream, B >= 64), "front-end sync");
     if (dbg) {
         for (int k = 0; k < n_chunks && wave_host && feat_host; ++k) {
             float a = 0, b = 0, d = 0;
@@ -632,7 +643,7 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
     CK(finish_out<float>(c, states_2, s2_dev, n_state, s2_h), "states_2 D2H");
     int32_t n_failed = 0;
     CK(cudaMemcpyAsync(&n_failed, decoder_fail_count_dev(c), sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream), "status D2H");
-    CK(cudaStreamSynchronize(c->stream), "greedy decode sync");
+    CK(wait_stream(c, c->stream, B >= 64 && !slots_host), "greedy decode sync");
     // streams whose argmax left the embedding table and needed another step: the reference's next decoder_joint
     // call fails ("Decode step failed", src/asr/decoder_optimized.rs:148-152); their n_tokens is -1
     if (n_failed > 0) return fail(c, AMIRA_ERR_DECODE_STEP, "Decode step failed for " + std::to_string(n_failed) + " stream(s)");

@@ -131,6 +131,7 @@ struct Ctx {
     // ordered against `stream` with events from this pool
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_pool[4 * kMaxChunks] = {};
+    cudaEvent_t ev_block = nullptr;  // blocking-sync event: batch-sized calls sleep instead of spinning while the GPU works
 
     // staging for host-pointer arguments (slot per argument position)
     DevBuf stage[10];
