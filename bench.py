@@ -171,6 +171,8 @@ def run_reference(args, rank: int):
     if rank != 0:
         return
     threads = len(os.sched_getaffinity(0)) or 1
+    if args.ref_sample <= 0:
+        args.ref_sample = min(8 * threads, args.utterances)
     pcm, offsets, lens = make_workload(args.ref_sample, 4567)
     for _ in range(max(args.warmup, 0) and 1):
         cpu_reference(pcm, offsets, lens, min(2, args.ref_sample), threads)
@@ -232,8 +234,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--utterances", type=int, default=1024, help="utterances per GPU per step")
-    ap.add_argument("--ref-sample", type=int, default=24)
-    ap.add_argument("--cpu-sample", type=int, default=24)
+    ap.add_argument("--ref-sample", type=int, default=0, help="utterances per CPU step; 0 = 8 per host thread (balanced OpenMP rounds)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="utterances of the CPU baseline sample; 0 = 8 per host thread")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
@@ -469,6 +471,8 @@ def main():
         if ORIG_AFFINITY:
             os.sched_setaffinity(0, ORIG_AFFINITY)  # the CPU baseline uses every host core this process may use
         threads = len(os.sched_getaffinity(0)) or 1
+        if args.cpu_sample <= 0:
+            args.cpu_sample = min(8 * threads, B)
         r = cpu_reference(pcm, offsets, lens, args.cpu_sample, threads)
         out["cpu_baseline"] = {"value": r["value"], "unit": "audio-s/s", "cores": threads, "kind": "port",
                                "sample": f"first {min(args.cpu_sample, B)} utterances of this workload ({r['audio_s']:.0f} audio-s): "
