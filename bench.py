@@ -407,8 +407,10 @@ def main():
         ms_e2e = timed(lambda: run_steps(args.steps), 1) / args.steps
         for k in workers:
             assert np.array_equal(k["ntok"].numpy().astype(np.int64), ntok), "host-buffer path disagrees with the resident path"
+        # for transparency: the same step with nothing else in flight (one blocking pair of calls at a time)
+        ms_single = timed(lambda: [step_host(0) for _ in range(3)], 1) / 3
         e2e = {"value": total_audio / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e, "layout": args.e2e_layout,
-               "steps_in_flight": n_fl,
+               "steps_in_flight": n_fl, "ms_per_step_one_in_flight": ms_single,
                "h2d_bytes_per_step": int(pcm.nbytes + enc_pin.numel() * 4 + offsets.nbytes + elens.nbytes),
                "d2h_bytes_per_step": int(workers[0]["feats"].numel() * 4 + workers[0]["tok"].numel() * 4 + B * 4)}
         launches_e2e = workers[0]["fe"].launch_count()
