@@ -106,3 +106,24 @@ def test_oracle_buffer_keeps_leading_context_on_overflow():
     b2 = S.OverlappingAudioBuffer(1000, 2.0, 1.0, 0.5)
     b2.add_samples(np.ones(1500, np.float32))  # longer than the capacity: truncated, amplitude untouched (audio.rs:236-241)
     assert b2.length == 1000 and b2.mean_amplitude == 0.0
+
+
+def test_golden_streaming_fixture(st):
+    """tests/golden/streaming_golden.json (made by make_streaming_golden.py from the oracle): the C++ behind the C ABI
+    reproduces every committed vector."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "streaming_golden.json"), encoding="utf-8"))
+    for c in g["weave"]:
+        o, s = st.best_alignment(c["first"], c["second"], c["pct"])
+        assert abs(s - c["score"]) <= 1e-5 * max(1.0, abs(c["score"]))
+        if o == c["overlap"]:
+            assert st.weave_transcript_segs(c["first"], c["second"], c["pct"]) == c["woven"], c
+    for c in g["windows"]:
+        w = st.window_sequence(*c["args"])
+        assert [[a[0], a[1], b[0], b[1]] for a, b, _ in w] == c["slices"]
+        assert [float(o) for _, _, o in w] == c["overlap"]
+    for c in g["silence"]:
+        a = np.array(c["audio"], np.float32)
+        assert st.mean_amplitude(a) == c["mean_abs"]
+        assert st.is_overlap_silence(a, c["mean_amplitude"]) == c["silent"]
