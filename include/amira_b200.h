@@ -118,7 +118,8 @@ int32_t amira_preprocess_pcm16(amira_ctx *ctx, const int16_t *pcm, const int64_t
                                float *features, int64_t t_stride, int64_t *features_lens);
 /* Same, ragged output: utterance b's features are a dense [128][features_lens[b]] block at features + feat_offsets[b]
  * (element offsets, int64[B+1], host, non-decreasing, block >= 128 * features_len) — the shape the reference hands its
- * encoder per request (features [1][128][T_b], src/triton/model.rs:126-141) without padding every utterance of a batch
+ * encoder per request (features [1][128][T_b] with features.len() == 128 * features_len, src/asr/pipeline.rs:298-301,
+ * src/triton/model.rs:126-141) without padding every utterance of a batch
  * to the longest one; only valid frames cross PCIe.  Elements of a block beyond 128 * features_len are unspecified. */
 int32_t amira_preprocess_pcm16_packed(amira_ctx *ctx, const int16_t *pcm, const int64_t *offsets, int32_t B,
                                       float *features, const int64_t *feat_offsets, int64_t *features_lens);
