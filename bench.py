@@ -205,7 +205,9 @@ def run_streaming(A, torch, dev, ctx, n_streams: int, ticks: int, warm: int):
     rng = np.random.default_rng(99)
     pcm = torch.from_numpy((rng.standard_normal(n_streams * chunk) * 3000).astype(np.int16)).pin_memory()
     offsets = np.arange(n_streams + 1, dtype=np.int64) * chunk
-    feats = torch.empty((n_streams, 128, 32), dtype=torch.float32).pin_memory()
+    flen = chunk // 160 + 1  # 17 frames per 160 ms chunk: per-stream [128][17] blocks, nothing padded
+    foff = np.arange(n_streams + 1, dtype=np.int64) * (128 * flen)
+    feats = torch.empty(n_streams * 128 * flen, dtype=torch.float32).pin_memory()
     enc = torch.from_numpy((0.5 * rng.standard_normal((n_streams, 1024, T))).astype(np.float32)).pin_memory()
     tok = torch.zeros((n_streams, ctx.max_total_tokens), dtype=torch.int32).pin_memory()
     ntok = torch.zeros(n_streams, dtype=torch.int32).pin_memory()
@@ -214,7 +216,7 @@ def run_streaming(A, torch, dev, ctx, n_streams: int, ticks: int, warm: int):
     lat = []
     for i in range(warm + ticks):
         t0 = time.perf_counter()
-        ctx.preprocess_pcm16_raw(pcm.data_ptr(), offsets, n_streams, feats.data_ptr(), 32, flens)
+        ctx.preprocess_pcm16_packed_raw(pcm.data_ptr(), offsets, n_streams, feats.data_ptr(), foff, flens)
         ctx.stream_decode_raw(slots, enc.data_ptr(), T, None, tok.data_ptr(), ntok.data_ptr(), None)
         if i >= warm:
             lat.append((time.perf_counter() - t0) * 1e3)
