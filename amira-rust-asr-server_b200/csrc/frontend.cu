@@ -26,6 +26,9 @@ namespace amira {
 
 namespace {
 
+#ifndef FE_LOG
+#define FE_LOG logf
+#endif
 constexpr int TF = 32;                             // frames per tile
 constexpr int FE_THREADS = 128;                    // 4 warps, 8 frames each
 constexpr int FE_WARPS = FE_THREADS / 32;
@@ -325,25 +328,32 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
                 }
             }
             __syncwarp();
-            // banded mel reduction, both frames in turn with all 32 lanes: lane owns filters lane + 32 g
-#pragma unroll 1
-            for (int hh = 0; hh < 2; ++hh) {
-                const int f = 2 * fp + hh;
-                if (f >= nf) break;
-                const float *ppw = pw + (warp * 2 + hh) * PPAD;
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            // banded mel reduction with all 32 lanes, both frames of the pair at once (each filter weight is loaded once and
+            // applied to both power spectra): lane owns filters lane + 32 g.  A second frame past the tile's end reads a
+            // stale-but-finite spectrum and is not stored.
+            {
+                const float *ppw0 = pw + (warp * 2) * PPAD, *ppw1 = ppw0 + PPAD;
+                float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
                 auto band = [&](int g, int ra, int rb) {  // rows past a filter's support carry zero weights and read the zero padding
-                    const float *pk = ppw + mk[g];
+                    const float *pk0 = ppw0 + mk[g], *pk1 = ppw1 + mk[g];
                     const float *wk = melw + ra * 32 + lane;
 #pragma unroll 4
-                    for (int r = 0; r < rb - ra; ++r) acc[g] = fmaf(wk[r * 32], pk[r], acc[g]);
+                    for (int r = 0; r < rb - ra; ++r) {
+                        const float w = wk[r * 32];
+                        acc0[g] = fmaf(w, pk0[r], acc0[g]);
+                        acc1[g] = fmaf(w, pk1[r], acc1[g]);
+                    }
                 };
                 band(0, r0, r1);
                 band(1, r1, r2);
                 band(2, r2, r3);
                 band(3, r3, r4);
+                const int f = 2 * fp;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) outt[(lane + 32 * g) * OUT_LD + f] = logf(acc[g] + 5.9604644775390625e-08f);
+                for (int g = 0; g < 4; ++g) {
+                    outt[(lane + 32 * g) * OUT_LD + f] = FE_LOG(acc0[g] + 5.9604644775390625e-08f);
+                    if (f + 1 < nf) outt[(lane + 32 * g) * OUT_LD + f + 1] = FE_LOG(acc1[g] + 5.9604644775390625e-08f);
+                }
             }
             __syncwarp();
         }
