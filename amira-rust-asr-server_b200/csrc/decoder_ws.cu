@@ -67,7 +67,6 @@ constexpr int W_NACC = 4;                                   // TMEM accumulators
 constexpr int W_Q = 4;                                      // descriptor queue depth (= signal slots: bounds the epilogue's run-ahead)
 constexpr int W_EPI_WARPS = 8, W_EPI_THREADS = W_EPI_WARPS * 32;
 constexpr int W_THREADS = (4 + W_EPI_WARPS) * 32;           // 384: warp 0 TMA, 1 MMA, 2 scheduler, 3 idle, 4..11 epilogue
-constexpr int W_NPART = 2 * W_ND2;                          // argmax partial slots per row (32 columns each; 2*W_ND used without clusters)
 constexpr int W_MAX_MT = 256;
 constexpr long long W_SPIN_LIMIT = 6000000000LL;            // ~3 s of SM clocks
 constexpr int W_TRACE_ITS = 512;

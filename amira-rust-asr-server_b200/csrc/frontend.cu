@@ -26,9 +26,6 @@ namespace amira {
 
 namespace {
 
-#ifndef FE_LOG
-#define FE_LOG logf
-#endif
 constexpr int TF = 32;                             // frames per tile
 constexpr int FE_THREADS = 128;                    // 4 warps, 8 frames each
 constexpr int FE_WARPS = FE_THREADS / 32;
@@ -57,8 +54,6 @@ __device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
     return i < n ? i : p - i;
 }
 
-__device__ __forceinline__ int rev5(int x) { return (int)(__brev((unsigned)x) >> 27); }
-
 struct cplx {
     double x, y;
 };
@@ -66,39 +61,6 @@ __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.x * b.x - a.y *
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.x + b.x, a.y + b.y}; }
 __device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.x - b.x, a.y - b.y}; }
 __device__ __forceinline__ cplx mul_mi(cplx a) { return {a.y, -a.x}; }  // a * (-i)
-__device__ __forceinline__ cplx twiddle(int num, int den) {            // exp(-2*pi*i*num/den)
-    double s, c;
-    sincospi(-2.0 * (double)num / (double)den, &s, &c);
-    return {c, s};
-}
-__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
-// in-register 8-point DFT (decimation in frequency, output in natural order)
-__device__ __forceinline__ void dft8(cplx (&a)[8]) {
-    const double r = 0.70710678118654752440;
-    cplx b[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        b[j] = cadd(a[j], a[j + 4]);
-        b[j + 4] = csub(a[j], a[j + 4]);
-    }
-    // twiddles W8^j on the odd half
-    b[5] = {r * (b[5].x + b[5].y), r * (b[5].y - b[5].x)};
-    b[6] = mul_mi(b[6]);
-    b[7] = {r * (b[7].y - b[7].x), -r * (b[7].x + b[7].y)};
-    // two 4-point DFTs: even outputs from b[0..3], odd outputs from b[4..7]
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const cplx s0 = cadd(b[4 * h + 0], b[4 * h + 2]), d0 = csub(b[4 * h + 0], b[4 * h + 2]);
-        const cplx s1 = cadd(b[4 * h + 1], b[4 * h + 3]), d1 = mul_mi(csub(b[4 * h + 1], b[4 * h + 3]));
-        a[h + 0] = cadd(s0, s1);
-        a[h + 4] = csub(s0, s1);
-        a[h + 2] = cadd(d0, d1);
-        a[h + 6] = csub(d0, d1);
-    }
-}
-
 
 // ---- 16-point DFT in registers (two radix-4 passes; forward transform, W = exp(-2 pi i / 16)), natural order in/out ----
 __device__ __forceinline__ void radix4(cplx &x0, cplx &x1, cplx &x2, cplx &x3) {
@@ -351,8 +313,8 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
                 const int f = 2 * fp;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    outt[(lane + 32 * g) * OUT_LD + f] = FE_LOG(acc0[g] + 5.9604644775390625e-08f);
-                    if (f + 1 < nf) outt[(lane + 32 * g) * OUT_LD + f + 1] = FE_LOG(acc1[g] + 5.9604644775390625e-08f);
+                    outt[(lane + 32 * g) * OUT_LD + f] = logf(acc0[g] + 5.9604644775390625e-08f);
+                    if (f + 1 < nf) outt[(lane + 32 * g) * OUT_LD + f + 1] = logf(acc1[g] + 5.9604644775390625e-08f);
                 }
             }
             __syncwarp();
