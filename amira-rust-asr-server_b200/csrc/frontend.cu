@@ -221,8 +221,11 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
 #pragma unroll 4
             for (int p = 2 * tid; p < span; p += 2 * FE_THREADS) {
                 const RawT x0 = rq[p], x1 = rq[p + 1], x2 = rq[p + 2];
-                ystage[p] = Stage<RawT>::make(x1, x0, false);
-                if (p + 1 < span) ystage[p + 1] = Stage<RawT>::make(x2, x1, false);
+                const StT ya = Stage<RawT>::make(x1, x0, false), yb = Stage<RawT>::make(x2, x1, false);
+                // span is even and p is even: one 8- / 16-byte store per pair (two 4-byte stores at lane stride 2 are a
+                // 2-way bank conflict each)
+                if constexpr (sizeof(StT) == 4) *reinterpret_cast<float2 *>(ystage + p) = make_float2((float)ya, (float)yb);
+                else *reinterpret_cast<double2 *>(ystage + p) = make_double2((double)ya, (double)yb);
             }
         } else {
             for (int p = tid; p < span; p += FE_THREADS) {
