@@ -133,6 +133,11 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
     float *pw = outt + kMel * OUT_LD;                                                 // [FE_HALVES][PPAD]
     float *melw = pw + FE_HALVES * PPAD;                                              // [kMelRowsMax][32]
     RawT *raw = reinterpret_cast<RawT *>(xbuf);  // [RAW_CAP] raw samples are staged before, the exchange buffers used after, the barrier
+    // 16-bit input only: a second staging buffer that does NOT alias the exchange buffers, filled with cp.async for the NEXT
+    // tile of this CTA while the current tile's frames are transformed (the DRAM latency of the staging loads was 14 % of
+    // the kernel's stall samples)
+    constexpr bool kPrefetch = sizeof(RawT) == 2;
+    RawT *raw2 = reinterpret_cast<RawT *>(melw + kMelRowsMax * 32);  // [RAW_CAP], 16-byte aligned
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, hl = lane & 15;  // half-warp and lane within it
@@ -157,42 +162,78 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
     for (int i = tid; i < FE_HALVES * PPAD; i += FE_THREADS) pw[i] = 0.f;  // the padding beyond bin 256 stays zero
     double2 *myx = xbuf + (warp * 2 + half) * TBUF;
 
-    for (int tile = blockIdx.x; tile < meta.n_tiles; tile += gridDim.x) {
-        // ---- locate (utterance, first frame) ----
+    struct TileLoc {
+        int b, f0, nf, span, delta, nvec;
+        int64_t n, L, i0, g_lo, g_hi;
+        const RawT *x;
+        const int4 *src;
+        bool fits, fast;
+    };
+    constexpr int PER = 16 / sizeof(RawT);
+    auto locate = [&](int tile) -> TileLoc {  // (utterance, first frame) of a tile and the signal span it needs
+        TileLoc t;
         int lo = 0, hi = meta.B;  // largest b with tile_pfx[b] <= tile
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (meta.tile_pfx[mid] <= tile) lo = mid; else hi = mid;
         }
-        const int b = lo;
-        const int64_t n = meta.lens[b];
-        const RawT *x = wave + meta.starts[b];
-        const int64_t L = n / kHop + 1;
-        const int f0 = (tile - meta.tile_pfx[b]) * TF;
-        const int nf = (int)min((int64_t)TF, L - f0);
-        const int span = (nf - 1) * kHop + kNfft;
-        const int64_t i0 = (int64_t)f0 * kHop - kNfft / 2;  // signal index of padded sample 0 of the tile
+        t.b = lo;
+        t.n = meta.lens[t.b];
+        t.x = wave + meta.starts[t.b];
+        t.L = t.n / kHop + 1;
+        t.f0 = (tile - meta.tile_pfx[t.b]) * TF;
+        t.nf = (int)min((int64_t)TF, t.L - t.f0);
+        t.span = (t.nf - 1) * kHop + kNfft;
+        t.i0 = (int64_t)t.f0 * kHop - kNfft / 2;  // signal index of padded sample 0 of the tile
+        t.g_lo = t.i0 - 1;
+        t.g_hi = t.i0 + t.span;
+        if (t.g_lo < 0) { t.g_lo = 0; t.g_hi = max(t.g_hi, (int64_t)(kNfft / 2 + 2)); }
+        if (t.g_hi > t.n) { t.g_hi = t.n; t.g_lo = min(t.g_lo, t.n - (kNfft / 2 + 2)); }
+        if (t.g_lo < 0) t.g_lo = 0;
+        t.fits = (t.g_hi - t.g_lo) <= RAW_CAP;  // false only for pathological tiny signals with long reflections
+        // common case: the tile lies well inside its utterance — copy the 16-byte aligned image of x[i0-1 ..]
+        // (raw[q + delta] = x[i0 - 1 + q])
+        t.fast = t.fits && t.i0 >= 1 + PER && t.i0 + t.span + PER <= t.n;
+        t.delta = 0;
+        t.src = nullptr;
+        t.nvec = 0;
+        if (t.fast) {
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(t.x + (t.i0 - 1));
+            t.delta = (int)((ga & 15) / sizeof(RawT));
+            t.src = reinterpret_cast<const int4 *>(ga & ~(uintptr_t)15);
+            t.nvec = (t.span + 1 + t.delta + PER - 1) / PER;  // <= RAW_CAP / PER
+        }
+        return t;
+    };
+    auto prefetch = [&](const TileLoc &t) {  // asynchronous staging of a fast tile into raw2 (one commit group per call)
+        if (t.fast) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(raw2);
+            for (int v = tid; v < t.nvec; v += FE_THREADS)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)v), "l"(t.src + v) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    TileLoc cur;
+    if ((int)blockIdx.x < meta.n_tiles) {
+        cur = locate(blockIdx.x);
+        if (kPrefetch) prefetch(cur);
+    }
+
+    for (int tile = blockIdx.x; tile < meta.n_tiles; tile += gridDim.x) {
+        const int b = cur.b, f0 = cur.f0, nf = cur.nf, span = cur.span;
+        const int64_t n = cur.n, L = cur.L, i0 = cur.i0, g_lo = cur.g_lo, g_hi = cur.g_hi;
+        const RawT *x = cur.x;
+        const bool fits = cur.fits, fast = cur.fast;
+        const int delta = cur.delta;
 
         __syncthreads();  // previous tile fully consumed (ystage/outt/raw reuse); melw visible on first pass
         // ---- stage the signal span [g_lo, g_hi) needed by this tile ----
-        int64_t g_lo = i0 - 1, g_hi = i0 + span;
-        if (g_lo < 0) { g_lo = 0; g_hi = max(g_hi, (int64_t)(kNfft / 2 + 2)); }
-        if (g_hi > n) { g_hi = n; g_lo = min(g_lo, n - (kNfft / 2 + 2)); }
-        if (g_lo < 0) g_lo = 0;
-        const bool fits = (g_hi - g_lo) <= RAW_CAP;  // false only for pathological tiny signals with long reflections
-        constexpr int PER = 16 / sizeof(RawT);
-        // common case: the tile lies well inside its utterance — copy the 16-byte aligned image of x[i0-1 ..] (one 128-bit load and
-        // one 128-bit shared store per thread and step; raw[q + delta] = x[i0 - 1 + q])
-        const bool fast = fits && i0 >= 1 + PER && i0 + span + PER <= n;
-        int delta = 0;
-        if (fast) {
-            const uintptr_t ga = reinterpret_cast<uintptr_t>(x + (i0 - 1));
-            delta = (int)((ga & 15) / sizeof(RawT));
-            const int4 *src = reinterpret_cast<const int4 *>(ga & ~(uintptr_t)15);
-            const int nvec = (span + 1 + delta + PER - 1) / PER;  // <= RAW_CAP / PER
+        if (fast && kPrefetch) {
+            asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's share of the tile, requested during the previous tile
+        } else if (fast) {
             int4 *dst = reinterpret_cast<int4 *>(raw);
 #pragma unroll 4
-            for (int v = tid; v < nvec; v += FE_THREADS) dst[v] = __ldg(src + v);
+            for (int v = tid; v < cur.nvec; v += FE_THREADS) dst[v] = __ldg(cur.src + v);
         } else if (fits) {
             const int cnt = (int)(g_hi - g_lo);
             // 128-bit path over the 16-byte aligned interior, scalar head/tail
@@ -217,7 +258,7 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
         if (interior) {
             // rq[q] = x[i0 - 1 + q]; two consecutive samples per thread and step (one staged pair store), unrolled for ILP:
             // this loop is pure shared-memory latency otherwise (it showed up with a quarter of the kernel's stall samples)
-            const RawT *rq = raw + delta;
+            const RawT *rq = ((fast && kPrefetch) ? raw2 : raw) + delta;
 #pragma unroll 4
             for (int p = 2 * tid; p < span; p += 2 * FE_THREADS) {
                 const RawT x0 = rq[p], x1 = rq[p + 1], x2 = rq[p + 2];
@@ -242,6 +283,12 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
             }
         }
         __syncthreads();
+        // raw2 has been consumed: request the next tile of this CTA now, its loads fly during the transforms below
+        TileLoc nxt = cur;
+        if (tile + (int)gridDim.x < meta.n_tiles) {
+            nxt = locate(tile + gridDim.x);
+            if (kPrefetch) prefetch(nxt);
+        }
 
         // ---- a half-warp per frame, two frames per warp at a time: 512-point real FFT = 256-point complex FFT (z[m] = x[2m] +
         // i x[2m+1]) as 16 x 16: radix-16 in registers over m1 (m = 16 m1 + lane), twiddle W256^(lane k1), transpose through
@@ -342,6 +389,7 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
         float *dst = features + meta.foff[b] + f0;
         for (int m = warp; m < kMel; m += FE_WARPS)
             if (lane < nf) dst[(size_t)m * ld + lane] = outt[m * OUT_LD + lane];
+        cur = nxt;
     }
 }
 
@@ -465,7 +513,8 @@ __global__ void bytes_to_f32_kernel(const uint8_t *__restrict__ in, size_t n_byt
 template <typename RawT>
 size_t fe_smem_bytes() {
     return sizeof(double2) * (FE_HALVES * TBUF + 256 + 130 + 256) + sizeof(typename Stage<RawT>::T) * SPAN +
-           sizeof(float) * (kMel * OUT_LD + FE_HALVES * PPAD + kMelRowsMax * 32);
+           sizeof(float) * (kMel * OUT_LD + FE_HALVES * PPAD + kMelRowsMax * 32) +
+           (sizeof(RawT) == 2 ? ((RAW_CAP * sizeof(RawT) + 15) & ~(size_t)15) : 0);  // raw2 (16-bit input: prefetched staging)
 }
 
 }  // namespace
