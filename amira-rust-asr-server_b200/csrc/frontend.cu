@@ -41,6 +41,7 @@ struct FeMeta {
     const int64_t *starts;   // [B] first element of each utterance
     const int64_t *lens;     // [B] samples
     const int32_t *tile_pfx; // [B+1] prefix sum of tiles per utterance
+    const int32_t *tile_b;   // [n_tiles] utterance of every tile
     const int64_t *foff;     // [B] first element of each utterance's [128][ld] feature block
     int B;
     int n_tiles;
@@ -164,7 +165,7 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
 
     struct TileLoc {
         int b, f0, nf, span, delta, nvec;
-        int64_t n, L, i0, g_lo, g_hi;
+        int64_t n, L, i0, g_lo, g_hi, foff;
         const RawT *x;
         const int4 *src;
         bool fits, fast;
@@ -172,14 +173,10 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
     constexpr int PER = 16 / sizeof(RawT);
     auto locate = [&](int tile) -> TileLoc {  // (utterance, first frame) of a tile and the signal span it needs
         TileLoc t;
-        int lo = 0, hi = meta.B;  // largest b with tile_pfx[b] <= tile
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (meta.tile_pfx[mid] <= tile) lo = mid; else hi = mid;
-        }
-        t.b = lo;
+        t.b = meta.tile_b[tile];
         t.n = meta.lens[t.b];
         t.x = wave + meta.starts[t.b];
+        t.foff = meta.foff[t.b];
         t.L = t.n / kHop + 1;
         t.f0 = (tile - meta.tile_pfx[t.b]) * TF;
         t.nf = (int)min((int64_t)TF, t.L - t.f0);
@@ -221,7 +218,7 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
 
     for (int tile = blockIdx.x; tile < meta.n_tiles; tile += gridDim.x) {
         const int b = cur.b, f0 = cur.f0, nf = cur.nf, span = cur.span;
-        const int64_t n = cur.n, L = cur.L, i0 = cur.i0, g_lo = cur.g_lo, g_hi = cur.g_hi;
+        const int64_t n = cur.n, L = cur.L, i0 = cur.i0, g_lo = cur.g_lo, g_hi = cur.g_hi, foff_b = cur.foff;
         const RawT *x = cur.x;
         const bool fits = cur.fits, fast = cur.fast;
         const int delta = cur.delta;
@@ -386,7 +383,7 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
         }
         // row stride: t_stride (padded layout) or, packed (t_stride == 0), the utterance's own frame count
         const int64_t ld = t_stride > 0 ? t_stride : n / kHop + 1;
-        float *dst = features + meta.foff[b] + f0;
+        float *dst = features + foff_b + f0;
         for (int m = warp; m < kMel; m += FE_WARPS)
             if (lane < nf) dst[(size_t)m * ld + lane] = outt[m * OUT_LD + lane];
         cur = nxt;
@@ -526,8 +523,14 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
     if (slot < 0 || slot >= Ctx::kMaxChunks) return cudaErrorInvalidValue;
     DevBuf &fe_meta = c->fe_meta[slot], &fe_partials = c->fe_partials[slot];
     PinBuf &fe_meta_pin = c->fe_meta_pin[slot];
-    // host metadata: starts, lens, tile prefix -> one pinned block, one async copy
-    const size_t meta_bytes = sizeof(int64_t) * 3 * (size_t)B + sizeof(int32_t) * ((size_t)B + 1);
+    // host metadata: starts, lens, feature offsets, tile prefix, utterance of every tile -> one pinned block, one async copy
+    int64_t tiles = 0;
+    for (int b = 0; b < B; ++b) {
+        const int64_t L = lens_host[b] <= 0 ? 0 : lens_host[b] / kHop + 1;
+        tiles += (L + TF - 1) / TF;
+    }
+    if (tiles > 0x7fffffff) return cudaErrorInvalidValue;
+    const size_t meta_bytes = sizeof(int64_t) * 3 * (size_t)B + sizeof(int32_t) * ((size_t)B + 1 + (size_t)tiles);
     cudaError_t e;
     if ((e = fe_meta_pin.reserve(meta_bytes)) != cudaSuccess) return e;
     if ((e = fe_meta.reserve(meta_bytes)) != cudaSuccess) return e;
@@ -535,14 +538,17 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
     int64_t *h_lens = h_starts + B;
     int64_t *h_foff = h_lens + B;
     int32_t *h_pfx = reinterpret_cast<int32_t *>(h_foff + B);
-    int64_t tiles = 0;
+    int32_t *h_tile_b = h_pfx + B + 1;  // one load instead of a binary search over tile_pfx per tile
+    tiles = 0;
     for (int b = 0; b < B; ++b) {
         h_starts[b] = starts_host[b];
         h_lens[b] = lens_host[b];
         h_foff[b] = foff_host ? foff_host[b] : (int64_t)b * kMel * t_stride;
         h_pfx[b] = (int32_t)tiles;
         const int64_t L = lens_host[b] <= 0 ? 0 : lens_host[b] / kHop + 1;
-        tiles += (L + TF - 1) / TF;
+        const int64_t nt = (L + TF - 1) / TF;
+        for (int64_t t = 0; t < nt; ++t) h_tile_b[tiles + t] = b;
+        tiles += nt;
     }
     h_pfx[B] = (int32_t)tiles;
     if (tiles > 0x7fffffff) return cudaErrorInvalidValue;
@@ -557,6 +563,7 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
     meta.lens = meta.starts + B;
     meta.foff = meta.lens + B;
     meta.tile_pfx = reinterpret_cast<const int32_t *>(meta.foff + B);
+    meta.tile_b = meta.tile_pfx + B + 1;
     meta.B = B;
     meta.n_tiles = (int)tiles;
     if ((e = fe_partials.reserve(sizeof(double2) * (size_t)std::max<int64_t>(tiles, 1) * kMel)) != cudaSuccess) return e;
