@@ -33,7 +33,7 @@ F_FRAME = 1_310_720      # flop per (stream, encoder frame): hoisted encoder pro
 BYTES_PER_AUDIO_S = 83_200  # front end, i16 in + f32 [128, T'] out
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this command's default workload
 # (profiles/r1e_ncu_full_raw.csv); reported as roofline.traffic only for that workload
-NCU_DRAM_BYTES = {"greedy": 651_576_576, "fe_logmel": 1_549_147_392}
+NCU_DRAM_BYTES = {"greedy": 649_477_376, "fe_logmel": 1_550_140_928}
 ENGINE_NAMES = {0: ("greedy_ws_kernel", "tcgen05 split-bf16 weight-stationary dataflow kernel"),
                 1: ("greedy_persistent_kernel", "fp32 persistent cooperative kernel"),
                 2: ("greedy_tc_kernel", "tcgen05 split-bf16 grid-synchronised kernel"),
