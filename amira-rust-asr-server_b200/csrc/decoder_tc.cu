@@ -1202,7 +1202,8 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
         // three uploads are queued at a time (the host waits on the event of chunk k-3): the copy engine is FIFO across
         // streams, and a burst of bulk copies would starve the copies of any other context sharing the GPU.
         const size_t enc_bytes = sizeof(float) * (enc_off_host ? (size_t)enc_off_host[B] : (size_t)B * kEnc * T);
-        const int by_bytes = (int)std::min<size_t>((size_t)2 * Ctx::kMaxChunks, enc_bytes / ((size_t)24 << 20));  // >= 24 MB per chunk
+        int by_bytes = (int)std::min<size_t>((size_t)2 * Ctx::kMaxChunks, enc_bytes / ((size_t)24 << 20));  // >= 24 MB per chunk
+        if (const char *f = getenv("AMIRA_FORCE_CHUNKS")) by_bytes = std::min(2 * Ctx::kMaxChunks, atoi(f));  // tests: chunked path at small sizes
         const int n_chunks = enc_host ? std::max(1, std::min(by_bytes, B / 32)) : 1;
         for (int k = 0; k < n_chunks; ++k) {
             const int b0 = (int)((long long)B * k / n_chunks), b1 = (int)((long long)B * (k + 1) / n_chunks);

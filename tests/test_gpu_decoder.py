@@ -227,6 +227,7 @@ def test_full_size_batch_256_properties(ctx, amira):
 def test_pipelined_host_upload_equals_resident_decode(amira):
     """Encoder outputs in host memory are uploaded chunk by chunk, overlapped with the projection of the chunks already on
     the device (>= 64 streams => several chunks); the tokens must equal the device-resident decode of the same batch."""
+    import os
     import torch
     rng = np.random.default_rng(21)
     B, T = 96, 24
@@ -234,7 +235,14 @@ def test_pipelined_host_upload_equals_resident_decode(amira):
     lens = rng.integers(1, T + 1, size=B).astype(np.int64)
     with amira.Context(device_id=0) as c:
         c.load_weights(amira.synthetic_weights(3456))
-        toks_h, _, steps_h = c.greedy_decode(enc, lens)
+        os.environ["AMIRA_FORCE_CHUNKS"] = "3"  # the library chunks by bytes (>= 24 MB per chunk): force the chunked path here
+        try:
+            toks_h, _, steps_h = c.greedy_decode(enc, lens)
+            ragged = [np.ascontiguousarray(enc[b, :, :int(lens[b])]) for b in range(B)]
+            toks_k, _, steps_k = c.greedy_decode_packed(ragged)
+        finally:
+            os.environ.pop("AMIRA_FORCE_CHUNKS", None)
+        assert toks_k == toks_h and steps_k.tolist() == steps_h.tolist()
         enc_d = torch.from_numpy(enc).cuda()
         tok_d = torch.zeros((B, c.max_total_tokens), dtype=torch.int32, device="cuda")
         nt_d = torch.zeros(B, dtype=torch.int32, device="cuda")
