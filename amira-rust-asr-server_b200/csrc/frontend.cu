@@ -436,40 +436,40 @@ fe_normalize_kernel(FeMeta meta, float *__restrict__ features, int64_t t_stride,
     const double sd = L > 1 ? sqrt(cm2 / (double)(L - 1)) : 0.0;
     const float mu = (float)cmean;
     const float inv = (float)(1.0 / (sd + 1e-5));
-    const bool vec = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 4 == 0);
-    if (vec) {
-        float4 *p4 = reinterpret_cast<float4 *>(p);
-        const int64_t n4 = ld / 4;
-        // four independent 128-bit loads in flight per lane before the first store (the row is read and written through
-        // the same pointer, so the compiler keeps load -> store order; batching restores the memory-level parallelism)
-        for (int64_t i0 = lane; i0 < n4; i0 += 128) {
-            float4 v[4];
+    // scalar head up to the first 16-byte boundary (rows of the ragged layout start anywhere), 128-bit body, scalar tail
+    const int64_t head = min(ld, (int64_t)(((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) / sizeof(float)));
+    if (lane < head) p[lane] = lane < L ? (p[lane] - mu) * inv : 0.f;
+    float4 *p4 = reinterpret_cast<float4 *>(p + head);
+    const int64_t n4 = (ld - head) / 4;
+    // four independent 128-bit loads in flight per lane before the first store (the row is read and written through
+    // the same pointer, so the compiler keeps load -> store order; batching restores the memory-level parallelism)
+    for (int64_t i0 = lane; i0 < n4; i0 += 128) {
+        float4 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t i = i0 + 32 * u;
-                v[u] = (i < n4 && i * 4 < L) ? p4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t i = i0 + 32 * u, t = i * 4;
-                if (i >= n4) continue;
-                float4 w = v[u];
-                if (t + 3 < L) {
-                    w.x = (w.x - mu) * inv; w.y = (w.y - mu) * inv; w.z = (w.z - mu) * inv; w.w = (w.w - mu) * inv;
-                } else if (t >= L) {
-                    w = make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
-                    w.x = (w.x - mu) * inv;
-                    w.y = t + 1 < L ? (w.y - mu) * inv : 0.f;
-                    w.z = t + 2 < L ? (w.z - mu) * inv : 0.f;
-                    w.w = 0.f;
-                }
-                p4[i] = w;
-            }
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + 32 * u;
+            v[u] = (i < n4 && head + i * 4 < L) ? p4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    } else {
-        for (int64_t t = lane; t < ld; t += 32) p[t] = t < L ? (p[t] - mu) * inv : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + 32 * u, t = head + i * 4;
+            if (i >= n4) continue;
+            float4 w = v[u];
+            if (t + 3 < L) {
+                w.x = (w.x - mu) * inv; w.y = (w.y - mu) * inv; w.z = (w.z - mu) * inv; w.w = (w.w - mu) * inv;
+            } else if (t >= L) {
+                w = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                w.x = (w.x - mu) * inv;
+                w.y = t + 1 < L ? (w.y - mu) * inv : 0.f;
+                w.z = t + 2 < L ? (w.z - mu) * inv : 0.f;
+                w.w = 0.f;
+            }
+            p4[i] = w;
+        }
     }
+    const int64_t t_tail = head + n4 * 4 + lane;
+    if (t_tail < ld) p[t_tail] = t_tail < L ? (p[t_tail] - mu) * inv : 0.f;
 }
 
 __global__ void bytes_to_f32_kernel(const uint8_t *__restrict__ in, size_t n_bytes, int drop_odd, float *__restrict__ out) {

@@ -283,7 +283,10 @@ def main():
 
     pcm_pin = torch.from_numpy(pcm).pin_memory()
     pcm_dev = pcm_pin.to(dev)
-    feats_dev = torch.empty((B, 128, t_stride), dtype=torch.float32, device=dev)
+    # features in the ragged layout the reference hands its encoder per request ([128][features_len_b] blocks, nothing padded)
+    foff_dev = np.zeros(B + 1, np.int64)
+    foff_dev[1:] = np.cumsum(128 * flens)
+    feats_dev = torch.empty(int(foff_dev[-1]), dtype=torch.float32, device=dev)
     g = torch.Generator(device=dev)
     g.manual_seed(2345 + rank)
     enc_dev = torch.randn((B, 1024, T), generator=g, device=dev, dtype=torch.float32) * 0.5
@@ -294,7 +297,7 @@ def main():
     torch.cuda.synchronize()
 
     def step_device():
-        ctx.preprocess_pcm16_raw(pcm_dev.data_ptr(), offsets, B, feats_dev.data_ptr(), t_stride, flens_out)
+        ctx.preprocess_pcm16_packed_raw(pcm_dev.data_ptr(), offsets, B, feats_dev.data_ptr(), foff_dev, flens_out)
         ctx.greedy_decode_raw(enc_dev.data_ptr(), B, T, elens, tok_dev.data_ptr(), ntok_dev.data_ptr(), nsteps_dev.data_ptr())
 
     def barrier():
