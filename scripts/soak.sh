@@ -1,11 +1,11 @@
 #!/bin/bash
 # stability soak: repeated decode benches and test runs; any non-zero exit or timeout is reported
 fail=0
-for i in $(seq 1 12); do
+for i in $(seq 1 8); do
   timeout 120 python bench.py --steps 4 --warmup 2 --no-cpu --no-stream > gpurun_out/soak_$i.json 2> gpurun_out/soak_$i.err || { echo "bench run $i FAILED rc=$?"; fail=1; }
 done
-for i in 1 2 3; do
-  timeout 300 python -m pytest tests/test_gpu_decoder.py tests/test_gpu_streaming.py -q -x 2>&1 | tail -1
+for i in 1 2; do
+  timeout 300 python -m pytest tests -q -x -m gpu 2>&1 | tail -1
 done
 python - <<'PY'
 import json, glob
