@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 
 #include "common.h"
@@ -86,6 +87,22 @@ cudaError_t finish_out(Ctx *c, T *host, const T *dev, size_t count, bool is_host
     return cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream);
 }
 
+// A failing call must not leave copies in flight that still target the caller's host buffers or this context's pinned /
+// staging buffers (the caller may free its buffers after the error, the next call reuses ours): every exit that is not the
+// success path waits for the three streams first.
+struct DrainOnError {
+    Ctx *c;
+    bool armed = true;
+    explicit DrainOnError(Ctx *ctx) : c(ctx) {}
+    ~DrainOnError() {
+        if (!armed) return;
+        if (c->h2d_stream) cudaStreamSynchronize(c->h2d_stream);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
+        cudaGetLastError();
+    }
+};
+
 #define CK(call, what)                                      \
     do {                                                    \
         cudaError_t _e = (call);                            \
@@ -156,8 +173,7 @@ int32_t amira_ctx_create(const amira_config *cfg, amira_ctx **out) {
     amira_config_default(&dflt);
     if (!cfg) cfg = &dflt;
     if (cfg->max_symbols_per_step <= 0 || cfg->max_total_tokens <= 0 || cfg->blank_id < 0 || cfg->blank_id >= kV ||
-        cfg->max_streams < 0 || cfg->joint_activation < 0 || cfg->joint_activation > 1 || cfg->decode_engine < 0 ||
-        cfg->decode_engine > 4)
+        cfg->max_streams < 0 || cfg->joint_activation < 0 || cfg->joint_activation > 1 || (cfg->decode_engine != 0 && cfg->decode_engine != 1 && cfg->decode_engine != 4))
         return fail(nullptr, AMIRA_ERR_INVALID_VALUE, "invalid amira_config");
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -197,11 +213,16 @@ int32_t amira_ctx_create(const amira_config *cfg, amira_ctx **out) {
     for (cudaEvent_t &ev : c->ev_pool)  // blocking sync: a host thread throttled on one of these yields its core
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&c->ev_block, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) return bail(e, "event");
-    FrontendTables *ht = new FrontendTables();
-    build_frontend_tables(ht);
-    e = cudaMalloc(&c->tables_dev, sizeof(FrontendTables));
-    if (e == cudaSuccess) e = cudaMemcpy(c->tables_dev, ht, sizeof(FrontendTables), cudaMemcpyHostToDevice);
-    delete ht;
+    try {  // host allocations below may throw: no exception crosses the C boundary, and the half-built context is released
+        std::unique_ptr<FrontendTables> ht(new FrontendTables());
+        build_frontend_tables(ht.get());
+        e = cudaMalloc(&c->tables_dev, sizeof(FrontendTables));
+        if (e == cudaSuccess) e = cudaMemcpy(c->tables_dev, ht.get(), sizeof(FrontendTables), cudaMemcpyHostToDevice);
+        if (cfg->max_streams > 0) c->slot_used.assign((size_t)cfg->max_streams, 0);
+    } catch (...) {
+        amira_ctx_destroy(c);
+        return fail(nullptr, AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
     if (e != cudaSuccess) return bail(e, "front-end tables");
     if (cfg->max_streams > 0) {
         const size_t bytes = sizeof(float) * (size_t)cfg->max_streams * 2 * kH;
@@ -209,7 +230,6 @@ int32_t amira_ctx_create(const amira_config *cfg, amira_ctx **out) {
         if ((e = cudaMalloc(&c->slot_s2, bytes)) != cudaSuccess) return bail(e, "stream slots");
         cudaMemset(c->slot_s1, 0, bytes);
         cudaMemset(c->slot_s2, 0, bytes);
-        c->slot_used.assign((size_t)cfg->max_streams, 0);
     }
     *out = c;
     return AMIRA_OK;
@@ -370,6 +390,7 @@ static int32_t preprocess_common(amira_ctx *c, const void *wave, bool pcm16, con
     } else if (t_stride < max_len || t_stride <= 0) {
         return fail(c, AMIRA_ERR_INVALID_VALUE, "t_stride smaller than the longest features_len");
     }
+    DrainOnError drain(c);
     const size_t esz = pcm16 ? sizeof(int16_t) : sizeof(float);
     const size_t feat_count = feat_offsets ? (size_t)feat_offsets[B] : (size_t)B * kMel * (size_t)t_stride;
     auto feat_elem = [&](int b) -> size_t { return feat_offsets ? (size_t)feat_offsets[b] : (size_t)b * kMel * (size_t)t_stride; };
@@ -440,6 +461,7 @@ static int32_t preprocess_common(amira_ctx *c, const void *wave, bool pcm16, con
         }
         for (auto &ev : dbg_ev) cudaEventDestroy(ev);
     }
+    drain.armed = false;
     return AMIRA_OK;
 }
 
@@ -610,6 +632,7 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
             if (enc_offsets[b + 1] - enc_offsets[b] < (int64_t)kEnc * h_lens[b])
                 return fail(c, AMIRA_ERR_INVALID_VALUE, "enc_offsets: block smaller than 1024 x encoded_length");
     }
+    DrainOnError drain(c);
     CK(c->stage[9].reserve(sizeof(int32_t) * 2 * (size_t)B), "lens dev");
     CK(cudaMemcpyAsync(c->stage[9].p, h_lens, sizeof(int32_t) * 2 * (size_t)B, cudaMemcpyHostToDevice, c->stream), "lens H2D");
     const int32_t *lens_dev = c->stage[9].as<int32_t>();
@@ -648,6 +671,7 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
     int32_t n_failed = 0;
     CK(cudaMemcpyAsync(&n_failed, decoder_fail_count_dev(c), sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream), "status D2H");
     CK(wait_stream(c, c->stream, B >= 64 && !slots_host), "greedy decode sync");
+    drain.armed = false;
     // streams whose argmax left the embedding table and needed another step: the reference's next decoder_joint
     // call fails ("Decode step failed", src/asr/decoder_optimized.rs:148-152); their n_tokens is -1
     if (n_failed > 0) return fail(c, AMIRA_ERR_DECODE_STEP, "Decode step failed for " + std::to_string(n_failed) + " stream(s)");

@@ -334,7 +334,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) greedy_persistent_kernel(DecAr
                 for (int j = 0; j < 4; ++j) {
                     const int n = nt * TN + tx * 4 + j;
                     const float v = acc[i][j] + bbv[j];
-                    if (n < kV && (v > bv || bi == 0x7fffffff)) { bv = v; bi = n; }
+                    // zero_copy.rs:190-232: seed (logits[0], 0), replace on strict '>': NaN is returned only from index 0
+                    if (n < kV && (n == 0 || v > bv || (bi == 0x7fffffff && v == v))) { bv = v; bi = n; }
                 }
 #pragma unroll
                 for (int o = 8; o >= 1; o >>= 1) {
@@ -621,8 +622,8 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, const float *enc_host, int B, int T, const int32_t *lens_dev,
                                  const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev,
                                  int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev, const int64_t *enc_off_host) {
-    // decode_engine: 1 = fp32 CUDA-core persistent kernel (this file); tcgen05 split-bf16 (decoder_tc.cu): 2 = grid-synchronised,
-    // 3 = dataflow; 0 = auto (3)
+    // decode_engine: 1 = fp32 CUDA-core persistent kernel (this file, the numerics anchor); 0 = auto = 4 = tcgen05 split-bf16
+    // weight-stationary dataflow kernel (decoder_ws.cu, launched from decoder_tc.cu)
     if (c->cfg.decode_engine != 1)
         return launch_greedy_decode_tc(c, enc_dev, enc_host, B, T, lens_dev, lens_host, slots_dev, s1_dev, s2_dev, tokens_dev, ntok_dev,
                                        nsteps_dev, enc_off_host);

@@ -1031,15 +1031,18 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     for (int j = 0; j < 32; ++j) {
                         const int n = nb + j;
                         if (n < kV) {
+                            // zero_copy.rs:190-232 seeds (max, idx) with (logits[0], 0) and replaces on strict '>': a NaN can
+                            // only be returned from index 0 (nothing compares greater than it), a NaN anywhere else never wins
                             const float v = bof[j];
-                            if (v > best_v || best_i == 0x7fffffff) { best_v = v; best_i = n; }
+                            if (n == 0 || v > best_v || (best_i == 0x7fffffff && v == v)) { best_v = v; best_i = n; }
                         }
                     }
                     if (best_i != 0x7fffffff) {
                         // order-preserving map of the float, then ~column: the maximum key is the largest logit and, among equal
-                        // logits, the smallest column — the strict-'>' first-max rule of zero_copy.rs:190-232
-                        const unsigned fb = __float_as_uint(best_v);
-                        const unsigned ord = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+                        // logits, the smallest column — the strict-'>' first-max rule of zero_copy.rs:190-232.  -0.0 == +0.0
+                        // there, so both map to one key; a NaN seed (column 0 only) maps above every number.
+                        const unsigned fb = best_v == 0.f ? 0u : __float_as_uint(best_v);
+                        const unsigned ord = best_v != best_v ? 0xFFFFFFFFu : ((fb & 0x80000000u) ? ~fb : (fb | 0x80000000u));
                         atomicMax(p.amax + (size_t)(it & 1) * p.Mpad + row, ((unsigned long long)ord << 32) | (0xFFFFFFFFu - (unsigned)best_i));
                     }
                 }
@@ -1080,29 +1083,8 @@ cudaError_t decoder_ws_prepare(Ctx *c) {
     if ((e = make_tmap_bf16(&w->s_wp_lo, w->wp_lo, kH, kH, kH, W_SL)) != cudaSuccess) return e;
     if ((e = make_tmap_bf16(&w->s_wo_hi, w->wo_hi, W_ND * W_SL, kH, kH, W_SL)) != cudaSuccess) return e;
     if ((e = make_tmap_bf16(&w->s_wo_lo, w->wo_lo, W_ND * W_SL, kH, kH, W_SL)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(greedy_ws_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(greedy_ws_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(greedy_ws_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
-    // cluster variant: all 74 CTA pairs must be co-resident (one pair per TPC)
     w->ws_cluster = false;
-    // Opt-in (AMIRA_WS_CLUSTER=1): measured on B200 the pair variant halves the kernel's L2 read traffic but is ~8 % slower —
-    // the per-unit cost is the SM's shared-memory port (TMA writes + tcgen05 operand reads), not L2, and the lock step between
-    // the two CTAs adds hand-off latency.  Kept as a validated building block for a cta_group::2 version.
-    if (c->sm_count >= W_CTAS2 && getenv("AMIRA_WS_CLUSTER") && atoi(getenv("AMIRA_WS_CLUSTER")) == 1) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(W_CTAS2);
-        cfg.blockDim = dim3(W_THREADS);
-        cfg.dynamicSmemBytes = W_SMEM;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        int n_clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&n_clusters, greedy_ws_kernel<2, false>, &cfg) == cudaSuccess && n_clusters >= W_CTAS2 / 2)
-            w->ws_cluster = true;
-        cudaGetLastError();
-    }
     w->ws_ready = true;
     return cudaSuccess;
 }
@@ -1144,11 +1126,10 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     p.h0b_hi = reinterpret_cast<__nv_bfloat16 *>(work + oh0h); p.h0b_lo = reinterpret_cast<__nv_bfloat16 *>(work + oh0l);
     p.h1b_hi = reinterpret_cast<__nv_bfloat16 *>(work + oh1h); p.h1b_lo = reinterpret_cast<__nv_bfloat16 *>(work + oh1l);
     p.zb_hi = reinterpret_cast<__nv_bfloat16 *>(work + ozh); p.zb_lo = reinterpret_cast<__nv_bfloat16 *>(work + ozl);
-    const bool cluster = w->ws_cluster;
-    // TS form, one M-tile with few streams (the reference's B = 1 request, small micro-batches): a unit loads and multiplies only
+    const bool cluster = false;
+    // one M-tile with few streams (the reference's B = 1 request, small micro-batches): a unit loads and multiplies only
     // the first 32 / 64 rows of the tile — the activation ingest (327 KB per unit at 128 rows) is what a chain phase waits for
-    const bool use_ts_form = !cluster && !(getenv("AMIRA_WS_TS") && atoi(getenv("AMIRA_WS_TS")) == 0);
-    p.nrows = (use_ts_form && MT == 1 && !getenv("AMIRA_WS_FULLROWS")) ? (B <= 32 ? 32 : B <= 64 ? 64 : W_BM) : W_BM;
+    p.nrows = (MT == 1 && !getenv("AMIRA_WS_FULLROWS")) ? (B <= 32 ? 32 : B <= 64 ? 64 : W_BM) : W_BM;
     const uint32_t box_rows = cluster ? W_BM / 2 : (uint32_t)p.nrows;  // the cluster variant loads half a tile per CTA and multicasts it
     if ((e = make_tmap_bf16(&p.h0_hi, p.h0b_hi, 2 * (uint64_t)Mpad, kH, kH, box_rows)) != cudaSuccess) return e;
     if ((e = make_tmap_bf16(&p.h0_lo, p.h0b_lo, 2 * (uint64_t)Mpad, kH, kH, box_rows)) != cudaSuccess) return e;
@@ -1188,26 +1169,7 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
 
     void *params[] = {&p};
     ProfScope prof(c, PK_GREEDY);
-    if (cluster) {  // cooperative (grid.sync in the prologue) + clusters of two
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(W_CTAS2);
-        cfg.blockDim = dim3(W_THREADS);
-        cfg.dynamicSmemBytes = W_SMEM;
-        cfg.stream = c->stream;
-        cudaLaunchAttribute at[2];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        at[1].id = cudaLaunchAttributeCooperative;
-        at[1].val.cooperative = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 2;
-        e = cudaLaunchKernelExC(&cfg, (const void *)greedy_ws_kernel<2, false>, params);
-    } else {
-        // default: weights in tensor memory (TS); AMIRA_WS_TS=0 selects the shared-memory-stationary variant
-        const bool ts = !(getenv("AMIRA_WS_TS") && atoi(getenv("AMIRA_WS_TS")) == 0);
-        e = cudaLaunchCooperativeKernel(ts ? (const void *)greedy_ws_kernel<1, true> : (const void *)greedy_ws_kernel<1, false>, dim3(W_CTAS),
-                                        dim3(W_THREADS), params, W_SMEM, c->stream);
-    }
+    e = cudaLaunchCooperativeKernel((const void *)greedy_ws_kernel<1, true>, dim3(W_CTAS), dim3(W_THREADS), params, W_SMEM, c->stream);
     c->launches++;
     return e;
 }

@@ -42,6 +42,7 @@ int32_t run_request(amira_pipeline *p, const uint8_t *bytes, size_t n_bytes, con
     if (!p) return pfail(nullptr, AMIRA_ERR_INVALID_VALUE, "null pipeline");
     std::lock_guard<std::mutex> lock(p->mu);
     if (!out) return pfail(p, AMIRA_ERR_INVALID_VALUE, "null transcription");
+    if (tokens_cap < 0) return pfail(p, AMIRA_ERR_INVALID_VALUE, "negative tokens_cap");
     std::memset(out, 0, sizeof(*out));
     if (!p->ctx) return pfail(p, AMIRA_ERR_NO_DEVICE, "pipeline was created without a GPU context (vocabulary only)");
     if (text && text_cap) text[0] = '\0';
@@ -80,12 +81,15 @@ int32_t run_request(amira_pipeline *p, const uint8_t *bytes, size_t n_bytes, con
         return pfail(p, AMIRA_ERR_UNKNOWN, "encoder callback failed");
     out->encoded_length = enc_len;
     // step 3: greedy decode (:313-356) — one persistent kernel instead of one RPC per step
-    p->tokens.assign(AMIRA_MAX_TOTAL_TOKENS * 8, 0);  // >= max_total_tokens of any sane config
+    int32_t row_cap = AMIRA_MAX_TOTAL_TOKENS;  // the decode entry writes max_total_tokens ids per stream: size the row from the context
+    if ((rc = amira_ctx_max_total_tokens(p->ctx, &row_cap)) != 0 || row_cap <= 0) return pfail(p, rc ? rc : AMIRA_ERR_UNKNOWN, "cannot query max_total_tokens");
+    p->tokens.assign((size_t)row_cap, 0);
     int32_t ntok = 0;
     if (enc_len > 0) {
         rc = amira_greedy_decode(p->ctx, enc, 1, (int32_t)enc_len, &enc_len, states_1, states_2, p->tokens.data(), &ntok, nullptr);
         if (rc) return pfail(p, rc, amira_last_error(p->ctx));
     }
+    ntok = std::max(0, std::min(ntok, row_cap));
     out->n_tokens = ntok;
     if (tokens) std::memcpy(tokens, p->tokens.data(), sizeof(int32_t) * (size_t)std::min(ntok, tokens_cap));
     // step 4: tokens -> text (:361-363)
@@ -275,7 +279,9 @@ void run_batch(amira_batcher *b, std::vector<BatchReq *> &reqs) {
     std::lock_guard<std::mutex> plock(p->mu);  // the pipeline's context calls are serialised like single requests
     const int B = (int)reqs.size();
     auto fail_all = [&](int32_t rc, const std::string &m) {
-        for (BatchReq *r : reqs) finish_req(b, r, rc, m);
+        // a finished request is nulled in `reqs` (its owner may destroy it the moment it is marked done): skip those
+        for (BatchReq *&r : reqs)
+            if (r) { finish_req(b, r, rc, m); r = nullptr; }
     };
     try {
         b->offsets.assign((size_t)B + 1, 0);
@@ -326,6 +332,7 @@ void run_batch(amira_batcher *b, std::vector<BatchReq *> &reqs) {
             const int32_t n = b->ntok[(size_t)i];
             if (n < 0) {  // this stream's argmax left the embedding table ("Decode step failed", decoder_optimized.rs:148-152)
                 finish_req(b, r, AMIRA_ERR_DECODE_STEP, "Decode step failed");
+                reqs[(size_t)i] = nullptr;
                 continue;
             }
             const int32_t *tk = b->tokens.data() + (size_t)i * (size_t)row_cap;
@@ -333,7 +340,7 @@ void run_batch(amira_batcher *b, std::vector<BatchReq *> &reqs) {
             r->out->features_length = b->flens[(size_t)i];
             r->out->encoded_length = b->elens[(size_t)i];
             r->out->n_tokens = n;
-            if (r->tokens) std::memcpy(r->tokens, tk, sizeof(int32_t) * (size_t)std::min(n, r->tokens_cap));
+            if (r->tokens && r->tokens_cap > 0) std::memcpy(r->tokens, tk, sizeof(int32_t) * (size_t)std::min(n, r->tokens_cap));
             const std::string s = p->vocab.decode(tk, n);
             r->out->text_len = (int32_t)s.size();
             if (r->text && r->text_cap) {
@@ -341,14 +348,13 @@ void run_batch(amira_batcher *b, std::vector<BatchReq *> &reqs) {
                 std::memcpy(r->text, s.data(), m);
                 r->text[m] = '\0';
             }
+            reqs[(size_t)i] = nullptr;  // before the hand-back: the owner may free the request once it is done
             finish_req(b, r, AMIRA_OK, "");
         }
     } catch (const std::bad_alloc &) {
-        for (BatchReq *r : reqs)
-            if (r && !r->done) finish_req(b, r, AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed");
+        fail_all(AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed");
     } catch (...) {
-        for (BatchReq *r : reqs)
-            if (r && !r->done) finish_req(b, r, AMIRA_ERR_UNKNOWN, "unexpected exception");
+        fail_all(AMIRA_ERR_UNKNOWN, "unexpected exception");
     }
 }
 

@@ -448,23 +448,34 @@ void copy_text(const std::string &s, char *text, size_t cap, int32_t *len) {
 
 }  // namespace
 
+// no exception crosses the C boundary (std::bad_alloc / std::length_error from the string and vector work below)
+#define HS_TRY try {
+#define HS_CATCH(g_)                                                                                            \
+    } catch (const std::bad_alloc &) { return gfail((g_), AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed"); } \
+    catch (const std::exception &ex) { return gfail((g_), AMIRA_ERR_UNKNOWN, ex.what()); }                     \
+    catch (...) { return gfail((g_), AMIRA_ERR_UNKNOWN, "unexpected exception"); }
+
 extern "C" {
 
 int32_t amira_weave_transcript_segs(const char *first_seg, const char *second_seg, float percent_time_overlap, float min_alignment_score,
                                     char *out, size_t out_cap, int32_t *out_len) {
     if (!first_seg || !second_seg) return AMIRA_ERR_INVALID_VALUE;
+    HS_TRY
     copy_text(encode_utf8(weave_transcript_segs(decode_utf8(first_seg), decode_utf8(second_seg), percent_time_overlap, min_alignment_score)),
               out, out_cap, out_len);
     return AMIRA_OK;
+    HS_CATCH(nullptr)
 }
 
 int32_t amira_best_alignment(const char *first, const char *second, float percent_time_overlap, int32_t *overlap, float *score) {
     if (!first || !second || !overlap || !score) return AMIRA_ERR_INVALID_VALUE;
+    HS_TRY
     const u32s a = decode_utf8(first), b = decode_utf8(second);
     size_t o;
     best_alignment({a.data(), a.size()}, {b.data(), b.size()}, percent_time_overlap, &o, score);
     *overlap = (int32_t)o;
     return AMIRA_OK;
+    HS_CATCH(nullptr)
 }
 
 int32_t amira_is_overlap_silence(const float *overlap_audio, size_t n, float mean_amplitude, int32_t *silent) {
@@ -484,6 +495,7 @@ int32_t amira_window_sequence(int64_t total_len, int64_t window_size, int64_t le
     if (total_len < 0 || window_size <= 0 || leading_context < 0 || trailing_context < 0 || !n_windows ||
         window_size <= leading_context + trailing_context)
         return AMIRA_ERR_INVALID_VALUE;
+    HS_TRY
     const std::vector<Window> w = window_sequence((size_t)total_len, (size_t)window_size, (size_t)leading_context, (size_t)trailing_context);
     *n_windows = (int32_t)w.size();
     for (int32_t i = 0; i < *n_windows && i < cap; ++i) {
@@ -494,6 +506,7 @@ int32_t amira_window_sequence(int64_t total_len, int64_t window_size, int64_t le
         if (overlap_ratio) overlap_ratio[i] = w[(size_t)i].overlap;
     }
     return AMIRA_OK;
+    HS_CATCH(nullptr)
 }
 
 int32_t amira_stream_group_create(amira_pipeline *p, int32_t n_streams, float chunk_size, float leading_context, float trailing_context,
@@ -512,7 +525,7 @@ int32_t amira_stream_group_create(amira_pipeline *p, int32_t n_streams, float ch
             s->reset_state();
             g->sessions.push_back(std::move(s));
         }
-    } catch (const std::bad_alloc &) {
+    } catch (...) {
         delete g;
         return AMIRA_ERR_OUT_OF_MEMORY;
     }
@@ -541,7 +554,7 @@ int32_t amira_stream_group_process_chunks(amira_stream_group *g, int32_t n, cons
     std::lock_guard<std::mutex> lock(g->mu);
     if (n < 0 || (n > 0 && (!streams || !audio_bytes || !n_bytes))) return gfail(g, AMIRA_ERR_INVALID_VALUE, "process_chunks: bad arguments");
     if (!g->p->ctx) return gfail(g, AMIRA_ERR_NO_DEVICE, "pipeline was created without a GPU context");
-    try {
+    HS_TRY
         std::vector<char> seen(g->sessions.size(), 0);
         for (int32_t i = 0; i < n; ++i) {
             if (streams[i] < 0 || (size_t)streams[i] >= g->sessions.size() || seen[(size_t)streams[i]])
@@ -573,16 +586,16 @@ int32_t amira_stream_group_process_chunks(amira_stream_group *g, int32_t n, cons
             if (rcs[a] && !worst) worst = rcs[a];
         }
         return worst;
-    } catch (const std::bad_alloc &) {
-        return gfail(g, AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed");
-    }
+    HS_CATCH(g)
 }
 
 int32_t amira_stream_group_transcript(amira_stream_group *g, int32_t stream, char *text, size_t text_cap, int32_t *text_len) {
     if (!g || stream < 0 || (size_t)stream >= g->sessions.size()) return AMIRA_ERR_INVALID_VALUE;
     std::lock_guard<std::mutex> lock(g->mu);
+    HS_TRY
     copy_text(encode_utf8(g->sessions[(size_t)stream]->transcript), text, text_cap, text_len);
     return AMIRA_OK;
+    HS_CATCH(g)
 }
 
 int32_t amira_stream_group_tokens(amira_stream_group *g, int32_t stream, int32_t *tokens, int32_t tokens_cap, int32_t *n_tokens) {
@@ -614,7 +627,7 @@ int32_t amira_stream_group_process_batch(amira_stream_group *g, int32_t stream, 
         if (rc) g->err = amira_pipeline_last_error(g->p);
         return rc;
     }
-    try {
+    HS_TRY
         std::vector<float> samples(ns);
         for (size_t k = 0; k < ns; ++k) {
             const int16_t v = (int16_t)((uint16_t)audio_bytes[2 * k] | ((uint16_t)audio_bytes[2 * k + 1] << 8));
@@ -631,9 +644,7 @@ int32_t amira_stream_group_process_batch(amira_stream_group *g, int32_t stream, 
         if (tokens && tokens_cap > 0) std::memcpy(tokens, s.token_ids.data(), sizeof(int32_t) * std::min<size_t>(s.token_ids.size(), (size_t)tokens_cap));
         copy_text(encode_utf8(s.transcript), text, text_cap, &out->text_len);
         return AMIRA_OK;
-    } catch (const std::bad_alloc &) {
-        return gfail(g, AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed");
-    }
+    HS_CATCH(g)
 }
 
 int32_t amira_stream_group_stats(amira_stream_group *g, int64_t *n_pipeline_calls, int64_t *n_rounds) {

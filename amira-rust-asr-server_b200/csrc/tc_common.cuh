@@ -125,9 +125,7 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bflo
 struct TcWeights {
     __nv_bfloat16 *whh0_hi = nullptr, *whh0_lo = nullptr, *w1_hi = nullptr, *w1_lo = nullptr, *wp_hi = nullptr, *wp_lo = nullptr,
                   *wo_hi = nullptr, *wo_lo = nullptr, *we_hi = nullptr, *we_lo = nullptr;
-    CUtensorMap m_whh0_hi, m_whh0_lo, m_w1_hi, m_w1_lo, m_wp_hi, m_wp_lo, m_wo_hi, m_wo_lo;          // box {64 k, 128 rows}
     CUtensorMap s_whh0_hi, s_whh0_lo, s_w1_hi, s_w1_lo, s_wp_hi, s_wp_lo, s_wo_hi, s_wo_lo;          // box {64 k, 64 rows}
-    int coop_blocks_per_sm = 0;
     bool ws_ready = false;    // decoder_ws.cu: kernel attributes set
     bool ws_cluster = false;  // decoder_ws.cu: the 74-CTA-pair cluster variant fits this device
 };

@@ -36,8 +36,6 @@ BYTES_PER_AUDIO_S = 83_200  # front end, i16 in + f32 [128, T'] out (SURVEY.md 8
 NCU_DRAM_BYTES = {"greedy": 649_477_376, "fe_logmel": 1_550_140_928}
 ENGINE_NAMES = {0: ("greedy_ws_kernel", "tcgen05 split-bf16 weight-stationary dataflow kernel"),
                 1: ("greedy_persistent_kernel", "fp32 persistent cooperative kernel"),
-                2: ("greedy_tc_kernel", "tcgen05 split-bf16 grid-synchronised kernel"),
-                3: ("greedy_df_kernel", "tcgen05 split-bf16 dataflow kernel"),
                 4: ("greedy_ws_kernel", "tcgen05 split-bf16 weight-stationary dataflow kernel")}
 
 
@@ -143,28 +141,60 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference(pcm, offsets, lens, sample: int, threads: int):
-    """The CPU restatement of the reference path (oracle/; the reference binary itself needs cargo + Triton + ONNX
-    weights, none of which exist here) on a bounded sample of the workload, all host threads."""
+def oracle_module():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
+    return O
+
+
+def synthetic_weights_cpu(O, seed: int = 3456):
+    """The benchmark model (amira_b200.synthetic_weights) built WITHOUT libamira_b200.so: the oracle's own generator
+    (bit-identical to amira_weights_random_init, tests/test_abi.py::test_library_random_init_equals_oracle_generator) plus
+    the rescaling recipe, whose constants are plain Python in amira_b200 (importing the module does not load the library)."""
     import amira_b200 as A
-    sample = min(sample, lens.size)
-    t_stride = int(max(l // 160 + 1 for l in lens[:sample]))
-    t0 = time.perf_counter()
-    feats, flens = O.preprocess_pcm16_batch(pcm[:offsets[sample]], offsets[:sample + 1], t_stride, threads)
-    t_fe = time.perf_counter() - t0
-    elens = np.array([encoded_len(int(x)) for x in flens], np.int64)
-    T = int(elens.max())
-    rng = np.random.default_rng(2345)
-    enc = (0.5 * rng.standard_normal((sample, 1024, T))).astype(np.float32)
-    model = O.Model(blob=A.synthetic_weights(3456))
-    t0 = time.perf_counter()
-    r = O.greedy_decode_batch(model, enc, enc_lens=elens, threads=threads)
-    t_dec = time.perf_counter() - t0
-    audio_s = float(lens[:sample].sum()) / 16000.0
-    return {"audio_s": audio_s, "t_fe": t_fe, "t_dec": t_dec, "value": audio_s / (t_fe + t_dec),
-            "steps": int(r["n_steps"].sum()), "tokens": int(r["n_tokens"].sum())}
+    blob = O.Model(seed=seed).blob.copy()
+    t = A.blob_views(blob)
+    for k, v in A.SYNTH_SCALE.items():
+        t[k] *= np.float32(v)
+    t["b_out"][1025:1030] -= np.float32(100.0)
+    t["b_out"][A.BLANK_ID] += np.float32(A.SYNTH_BLANK_BIAS)
+    return blob
+
+
+def sample_encoder_outputs(elens: np.ndarray, seed: int = 2345) -> np.ndarray:
+    """Seeded synthetic encoder outputs [n, 1024, max T] for the CPU sample; the GPU arm decodes the SAME tensors in those rows
+    (rank 0), so tokens can be compared (the `parity` key)."""
+    rng = np.random.default_rng(seed)
+    return (0.5 * rng.standard_normal((elens.size, 1024, int(elens.max())))).astype(np.float32)
+
+
+class CpuReference:
+    """The CPU restatement of the reference path (oracle/; the reference binary itself needs cargo + Triton + ONNX weights,
+    none of which exist here) on a bounded sample of the workload, all host threads.  Everything that is not the path itself —
+    synthetic inputs, weights, output buffers' first touch — is built in __init__, outside any timed region."""
+
+    def __init__(self, pcm, offsets, lens, sample: int, threads: int):
+        self.O = oracle_module()
+        self.n = n = min(sample, lens.size)
+        self.threads = threads
+        self.pcm, self.offsets, self.lens = pcm[:offsets[n]], offsets[:n + 1], lens[:n]
+        flens = self.lens // 160 + 1
+        self.t_stride = int(flens.max())
+        self.elens = np.array([encoded_len(int(x)) for x in flens], np.int64)
+        self.enc = sample_encoder_outputs(self.elens)
+        self.model = self.O.Model(blob=synthetic_weights_cpu(self.O))
+        self.audio_s = float(self.lens.sum()) / 16000.0
+        self.O.lib()
+
+    def run(self):
+        t0 = time.perf_counter()
+        feats, flens = self.O.preprocess_pcm16_batch(self.pcm, self.offsets, self.t_stride, self.threads)
+        t1 = time.perf_counter()
+        r = self.O.greedy_decode_batch(self.model, self.enc, enc_lens=self.elens, threads=self.threads)
+        t2 = time.perf_counter()
+        assert np.array_equal(np.array([encoded_len(int(x)) for x in flens], np.int64), self.elens)
+        return {"audio_s": self.audio_s, "t_fe": t1 - t0, "t_dec": t2 - t1, "value": self.audio_s / (t2 - t0),
+                "steps": int(r["n_steps"].sum()), "tokens": int(r["n_tokens"].sum()), "decode": r}
 
 
 def run_reference(args, rank: int):
@@ -173,23 +203,25 @@ def run_reference(args, rank: int):
     threads = len(os.sched_getaffinity(0)) or 1
     if args.ref_sample <= 0:
         args.ref_sample = min(8 * threads, args.utterances)
-    pcm, offsets, lens = make_workload(args.ref_sample, 4567)
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_reference(pcm, offsets, lens, min(2, args.ref_sample), threads)
+    pcm, offsets, lens = make_workload(args.utterances, 4567)  # the b200 arm's rank-0 workload; the sample is its first utterances
+    ref = CpuReference(pcm, offsets, lens, args.ref_sample, threads)
+    if args.warmup > 0:
+        CpuReference(pcm, offsets, lens, min(2, args.ref_sample), threads).run()
     ts, last = [], None
     for _ in range(args.steps):
-        t0 = time.perf_counter()
-        last = cpu_reference(pcm, offsets, lens, args.ref_sample, threads)
-        ts.append(time.perf_counter() - t0)
+        last = ref.run()
+        ts.append(last["t_fe"] + last["t_dec"])
     ms = 1e3 * float(np.mean(ts))
     val = last["audio_s"] / (ms / 1e3)
-    sample = f"{args.ref_sample} utterances ({last['audio_s']:.0f} audio-s) of the same seeded workload per step"
+    sample = (f"first {ref.n} utterances ({last['audio_s']:.0f} audio-s) of the b200 arm's seeded rank-0 workload per step "
+              f"(a rate: same_config apart from the sample size); inputs, weights and encoder tensors are built before the timed loop")
     print(json.dumps({
         "impl": "reference", "metric": "audio-sec/sec (preproc + RNN-T greedy decode)", "value": val, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64 fft / f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (reference precision: fp32 front end, fp32 LSTM/joint)", "data": "synthetic",
         "config": {"workload": "cfg5 shard: 5-30 s mixed utterances, front end + greedy decode (CPU restatement of the "
-                               "reference path; no gRPC/Triton cost, so optimistic for the reference)", "sample": sample},
+                               "reference path; no gRPC/Triton cost, so optimistic for the reference)", "sample": sample,
+                   "front_end_s": last["t_fe"], "decode_s": last["t_dec"]},
         "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -228,6 +260,57 @@ def run_streaming(A, torch, dev, ctx, n_streams: int, ticks: int, warm: int):
             "audio_s_per_s": float(n_streams * 0.16 / (np.mean(lat) / 1e3)), "tokens_last_tick": int(ntok.numpy().clip(min=0).sum())}
 
 
+# ------------------------------------------------------------------------------------------------ cfg2 / cfg3 stand-alone
+def run_extras(A, torch, dev, ctx, stream, hbm_peak, tf_peak):
+    """BASELINE configs 2 and 3 on their own (device-resident inputs, CUDA events on the launching stream), so the driver's
+    record carries them: cfg2 = preprocessor only, 64 x 30 s; cfg3 = greedy loop only, 256 streams, T = 126 and 376."""
+    def timed_ms(fn, iters, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(iters):
+                fn()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out = {}
+    # cfg2
+    Bp, n = 64, 480000
+    pcm, offsets, _ = make_workload(Bp, 1234, 30.0, 30.0)
+    pcm_dev = torch.from_numpy(pcm).to(dev)
+    L = n // 160 + 1
+    feats = torch.empty((Bp, 128, L), dtype=torch.float32, device=dev)
+    flens = np.zeros(Bp, np.int64)
+    ms = timed_ms(lambda: ctx.preprocess_pcm16_raw(pcm_dev.data_ptr(), offsets, Bp, feats.data_ptr(), L, flens), 10)
+    byts = 2.0 * Bp * n + 4.0 * 128 * L * Bp + 16 * Bp
+    out["cfg2_preprocessor_64x30s"] = {"ms": ms, "audio_s_per_s": Bp * 30.0 / (ms / 1e3), "algorithmic_GBps": byts / (ms / 1e3) / 1e9,
+                                       "frac_of_hbm_peak": byts / (ms / 1e3) / 1e9 / hbm_peak,
+                                       "note": "both front-end kernels, resident PCM in, resident [64,128,3001] f32 out"}
+    del pcm_dev, feats
+    # cfg3
+    for T in (126, 376):
+        Bd = 256
+        g = torch.Generator(device=dev)
+        g.manual_seed(2345)
+        enc = torch.randn((Bd, 1024, T), generator=g, device=dev, dtype=torch.float32) * 0.5
+        tok = torch.zeros((Bd, ctx.max_total_tokens), dtype=torch.int32, device=dev)
+        nt = torch.zeros(Bd, dtype=torch.int32, device=dev)
+        ns = torch.zeros(Bd, dtype=torch.int32, device=dev)
+        ms = timed_ms(lambda: ctx.greedy_decode_raw(enc.data_ptr(), Bd, T, None, tok.data_ptr(), nt.data_ptr(), ns.data_ptr()), 5)
+        steps = int(ns.cpu().numpy().astype(np.int64).sum())
+        fl = steps * F_STEP + Bd * T * F_FRAME
+        out[f"cfg3_greedy_256xT{T}"] = {"ms": ms, "audio_s_per_s": Bd * T * 0.08 / (ms / 1e3), "decode_steps": steps,
+                                         "tokens": int(nt.cpu().numpy().clip(min=0).sum()), "algorithmic_TFLOPs": fl / (ms / 1e3) / 1e12,
+                                         "frac_of_tensor_peak": fl / (ms / 1e3) / 1e12 / tf_peak,
+                                         "note": "encoder projection + persistent decode kernel, resident inputs and outputs"}
+        del enc
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def main():
     ap = argparse.ArgumentParser()
@@ -241,6 +324,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the stand-alone cfg2 / cfg3 measurements")
     ap.add_argument("--e2e-inflight", type=int, default=2, help="steps in flight in the e2e leg (each on its own contexts)")
     ap.add_argument("--e2e-layout", choices=["packed", "padded"], default="packed",
                     help="host buffers of the e2e leg: ragged per-utterance blocks (default) or batch tensors padded to the longest")
@@ -290,6 +374,13 @@ def main():
     g = torch.Generator(device=dev)
     g.manual_seed(2345 + rank)
     enc_dev = torch.randn((B, 1024, T), generator=g, device=dev, dtype=torch.float32) * 0.5
+    cpu_ref = None
+    if rank == 0 and not args.no_cpu:
+        # rows [0, n) of the encoder tensor are the CPU sample's seeded numpy tensors, so both arms decode the same inputs there
+        # (`parity`); built here, outside every timed region
+        threads = len(ORIG_AFFINITY or os.sched_getaffinity(0)) or 1  # the CPU baseline uses every host core this process may use
+        cpu_ref = CpuReference(pcm, offsets, lens, args.cpu_sample if args.cpu_sample > 0 else min(8 * threads, B), threads)
+        enc_dev[:cpu_ref.n, :, :cpu_ref.enc.shape[2]].copy_(torch.from_numpy(cpu_ref.enc))
     tok_dev = torch.zeros((B, ctx.max_total_tokens), dtype=torch.int32, device=dev)
     ntok_dev = torch.zeros(B, dtype=torch.int32, device=dev)
     nsteps_dev = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -459,6 +550,7 @@ def main():
                    "global_utterances": B * world, "parallelism": f"dp{world} by utterance, no collective",
                    "cache": "inputs larger than L2 (PCM + encoder outputs > 2 GB per step)",
                    "decode_steps_per_step": int(nsteps.sum()), "tokens_per_step": int(ntok[ntok > 0].sum()),
+                   "tokens_per_encoder_frame": float(ntok[ntok > 0].sum()) / float(elens.sum()),
                    "decode_engine": ENGINE_NAMES[args.engine][1]},
         "clocks": clocks,
         "gpu_launches": int(launches),
@@ -474,16 +566,43 @@ def main():
         out["streaming"] = streaming
     if e2e:
         out["e2e"] = e2e
-    if not args.no_cpu:
+    extras = run_extras(A, torch, dev, ctx, stream, hbm_peak, tf_peak) if not args.no_extras else None
+    if extras:
+        out["extra"] = extras
+    if cpu_ref is not None:
         if ORIG_AFFINITY:
-            os.sched_setaffinity(0, ORIG_AFFINITY)  # the CPU baseline uses every host core this process may use
-        threads = len(os.sched_getaffinity(0)) or 1
-        if args.cpu_sample <= 0:
-            args.cpu_sample = min(8 * threads, B)
-        r = cpu_reference(pcm, offsets, lens, args.cpu_sample, threads)
-        out["cpu_baseline"] = {"value": r["value"], "unit": "audio-s/s", "cores": threads, "kind": "port",
-                               "sample": f"first {min(args.cpu_sample, B)} utterances of this workload ({r['audio_s']:.0f} audio-s): "
-                                         f"front end {r['t_fe']:.2f} s + decode {r['t_dec']:.2f} s, OpenMP over utterances"}
+            os.sched_setaffinity(0, ORIG_AFFINITY)
+        r = cpu_ref.run()
+        out["cpu_baseline"] = {"value": r["value"], "unit": "audio-s/s", "cores": cpu_ref.threads, "kind": "port",
+                               "sample": f"first {cpu_ref.n} utterances of this workload ({r['audio_s']:.0f} audio-s): "
+                                         f"front end {r['t_fe']:.2f} s + decode {r['t_dec']:.2f} s, OpenMP over utterances; "
+                                         "inputs, weights and encoder tensors built outside the timed region"}
+        # ---- parity of THIS run's GPU results with the oracle on the same inputs (outside every timed region) ----
+        tok_gpu = tok_dev.cpu().numpy()
+        d = r["decode"]
+        exact = near_tie = wrong = 0
+        for b in range(cpu_ref.n):
+            same = ntok[b] == d["n_tokens"][b] and np.array_equal(tok_gpu[b, :ntok[b]], d["tokens"][b, :ntok[b]]) and \
+                nsteps[b] == d["n_steps"][b]
+            if same:
+                exact += 1
+            elif float(d["min_margin"][b]) < 2e-4:
+                near_tie += 1
+            else:
+                wrong += 1
+        n_f = min(8, cpu_ref.n)
+        feats_host = feats_dev.cpu().numpy()
+        ferr = 0.0
+        for b in range(n_f):
+            w = pcm[offsets[b]:offsets[b + 1]].astype(np.float32) / 32768.0
+            ref_f, L = cpu_ref.O.preprocess(w, "f64")
+            got = feats_host[foff_dev[b]:foff_dev[b + 1]].reshape(128, -1)
+            ferr = max(ferr, float(np.abs(got[:, :L] - ref_f).max()))
+        out["parity"] = {"streams": cpu_ref.n, "exact": exact, "near_tie": near_tie, "mismatch": wrong, "near_tie_margin": 2e-4,
+                         "decode_steps_compared": int(d["n_steps"].sum()), "feature_utterances": n_f, "max_feat_err": ferr,
+                         "feat_tol": 1e-4, "oracle": "oracle/ (tokens: fp32 restatement on the same encoder tensors; features: f64)"}
+        if wrong or ferr > 1e-4:
+            out["parity"]["FAILED"] = True
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

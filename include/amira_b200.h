@@ -60,9 +60,9 @@ typedef struct {
     int32_t max_total_tokens;     /* 200 */
     int32_t blank_id;             /* 1024 */
     int32_t joint_activation;     /* 0 = tanh (north_star), 1 = relu */
-    int32_t decode_engine;        /* 0 = auto (4); 1 = fp32 CUDA-core persistent kernel; tcgen05 split-bf16 persistent
-                                   * kernels: 2 = grid-synchronised phases, 3 = dataflow (per-M-tile dependency counters),
-                                   * 4 = weight-stationary dataflow (weights resident in shared memory, one slice per SM) */
+    int32_t decode_engine;        /* 0 = auto (4); 1 = fp32 CUDA-core persistent kernel (numerics anchor); 4 = tcgen05 split-bf16
+                                   * weight-stationary dataflow kernel (one 64-feature weight slice resident in the tensor
+                                   * memory of each of 147 SMs).  Other values are rejected. */
     int32_t max_streams;          /* resident stream-state slots for the WebSocket path (default 1024) */
     int32_t reserved;
 } amira_config;
@@ -157,7 +157,7 @@ int32_t amira_greedy_decode(amira_ctx *ctx, const float *encoder_outputs, int32_
 /* Same, ragged input: stream b's encoder output is a dense [1024][encoded_lengths[b]] block at
  * encoder_outputs + enc_offsets[b] (element offsets, int64[B+1], host) — the per-request tensor of
  * EncoderModel::infer (src/triton/model.rs:298-420, outputs [1][1024][T_b]) as it is, instead of a batch padded to
- * the longest stream.  decode_engine 0/2/3/4. */
+ * the longest stream.  decode_engine 0 / 4. */
 int32_t amira_greedy_decode_packed(amira_ctx *ctx, const float *encoder_outputs, const int64_t *enc_offsets, int32_t B,
                                    const int64_t *encoded_lengths, float *states_1, float *states_2, int32_t *tokens,
                                    int32_t *n_tokens, int32_t *n_steps);
