@@ -121,13 +121,11 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bflo
 
 }  // namespace tc
 
-// device-resident split-bf16 operands of the decoder weights + their TMA maps (built by decoder_tc_prepare_weights)
+// device-resident split-bf16 operands of the decoder weights (built by decoder_tc_prepare_weights)
 struct TcWeights {
     __nv_bfloat16 *whh0_hi = nullptr, *whh0_lo = nullptr, *w1_hi = nullptr, *w1_lo = nullptr, *wp_hi = nullptr, *wp_lo = nullptr,
                   *wo_hi = nullptr, *wo_lo = nullptr, *we_hi = nullptr, *we_lo = nullptr;
-    CUtensorMap s_whh0_hi, s_whh0_lo, s_w1_hi, s_w1_lo, s_wp_hi, s_wp_lo, s_wo_hi, s_wo_lo;          // box {64 k, 64 rows}
     bool ws_ready = false;    // decoder_ws.cu: kernel attributes set
-    bool ws_cluster = false;  // decoder_ws.cu: the 74-CTA-pair cluster variant fits this device
 };
 
 // host: 2-D bf16 row-major [rows][cols] tensor map with box {64 cols, box_rows}, 128-byte swizzle
