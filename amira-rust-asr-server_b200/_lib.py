@@ -34,7 +34,8 @@ EXPORTS = ["amira_device_count", "amira_config_default", "amira_ctx_create", "am
            "amira_is_overlap_silence", "amira_mean_amplitude", "amira_window_sequence", "amira_stream_group_create",
            "amira_stream_group_destroy", "amira_stream_group_last_error", "amira_stream_group_clear",
            "amira_stream_group_process_chunks", "amira_stream_group_transcript", "amira_stream_group_tokens",
-           "amira_stream_group_audio_length", "amira_stream_group_process_batch", "amira_stream_group_stats"]
+           "amira_stream_group_audio_length", "amira_stream_group_process_batch", "amira_stream_group_stats", "amira_ctx_fork", "amira_device_alloc",
+           "amira_device_free", "amira_ipc_export", "amira_ipc_import", "amira_ipc_close"]
 
 
 class AmiraError(RuntimeError):
@@ -71,6 +72,12 @@ def load_library():
     L.amira_config_default.argtypes = [C.POINTER(_Config)]
     L.amira_ctx_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
     L.amira_ctx_destroy.argtypes = [vp]
+    L.amira_ctx_fork.argtypes = [vp, C.POINTER(vp)]
+    L.amira_device_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.amira_device_free.argtypes = [vp, vp]
+    L.amira_ipc_export.argtypes = [vp, vp, vp]
+    L.amira_ipc_import.argtypes = [vp, vp, C.POINTER(vp)]
+    L.amira_ipc_close.argtypes = [vp, vp]
     L.amira_last_error.argtypes = [vp]
     L.amira_last_error.restype = C.c_char_p
     L.amira_ctx_set_stream.argtypes = [vp, vp]
@@ -230,6 +237,36 @@ class Context:
             raise AmiraError(rc, (self._L.amira_last_error(None) or b"").decode())
 
     # -- lifecycle
+    def fork(self) -> "Context":
+        """Another submission lane on the same GPU sharing this context's weights (amira_ctx_fork)."""
+        lane = object.__new__(Context)
+        lane._L, lane.max_total_tokens, lane._h = self._L, self.max_total_tokens, C.c_void_p()
+        self._check(self._L.amira_ctx_fork(self._h, C.byref(lane._h)))
+        return lane
+
+    # -- device-resident hand-off (src/cuda/cuda_helper.cu:63-183)
+    def device_alloc(self, n_bytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._L.amira_device_alloc(self._h, n_bytes, C.byref(p)))
+        return int(p.value)
+
+    def device_free(self, dev_ptr: int):
+        self._check(self._L.amira_device_free(self._h, C.c_void_p(dev_ptr)))
+
+    def ipc_export(self, dev_ptr: int) -> bytes:
+        h = (C.c_ubyte * 64)()
+        self._check(self._L.amira_ipc_export(self._h, C.c_void_p(dev_ptr), C.cast(h, C.c_void_p)))
+        return bytes(h)
+
+    def ipc_import(self, handle: bytes) -> int:
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self._L.amira_ipc_import(self._h, C.cast(h, C.c_void_p), C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, dev_ptr: int):
+        self._check(self._L.amira_ipc_close(self._h, C.c_void_p(dev_ptr)))
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self._L.amira_ctx_destroy(self._h)

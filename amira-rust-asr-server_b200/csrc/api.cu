@@ -214,10 +214,14 @@ int32_t amira_ctx_create(const amira_config *cfg, amira_ctx **out) {
         if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&c->ev_block, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess) return bail(e, "event");
     try {  // host allocations below may throw: no exception crosses the C boundary, and the half-built context is released
+        c->shared = std::make_shared<SharedDev>();
+        c->shared->device = c->device;
         std::unique_ptr<FrontendTables> ht(new FrontendTables());
         build_frontend_tables(ht.get());
-        e = cudaMalloc(&c->tables_dev, sizeof(FrontendTables));
-        if (e == cudaSuccess) e = cudaMemcpy(c->tables_dev, ht.get(), sizeof(FrontendTables), cudaMemcpyHostToDevice);
+        e = cudaMalloc(&c->shared->tables_dev, sizeof(FrontendTables));
+        if (e == cudaSuccess) e = cudaMemcpy(c->shared->tables_dev, ht.get(), sizeof(FrontendTables), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = frontend_upload_tables(ht.get());
+        c->tables_dev = c->shared->tables_dev;
         if (cfg->max_streams > 0) c->slot_used.assign((size_t)cfg->max_streams, 0);
     } catch (...) {
         amira_ctx_destroy(c);
@@ -239,9 +243,12 @@ int32_t amira_ctx_destroy(amira_ctx *c) {
     if (!c) return AMIRA_OK;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    decoder_release(c);
-    if (c->tables_dev) cudaFree(c->tables_dev);
-    if (c->w_blob) cudaFree(c->w_blob);
+    decoder_release(c);  // this lane's workspace; tables and weights are freed with the last holder of `shared`
+    if (c->h2d_stream) cudaStreamSynchronize(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
+    c->tables_dev = nullptr;
+    c->w_blob = nullptr;
+    c->shared.reset();
     if (c->slot_s1) cudaFree(c->slot_s1);
     if (c->slot_s2) cudaFree(c->slot_s2);
     for (int k = 0; k < Ctx::kMaxChunks; ++k) {
@@ -323,7 +330,11 @@ int32_t amira_ctx_load_weights(amira_ctx *c, const float *blob, size_t n_params)
     API_BEGIN(c)
     if (!blob || n_params != (size_t)AMIRA_N_PARAMS || blob_layout().total != (size_t)AMIRA_N_PARAMS)
         return fail(c, AMIRA_ERR_INVALID_VALUE, "weight blob must hold exactly AMIRA_N_PARAMS fp32 values");
-    if (!c->w_blob) CK(cudaMalloc(&c->w_blob, sizeof(float) * n_params), "weights alloc");
+    // the weights live in `shared`: every lane forked from this context sees the new ones at its next call (the caller keeps the
+    // other lanes idle during a reload, as it would for any model swap)
+    std::lock_guard<std::mutex> wlock(c->shared->mu);
+    if (!c->shared->w_blob) CK(cudaMalloc(&c->shared->w_blob, sizeof(float) * n_params), "weights alloc");
+    c->w_blob = c->shared->w_blob;
     CK(cudaMemcpyAsync(c->w_blob, blob, sizeof(float) * n_params,
                        is_device_ptr(blob) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream),
        "weights copy");
@@ -332,6 +343,38 @@ int32_t amira_ctx_load_weights(amira_ctx *c, const float *blob, size_t n_params)
     c->has_weights = true;
     return AMIRA_OK;
     API_END(c)
+}
+
+// More submission lanes on the same GPU: the new context has its own streams, staging buffers and decode workspace and shares the
+// parent's weights and tables (read-only).  Calls on different lanes run concurrently: the upload of one batch overlaps the
+// kernels of another without a second copy of the model.  Stream slots stay with the parent (max_streams = 0 in the fork).
+int32_t amira_ctx_fork(amira_ctx *parent, amira_ctx **out) {
+    if (!out) return fail(parent, AMIRA_ERR_INVALID_VALUE, "null out pointer");
+    *out = nullptr;
+    if (!parent) return fail(nullptr, AMIRA_ERR_INVALID_VALUE, "null context");
+    amira_config cfg;
+    std::shared_ptr<SharedDev> sh;
+    {
+        std::lock_guard<std::mutex> lock(parent->mu);
+        cfg = parent->cfg;
+        sh = parent->shared;
+    }
+    cfg.max_streams = 0;
+    amira_ctx *c = nullptr;
+    const int32_t rc = amira_ctx_create(&cfg, &c);
+    if (rc) { parent->err = g_create_error; return rc; }
+    try {
+        std::lock_guard<std::mutex> lock(c->mu);
+        c->shared = sh;  // drops the fork's own (tables only) shared block
+        c->tables_dev = sh->tables_dev;
+        std::lock_guard<std::mutex> wlock(sh->mu);
+        decoder_adopt_shared(c);
+    } catch (...) {
+        amira_ctx_destroy(c);
+        return fail(parent, AMIRA_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+    *out = c;
+    return AMIRA_OK;
 }
 
 int32_t amira_ctx_load_weights_file(amira_ctx *c, const char *path) {
@@ -551,6 +594,7 @@ int32_t amira_decoder_joint(amira_ctx *c, const float *encoder_outputs, int32_t 
                             const float *input_states_2, float *outputs, int32_t *prednet_lengths,
                             float *output_states_1, float *output_states_2) {
     API_BEGIN(c)
+    if (c->shared && c->shared->version != c->weights_version) decoder_adopt_shared(c);
     if (!c->has_weights) return fail(c, AMIRA_ERR_NO_WEIGHTS, "amira_decoder_joint: no weights loaded");
     if (B <= 0 || T <= 0 || U <= 0 || !encoder_outputs || !targets || !outputs)
         return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_decoder_joint: bad arguments");
@@ -593,6 +637,7 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
                              const int64_t *encoded_lengths, const int32_t *slots_host, float *states_1, float *states_2,
                              int32_t *tokens, int32_t *n_tokens, int32_t *n_steps, const int64_t *enc_offsets = nullptr) {
     // enc_offsets != nullptr: packed encoder outputs — stream b is a [1024][encoded_lengths[b]] block at encoder_outputs + enc_offsets[b]
+    if (c->shared && c->shared->version != c->weights_version) decoder_adopt_shared(c);  // a sibling lane loaded weights
     if (!c->has_weights) return fail(c, AMIRA_ERR_NO_WEIGHTS, "greedy decode: no weights loaded");
     if (B < 0 || T < 0 || !tokens || !n_tokens || (B > 0 && T > 0 && !encoder_outputs))
         return fail(c, AMIRA_ERR_INVALID_VALUE, "greedy decode: bad arguments");
@@ -757,6 +802,57 @@ int32_t amira_stream_decode(amira_ctx *c, const int32_t *slots, int32_t n, const
     API_BEGIN(c)
     if (!slots && n > 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "null slots");
     return greedy_common(c, encoder_outputs, n, T, encoded_lengths, slots, nullptr, nullptr, tokens, n_tokens, n_steps);
+    API_END(c)
+}
+
+// ---------------------------------------------------------------------------------------------- device-resident hand-off
+// (the reference's CUDA shared-memory regions, src/cuda/cuda_helper.cu:63-183)
+int32_t amira_device_alloc(amira_ctx *c, size_t bytes, void **dev_ptr) {
+    API_BEGIN(c)
+    if (!dev_ptr || bytes == 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_device_alloc: bad arguments");
+    *dev_ptr = nullptr;
+    CK(cudaMalloc(dev_ptr, bytes), "device region alloc");
+    return AMIRA_OK;
+    API_END(c)
+}
+
+int32_t amira_device_free(amira_ctx *c, void *dev_ptr) {
+    API_BEGIN(c)
+    if (!dev_ptr) return AMIRA_OK;
+    CK(cudaStreamSynchronize(c->stream), "device region free sync");
+    CK(cudaFree(dev_ptr), "device region free");
+    return AMIRA_OK;
+    API_END(c)
+}
+
+int32_t amira_ipc_export(amira_ctx *c, const void *dev_ptr, amira_ipc_handle *handle) {
+    API_BEGIN(c)
+    static_assert(sizeof(amira_ipc_handle) == sizeof(cudaIpcMemHandle_t), "amira_ipc_handle is a cudaIpcMemHandle_t");
+    if (!dev_ptr || !handle || !is_device_ptr(dev_ptr)) return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_ipc_export: not a device pointer");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)), "cudaIpcGetMemHandle");
+    std::memcpy(handle->reserved, &h, sizeof(h));
+    return AMIRA_OK;
+    API_END(c)
+}
+
+int32_t amira_ipc_import(amira_ctx *c, const amira_ipc_handle *handle, void **dev_ptr) {
+    API_BEGIN(c)
+    if (!handle || !dev_ptr) return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_ipc_import: bad arguments");
+    *dev_ptr = nullptr;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle->reserved, sizeof(h));
+    CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    return AMIRA_OK;
+    API_END(c)
+}
+
+int32_t amira_ipc_close(amira_ctx *c, void *dev_ptr) {
+    API_BEGIN(c)
+    if (!dev_ptr) return AMIRA_OK;
+    CK(cudaStreamSynchronize(c->stream), "ipc close sync");
+    CK(cudaIpcCloseMemHandle(dev_ptr), "cudaIpcCloseMemHandle");
+    return AMIRA_OK;
     API_END(c)
 }
 

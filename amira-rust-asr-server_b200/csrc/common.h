@@ -5,6 +5,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -92,7 +93,21 @@ struct PinBuf {
 };
 
 struct TcWeights;  // decoder_tc.cu
-struct DecoderPriv {  // derived weight tables (decoder.cu) + tcgen05 operands (decoder_tc.cu)
+// Device memory that a context and its forks (amira_ctx_fork: more submission lanes on the same GPU) share read-only: front-end
+// tables, the fp32 weight blob, the derived weight tables and the split-bf16 tcgen05 operands.  Freed with the last context that
+// holds it.  `version` counts weight loads: a lane refreshes its cached pointers when it falls behind.
+struct SharedDev {
+    int device = 0;
+    FrontendTables *tables_dev = nullptr;
+    float *w_blob = nullptr;
+    float *g0p = nullptr, *whh0p = nullptr, *w1p = nullptr, *b1p = nullptr, *bjoint = nullptr, *woutp = nullptr, *boutp = nullptr;
+    TcWeights *tc = nullptr;
+    int coop_blocks_per_sm = 0;
+    int version = 0;  // 0 = no weights loaded
+    std::mutex mu;    // weight loads
+    ~SharedDev();     // decoder.cu
+};
+struct DecoderPriv {  // per-context view of the shared weight tables + this context's decode workspace
     float *g0p = nullptr, *whh0p = nullptr, *w1p = nullptr, *b1p = nullptr, *bjoint = nullptr, *woutp = nullptr, *boutp = nullptr;
     DevBuf work;
     int coop_blocks_per_sm = 0;
@@ -138,8 +153,10 @@ struct Ctx {
     PinBuf pin[10];
 
     // decoder
+    std::shared_ptr<SharedDev> shared;  // owner of tables_dev, w_blob and the weight tables behind `dec`
+    int weights_version = 0;            // version of `shared` this context's cached pointers belong to
     bool has_weights = false;
-    float *w_blob = nullptr;  // fp32 blob as loaded
+    float *w_blob = nullptr;  // fp32 blob as loaded (owned by `shared`)
     DecoderPriv *dec = nullptr;
 
     // stream slots (WebSocket path): device-resident LSTM state
@@ -170,10 +187,12 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
                             const int64_t *lens_host, int B, float *features_dev, int64_t t_stride, int slot = 0, int phase = 0,
                             const int64_t *foff_host = nullptr);
 cudaError_t launch_bytes_to_f32(Ctx *c, const uint8_t *bytes_dev, size_t n_bytes, bool drop_odd, float *out_dev);
+cudaError_t frontend_upload_tables(const FrontendTables *t);  // mel filterbank -> constant memory of the current device
 
 // decoder.cu ---------------------------------------------------------------------------------------------------
-cudaError_t decoder_prepare_weights(Ctx *c);  // derived tables from c->w_blob
-void decoder_release(Ctx *c);
+cudaError_t decoder_prepare_weights(Ctx *c);  // derived tables from c->w_blob, published in c->shared
+void decoder_adopt_shared(Ctx *c);            // refresh this context's cached weight pointers from c->shared (after a load / fork)
+void decoder_release(Ctx *c);                 // this context's workspace only; the weights go with the last holder of c->shared
 // enc_dev [B][1024][T]; lens_dev int32[B]; slots_dev nullable: when given, states live in c->slot_s1/2 rows
 // slots[b] ([slot][2][640]); otherwise s1/s2 are [2][B][640] in/out (nullable => zero start, result dropped).
 // enc_host != nullptr: the encoder outputs still live in host memory; the launcher uploads them into enc_dev chunk by
@@ -189,7 +208,7 @@ cudaError_t launch_decoder_joint(Ctx *c, const float *enc_dev, int B, int T, con
 
 // decoder_tc.cu (tcgen05 paths) --------------------------------------------------------------------------------
 cudaError_t decoder_tc_prepare_weights(Ctx *c);
-void decoder_tc_release(Ctx *c);
+void decoder_tc_free(TcWeights *w);
 cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *enc_host, int B, int T, const int32_t *lens_dev,
                                     const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev,
                                     int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev, const int64_t *enc_off_host = nullptr);
@@ -203,7 +222,7 @@ cudaError_t launch_split_transpose_enc(Ctx *c, const float *enc, int B, int T, c
 
 // decoder_ws.cu (weight-stationary dataflow engine, decode_engine = 4) ------------------------------------------
 bool decoder_ws_supported(const Ctx *c);
-cudaError_t decoder_ws_prepare(Ctx *c);
+cudaError_t decoder_ws_prepare(Ctx *c, TcWeights *w);
 // work == nullptr: size query (*work_bytes receives the workspace size).  E [B*T][640] and perm_dev [Mpad] from the caller.
 cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t *lens_dev, const int *perm_dev,
                              const int *eoff_dev, const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,

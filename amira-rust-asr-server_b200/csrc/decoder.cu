@@ -564,18 +564,37 @@ const int32_t *decoder_fail_count_dev(Ctx *c) { return c->dec ? c->dec->fail_cou
 
 void decoder_release(Ctx *c) {
     if (!c->dec) return;
-    DecoderPriv *d = c->dec;
-    for (float *p : {d->g0p, d->whh0p, d->w1p, d->b1p, d->bjoint, d->woutp, d->boutp})
-        if (p) cudaFree(p);
-    decoder_tc_release(c);
-    d->work.release();
-    delete d;
+    c->dec->work.release();
+    delete c->dec;
     c->dec = nullptr;
 }
 
-cudaError_t decoder_prepare_weights(Ctx *c) {
+SharedDev::~SharedDev() {
+    cudaSetDevice(device);
+    for (float *p : {g0p, whh0p, w1p, b1p, bjoint, woutp, boutp, w_blob})
+        if (p) cudaFree(p);
+    if (tables_dev) cudaFree(tables_dev);
+    decoder_tc_free(tc);
+    cudaGetLastError();
+}
+
+void decoder_adopt_shared(Ctx *c) {
+    SharedDev *sh = c->shared.get();
+    if (!sh || sh->version == 0) return;
     if (!c->dec) c->dec = new DecoderPriv();
     DecoderPriv *d = c->dec;
+    d->g0p = sh->g0p; d->whh0p = sh->whh0p; d->w1p = sh->w1p; d->b1p = sh->b1p; d->bjoint = sh->bjoint; d->woutp = sh->woutp; d->boutp = sh->boutp;
+    d->tc = sh->tc;
+    d->coop_blocks_per_sm = sh->coop_blocks_per_sm;
+    c->w_blob = sh->w_blob;
+    c->tables_dev = sh->tables_dev;
+    c->weights_version = sh->version;
+    c->has_weights = true;
+}
+
+cudaError_t decoder_prepare_weights(Ctx *c) {
+    SharedDev *d = c->shared.get();  // the tables are allocated once and rewritten in place by later loads
+    if (!c->dec) c->dec = new DecoderPriv();
     const BlobLayout L = blob_layout();
     const float *w = c->w_blob;
     cudaError_t e;
@@ -614,7 +633,10 @@ cudaError_t decoder_prepare_weights(Ctx *c) {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, greedy_persistent_kernel, DEC_THREADS, 0);
     if (e != cudaSuccess) return e;
     d->coop_blocks_per_sm = nb < 1 ? 1 : nb;
-    return decoder_tc_prepare_weights(c);
+    if ((e = decoder_tc_prepare_weights(c)) != cudaSuccess) return e;
+    d->version += 1;
+    decoder_adopt_shared(c);
+    return cudaSuccess;
 }
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }

@@ -298,17 +298,15 @@ cudaError_t launch_split_transpose_enc(Ctx *c, const float *enc, int B, int T, c
 // ---- host side: split-bf16 weight operands, the hoisted encoder projection, and the launch of the decode kernel ----
 constexpr int V_PAD_WS = 17 * 64;  // vocabulary rows padded to whole 64-row slices (decoder_ws.cu)
 
-void decoder_tc_release(Ctx *c) {
-    if (!c->dec || !c->dec->tc) return;
-    TcWeights *w = c->dec->tc;
+void decoder_tc_free(TcWeights *w) {
+    if (!w) return;
     for (__nv_bfloat16 *p : {w->whh0_hi, w->whh0_lo, w->w1_hi, w->w1_lo, w->wp_hi, w->wp_lo, w->wo_hi, w->wo_lo, w->we_hi, w->we_lo})
         if (p) cudaFree(p);
     delete w;
-    c->dec->tc = nullptr;
 }
 
 cudaError_t decoder_tc_prepare_weights(Ctx *c) {
-    DecoderPriv *d = c->dec;
+    SharedDev *d = c->shared.get();
     if (!d->tc) d->tc = new (std::nothrow) TcWeights();
     if (!d->tc) return cudaErrorMemoryAllocation;
     TcWeights *w = d->tc;
@@ -327,7 +325,7 @@ cudaError_t decoder_tc_prepare_weights(Ctx *c) {
     if ((e = launch_split_rows(c, c->w_blob + L.w_pred, kH, w->wp_hi, w->wp_lo, kH, kH, kH)) != cudaSuccess) return e;
     if ((e = launch_split_rows(c, c->w_blob + L.w_out, kH, w->wo_hi, w->wo_lo, kH, kV, kH)) != cudaSuccess) return e;
     if ((e = launch_split_rows(c, c->w_blob + L.w_enc, kEnc, w->we_hi, w->we_lo, kEnc, kH, kEnc)) != cudaSuccess) return e;
-    return decoder_ws_prepare(c);
+    return decoder_ws_prepare(c, w);
 }
 
 static size_t tc_align(size_t x) { return (x + 1023) & ~(size_t)1023; }

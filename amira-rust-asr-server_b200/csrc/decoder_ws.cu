@@ -816,8 +816,8 @@ size_t ws_align(size_t x) { return (x + 1023) & ~(size_t)1023; }
 
 bool decoder_ws_supported(const Ctx *c) { return c->sm_count >= W_CTAS; }
 
-cudaError_t decoder_ws_prepare(Ctx *c) {
-    TcWeights *w = c->dec->tc;
+cudaError_t decoder_ws_prepare(Ctx *c, TcWeights *w) {
+    (void)c;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(greedy_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM)) != cudaSuccess) return e;
     w->ws_ready = true;

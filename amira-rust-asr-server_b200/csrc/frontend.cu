@@ -5,19 +5,23 @@
 //   PreprocessorModel::infer_zero_copy (src/triton/model.rs:71-160)               waveform -> [1,128,T'] features
 // Spec of the (absent, LFS) preprocessor ONNX: SURVEY.md 8(c).
 //
-// Kernel 1 (fe_logmel_kernel, persistent, 32-frame tiles, a half-warp per frame):
-//   global i16/f32 -> smem (128-bit loads) -> pre-emphasis + reflect padding staged in smem (exact: for PCM the
-//   pre-emphasised sample 100*s[n]-97*s[n-1] is an integer < 2^24) -> Hann window -> 512-point real FFT as a
-//   256-point complex FFT factored 16 x 16: radix-16 in registers, twiddle, 16x16 transpose through shared memory,
-//   radix-16 in registers; real-input split against the mirrored bin -> |X|^2 -> banded mel reduction (each lane owns
-//   4 filters) -> log -> smem tile -> coalesced stores of the un-normalised log-mel tile + per-tile (mean, M2) partials.
+// ONE kernel (fe_fused_kernel), persistent CTAs that pull 32-frame tiles from an atomic counter (longest utterances first):
+//   global i16/f32 -> smem (128-bit loads, the next tile's samples prefetched with cp.async) -> pre-emphasis + reflect padding
+//   staged in smem (exact: for PCM the pre-emphasised sample 100*s[n]-97*s[n-1] is an integer < 2^24) -> a half-warp per frame:
+//   Hann window -> 512-point real FFT as a 256-point complex FFT factored 16 x 16 (radix-16 in registers, twiddle, 16x16
+//   transpose through shared memory, radix-16 in registers) -> real-input split against the mirrored bin, whose values sit in
+//   the partner lane (16 - lane) and come over with warp shuffles -> |X|^2 of the tile's 32 frames in shared memory;
+//   then the mel reduction with a LANE PER FRAME: every filter weight is a warp-uniform constant-memory operand, each power bin
+//   one conflict-free shared-memory load -> log -> tile of un-normalised log-mel + per-tile (mean, M2) partials -> coalesced
+//   stores.  The CTA that completes the LAST tile of an utterance (atomic counter) merges the partials (Chan, fp64) and
+//   normalises the utterance in place while its features are still in L2: (x - mean) / (std + 1e-5), frames >= features_len
+//   zeroed — no second kernel, no second pass over HBM.
 //   The FFT runs in fp64: an fp32 FFT leaves ~2e-4 max-abs error after normalisation on low mel bins (deep
 //   fades under pre-emphasis), above the 1e-4 contract; B200 has a 1:2 fp64 pipe (DESIGN.md "front end").
-// Kernel 2 (fe_normalize_kernel, one warp per (utterance, mel) row): Chan-merge of the partials in fp64,
-//   (x - mean) / (std + 1e-5) in place with 128-bit accesses, frames >= features_len zeroed.
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.h"
@@ -31,7 +35,7 @@ constexpr int FE_THREADS = 128;                    // 4 warps, 8 frames each
 constexpr int FE_WARPS = FE_THREADS / 32;
 constexpr int SPAN = (TF - 1) * kHop + kNfft;      // 5472 padded samples per tile
 constexpr int RAW_CAP = SPAN + 16;                 // raw samples staged per tile (+ previous sample, alignment slack)
-constexpr int PPAD = 320;                          // power spectrum row: 257 bins + zero padding read by the padded filter rows
+constexpr int P_LD = kNbin;                        // power spectrum row stride (257: odd, so a lane per frame is conflict-free)
 constexpr int OUT_LD = TF + 1;
 constexpr int FE_HALVES = 2 * FE_WARPS;            // a half-warp (16 lanes) transforms one frame
 constexpr int TLD = 17;                            // row stride (complex doubles) of the 16x16 transpose buffer
@@ -40,12 +44,22 @@ constexpr int TBUF = 16 * TLD;                     // complex doubles per half-w
 struct FeMeta {
     const int64_t *starts;   // [B] first element of each utterance
     const int64_t *lens;     // [B] samples
-    const int32_t *tile_pfx; // [B+1] prefix sum of tiles per utterance
-    const int32_t *tile_b;   // [n_tiles] utterance of every tile
+    const int32_t *tile_pfx; // [B+1] first tile of each utterance in the launch's tile order (+ its tile count, see tile_cnt)
+    const int32_t *tile_cnt; // [B] tiles of each utterance
+    const int32_t *tile_b;   // [n_tiles] utterance of every tile (utterances in descending length order)
     const int64_t *foff;     // [B] first element of each utterance's [128][ld] feature block
+    int32_t *done;           // [B] tiles finished per utterance (zero at launch); [B] = the tile counter
     int B;
     int n_tiles;
+    int debug;               // AMIRA_FE_DEBUG bit mask (timing attribution only): 1 skip the normalisation, 2 skip the mel phase,
+                             // 8 skip the transforms
 };
+
+// mel filterbank in constant memory (filled per device by frontend_upload_tables): filter m covers bins
+// [c_mel_kstart[m], + c_mel_kcnt[m]) with weights c_mel_w[c_mel_off[m] ..]; every access below is warp-uniform
+__constant__ float c_mel_w[512];
+__constant__ int c_mel_kstart[kMel], c_mel_kcnt[kMel], c_mel_off[kMel];
+__constant__ int c_mel_split[FE_WARPS + 1];  // filters of warp w: [c_mel_split[w], c_mel_split[w+1]) — equal non-zero counts
 
 __device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
     if (n <= 1) return 0;
@@ -119,49 +133,85 @@ struct Stage<float> {
     }
 };
 
+// (x - mu) * inv in place over one feature row of `ld` floats, frames >= L zeroed; one warp per row.  The row was written by other
+// SMs moments ago: loads bypass L1 (ld.global.cg).  Scalar head up to the first 16-byte boundary (rows of the ragged layout start
+// anywhere), 128-bit body with four loads in flight per lane, scalar tail.
+__device__ __forceinline__ void normalize_row(float *p, int64_t ld, int64_t L, float mu, float inv, int lane) {
+    const int64_t head = min(ld, (int64_t)(((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) / sizeof(float)));
+    if (lane < head) p[lane] = lane < L ? (__ldcg(p + lane) - mu) * inv : 0.f;
+    float4 *p4 = reinterpret_cast<float4 *>(p + head);
+    const int64_t n4 = (ld - head) / 4;
+    for (int64_t i0 = lane; i0 < n4; i0 += 128) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + 32 * u;
+            v[u] = (i < n4 && head + i * 4 < L) ? __ldcg(p4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + 32 * u, t = head + i * 4;
+            if (i >= n4) continue;
+            float4 w = v[u];
+            if (t + 3 < L) {
+                w.x = (w.x - mu) * inv; w.y = (w.y - mu) * inv; w.z = (w.z - mu) * inv; w.w = (w.w - mu) * inv;
+            } else if (t >= L) {
+                w = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                w.x = (w.x - mu) * inv;
+                w.y = t + 1 < L ? (w.y - mu) * inv : 0.f;
+                w.z = t + 2 < L ? (w.z - mu) * inv : 0.f;
+                w.w = 0.f;
+            }
+            p4[i] = w;
+        }
+    }
+    const int64_t t_tail = head + n4 * 4 + lane;
+    if (t_tail < ld) p[t_tail] = t_tail < L ? (__ldcg(p + t_tail) - mu) * inv : 0.f;
+}
+
 template <typename RawT>
 __global__ void __launch_bounds__(FE_THREADS, 2)
-fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables *__restrict__ tab,
-                 float *__restrict__ features, int64_t t_stride, double2 *__restrict__ partials) {
+fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables *__restrict__ tab,
+                float *__restrict__ features, int64_t t_stride, double2 *__restrict__ partials) {
     using StT = typename Stage<RawT>::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *xbuf = reinterpret_cast<double2 *>(smem_raw);                            // [FE_HALVES][TBUF] transpose / spectrum exchange
+    double2 *xbuf = reinterpret_cast<double2 *>(smem_raw);                            // [FE_HALVES][TBUF] transpose exchange
     double2 *tw256 = xbuf + FE_HALVES * TBUF;                                         // [16][16] W256^(m2 k1) at [k1][m2]
     double2 *tw512 = tw256 + 256;                                                     // [129] exp(-2 pi i k / 512)
     double2 *winp = tw512 + 130;                                                      // [256] scaled window pairs (w[2m], w[2m+1])
-    StT *ystage = reinterpret_cast<StT *>(winp + 256);                                // [SPAN]
-    float *outt = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ystage) + sizeof(StT) * SPAN);  // [128][OUT_LD]
-    float *pw = outt + kMel * OUT_LD;                                                 // [FE_HALVES][PPAD]
-    float *melw = pw + FE_HALVES * PPAD;                                              // [kMelRowsMax][32]
+    StT *ystage = reinterpret_cast<StT *>(winp + 256);                                // [SPAN]; dead after the transforms ...
+    float *outt = reinterpret_cast<float *>(ystage);                                  // ... [128][OUT_LD] log-mel tile aliases it
+    float *pw = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(ystage) + sizeof(StT) * SPAN);  // [TF][P_LD] power spectra
     RawT *raw = reinterpret_cast<RawT *>(xbuf);  // [RAW_CAP] raw samples are staged before, the exchange buffers used after, the barrier
     // 16-bit input only: a second staging buffer that does NOT alias the exchange buffers, filled with cp.async for the NEXT
-    // tile of this CTA while the current tile's frames are transformed (the DRAM latency of the staging loads was 14 % of
-    // the kernel's stall samples)
+    // tile of this CTA while the current tile's frames are transformed
     constexpr bool kPrefetch = sizeof(RawT) == 2;
-    RawT *raw2 = reinterpret_cast<RawT *>(melw + kMelRowsMax * 32);  // [RAW_CAP], 16-byte aligned
+    RawT *raw2 = reinterpret_cast<RawT *>(pw + TF * P_LD);  // [RAW_CAP], 16-byte aligned
+    __shared__ int s_tile[2];   // tile being processed / next tile of this CTA
+    __shared__ int s_last;      // this CTA finished the last tile of the utterance
+    __shared__ float s_mu[kMel], s_inv[kMel];
+    static_assert(sizeof(float) * kMel * OUT_LD <= sizeof(StT) * SPAN, "the log-mel tile must fit the staging buffer it aliases");
+    static_assert((TF * P_LD * 4) % 16 == 0 && (SPAN * 4) % 16 == 0, "raw2 alignment");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, hl = lane & 15;  // half-warp and lane within it
 
-    // ---- loop-invariant tables (shared memory) and per-lane constants ----
+    // ---- loop-invariant tables (shared memory) ----
+    // the window carries the input scale and the 1/2 of the real-input split (E = (Z + conj Z') / 2, ...)
     for (int i = tid; i < 256; i += FE_THREADS) {
         double sn, cs;
         sincospi(-2.0 * (double)(((i >> 4) * (i & 15)) & 255) / 256.0, &sn, &cs);  // entry [k1][m2] = W256^(m2 k1): lanes read consecutively
         tw256[i] = make_double2(cs, sn);
-        winp[i] = make_double2((double)tab->win[2 * i] * Stage<RawT>::kScale, (double)tab->win[2 * i + 1] * Stage<RawT>::kScale);
+        winp[i] = make_double2((double)tab->win[2 * i] * (0.5 * Stage<RawT>::kScale), (double)tab->win[2 * i + 1] * (0.5 * Stage<RawT>::kScale));
     }
     for (int i = tid; i < 129; i += FE_THREADS) {
         double sn, cs;
         sincospi(-2.0 * (double)i / 512.0, &sn, &cs);
         tw512[i] = make_double2(cs, sn);
     }
-    int mk[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) mk[g] = tab->kstart[lane + 32 * g];
-    const int r0 = tab->melRow[0], r1 = tab->melRow[1], r2 = tab->melRow[2], r3 = tab->melRow[3], r4 = tab->melRow[4];
-    for (int i = tid; i < kMelRowsMax * 32; i += FE_THREADS) melw[i] = (&tab->melw_t[0][0])[i];
-    for (int i = tid; i < FE_HALVES * PPAD; i += FE_THREADS) pw[i] = 0.f;  // the padding beyond bin 256 stays zero
     double2 *myx = xbuf + (warp * 2 + half) * TBUF;
+    int32_t *tile_counter = meta.done + meta.B;
 
     struct TileLoc {
         int b, f0, nf, span, delta, nvec;
@@ -210,20 +260,37 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+
+    // utterances without samples have no tile: their rows of the padded layout are all padding
+    if (t_stride > 0)
+        for (int b = blockIdx.x; b < meta.B; b += gridDim.x)
+            if (meta.tile_cnt[b] == 0) {
+                float *ub = features + meta.foff[b];
+                for (int64_t i = tid; i < (int64_t)kMel * t_stride; i += FE_THREADS) ub[i] = 0.f;
+            }
+
+    // ---- dynamic tile scheduler: every CTA holds the tile it works on and the one after it (whose samples are in flight) ----
+    if (tid == 0) {
+        s_tile[0] = atomicAdd(tile_counter, 1);
+        s_tile[1] = atomicAdd(tile_counter, 1);
+    }
+    __syncthreads();  // also: tables visible
+    int tile = s_tile[0], next_tile = s_tile[1];
     TileLoc cur;
-    if ((int)blockIdx.x < meta.n_tiles) {
-        cur = locate(blockIdx.x);
+    if (tile < meta.n_tiles) {
+        cur = locate(tile);
         if (kPrefetch) prefetch(cur);
     }
 
-    for (int tile = blockIdx.x; tile < meta.n_tiles; tile += gridDim.x) {
+    while (tile < meta.n_tiles) {
         const int b = cur.b, f0 = cur.f0, nf = cur.nf, span = cur.span;
         const int64_t n = cur.n, L = cur.L, i0 = cur.i0, g_lo = cur.g_lo, g_hi = cur.g_hi, foff_b = cur.foff;
         const RawT *x = cur.x;
         const bool fits = cur.fits, fast = cur.fast;
         const int delta = cur.delta;
 
-        __syncthreads();  // previous tile fully consumed (ystage/outt/raw reuse); melw visible on first pass
+        __syncthreads();  // previous tile fully consumed (ystage/outt/pw/raw reuse, s_tile read)
+        if (tid == 0) s_tile[0] = atomicAdd(tile_counter, 1);  // the tile after next; read after the next barrier
         // ---- stage the signal span [g_lo, g_hi) needed by this tile ----
         if (fast && kPrefetch) {
             asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's share of the tile, requested during the previous tile
@@ -250,52 +317,53 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
             for (int i = head + nvec * PER + tid; i < cnt; i += FE_THREADS) raw[i] = x[g_lo + i];
         }
         __syncthreads();
+        const int after_next = s_tile[0];
         // ---- pre-emphasis (y[0] = x[0]; y[i] = x[i] - 0.97 x[i-1]) + reflect padding ----
         const bool interior = fits && i0 >= 1 && i0 + span <= n;
         if (interior) {
-            // rq[q] = x[i0 - 1 + q]; two consecutive samples per thread and step (one staged pair store), unrolled for ILP:
-            // this loop is pure shared-memory latency otherwise (it showed up with a quarter of the kernel's stall samples)
+            // rq[q] = x[i0 - 1 + q]; two consecutive samples per thread and step (one staged pair store), unrolled for ILP
             const RawT *rq = ((fast && kPrefetch) ? raw2 : raw) + delta;
 #pragma unroll 4
             for (int p = 2 * tid; p < span; p += 2 * FE_THREADS) {
                 const RawT x0 = rq[p], x1 = rq[p + 1], x2 = rq[p + 2];
                 const StT ya = Stage<RawT>::make(x1, x0, false), yb = Stage<RawT>::make(x2, x1, false);
-                // span is even and p is even: one 8- / 16-byte store per pair (two 4-byte stores at lane stride 2 are a
-                // 2-way bank conflict each)
                 if constexpr (sizeof(StT) == 4) *reinterpret_cast<float2 *>(ystage + p) = make_float2((float)ya, (float)yb);
                 else *reinterpret_cast<double2 *>(ystage + p) = make_double2((double)ya, (double)yb);
             }
         } else {
             for (int p = tid; p < span; p += FE_THREADS) {
                 const int64_t r = reflect_index(i0 + p, n);
-                RawT cur, prev = RawT(0);
+                RawT cur_s, prev = RawT(0);
                 if (fits) {
-                    cur = raw[r - g_lo];
+                    cur_s = raw[r - g_lo];
                     if (r > 0) prev = raw[r - 1 - g_lo];
                 } else {
-                    cur = x[r];
+                    cur_s = x[r];
                     if (r > 0) prev = x[r - 1];
                 }
-                ystage[p] = Stage<RawT>::make(cur, prev, r == 0);
+                ystage[p] = Stage<RawT>::make(cur_s, prev, r == 0);
             }
         }
         __syncthreads();
         // raw2 has been consumed: request the next tile of this CTA now, its loads fly during the transforms below
         TileLoc nxt = cur;
-        if (tile + (int)gridDim.x < meta.n_tiles) {
-            nxt = locate(tile + gridDim.x);
+        if (next_tile < meta.n_tiles) {
+            nxt = locate(next_tile);
             if (kPrefetch) prefetch(nxt);
         }
 
         // ---- a half-warp per frame, two frames per warp at a time: 512-point real FFT = 256-point complex FFT (z[m] = x[2m] +
         // i x[2m+1]) as 16 x 16: radix-16 in registers over m1 (m = 16 m1 + lane), twiddle W256^(lane k1), transpose through
-        // shared memory, radix-16 over m2; then the real-input split against the mirrored bin, |X|^2, banded mel, log ----
-        for (int fp = warp; 2 * fp < nf; fp += FE_WARPS) {
-            const int fl = 2 * fp + half;  // frames >= nf transform stale-but-finite staging data; their results are not stored
+        // shared memory, radix-16 over m2; then the real-input split against the mirrored bin and |X|^2 ----
+        for (int fp = warp; 2 * fp < nf && !(meta.debug & 8); fp += FE_WARPS) {
+            const int fl = 2 * fp + half;  // frames >= nf transform stale-but-finite staging data; their results are not used
             const StT *fr = ystage + min(fl, TF - 1) * kHop;
             cplx a[16];
+            // the centred 400-sample window is zero outside [56, 456): the terms m1 = 0 and m1 = 15 vanish for every lane
+            a[0] = cplx{0.0, 0.0};
+            a[15] = cplx{0.0, 0.0};
 #pragma unroll
-            for (int m1 = 0; m1 < 16; ++m1) {
+            for (int m1 = 1; m1 < 15; ++m1) {
                 const int m = 16 * m1 + hl;
                 const double2 w = winp[m];
                 a[m1].x = (double)fr[2 * m] * w.x;
@@ -315,161 +383,107 @@ fe_logmel_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTable
                 const double2 t = myx[hl * TLD + m2];
                 a[m2] = cplx{t.x, t.y};
             }
-            dft16(a);  // Z[hl + 16 k2] = sum_m2 (...) W16^(m2 k2)
+            dft16(a);  // Z[hl + 16 k2] = sum_m2 (...) W16^(m2 k2), already halved by the window scale
             __syncwarp();
+            // X[k] = E + W512^k O, X[256-k] = conj(E - W512^k O) with E = Z[k] + conj Z[256-k], O = (Z[k] - conj Z[256-k]) / i.
+            // Lane hl owns the pairs k = hl + 16 k2, k2 = 0..7; the mirrored bins 256 - k = (16 - hl) + 16 (15 - k2) are
+            // registers 15 - k2 of the partner lane (16 - hl) & 15: eight complex values cross by warp shuffle.  Lane 0 is its
+            // own partner with the registers shifted by one (256 - 16 k2 = 16 (16 - k2)); it also owns the self-paired bin 128.
+            float *mypw = pw + min(fl, TF - 1) * P_LD;
+            const int src_lane = (lane & 16) | ((16 - hl) & 15);
+            cplx rv[8];
 #pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) myx[hl + 16 * k2] = make_double2(a[k2].x, a[k2].y);
-            __syncwarp();
-            // X[k] = E + W512^k O, X[256-k] = conj(E - W512^k O) with E = (Z[k] + conj Z[256-k]) / 2, O = (Z[k] - conj Z[256-k]) / (2i)
-            float *mypw = pw + (warp * 2 + half) * PPAD;
+            for (int k2 = 0; k2 < 8; ++k2) {
+                rv[k2].x = __shfl_sync(0xffffffffu, a[15 - k2].x, src_lane);
+                rv[k2].y = __shfl_sync(0xffffffffu, a[15 - k2].y, src_lane);
+            }
+            const bool store = fl < nf;
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                const int k = hl + 16 * j;
-                if (k <= 128) {
-                    const double2 z = myx[k], zp = myx[(256 - k) & 255], w = tw512[k];
-                    const double ex = 0.5 * (z.x + zp.x), ey = 0.5 * (z.y - zp.y);
-                    const double dx = 0.5 * (z.x - zp.x), dy = 0.5 * (z.y + zp.y);  // (Z[k] - conj Z[256-k]) / 2
-                    const double ox = dy, oy = -dx;                                  // / i
-                    const double wx = w.x * ox - w.y * oy, wy = w.x * oy + w.y * ox;
-                    const double px = ex + wx, py = ey + wy, qx = ex - wx, qy = ey - wy;
+            for (int k2 = 0; k2 <= 8; ++k2) {
+                const int k = k2 < 8 ? hl + 16 * k2 : 128;
+                cplx z = a[k2], zp;
+                if (k2 == 8) zp = a[8];                                    // bin 128 (lane 0 only): its own mirror
+                else if (k2 == 0) zp = hl == 0 ? a[0] : rv[0];             // bin 0 pairs with itself (-> X[0], X[256])
+                else zp = hl == 0 ? rv[k2 - 1] : rv[k2];
+                const double2 w = tw512[k];
+                const double ex = z.x + zp.x, ey = z.y - zp.y;
+                const double dx = z.x - zp.x, dy = z.y + zp.y;
+                const double ox = dy, oy = -dx;                            // (Z[k] - conj Z[256-k]) / i
+                const double wx = w.x * ox - w.y * oy, wy = w.x * oy + w.y * ox;
+                const double px = ex + wx, py = ey + wy, qx = ex - wx, qy = ey - wy;
+                if (store && (k2 < 8 || hl == 0)) {
                     mypw[k] = (float)(px * px + py * py);
-                    if (k != 128) mypw[256 - k] = (float)(qx * qx + qy * qy);
+                    if (k2 < 8) mypw[256 - k] = (float)(qx * qx + qy * qy);
                 }
             }
             __syncwarp();
-            // banded mel reduction with all 32 lanes, both frames of the pair at once (each filter weight is loaded once and
-            // applied to both power spectra): lane owns filters lane + 32 g.  A second frame past the tile's end reads a
-            // stale-but-finite spectrum and is not stored.
-            {
-                const float *ppw0 = pw + (warp * 2) * PPAD, *ppw1 = ppw0 + PPAD;
-                float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-                auto band = [&](int g, int ra, int rb) {  // rows past a filter's support carry zero weights and read the zero padding
-                    const float *pk0 = ppw0 + mk[g], *pk1 = ppw1 + mk[g];
-                    const float *wk = melw + ra * 32 + lane;
-#pragma unroll 4
-                    for (int r = 0; r < rb - ra; ++r) {
-                        const float w = wk[r * 32];
-                        acc0[g] = fmaf(w, pk0[r], acc0[g]);
-                        acc1[g] = fmaf(w, pk1[r], acc1[g]);
-                    }
-                };
-                band(0, r0, r1);
-                band(1, r1, r2);
-                band(2, r2, r3);
-                band(3, r3, r4);
-                const int f = 2 * fp;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    outt[(lane + 32 * g) * OUT_LD + f] = logf(acc0[g] + 5.9604644775390625e-08f);
-                    if (f + 1 < nf) outt[(lane + 32 * g) * OUT_LD + f + 1] = logf(acc1[g] + 5.9604644775390625e-08f);
-                }
+        }
+        __syncthreads();  // all power spectra of the tile are in shared memory; the staging buffer is dead (outt may overwrite it)
+
+        // ---- mel reduction, a lane per frame: filter weights are warp-uniform constant-memory operands, every power bin is one
+        // conflict-free load (row stride 257); warp w owns a contiguous range of filters with a quarter of the non-zero weights ----
+        {
+            const float *prow = pw + lane * P_LD;  // lanes >= nf read stale-but-finite spectra; their results are not used
+            const int m_lo = c_mel_split[warp], m_hi = c_mel_split[warp + 1];
+            for (int m = m_lo; m < m_hi && !(meta.debug & 2); ++m) {
+                const int k0 = c_mel_kstart[m], cnt = c_mel_kcnt[m], o = c_mel_off[m];
+                float acc = 0.f;
+                for (int r = 0; r < cnt; ++r) acc = fmaf(c_mel_w[o + r], prow[k0 + r], acc);
+                outt[m * OUT_LD + lane] = logf(acc + 5.9604644775390625e-08f);
             }
-            __syncwarp();
         }
         __syncthreads();
 
         // ---- per-tile statistics (one thread per mel row) + coalesced store of the tile ----
         {
             const int m = tid;  // FE_THREADS == kMel
-            double s = 0.0;
-            for (int f = 0; f < nf; ++f) s += (double)outt[m * OUT_LD + f];
-            const double mean = s / nf;
-            double m2 = 0.0;
+            // mean in fp64 (it is subtracted from values of magnitude ~10 whose spread may be 1e-2), M2 in fp32 relative to it
+            double sum = 0.0;
+            for (int f = 0; f < nf; ++f) sum += (double)outt[m * OUT_LD + f];
+            const double mean = sum / nf;
+            const float mf = (float)mean, ml = (float)(mean - (double)mf);
+            float m2 = 0.f;
             for (int f = 0; f < nf; ++f) {
-                const double d = (double)outt[m * OUT_LD + f] - mean;
-                m2 += d * d;
+                const float d = (outt[m * OUT_LD + f] - mf) - ml;
+                m2 = fmaf(d, d, m2);
             }
-            partials[(size_t)tile * kMel + m] = make_double2(mean, m2);
+            if (!(meta.debug & 4)) partials[(size_t)tile * kMel + m] = make_double2(mean, (double)m2);
         }
         // row stride: t_stride (padded layout) or, packed (t_stride == 0), the utterance's own frame count
-        const int64_t ld = t_stride > 0 ? t_stride : n / kHop + 1;
+        const int64_t ld = t_stride > 0 ? t_stride : L;
         float *dst = features + foff_b + f0;
         for (int m = warp; m < kMel; m += FE_WARPS)
             if (lane < nf) dst[(size_t)m * ld + lane] = outt[m * OUT_LD + lane];
-        cur = nxt;
-    }
-}
 
-// one warp per (utterance, mel) row
-__global__ void __launch_bounds__(256)
-fe_normalize_kernel(FeMeta meta, float *__restrict__ features, int64_t t_stride, const double2 *__restrict__ partials) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= (int64_t)meta.B * kMel) return;
-    const int b = (int)(row / kMel), m = (int)(row % kMel);
-    const int64_t n = meta.lens[b];
-    const int64_t L = n <= 0 ? 0 : n / kHop + 1;
-    const int64_t ld = t_stride > 0 ? t_stride : L;  // packed layout (t_stride == 0): rows are exactly L long
-    float *p = features + meta.foff[b] + (int64_t)m * ld;
-    // Chan et al. pairwise merge of (count, mean, M2)
-    double cn = 0.0, cmean = 0.0, cm2 = 0.0;
-    auto merge = [&](double n2, double mean2, double m22) {
-        if (n2 == 0.0) return;
-        const double nt = cn + n2, d = mean2 - cmean;
-        cmean += d * (n2 / nt);
-        cm2 += m22 + d * d * (cn * n2 / nt);
-        cn = nt;
-    };
-    if (L > 0) {
-        const int t0 = meta.tile_pfx[b], nt = meta.tile_pfx[b + 1] - t0;
-        for (int t = lane; t < nt; t += 32) {
-            const double2 q = partials[(size_t)(t0 + t) * kMel + m];
-            const double cnt = (double)min((int64_t)TF, L - (int64_t)t * TF);
-            merge(cnt, q.x, q.y);
-        }
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-            const double n2 = __shfl_xor_sync(0xffffffffu, cn, o);
-            const double mean2 = __shfl_xor_sync(0xffffffffu, cmean, o);
-            const double m22 = __shfl_xor_sync(0xffffffffu, cm2, o);
-            // symmetric merge so both partners end with identical values
-            const double nt2 = cn + n2;
-            if (nt2 > 0.0) {
-                const double d = mean2 - cmean;
-                const double nm = (cn * cmean + n2 * mean2) / nt2;
-                cm2 = cm2 + m22 + d * d * (cn * n2 / nt2);
-                cmean = nm;
-                cn = nt2;
+        // ---- the CTA that finishes the LAST tile of the utterance normalises it, from L2 ----
+        __threadfence();  // this thread's feature and partial stores, before the counter
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(meta.done + b, 1) == meta.tile_cnt[b] - 1;
+        __syncthreads();
+        if (s_last && !(meta.debug & 1)) {
+            __threadfence();  // acquire side of the counter: every other CTA's stores of this utterance are visible
+            {   // Chan et al. merge of the per-tile (count, mean, M2), one thread per mel row
+                const int m = tid, t0 = meta.tile_pfx[b], nt = meta.tile_cnt[b];
+                double cn = 0.0, cmean = 0.0, cm2 = 0.0;
+                for (int t = 0; t < nt; ++t) {
+                    const double2 q = __ldcg(partials + (size_t)(t0 + t) * kMel + m);
+                    const double n2 = (double)min((int64_t)TF, L - (int64_t)t * TF), nt2 = cn + n2, d = q.x - cmean;
+                    cmean += d * (n2 / nt2);
+                    cm2 += q.y + d * d * (cn * n2 / nt2);
+                    cn = nt2;
+                }
+                const double sd = L > 1 ? sqrt(cm2 / (double)(L - 1)) : 0.0;
+                s_mu[m] = (float)cmean;
+                s_inv[m] = (float)(1.0 / (sd + 1e-5));
             }
+            __syncthreads();
+            float *ub = features + foff_b;
+            for (int m = warp; m < kMel; m += FE_WARPS) normalize_row(ub + (int64_t)m * ld, ld, L, s_mu[m], s_inv[m], lane);
         }
+        cur = nxt;
+        tile = next_tile;
+        next_tile = after_next;
     }
-    const double sd = L > 1 ? sqrt(cm2 / (double)(L - 1)) : 0.0;
-    const float mu = (float)cmean;
-    const float inv = (float)(1.0 / (sd + 1e-5));
-    // scalar head up to the first 16-byte boundary (rows of the ragged layout start anywhere), 128-bit body, scalar tail
-    const int64_t head = min(ld, (int64_t)(((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) / sizeof(float)));
-    if (lane < head) p[lane] = lane < L ? (p[lane] - mu) * inv : 0.f;
-    float4 *p4 = reinterpret_cast<float4 *>(p + head);
-    const int64_t n4 = (ld - head) / 4;
-    // four independent 128-bit loads in flight per lane before the first store (the row is read and written through
-    // the same pointer, so the compiler keeps load -> store order; batching restores the memory-level parallelism)
-    for (int64_t i0 = lane; i0 < n4; i0 += 128) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t i = i0 + 32 * u;
-            v[u] = (i < n4 && head + i * 4 < L) ? p4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t i = i0 + 32 * u, t = head + i * 4;
-            if (i >= n4) continue;
-            float4 w = v[u];
-            if (t + 3 < L) {
-                w.x = (w.x - mu) * inv; w.y = (w.y - mu) * inv; w.z = (w.z - mu) * inv; w.w = (w.w - mu) * inv;
-            } else if (t >= L) {
-                w = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                w.x = (w.x - mu) * inv;
-                w.y = t + 1 < L ? (w.y - mu) * inv : 0.f;
-                w.z = t + 2 < L ? (w.z - mu) * inv : 0.f;
-                w.w = 0.f;
-            }
-            p4[i] = w;
-        }
-    }
-    const int64_t t_tail = head + n4 * 4 + lane;
-    if (t_tail < ld) p[t_tail] = t_tail < L ? (p[t_tail] - mu) * inv : 0.f;
 }
 
 __global__ void bytes_to_f32_kernel(const uint8_t *__restrict__ in, size_t n_bytes, int drop_odd, float *__restrict__ out) {
@@ -509,12 +523,41 @@ __global__ void bytes_to_f32_kernel(const uint8_t *__restrict__ in, size_t n_byt
 
 template <typename RawT>
 size_t fe_smem_bytes() {
-    return sizeof(double2) * (FE_HALVES * TBUF + 256 + 130 + 256) + sizeof(typename Stage<RawT>::T) * SPAN +
-           sizeof(float) * (kMel * OUT_LD + FE_HALVES * PPAD + kMelRowsMax * 32) +
+    return sizeof(double2) * (FE_HALVES * TBUF + 256 + 130 + 256) + sizeof(typename Stage<RawT>::T) * SPAN + sizeof(float) * TF * P_LD +
            (sizeof(RawT) == 2 ? ((RAW_CAP * sizeof(RawT) + 15) & ~(size_t)15) : 0);  // raw2 (16-bit input: prefetched staging)
 }
 
 }  // namespace
+
+// mel filterbank -> constant memory of the current device (called once per context)
+cudaError_t frontend_upload_tables(const FrontendTables *t) {
+    std::vector<float> fb((size_t)kMel * kNbin);
+    build_mel_filterbank(fb.data());
+    float w[512] = {};
+    int off[kMel], split[FE_WARPS + 1];
+    int o = 0;
+    for (int m = 0; m < kMel; ++m) {
+        off[m] = o;
+        for (int r = 0; r < t->kcnt[m]; ++r) {
+            if (o >= 512) return cudaErrorInvalidValue;
+            w[o++] = fb[(size_t)m * kNbin + t->kstart[m] + r];
+        }
+    }
+    // contiguous filter ranges with equal shares of the non-zero weights (the work of a warp in the mel phase)
+    split[0] = 0;
+    for (int q = 1; q < FE_WARPS; ++q) {
+        int m = split[q - 1];
+        while (m < kMel && off[m] < o * q / FE_WARPS) ++m;
+        split[q] = m;
+    }
+    split[FE_WARPS] = kMel;
+    cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(c_mel_w, w, sizeof(w))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_mel_kstart, t->kstart, sizeof(int) * kMel)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_mel_kcnt, t->kcnt, sizeof(int) * kMel)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_mel_off, off, sizeof(off))) != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_mel_split, split, sizeof(split));
+}
 
 cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const int64_t *starts_host,
                             const int64_t *lens_host, int B, float *features_dev, int64_t t_stride, int slot, int phase,
@@ -523,14 +566,14 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
     if (slot < 0 || slot >= Ctx::kMaxChunks) return cudaErrorInvalidValue;
     DevBuf &fe_meta = c->fe_meta[slot], &fe_partials = c->fe_partials[slot];
     PinBuf &fe_meta_pin = c->fe_meta_pin[slot];
-    // host metadata: starts, lens, feature offsets, tile prefix, utterance of every tile -> one pinned block, one async copy
+    // host metadata: starts, lens, feature offsets, tile tables, zeroed completion counters -> one pinned block, one async copy
     int64_t tiles = 0;
     for (int b = 0; b < B; ++b) {
         const int64_t L = lens_host[b] <= 0 ? 0 : lens_host[b] / kHop + 1;
         tiles += (L + TF - 1) / TF;
     }
     if (tiles > 0x7fffffff) return cudaErrorInvalidValue;
-    const size_t meta_bytes = sizeof(int64_t) * 3 * (size_t)B + sizeof(int32_t) * ((size_t)B + 1 + (size_t)tiles);
+    const size_t meta_bytes = sizeof(int64_t) * 3 * (size_t)B + sizeof(int32_t) * (3 * (size_t)B + 2 + (size_t)tiles);
     cudaError_t e;
     if ((e = fe_meta_pin.reserve(meta_bytes)) != cudaSuccess) return e;
     if ((e = fe_meta.reserve(meta_bytes)) != cudaSuccess) return e;
@@ -538,65 +581,67 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
     int64_t *h_lens = h_starts + B;
     int64_t *h_foff = h_lens + B;
     int32_t *h_pfx = reinterpret_cast<int32_t *>(h_foff + B);
-    int32_t *h_tile_b = h_pfx + B + 1;  // one load instead of a binary search over tile_pfx per tile
+    int32_t *h_cnt = h_pfx + B;
+    int32_t *h_done = h_cnt + B;         // [B] tiles finished + [1] tile counter, all zero at launch
+    int32_t *h_tile_b = h_done + B + 1;  // one load instead of a binary search per tile
+    // tiles are handed out in this order: longest utterances first, so the normalisation that trails the last tile of the
+    // launch belongs to a short utterance
+    std::vector<int32_t> order((size_t)B);
+    for (int b = 0; b < B; ++b) order[(size_t)b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return lens_host[x] > lens_host[y]; });
     tiles = 0;
-    for (int b = 0; b < B; ++b) {
+    for (int i = 0; i < B; ++i) {
+        const int b = order[(size_t)i];
         h_starts[b] = starts_host[b];
         h_lens[b] = lens_host[b];
         h_foff[b] = foff_host ? foff_host[b] : (int64_t)b * kMel * t_stride;
-        h_pfx[b] = (int32_t)tiles;
         const int64_t L = lens_host[b] <= 0 ? 0 : lens_host[b] / kHop + 1;
         const int64_t nt = (L + TF - 1) / TF;
+        h_pfx[b] = (int32_t)tiles;
+        h_cnt[b] = (int32_t)nt;
+        h_done[b] = 0;
         for (int64_t t = 0; t < nt; ++t) h_tile_b[tiles + t] = b;
         tiles += nt;
     }
-    h_pfx[B] = (int32_t)tiles;
-    if (tiles > 0x7fffffff) return cudaErrorInvalidValue;
-    // phase 1 = metadata upload only, 2 = kernels only (metadata already uploaded for this slot), 0 = both.  Pipelined host
+    h_done[B] = 0;
+    // phase 1 = metadata upload only, 2 = kernel only (metadata already uploaded for this slot), 0 = both.  Pipelined host
     // calls upload every chunk's metadata BEFORE queueing the bulk copies: a small copy that becomes runnable later would
-    // wait in the copy engine behind all bulk copies already queued there, and its kernels with it.
+    // wait in the copy engine behind all bulk copies already queued there, and its kernel with it.
     if (phase != 2 && (e = cudaMemcpyAsync(fe_meta.p, fe_meta_pin.p, meta_bytes, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
         return e;
-    if (phase == 1) return fe_partials.reserve(sizeof(double2) * (size_t)std::max<int64_t>(tiles, 1) * kMel);
+    if ((e = fe_partials.reserve(sizeof(double2) * (size_t)std::max<int64_t>(tiles, 1) * kMel)) != cudaSuccess) return e;
+    if (phase == 1) return cudaSuccess;
     FeMeta meta;
     meta.starts = fe_meta.as<int64_t>();
     meta.lens = meta.starts + B;
     meta.foff = meta.lens + B;
     meta.tile_pfx = reinterpret_cast<const int32_t *>(meta.foff + B);
-    meta.tile_b = meta.tile_pfx + B + 1;
+    meta.tile_cnt = meta.tile_pfx + B;
+    meta.done = reinterpret_cast<int32_t *>(fe_meta.as<int64_t>() + 3 * (size_t)B) + 2 * (size_t)B;
+    meta.tile_b = meta.done + B + 1;
     meta.B = B;
     meta.n_tiles = (int)tiles;
-    if ((e = fe_partials.reserve(sizeof(double2) * (size_t)std::max<int64_t>(tiles, 1) * kMel)) != cudaSuccess) return e;
+    meta.debug = getenv("AMIRA_FE_DEBUG") ? atoi(getenv("AMIRA_FE_DEBUG")) : 0;
 
-    if (tiles > 0) {
-        ProfScope prof(c, PK_FE_LOGMEL);
-        const int grid = (int)std::min<int64_t>(tiles, (int64_t)c->sm_count * 2);
-        if (is_pcm16) {
-            const size_t smem = fe_smem_bytes<int16_t>();
-            if (!c->attr_fe_i16) {
-                if ((e = cudaFuncSetAttribute(fe_logmel_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-                c->attr_fe_i16 = true;
-            }
-            fe_logmel_kernel<int16_t><<<grid, FE_THREADS, smem, c->stream>>>(
-                static_cast<const int16_t *>(wave_dev), meta, c->tables_dev, features_dev, t_stride,
-                fe_partials.as<double2>());
-        } else {
-            const size_t smem = fe_smem_bytes<float>();
-            if (!c->attr_fe_f32) {
-                if ((e = cudaFuncSetAttribute(fe_logmel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-                c->attr_fe_f32 = true;
-            }
-            fe_logmel_kernel<float><<<grid, FE_THREADS, smem, c->stream>>>(
-                static_cast<const float *>(wave_dev), meta, c->tables_dev, features_dev, t_stride,
-                fe_partials.as<double2>());
+    ProfScope prof(c, PK_FE_LOGMEL);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)c->sm_count * 2));
+    if (is_pcm16) {
+        const size_t smem = fe_smem_bytes<int16_t>();
+        if (!c->attr_fe_i16) {
+            if ((e = cudaFuncSetAttribute(fe_fused_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            c->attr_fe_i16 = true;
         }
-        c->launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        fe_fused_kernel<int16_t><<<grid, FE_THREADS, smem, c->stream>>>(
+            static_cast<const int16_t *>(wave_dev), meta, c->tables_dev, features_dev, t_stride, fe_partials.as<double2>());
+    } else {
+        const size_t smem = fe_smem_bytes<float>();
+        if (!c->attr_fe_f32) {
+            if ((e = cudaFuncSetAttribute(fe_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            c->attr_fe_f32 = true;
+        }
+        fe_fused_kernel<float><<<grid, FE_THREADS, smem, c->stream>>>(
+            static_cast<const float *>(wave_dev), meta, c->tables_dev, features_dev, t_stride, fe_partials.as<double2>());
     }
-    const int64_t rows = (int64_t)B * kMel;
-    ProfScope prof(c, PK_FE_NORMALIZE);
-    fe_normalize_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, c->stream>>>(meta, features_dev, t_stride,
-                                                                            fe_partials.as<double2>());
     c->launches++;
     return cudaGetLastError();
 }

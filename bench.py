@@ -33,7 +33,7 @@ F_FRAME = 1_310_720      # flop per (stream, encoder frame): hoisted encoder pro
 BYTES_PER_AUDIO_S = 83_200  # front end, i16 in + f32 [128, T'] out
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this command's default workload
 # (profiles/r1e_ncu_full_raw.csv); reported as roofline.traffic only for that workload
-NCU_DRAM_BYTES = {"greedy": 649_477_376, "fe_logmel": 1_550_140_928}
+NCU_DRAM_BYTES = {"greedy": None, "fe_logmel": None}  # filled from profiles/r2_ncu_full_raw.csv once captured
 ENGINE_NAMES = {0: ("greedy_ws_kernel", "tcgen05 split-bf16 weight-stationary dataflow kernel"),
                 1: ("greedy_persistent_kernel", "fp32 persistent cooperative kernel"),
                 4: ("greedy_ws_kernel", "tcgen05 split-bf16 weight-stationary dataflow kernel")}
@@ -289,7 +289,7 @@ def run_extras(A, torch, dev, ctx, stream, hbm_peak, tf_peak):
     byts = 2.0 * Bp * n + 4.0 * 128 * L * Bp + 16 * Bp
     out["cfg2_preprocessor_64x30s"] = {"ms": ms, "audio_s_per_s": Bp * 30.0 / (ms / 1e3), "algorithmic_GBps": byts / (ms / 1e3) / 1e9,
                                        "frac_of_hbm_peak": byts / (ms / 1e3) / 1e9 / hbm_peak,
-                                       "note": "both front-end kernels, resident PCM in, resident [64,128,3001] f32 out"}
+                                       "note": "the fused front-end kernel, resident PCM in, resident [64,128,3001] f32 out"}
     del pcm_dev, feats
     # cfg3
     for T in (126, 376):
@@ -421,7 +421,7 @@ def main():
     ms_total = timed(step_device, args.steps)
     clocks = sampler.stop()
     launches = ctx.launch_count() - l0
-    kms = {k: ctx.kernel_ms(k) for k in ("fe_logmel", "fe_normalize", "enc_proj", "greedy")}
+    kms = {k: ctx.kernel_ms(k) for k in ("fe_logmel", "enc_proj", "greedy")}  # fe_logmel = the fused front-end kernel
     ctx.profile(False)
     ms_step = ms_total / args.steps
     nsteps = nsteps_dev.cpu().numpy().astype(np.int64)
@@ -435,7 +435,7 @@ def main():
     value = total_audio / (ms_step / 1e3)
 
     # ---- e2e: same calls, pinned host buffers in and out ----
-    e2e = None
+    e2e = handoff = None
     if not args.no_e2e:
         packed = args.e2e_layout == "packed"
         if packed:
@@ -459,16 +459,16 @@ def main():
         # outputs are synthetic), so the host drives them as the server would drive two requests: one blocking C-ABI call
         # each from its own thread, on two contexts of the same GPU; inside each call the library pipelines H2D copies,
         # kernels and D2H copies chunk by chunk.  `--e2e-inflight` steps are in flight at a time (default 2, each with its
-        # own pair of contexts and its own output buffers), as a server keeps several batches in flight: the upload of one
+        # own pair of lanes and its own output buffers), as a server keeps several batches in flight: the upload of one
         # step then overlaps the decode kernel of the other.  Every step still uploads all of its inputs and reads back
         # all of its results inside the timed region.
         n_fl = max(1, args.e2e_inflight)
         workers = []
         for w in range(n_fl):
-            cd = ctx if w == 0 else A.Context(device_id=local_rank, decode_engine=args.engine)
-            if w > 0:
-                cd.load_weights(A.synthetic_weights(3456))
-            workers.append({"dec": cd, "fe": A.Context(device_id=local_rank, decode_engine=args.engine),
+            # lanes of ONE context (amira_ctx_fork): own streams / staging / workspace, shared weights — the documented way to keep
+            # several batches in flight on one GPU
+            cd = ctx if w == 0 else ctx.fork()
+            workers.append({"dec": cd, "fe": ctx.fork(),
                             "feats": torch.empty(feat_shape, dtype=torch.float32).pin_memory(),
                             "tok": torch.zeros((B, ctx.max_total_tokens), dtype=torch.int32).pin_memory(),
                             "ntok": torch.zeros(B, dtype=torch.int32).pin_memory(), "flens": np.zeros(B, np.int64)})
@@ -509,6 +509,88 @@ def main():
                "steps_in_flight": n_fl, "ms_per_step_one_in_flight": ms_single,
                "h2d_bytes_per_step": int(pcm.nbytes + enc_pin.numel() * 4 + offsets.nbytes + elens.nbytes),
                "d2h_bytes_per_step": int(workers[0]["feats"].numel() * 4 + workers[0]["tok"].numel() * 4 + B * 4)}
+        # ---- what the box's host<->device path allows: the step's bytes and nothing else (pinned memory, both directions at
+        # once, every rank at the same time).  e2e above can not be faster than this; frac_of_host_io_ceiling says how close it is.
+        h2d_src = [pcm_pin, enc_pin]
+        h2d_dst = [torch.empty_like(pcm_pin, device=dev), torch.empty(enc_pin.shape, dtype=torch.float32, device=dev)]
+        d2h_src = [torch.empty(workers[0]["feats"].shape, dtype=torch.float32, device=dev), tok_dev]
+        d2h_dst = [workers[0]["feats"], workers[0]["tok"]]
+        s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def copy_only():
+            with torch.cuda.stream(s_up):
+                for a, b_ in zip(h2d_src, h2d_dst):
+                    b_.copy_(a, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                for a, b_ in zip(d2h_src, d2h_dst):
+                    b_.copy_(a, non_blocking=True)
+
+        def timed_wall(fn, reps):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            barrier()
+            ms = (time.perf_counter() - t0) * 1e3 / reps
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
+
+        copy_only()
+        torch.cuda.synchronize()
+        ms_io = timed_wall(copy_only, 4)
+        e2e["host_io_ceiling_ms"] = ms_io
+        e2e["frac_of_host_io_ceiling"] = ms_io / ms_e2e
+        e2e["host_io_GBps_per_gpu"] = (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) / (ms_io / 1e3) / 1e9
+        del h2d_dst, d2h_src
+
+        # ---- device-resident hand-off (extra key, not the headline): the tensors exchanged with the encoder stay in device
+        # regions shared by CUDA IPC handle (amira_device_alloc / amira_ipc_export, the reference's CUDA shared-memory regions,
+        # src/cuda/cuda_helper.cu:63-183) — PCM comes from host memory, tokens go back to it, features and encoder outputs never
+        # cross PCIe.  Same lanes, same two steps in flight.
+        handoff = None
+        if packed:
+            enc_region = ctx.device_alloc(int(eoff[-1]) * 4)
+            feat_regions = [ctx.device_alloc(int(foff[-1]) * 4) for _ in range(n_fl)]
+            handle = ctx.ipc_export(enc_region)  # what the encoder process would open
+            assert len(handle) == 64
+            from cuda import cudart  # cuda-python: fills the region as the encoder process would (any CUDA API can address it)
+            (err,) = cudart.cudaMemcpy(enc_region, enc_pin.data_ptr(), int(eoff[-1]) * 4, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice)
+            assert int(err) == 0, err
+
+            def step_handoff(w):
+                k = workers[w]
+                th = threading.Thread(target=k["fe"].preprocess_pcm16_packed_raw,
+                                      args=(pcm_pin.data_ptr(), offsets, B, feat_regions[w], foff, k["flens"]))
+                th.start()
+                k["dec"].greedy_decode_packed_raw(enc_region, eoff, B, elens, k["tok"].data_ptr(), k["ntok"].data_ptr(), None)
+                th.join()
+
+            def run_handoff(steps):
+                def loop(w):
+                    for _ in range(w, steps, n_fl):
+                        step_handoff(w)
+                ths = [threading.Thread(target=loop, args=(w,)) for w in range(1, n_fl)]
+                for th in ths:
+                    th.start()
+                loop(0)
+                for th in ths:
+                    th.join()
+
+            run_handoff(n_fl)
+            ms_h = timed(lambda: run_handoff(args.steps), 1) / args.steps
+            for k in workers:
+                assert np.array_equal(k["ntok"].numpy().astype(np.int64), ntok), "device hand-off path disagrees with the resident path"
+            handoff = {"value": total_audio / (ms_h / 1e3), "unit": "audio-s/s", "ms_per_step": ms_h, "steps_in_flight": n_fl,
+                       "h2d_bytes_per_step": int(pcm.nbytes + offsets.nbytes + elens.nbytes + eoff.nbytes + foff.nbytes),
+                       "d2h_bytes_per_step": int(workers[0]["tok"].numel() * 4 + B * 4),
+                       "note": "features written to / encoder outputs read from device regions exported by CUDA IPC handle"}
+            ctx.device_free(enc_region)
+            for r_ in feat_regions:
+                ctx.device_free(r_)
         launches_e2e = workers[0]["fe"].launch_count()
         for w, k in enumerate(workers):
             k["fe"].close()
@@ -558,7 +640,7 @@ def main():
         "roofline": {"kernel": ENGINE_NAMES[args.engine][0], "bound": "tensor", "achieved": ach_tf, "peak": tf_peak,
                      "unit": "TFLOP/s", "frac": ach_tf / tf_peak, "traffic": NCU_DRAM_BYTES["greedy"] if default_workload else None, "peak_kind": f"bf16 sustained, {peak_kind}",
                      "flops_per_launch": flops, "avg_launch_ms": dec_avg_ms},
-        "roofline_frontend": {"kernel": "fe_logmel_kernel", "bound": "hbm", "achieved": fe_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "roofline_frontend": {"kernel": "fe_fused_kernel", "bound": "hbm", "achieved": fe_gbs, "peak": hbm_peak, "unit": "GB/s",
                               "frac": fe_gbs / hbm_peak, "traffic": NCU_DRAM_BYTES["fe_logmel"] if default_workload else None, "peak_kind": peak_kind, "bytes_per_launch": fe_bytes,
                               "avg_launch_ms": fe_avg_ms},
     }
@@ -566,6 +648,8 @@ def main():
         out["streaming"] = streaming
     if e2e:
         out["e2e"] = e2e
+        if handoff:
+            out["e2e_device_handoff"] = handoff
     extras = run_extras(A, torch, dev, ctx, stream, hbm_peak, tf_peak) if not args.no_extras else None
     if extras:
         out["extra"] = extras

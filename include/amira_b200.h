@@ -52,7 +52,7 @@ typedef enum {
 #define AMIRA_N_MELS 128
 #define AMIRA_N_PARAMS 8946310u /* Embedding(1025x640)+2xLSTM(640)+joint(1024/640->640->1030) */
 
-typedef struct amira_ctx amira_ctx; /* opaque; one per GPU; thread-safe (internally serialised) */
+typedef struct amira_ctx amira_ctx; /* opaque; thread-safe (internally serialised); one per GPU + forked lanes (amira_ctx_fork) */
 
 typedef struct {
     int32_t device_id;            /* config `cuda_device_id` (src/config.rs:284-290) */
@@ -75,6 +75,12 @@ int32_t amira_config_default(amira_config *cfg);
 int32_t amira_ctx_create(const amira_config *cfg, amira_ctx **out);
 /* replaces CudaSharedMemoryRegionDestroy (src/cuda/cuda_helper.cu:113-142) */
 int32_t amira_ctx_destroy(amira_ctx *ctx);
+/* Another submission lane on the same GPU.  A context serialises its calls; the reference server has up to 10 + 50 requests in
+ * flight (src/config.rs:104-107).  A fork has its own streams, staging and workspace and SHARES the parent's weights (one copy
+ * of the model per GPU); calls on different lanes run concurrently, so the upload of one batch overlaps the kernels of another.
+ * Weights loaded through any lane are seen by all of them at their next call.  Stream slots stay with the parent.  Lanes are
+ * destroyed with amira_ctx_destroy in any order; the shared memory goes with the last one. */
+int32_t amira_ctx_fork(amira_ctx *parent, amira_ctx **out);
 /* message of the last failing call on this ctx (NULL ctx: last failing create on this thread); owned by the
  * library — replaces the Display impl of CudaSharedMemoryError (src/cuda/mod.rs:73-82) */
 const char *amira_last_error(amira_ctx *ctx);
@@ -85,7 +91,7 @@ int32_t amira_ctx_synchronize(amira_ctx *ctx);
 int32_t amira_ctx_launch_count(amira_ctx *ctx, int64_t *count);
 
 /* per-kernel device timing for bench.py's roofline: CUDA events on the context's stream around each launch.
- * kernel ids: 0 fe_logmel, 1 fe_normalize, 2 encoder projection GEMM, 3 persistent greedy-decode, 4 bytes_to_f32.
+ * kernel ids: 0 fused front end (log-mel + normalisation), 1 unused, 2 encoder projection GEMM, 3 persistent greedy-decode, 4 bytes_to_f32.
  * amira_ctx_profile(ctx, 1) resets the totals and starts recording; amira_ctx_kernel_ms reads them. */
 int32_t amira_ctx_profile(amira_ctx *ctx, int32_t enable);
 int32_t amira_ctx_kernel_ms(amira_ctx *ctx, int32_t kernel, double *total_ms, int64_t *launches);
@@ -258,6 +264,22 @@ int32_t amira_stream_group_process_batch(amira_stream_group *g, int32_t stream, 
 int32_t amira_stream_group_stats(amira_stream_group *g, int64_t *n_pipeline_calls, int64_t *n_rounds);
 /* configured max_total_tokens of a context (row stride of the tokens output of the decode entries) */
 int32_t amira_ctx_max_total_tokens(amira_ctx *ctx, int32_t *value);
+
+/* ---- device-resident hand-off (replaces the CUDA shared-memory regions of src/cuda/cuda_helper.cu:63-183: cudaMalloc +
+ * cudaIpcGetMemHandle, GetRawHandle).  The stages either side of the encoder exchange fp32 tensors with it (features out,
+ * encoder outputs in: 51 200 + 4 096 x frames bytes per audio-second over PCIe when they go through host memory).  Every
+ * compute entry already takes device pointers in place; these entries give the two processes a buffer to share:
+ *   the library side allocates a region and EXPORTS it (the encoder process opens the handle and reads features from it / writes
+ *   encoder outputs into it), or IMPORTS a region the encoder process exported.  The 64 bytes are a cudaIpcMemHandle_t;
+ *   a handle cannot be opened in the process that created it (CUDA rule). */
+typedef struct {
+    uint8_t reserved[64];
+} amira_ipc_handle;
+int32_t amira_device_alloc(amira_ctx *ctx, size_t bytes, void **dev_ptr);      /* CudaSharedMemoryRegionCreate */
+int32_t amira_device_free(amira_ctx *ctx, void *dev_ptr);                      /* CudaSharedMemoryRegionDestroy */
+int32_t amira_ipc_export(amira_ctx *ctx, const void *dev_ptr, amira_ipc_handle *handle); /* GetRawHandle */
+int32_t amira_ipc_import(amira_ctx *ctx, const amira_ipc_handle *handle, void **dev_ptr);
+int32_t amira_ipc_close(amira_ctx *ctx, void *dev_ptr);
 
 /* Multi-GPU: utterances are independent — longest-processing-time assignment of n utterances with
  * costs[i] (e.g. samples) to n_shards GPUs; shard_of[i] receives the shard index.  No collective follows. */

@@ -51,3 +51,31 @@ def calibrated_weights(O=None, seed=3456, blank_bias=None):
     """The synthetic benchmark model (amira_b200.synthetic_weights): seeded, rescaled, blank-calibrated."""
     import amira_b200 as A
     return A.synthetic_weights(seed) if blank_bias is None else A.synthetic_weights(seed, blank_bias)
+
+
+def oracle_row_sigma(oracle, wave):
+    """sigma over time of every un-normalised log-mel row, from the independent float64 numpy restatement."""
+    x = wave.astype(np.float64)
+    n = x.size
+    if n < 160:  # fewer than two frames
+        return np.zeros(128)
+    y = np.empty_like(x)
+    y[0] = x[0]
+    y[1:] = x[1:] - 0.97 * x[:-1]
+    idx = np.arange(-256, n + 256)
+    p = 2 * (n - 1)
+    idx = np.mod(idx, p)
+    idx = np.where(idx < n, idx, p - idx)
+    ypad = y[idx]
+    L = n // 160 + 1
+    win = oracle.hann_window_padded()
+    frames = np.stack([ypad[t * 160:t * 160 + 512] for t in range(L)]) * win[None, :]
+    power = np.abs(np.fft.rfft(frames, axis=1)) ** 2
+    logmel = np.log(power @ oracle.mel_filterbank().astype(np.float64).T + 2.0 ** -24)
+    return logmel.std(axis=0, ddof=1)
+
+
+def feature_bound(sigma, tol=1e-4):
+    """Per-row error bound of the normalised features: the contract's 1e-4, or two fp32 quanta of the log-mel intermediate over the
+    row's own sigma where the row is (nearly) constant in time (tests/test_gpu_parity_baseline.py explains why)."""
+    return np.maximum(tol, 4e-6 / (sigma + 1e-5))

@@ -18,7 +18,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import synth_pcm
+from conftest import feature_bound, oracle_row_sigma, synth_pcm
 from f64_decoder import greedy_decode_f64
 
 pytestmark = pytest.mark.gpu
@@ -187,9 +187,9 @@ def test_adversarial_signals_equal_f64_oracle(dctx, oracle):
         assert int(lens[b]) == L
         got = feats[b, :, :L]
         assert np.all(np.isfinite(got)), k
-        sigma = _oracle_row_sigma(oracle, w)
+        sigma = oracle_row_sigma(oracle, w)
         err = np.abs(got - ref).max(axis=1)
-        bound = np.maximum(FEAT_TOL, 4e-6 / (sigma + 1e-5))
+        bound = feature_bound(sigma, FEAT_TOL)
         regular = sigma >= 2e-2
         report[k] = (float(err[regular].max()) if regular.any() else 0.0, float((err / bound).max()), int((~regular).sum()))
         assert np.all(err <= bound), (k, int(np.argmax(err / bound)), float((err / bound).max()))
@@ -197,26 +197,6 @@ def test_adversarial_signals_equal_f64_oracle(dctx, oracle):
     print("adversarial front-end signals: (max err on rows with sigma >= 2e-2, max err / bound over all rows, rows below 2e-2)")
     for k, v in report.items():
         print(f"  {k:28s} {v[0]:.2e} {v[1]:.2f} {v[2]}")
-
-
-def _oracle_row_sigma(oracle, wave):
-    """sigma over time of every un-normalised log-mel row, from the independent float64 numpy restatement."""
-    x = wave.astype(np.float64)
-    n = x.size
-    y = np.empty_like(x)
-    y[0] = x[0]
-    y[1:] = x[1:] - 0.97 * x[:-1]
-    idx = np.arange(-256, n + 256)
-    p = 2 * (n - 1)
-    idx = np.mod(idx, p)
-    idx = np.where(idx < n, idx, p - idx)
-    ypad = y[idx]
-    L = n // 160 + 1
-    win = oracle.hann_window_padded()
-    frames = np.stack([ypad[t * 160:t * 160 + 512] for t in range(L)]) * win[None, :]
-    power = np.abs(np.fft.rfft(frames, axis=1)) ** 2
-    logmel = np.log(power @ oracle.mel_filterbank().astype(np.float64).T + 2.0 ** -24)
-    return logmel.std(axis=0, ddof=1)
 
 
 def test_one_frame_utterance_is_exactly_zero(dctx):

@@ -149,3 +149,94 @@ def test_two_gpus_in_one_process(amira):
             outs.append((feats, lens, toks, st.states_1, steps))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     assert outs[0][2] == outs[1][2] and np.array_equal(outs[0][3], outs[1][3]) and np.array_equal(outs[0][4], outs[1][4])
+
+
+def test_forked_lanes_share_weights_and_run_concurrently(amira, oracle):
+    """amira_ctx_fork: lanes of one context decode concurrently from several threads with ONE copy of the weights; a reload
+    through any lane is seen by all of them; lanes can be destroyed in any order (the parent first)."""
+    import threading
+    rng = np.random.default_rng(41)
+    enc = (0.5 * rng.standard_normal((6, 1024, 20))).astype(np.float32)
+    root = amira.Context(device_id=0)
+    root.load_weights(amira.synthetic_weights(3456))
+    want, _, want_steps = root.greedy_decode(enc)
+    lanes = [root.fork() for _ in range(3)]
+    got = [None] * 3
+
+    def run(i):
+        for _ in range(4):
+            got[i] = lanes[i].greedy_decode(enc)
+
+    ths = [threading.Thread(target=run, args=(i,)) for i in range(3)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for i in range(3):
+        assert got[i][0] == want and got[i][2].tolist() == want_steps.tolist()
+    # front end on a lane
+    pcm = (rng.standard_normal(16000) * 3000).astype(np.int16)
+    f0, _ = root.preprocess_pcm16(pcm, [0, pcm.size])
+    f1, _ = lanes[1].preprocess_pcm16(pcm, [0, pcm.size])
+    assert np.array_equal(f0, f1)
+    # a reload through one lane reaches the others; the parent goes first
+    lanes[2].load_weights(amira.synthetic_weights(777))
+    other, _, _ = lanes[0].greedy_decode(enc)
+    root.close()
+    again, _, _ = lanes[1].greedy_decode(enc)
+    assert other == again
+    model = oracle.Model(blob=amira.synthetic_weights(777))
+    r = oracle.greedy_decode(enc[0], 20, model)
+    assert again[0] == r.tokens or r.margins.min() < 2e-4
+    with pytest.raises(amira.AmiraError):
+        lanes[0].stream_open()  # stream slots stay with the parent
+    for lane in lanes:
+        lane.close()
+
+
+_IPC_CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+import amira_b200 as A
+handle = bytes.fromhex(sys.argv[2]); B, T = int(sys.argv[3]), int(sys.argv[4])
+with A.Context(device_id=0) as ctx:
+    ctx.load_weights(A.synthetic_weights(3456))
+    enc = ctx.ipc_import(handle)                      # the region the parent process exported
+    tok = np.zeros((B, 200), np.int32); nt = np.zeros(B, np.int32)
+    ctx.greedy_decode_raw(enc, B, T, None, tok.ctypes.data, nt.ctypes.data)
+    ctx.ipc_close(enc)
+    print("TOKENS", ";".join(",".join(str(x) for x in tok[b, :nt[b]]) for b in range(B)))
+"""
+
+
+def test_device_handoff_across_processes(amira, tmp_path):
+    """src/cuda/cuda_helper.cu:63-183 precedent: a device region allocated and exported by one process (amira_device_alloc +
+    amira_ipc_export) is opened by another (amira_ipc_import) and decoded in place — encoder outputs never touch host memory."""
+    import subprocess
+    import sys
+    from cuda import cudart
+    rng = np.random.default_rng(51)
+    B, T = 5, 16
+    enc = (0.5 * rng.standard_normal((B, 1024, T))).astype(np.float32)
+    with amira.Context(device_id=0) as ctx:
+        ctx.load_weights(amira.synthetic_weights(3456))
+        want, _, _ = ctx.greedy_decode(enc)
+        region = ctx.device_alloc(enc.nbytes)
+        (err,) = cudart.cudaMemcpy(region, enc.ctypes.data, enc.nbytes, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice)
+        assert int(err) == 0
+        handle = ctx.ipc_export(region)
+        assert len(handle) == 64 and any(handle)
+        # in-process: the exported region is used in place through its device pointer
+        tok = np.zeros((B, 200), np.int32)
+        nt = np.zeros(B, np.int32)
+        ctx.greedy_decode_raw(region, B, T, None, tok.ctypes.data, nt.ctypes.data)
+        assert [tok[b, :nt[b]].tolist() for b in range(B)] == want
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        script = tmp_path / "child.py"
+        script.write_text(_IPC_CHILD)
+        r = subprocess.run([sys.executable, str(script), root, handle.hex(), str(B), str(T)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = [l for l in r.stdout.splitlines() if l.startswith("TOKENS")][0][7:]
+        got = [[int(x) for x in part.split(",")] if part else [] for part in line.split(";")]
+        assert got == want
+        ctx.device_free(region)
