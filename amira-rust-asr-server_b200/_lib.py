@@ -35,7 +35,8 @@ EXPORTS = ["amira_device_count", "amira_config_default", "amira_ctx_create", "am
            "amira_stream_group_destroy", "amira_stream_group_last_error", "amira_stream_group_clear",
            "amira_stream_group_process_chunks", "amira_stream_group_transcript", "amira_stream_group_tokens",
            "amira_stream_group_audio_length", "amira_stream_group_process_batch", "amira_stream_group_stats", "amira_ctx_fork", "amira_device_alloc",
-           "amira_device_free", "amira_ipc_export", "amira_ipc_import", "amira_ipc_close"]
+           "amira_device_free", "amira_ipc_export", "amira_ipc_import", "amira_ipc_close", "amira_wire_classify_frame",
+           "amira_wire_parse_batch_request", "amira_wire_format_response"]
 
 
 class AmiraError(RuntimeError):
@@ -78,6 +79,10 @@ def load_library():
     L.amira_ipc_export.argtypes = [vp, vp, vp]
     L.amira_ipc_import.argtypes = [vp, vp, C.POINTER(vp)]
     L.amira_ipc_close.argtypes = [vp, vp]
+    L.amira_wire_classify_frame.argtypes = [vp, C.c_size_t, i32, C.POINTER(i32)]
+    L.amira_wire_parse_batch_request.argtypes = [C.c_char_p, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                                 C.POINTER(C.c_size_t), vp, C.c_size_t]
+    L.amira_wire_format_response.argtypes = [C.c_char_p, i32, C.c_char_p, vp, vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.amira_last_error.argtypes = [vp]
     L.amira_last_error.restype = C.c_char_p
     L.amira_ctx_set_stream.argtypes = [vp, vp]

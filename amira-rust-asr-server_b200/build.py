@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libamira_b200.so")
-SOURCES = ["api.cu", "frontend.cu", "decoder.cu", "decoder_tc.cu", "decoder_ws.cu", "tables.cpp", "host_pipeline.cpp", "host_stream.cpp"]
+SOURCES = ["api.cu", "frontend.cu", "decoder.cu", "decoder_tc.cu", "decoder_ws.cu", "tables.cpp", "host_pipeline.cpp", "host_stream.cpp", "host_wire.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-I", INCLUDE, "-I", CSRC]
 

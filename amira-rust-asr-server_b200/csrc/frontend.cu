@@ -11,8 +11,8 @@
 //   Hann window -> 512-point real FFT as a 256-point complex FFT factored 16 x 16 (radix-16 in registers, twiddle, 16x16
 //   transpose through shared memory, radix-16 in registers) -> real-input split against the mirrored bin, whose values sit in
 //   the partner lane (16 - lane) and come over with warp shuffles -> |X|^2 of the tile's 32 frames in shared memory;
-//   then the mel reduction with a LANE PER FRAME: every filter weight is a warp-uniform constant-memory operand, each power bin
-//   one conflict-free shared-memory load -> log -> tile of un-normalised log-mel + per-tile (mean, M2) partials -> coalesced
+//   then the mel reduction with a LANE PER FRAME, fully unrolled from the compile-time filterbank (weights are FFMA immediates,
+//   each power bin one conflict-free shared-memory load at an immediate offset) -> log -> tile of un-normalised log-mel + per-tile (mean, M2) partials -> coalesced
 //   stores.  The CTA that completes the LAST tile of an utterance (atomic counter) merges the partials (Chan, fp64) and
 //   normalises the utterance in place while its features are still in L2: (x - mean) / (std + 1e-5), frames >= features_len
 //   zeroed — no second kernel, no second pass over HBM.
@@ -22,8 +22,10 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
+#include "amira_mel128.h"
 #include "common.h"
 
 namespace amira {
@@ -55,11 +57,31 @@ struct FeMeta {
                              // 8 skip the transforms
 };
 
-// mel filterbank in constant memory (filled per device by frontend_upload_tables): filter m covers bins
-// [c_mel_kstart[m], + c_mel_kcnt[m]) with weights c_mel_w[c_mel_off[m] ..]; every access below is warp-uniform
-__constant__ float c_mel_w[512];
-__constant__ int c_mel_kstart[kMel], c_mel_kcnt[kMel], c_mel_off[kMel];
-__constant__ int c_mel_split[FE_WARPS + 1];  // filters of warp w: [c_mel_split[w], c_mel_split[w+1]) — equal non-zero counts
+// ---- mel reduction, fully unrolled from the compile-time filterbank (include/amira_mel128.h): for one frame (a lane), filter M is
+// sum_r w[M][r] * P[kStart[M] + r] with immediate weights and immediate shared-memory offsets ----
+template <int M, int R>
+__device__ __forceinline__ float mel_dot(const float *__restrict__ prow, float acc) {
+    if constexpr (R < mel128::kCount[M]) {
+        constexpr uint32_t wb = mel128::kWeightBits[mel128::kOffset[M] + R];
+        constexpr int k = mel128::kStart[M] + R;
+        return mel_dot<M, R + 1>(prow, fmaf(__uint_as_float(wb), prow[k], acc));
+    } else {
+        return acc;
+    }
+}
+template <int M, int M_END>
+__device__ __forceinline__ void mel_range(const float *__restrict__ prow, float *__restrict__ outcol) {
+    if constexpr (M < M_END) {
+        outcol[M * OUT_LD] = mel_dot<M, 0>(prow, 0.f);  // the logarithm follows in a rolled loop: 128 inlined logf bodies would
+        mel_range<M + 1, M_END>(prow, outcol);          // make this straight-line code instruction-fetch bound
+    }
+}
+template <int M0, int M1>
+__device__ __forceinline__ void mel_warp(const float *__restrict__ prow, float *__restrict__ outcol) {
+    mel_range<M0, M1>(prow, outcol);
+#pragma unroll 4
+    for (int m = M0; m < M1; ++m) outcol[m * OUT_LD] = logf(outcol[m * OUT_LD] + 5.9604644775390625e-08f);  // log(mel + 2^-24)
+}
 
 __device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
     if (n <= 1) return 0;
@@ -135,21 +157,22 @@ struct Stage<float> {
 
 // (x - mu) * inv in place over one feature row of `ld` floats, frames >= L zeroed; one warp per row.  The row was written by other
 // SMs moments ago: loads bypass L1 (ld.global.cg).  Scalar head up to the first 16-byte boundary (rows of the ragged layout start
-// anywhere), 128-bit body with four loads in flight per lane, scalar tail.
+// anywhere), 128-bit body with eight loads in flight per lane, scalar tail.
 __device__ __forceinline__ void normalize_row(float *p, int64_t ld, int64_t L, float mu, float inv, int lane) {
     const int64_t head = min(ld, (int64_t)(((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) / sizeof(float)));
     if (lane < head) p[lane] = lane < L ? (__ldcg(p + lane) - mu) * inv : 0.f;
     float4 *p4 = reinterpret_cast<float4 *>(p + head);
     const int64_t n4 = (ld - head) / 4;
-    for (int64_t i0 = lane; i0 < n4; i0 += 128) {
-        float4 v[4];
+    constexpr int NU = 8;  // independent 128-bit loads in flight per lane (the CTA is alone on this utterance: latency-bound)
+    for (int64_t i0 = lane; i0 < n4; i0 += 32 * NU) {
+        float4 v[NU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NU; ++u) {
             const int64_t i = i0 + 32 * u;
             v[u] = (i < n4 && head + i * 4 < L) ? __ldcg(p4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NU; ++u) {
             const int64_t i = i0 + 32 * u, t = head + i * 4;
             if (i >= n4) continue;
             float4 w = v[u];
@@ -420,34 +443,38 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
         }
         __syncthreads();  // all power spectra of the tile are in shared memory; the staging buffer is dead (outt may overwrite it)
 
-        // ---- mel reduction, a lane per frame: filter weights are warp-uniform constant-memory operands, every power bin is one
-        // conflict-free load (row stride 257); warp w owns a contiguous range of filters with a quarter of the non-zero weights ----
-        {
+        // ---- mel reduction, a lane per frame: every power bin is one conflict-free load (row stride 257) at an immediate offset,
+        // every weight an FFMA immediate; warp w owns a contiguous range of filters of equal modelled cost ----
+        if (!(meta.debug & 2)) {
             const float *prow = pw + lane * P_LD;  // lanes >= nf read stale-but-finite spectra; their results are not used
-            const int m_lo = c_mel_split[warp], m_hi = c_mel_split[warp + 1];
-            for (int m = m_lo; m < m_hi && !(meta.debug & 2); ++m) {
-                const int k0 = c_mel_kstart[m], cnt = c_mel_kcnt[m], o = c_mel_off[m];
-                float acc = 0.f;
-                for (int r = 0; r < cnt; ++r) acc = fmaf(c_mel_w[o + r], prow[k0 + r], acc);
-                outt[m * OUT_LD + lane] = logf(acc + 5.9604644775390625e-08f);
-            }
+            float *outcol = outt + lane;
+            constexpr int S0 = mel128::kSplit[0], S1 = mel128::kSplit[1], S2 = mel128::kSplit[2], S3 = mel128::kSplit[3], S4 = mel128::kSplit[4];
+            if (warp == 0) mel_warp<S0, S1>(prow, outcol);
+            else if (warp == 1) mel_warp<S1, S2>(prow, outcol);
+            else if (warp == 2) mel_warp<S2, S3>(prow, outcol);
+            else mel_warp<S3, S4>(prow, outcol);
         }
         __syncthreads();
 
         // ---- per-tile statistics (one thread per mel row) + coalesced store of the tile ----
         {
             const int m = tid;  // FE_THREADS == kMel
-            // mean in fp64 (it is subtracted from values of magnitude ~10 whose spread may be 1e-2), M2 in fp32 relative to it
-            double sum = 0.0;
-            for (int f = 0; f < nf; ++f) sum += (double)outt[m * OUT_LD + f];
-            const double mean = sum / nf;
+            // mean in fp64 (it is subtracted from values of magnitude ~10 whose spread may be 1e-2), M2 in fp32 relative to it;
+            // four independent chains each
+            const float *orow = outt + m * OUT_LD;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int f = 0;
+            for (; f + 3 < nf; f += 4) { s0 += (double)orow[f]; s1 += (double)orow[f + 1]; s2 += (double)orow[f + 2]; s3 += (double)orow[f + 3]; }
+            for (; f < nf; ++f) s0 += (double)orow[f];
+            const double mean = ((s0 + s1) + (s2 + s3)) / nf;
             const float mf = (float)mean, ml = (float)(mean - (double)mf);
-            float m2 = 0.f;
-            for (int f = 0; f < nf; ++f) {
-                const float d = (outt[m * OUT_LD + f] - mf) - ml;
-                m2 = fmaf(d, d, m2);
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+            for (f = 0; f + 3 < nf; f += 4) {
+                const float d0 = (orow[f] - mf) - ml, d1 = (orow[f + 1] - mf) - ml, d2 = (orow[f + 2] - mf) - ml, d3 = (orow[f + 3] - mf) - ml;
+                q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
             }
-            if (!(meta.debug & 4)) partials[(size_t)tile * kMel + m] = make_double2(mean, (double)m2);
+            for (; f < nf; ++f) { const float d = (orow[f] - mf) - ml; q0 = fmaf(d, d, q0); }
+            partials[(size_t)tile * kMel + m] = make_double2(mean, (double)((q0 + q1) + (q2 + q3)));
         }
         // row stride: t_stride (padded layout) or, packed (t_stride == 0), the utterance's own frame count
         const int64_t ld = t_stride > 0 ? t_stride : L;
@@ -456,9 +483,11 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
             if (lane < nf) dst[(size_t)m * ld + lane] = outt[m * OUT_LD + lane];
 
         // ---- the CTA that finishes the LAST tile of the utterance normalises it, from L2 ----
-        __threadfence();  // this thread's feature and partial stores, before the counter
-        __syncthreads();
-        if (tid == 0) s_last = atomicAdd(meta.done + b, 1) == meta.tile_cnt[b] - 1;
+        __syncthreads();  // every thread's feature and partial stores are ordered before thread 0's fence below (cumulativity)
+        if (tid == 0) {
+            __threadfence();
+            s_last = atomicAdd(meta.done + b, 1) == meta.tile_cnt[b] - 1;
+        }
         __syncthreads();
         if (s_last && !(meta.debug & 1)) {
             __threadfence();  // acquire side of the counter: every other CTA's stores of this utterance are visible
@@ -529,34 +558,20 @@ size_t fe_smem_bytes() {
 
 }  // namespace
 
-// mel filterbank -> constant memory of the current device (called once per context)
+// the compile-time mel filterbank of the kernel (include/amira_mel128.h) must be the table tables.cpp builds (and the oracle checks)
 cudaError_t frontend_upload_tables(const FrontendTables *t) {
     std::vector<float> fb((size_t)kMel * kNbin);
     build_mel_filterbank(fb.data());
-    float w[512] = {};
-    int off[kMel], split[FE_WARPS + 1];
     int o = 0;
     for (int m = 0; m < kMel; ++m) {
-        off[m] = o;
-        for (int r = 0; r < t->kcnt[m]; ++r) {
-            if (o >= 512) return cudaErrorInvalidValue;
-            w[o++] = fb[(size_t)m * kNbin + t->kstart[m] + r];
+        if (t->kstart[m] != mel128::kStart[m] || t->kcnt[m] != mel128::kCount[m] || mel128::kOffset[m] != o) return cudaErrorInvalidValue;
+        for (int r = 0; r < t->kcnt[m]; ++r, ++o) {
+            uint32_t bits;
+            std::memcpy(&bits, &fb[(size_t)m * kNbin + t->kstart[m] + r], sizeof(bits));
+            if (bits != mel128::kWeightBits[o]) return cudaErrorInvalidValue;
         }
     }
-    // contiguous filter ranges with equal shares of the non-zero weights (the work of a warp in the mel phase)
-    split[0] = 0;
-    for (int q = 1; q < FE_WARPS; ++q) {
-        int m = split[q - 1];
-        while (m < kMel && off[m] < o * q / FE_WARPS) ++m;
-        split[q] = m;
-    }
-    split[FE_WARPS] = kMel;
-    cudaError_t e;
-    if ((e = cudaMemcpyToSymbol(c_mel_w, w, sizeof(w))) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_mel_kstart, t->kstart, sizeof(int) * kMel)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_mel_kcnt, t->kcnt, sizeof(int) * kMel)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_mel_off, off, sizeof(off))) != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(c_mel_split, split, sizeof(split));
+    return o == mel128::kNonZero ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const int64_t *starts_host,

@@ -265,6 +265,34 @@ int32_t amira_stream_group_stats(amira_stream_group *g, int64_t *n_pipeline_call
 /* configured max_total_tokens of a context (row stride of the tokens output of the decode entries) */
 int32_t amira_ctx_max_total_tokens(amira_ctx *ctx, int32_t *value);
 
+/* ---- wire formats either side of the path (pure host code) ----
+ * WebSocket binary frames (StreamProcessor::handle_audio_chunk, src/server/stream.rs:215-281): one byte = control, otherwise
+ * 16-bit PCM.  The reference names two different pairs of control bytes: the server code matches END 0xFF / KEEPALIVE 0x00
+ * (src/constants.rs:243-246 via src/server/stream.rs:24-26), its configuration, README and example client say END 0x00 /
+ * KEEPALIVE 0x01 (src/config.rs:95-98, examples/simple_client.rs:87).  The caller picks the dialect; SERVER is what a running
+ * reference server accepts. */
+#define AMIRA_WIRE_DIALECT_SERVER 0
+#define AMIRA_WIRE_DIALECT_DOCUMENTED 1
+#define AMIRA_FRAME_AUDIO 0
+#define AMIRA_FRAME_END 1
+#define AMIRA_FRAME_KEEPALIVE 2
+#define AMIRA_FRAME_TOO_LARGE 3        /* > 1 MiB: "Audio chunk too large" */
+#define AMIRA_FRAME_UNKNOWN_CONTROL 4  /* "Unknown control byte" */
+#define AMIRA_FRAME_ODD_LENGTH 5       /* "Audio data length must be even for 16-bit PCM" */
+#define AMIRA_FRAME_EMPTY 6            /* "Empty audio chunk received" */
+int32_t amira_wire_classify_frame(const uint8_t *data, size_t n, int32_t dialect, int32_t *kind);
+/* JSON body of POST /v2/decode/batch/{model}: `BatchRequest` + `validate()` (src/server/handlers.rs:44-116).  audio_buffer is a
+ * JSON array of integers 0..255; `opaque` comes back as the span [*opaque_begin, +*opaque_len) of its raw value inside `json`
+ * (length 0 = absent / null); unknown keys are ignored as serde does.  A refused request returns AMIRA_ERR_INVALID_VALUE with the
+ * reference's validation message in err; audio_cap too small returns AMIRA_ERR_OUT_OF_MEMORY with the needed size in *n_audio. */
+int32_t amira_wire_parse_batch_request(const char *json, size_t n, uint8_t *audio, size_t audio_cap, size_t *n_audio,
+                                       size_t *opaque_begin, size_t *opaque_len, char *err, size_t err_cap);
+/* `AsrResponse` as serde writes it (src/asr/types.rs:236-272: camelCase keys, None omitted, status ACTIVE / COMPLETE / PAUSED /
+ * ERROR = 0..3) with the batch handler's metadata object (src/server/handlers.rs:192-206) when meta != NULL; opaque_json is
+ * spliced in verbatim.  *out_len receives the full length; a short buffer truncates and returns AMIRA_ERR_OUT_OF_MEMORY. */
+int32_t amira_wire_format_response(const char *transcription, int32_t status, const char *message, const amira_transcription *meta,
+                                   const int32_t *tokens, const char *opaque_json, char *out, size_t out_cap, size_t *out_len);
+
 /* ---- device-resident hand-off (replaces the CUDA shared-memory regions of src/cuda/cuda_helper.cu:63-183: cudaMalloc +
  * cudaIpcGetMemHandle, GetRawHandle).  The stages either side of the encoder exchange fp32 tensors with it (features out,
  * encoder outputs in: 51 200 + 4 096 x frames bytes per audio-second over PCIe when they go through host memory).  Every

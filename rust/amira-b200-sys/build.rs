@@ -16,6 +16,7 @@ const SOURCES: &[&str] = &[
     "tables.cpp",
     "host_pipeline.cpp",
     "host_stream.cpp",
+    "host_wire.cpp",
 ];
 
 fn main() {
