@@ -36,7 +36,7 @@ EXPORTS = ["amira_device_count", "amira_config_default", "amira_ctx_create", "am
            "amira_stream_group_process_chunks", "amira_stream_group_transcript", "amira_stream_group_tokens",
            "amira_stream_group_audio_length", "amira_stream_group_process_batch", "amira_stream_group_stats", "amira_ctx_fork", "amira_device_alloc",
            "amira_device_free", "amira_ipc_export", "amira_ipc_import", "amira_ipc_close", "amira_wire_classify_frame",
-           "amira_wire_parse_batch_request", "amira_wire_format_response"]
+           "amira_wire_parse_batch_request", "amira_wire_format_response", "amira_device_reset"]
 
 
 class AmiraError(RuntimeError):
@@ -71,6 +71,7 @@ def load_library():
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     L.amira_device_count.argtypes = [C.POINTER(i32)]
     L.amira_config_default.argtypes = [C.POINTER(_Config)]
+    L.amira_device_reset.argtypes = [i32]
     L.amira_ctx_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
     L.amira_ctx_destroy.argtypes = [vp]
     L.amira_ctx_fork.argtypes = [vp, C.POINTER(vp)]
@@ -138,6 +139,13 @@ def device_count() -> int:
     n = C.c_int32(0)
     load_library().amira_device_count(C.byref(n))
     return int(n.value)
+
+
+def device_reset(device_id: int = 0):
+    """cudaDeviceReset after a sticky device error; every Context of that device must have been closed first."""
+    rc = load_library().amira_device_reset(device_id)
+    if rc:
+        raise AmiraError(rc, "amira_device_reset")
 
 
 def features_len(n_samples: int) -> int:

@@ -153,6 +153,21 @@ int32_t amira_device_count(int32_t *count) {
     return AMIRA_OK;
 }
 
+// Recovery from a sticky device error.  The persistent kernels guard every spin loop with a cycle watchdog that traps instead of
+// hanging the GPU; a trap (like any device-side fault) leaves the process's CUDA context on that device unusable: every later call
+// of every amira_ctx on it fails with AMIRA_ERR_UNKNOWN.  The way back: destroy those contexts, call this, create new ones.
+int32_t amira_device_reset(int32_t device_id) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device_id < 0 || device_id >= n) {
+        cudaGetLastError();
+        return AMIRA_ERR_INVALID_VALUE;
+    }
+    if (cudaSetDevice(device_id) != cudaSuccess) { cudaGetLastError(); return AMIRA_ERR_UNKNOWN; }
+    const cudaError_t e = cudaDeviceReset();
+    cudaGetLastError();
+    return e == cudaSuccess ? AMIRA_OK : AMIRA_ERR_UNKNOWN;
+}
+
 int32_t amira_config_default(amira_config *cfg) {
     if (!cfg) return AMIRA_ERR_INVALID_VALUE;
     std::memset(cfg, 0, sizeof(*cfg));

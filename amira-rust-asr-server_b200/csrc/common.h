@@ -23,16 +23,23 @@ constexpr int kMel = AMIRA_N_MELS;        // 128
 constexpr int kNfft = 512, kNbin = 257, kWin = 400, kHop = 160;
 
 // ---- front-end tables (built on the host in double precision, tables.cpp) ----
-// Mel weights are stored "lane-transposed": lane l of a warp owns filters m = l + 32*g (g = 0..3); for group g
-// the warp walks rows melRow[g] .. melRow[g+1] of melw_t, row r holding the r-th non-zero weight of each
-// lane's filter (zero padded), so a warp reads one conflict-free 128 B row per step.
-constexpr int kMelRowsMax = 48;
+// Mel filterbank for the kernel: filters in groups of four consecutive ones.  A group walks `steps` = its longest support;
+// step s applies weight mel_w[woff + 4 s + j] (zero beyond filter j's own support) to power bin k0[j] + s.  Every table access is
+// warp-uniform (the kernel maps a lane to a frame), the loop body is a dozen instructions, and the filters of a warp are a
+// contiguous range of groups with about an eighth of the modelled cost each.
+constexpr int kMelGroupsMax = 40, kMelWeightsMax = 1024, kFeWarps = 8;
+struct alignas(16) MelGroup {
+    int m0, nf, steps, woff;  // first filter, filters in the group (1..4), term steps, first weight
+    int k0[4];                // first power bin of each filter
+};
 struct FrontendTables {
     float win[kNfft];               // Hann(400, symmetric) rounded to f32, centred in 512, zeros outside [56,456)
     int kstart[kMel];               // first non-zero FFT bin of each mel filter
     int kcnt[kMel];                 // number of non-zero bins
-    int melRow[5];                  // row range of each filter group in melw_t
-    float melw_t[kMelRowsMax][32];  // see above
+    int n_groups;
+    int warp_group[kFeWarps + 1];   // groups of warp w: [warp_group[w], warp_group[w+1])
+    alignas(16) MelGroup grp[kMelGroupsMax];
+    alignas(16) float mel_w[kMelWeightsMax];  // woff is a multiple of 4: float4 loads
 };
 void build_frontend_tables(FrontendTables *t);
 void build_mel_filterbank(float *fb /* [128][257] */);

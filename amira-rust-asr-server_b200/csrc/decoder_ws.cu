@@ -99,6 +99,7 @@ struct WsParams {
     int nrows;          // stream rows a unit loads and multiplies (32 / 64 when a single M-tile holds that few streams, else 128)
     int spec_depth[8];  // 0..W_DMAX: speculation depth while n M-tiles are alive, n = 1..8 (index n-1); 0 beyond
     long long *trace;   // nullable: [W_TRACE_ITS][32] globaltimer stamps of M-tile 0 (debug)
+    int force_trap;     // test hook (AMIRA_DEBUG_FORCE_TRAP): take the watchdog's exit on purpose
 };
 
 struct WsDesc {
@@ -215,6 +216,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
     float *ttile = reinterpret_cast<float *>(smem + W_NRING * W_UNIT);  // [128 feature parts][T_LD] accumulator transposition tile
     WsSmem &sm = *reinterpret_cast<WsSmem *>(smem + W_NRING * W_UNIT + W_BM * T_LD * 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (p.force_trap && blockIdx.x == 0 && tid == 0) __trap();  // what a spin-loop watchdog does when a dependency never arrives
 
     // role and slice of this CTA
     int role, slice;
@@ -912,6 +914,7 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
             }
         }
     }
+    p.force_trap = getenv("AMIRA_DEBUG_FORCE_TRAP") ? 1 : 0;
     if (getenv("AMIRA_WS_TRACE")) {
         p.trace = reinterpret_cast<long long *>(work + otrace);
         cudaMemsetAsync(p.trace, 0, sizeof(long long) * W_TRACE_ITS * 32, c->stream);

@@ -11,8 +11,8 @@
 //   Hann window -> 512-point real FFT as a 256-point complex FFT factored 16 x 16 (radix-16 in registers, twiddle, 16x16
 //   transpose through shared memory, radix-16 in registers) -> real-input split against the mirrored bin, whose values sit in
 //   the partner lane (16 - lane) and come over with warp shuffles -> |X|^2 of the tile's 32 frames in shared memory;
-//   then the mel reduction with a LANE PER FRAME, fully unrolled from the compile-time filterbank (weights are FFMA immediates,
-//   each power bin one conflict-free shared-memory load at an immediate offset) -> log -> tile of un-normalised log-mel + per-tile (mean, M2) partials -> coalesced
+//   then the mel reduction with a LANE PER FRAME (filters in groups of four, warp-uniform table loads, each power bin one
+//   conflict-free shared-memory load) -> log -> tile of un-normalised log-mel + per-tile (mean, M2) partials -> coalesced
 //   stores.  The CTA that completes the LAST tile of an utterance (atomic counter) merges the partials (Chan, fp64) and
 //   normalises the utterance in place while its features are still in L2: (x - mean) / (std + 1e-5), frames >= features_len
 //   zeroed — no second kernel, no second pass over HBM.
@@ -25,7 +25,6 @@
 #include <cstring>
 #include <vector>
 
-#include "amira_mel128.h"
 #include "common.h"
 
 namespace amira {
@@ -33,15 +32,16 @@ namespace amira {
 namespace {
 
 constexpr int TF = 32;                             // frames per tile
-constexpr int FE_THREADS = 128;                    // 4 warps, 8 frames each
+constexpr int FE_THREADS = 256;                    // 8 warps = 16 half-warps: half of a 32-frame tile is transformed at a time
 constexpr int FE_WARPS = FE_THREADS / 32;
+static_assert(FE_WARPS == kFeWarps, "the mel tables are split for this many warps");
 constexpr int SPAN = (TF - 1) * kHop + kNfft;      // 5472 padded samples per tile
 constexpr int RAW_CAP = SPAN + 16;                 // raw samples staged per tile (+ previous sample, alignment slack)
 constexpr int P_LD = kNbin;                        // power spectrum row stride (257: odd, so a lane per frame is conflict-free)
 constexpr int OUT_LD = TF + 1;
 constexpr int FE_HALVES = 2 * FE_WARPS;            // a half-warp (16 lanes) transforms one frame
 constexpr int TLD = 17;                            // row stride (complex doubles) of the 16x16 transpose buffer
-constexpr int TBUF = 16 * TLD;                     // complex doubles per half-warp exchange buffer (>= 256 for the Z spectrum)
+constexpr int TBUF = 16 * TLD;                     // doubles per half-warp exchange buffer (real and imaginary parts cross in turn)
 
 struct FeMeta {
     const int64_t *starts;   // [B] first element of each utterance
@@ -56,32 +56,6 @@ struct FeMeta {
     int debug;               // AMIRA_FE_DEBUG bit mask (timing attribution only): 1 skip the normalisation, 2 skip the mel phase,
                              // 8 skip the transforms
 };
-
-// ---- mel reduction, fully unrolled from the compile-time filterbank (include/amira_mel128.h): for one frame (a lane), filter M is
-// sum_r w[M][r] * P[kStart[M] + r] with immediate weights and immediate shared-memory offsets ----
-template <int M, int R>
-__device__ __forceinline__ float mel_dot(const float *__restrict__ prow, float acc) {
-    if constexpr (R < mel128::kCount[M]) {
-        constexpr uint32_t wb = mel128::kWeightBits[mel128::kOffset[M] + R];
-        constexpr int k = mel128::kStart[M] + R;
-        return mel_dot<M, R + 1>(prow, fmaf(__uint_as_float(wb), prow[k], acc));
-    } else {
-        return acc;
-    }
-}
-template <int M, int M_END>
-__device__ __forceinline__ void mel_range(const float *__restrict__ prow, float *__restrict__ outcol) {
-    if constexpr (M < M_END) {
-        outcol[M * OUT_LD] = mel_dot<M, 0>(prow, 0.f);  // the logarithm follows in a rolled loop: 128 inlined logf bodies would
-        mel_range<M + 1, M_END>(prow, outcol);          // make this straight-line code instruction-fetch bound
-    }
-}
-template <int M0, int M1>
-__device__ __forceinline__ void mel_warp(const float *__restrict__ prow, float *__restrict__ outcol) {
-    mel_range<M0, M1>(prow, outcol);
-#pragma unroll 4
-    for (int m = M0; m < M1; ++m) outcol[m * OUT_LD] = logf(outcol[m * OUT_LD] + 5.9604644775390625e-08f);  // log(mel + 2^-24)
-}
 
 __device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
     if (n <= 1) return 0;
@@ -199,8 +173,8 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
                 float *__restrict__ features, int64_t t_stride, double2 *__restrict__ partials) {
     using StT = typename Stage<RawT>::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *xbuf = reinterpret_cast<double2 *>(smem_raw);                            // [FE_HALVES][TBUF] transpose exchange
-    double2 *tw256 = xbuf + FE_HALVES * TBUF;                                         // [16][16] W256^(m2 k1) at [k1][m2]
+    double *xbuf = reinterpret_cast<double *>(smem_raw);                              // [FE_HALVES][TBUF] transpose exchange
+    double2 *tw256 = reinterpret_cast<double2 *>(xbuf + FE_HALVES * TBUF);            // [16][16] W256^(m2 k1) at [k1][m2]
     double2 *tw512 = tw256 + 256;                                                     // [129] exp(-2 pi i k / 512)
     double2 *winp = tw512 + 130;                                                      // [256] scaled window pairs (w[2m], w[2m+1])
     StT *ystage = reinterpret_cast<StT *>(winp + 256);                                // [SPAN]; dead after the transforms ...
@@ -215,7 +189,8 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
     __shared__ int s_last;      // this CTA finished the last tile of the utterance
     __shared__ float s_mu[kMel], s_inv[kMel];
     static_assert(sizeof(float) * kMel * OUT_LD <= sizeof(StT) * SPAN, "the log-mel tile must fit the staging buffer it aliases");
-    static_assert((TF * P_LD * 4) % 16 == 0 && (SPAN * 4) % 16 == 0, "raw2 alignment");
+    static_assert((TF * P_LD * 4) % 16 == 0 && (SPAN * 4) % 16 == 0 && (FE_HALVES * TBUF * 8) % 16 == 0, "alignment of the carve-up");
+    static_assert(sizeof(RawT) * RAW_CAP <= sizeof(double) * FE_HALVES * TBUF, "raw staging aliases the exchange buffers");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, hl = lane & 15;  // half-warp and lane within it
@@ -233,7 +208,7 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
         sincospi(-2.0 * (double)i / 512.0, &sn, &cs);
         tw512[i] = make_double2(cs, sn);
     }
-    double2 *myx = xbuf + (warp * 2 + half) * TBUF;
+    double *myx = xbuf + (warp * 2 + half) * TBUF;
     int32_t *tile_counter = meta.done + meta.B;
 
     struct TileLoc {
@@ -292,6 +267,32 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
                 for (int64_t i = tid; i < (int64_t)kMel * t_stride; i += FE_THREADS) ub[i] = 0.f;
             }
 
+    // ---- deferred normalisation: the CTA that finished the LAST tile of an utterance (atomic counter) normalises it, from L2 ----
+    int pend_b = -1, pend_old = 0;
+    int64_t pend_L = 0, pend_ld = 0, pend_foff = 0;
+    auto normalize_pending = [&]() {  // all threads; s_last was set by thread 0 and published by a barrier
+        if (s_last && !(meta.debug & 1)) {
+            __threadfence();  // acquire side of the counter: every other CTA's stores of this utterance are visible
+            if (tid < kMel) {  // Chan et al. merge of the per-tile (count, mean, M2), one thread per mel row
+                const int m = tid, t0 = meta.tile_pfx[pend_b], nt = meta.tile_cnt[pend_b];
+                double cn = 0.0, cmean = 0.0, cm2 = 0.0;
+                for (int t = 0; t < nt; ++t) {
+                    const double2 q = __ldcg(partials + (size_t)(t0 + t) * kMel + m);
+                    const double n2 = (double)min((int64_t)TF, pend_L - (int64_t)t * TF), nt2 = cn + n2, d = q.x - cmean;
+                    cmean += d * (n2 / nt2);
+                    cm2 += q.y + d * d * (cn * n2 / nt2);
+                    cn = nt2;
+                }
+                const double sd = pend_L > 1 ? sqrt(cm2 / (double)(pend_L - 1)) : 0.0;
+                s_mu[m] = (float)cmean;
+                s_inv[m] = (float)(1.0 / (sd + 1e-5));
+            }
+            __syncthreads();
+            float *ub = features + pend_foff;
+            for (int m = warp; m < kMel; m += FE_WARPS) normalize_row(ub + (int64_t)m * pend_ld, pend_ld, pend_L, s_mu[m], s_inv[m], lane);
+        }
+    };
+
     // ---- dynamic tile scheduler: every CTA holds the tile it works on and the one after it (whose samples are in flight) ----
     if (tid == 0) {
         s_tile[0] = atomicAdd(tile_counter, 1);
@@ -312,8 +313,14 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
         const bool fits = cur.fits, fast = cur.fast;
         const int delta = cur.delta;
 
+        // the next tile's location: five dependent global loads, issued here so that their latency hides behind the staging below
+        TileLoc nxt = cur;
+        if (next_tile < meta.n_tiles) nxt = locate(next_tile);
         __syncthreads();  // previous tile fully consumed (ystage/outt/pw/raw reuse, s_tile read)
-        if (tid == 0) s_tile[0] = atomicAdd(tile_counter, 1);  // the tile after next; read after the next barrier
+        if (tid == 0) {
+            s_tile[0] = atomicAdd(tile_counter, 1);  // the tile after next; read after the next barrier
+            s_last = pend_b >= 0 && pend_old == meta.tile_cnt[pend_b] - 1;  // the previous tile's completion count has arrived by now
+        }
         // ---- stage the signal span [g_lo, g_hi) needed by this tile ----
         if (fast && kPrefetch) {
             asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's share of the tile, requested during the previous tile
@@ -341,6 +348,7 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
         }
         __syncthreads();
         const int after_next = s_tile[0];
+        normalize_pending();  // the utterance whose last tile this CTA finished in its previous iteration (rare: once per utterance)
         // ---- pre-emphasis (y[0] = x[0]; y[i] = x[i] - 0.97 x[i-1]) + reflect padding ----
         const bool interior = fits && i0 >= 1 && i0 + span <= n;
         if (interior) {
@@ -369,11 +377,7 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
         }
         __syncthreads();
         // raw2 has been consumed: request the next tile of this CTA now, its loads fly during the transforms below
-        TileLoc nxt = cur;
-        if (next_tile < meta.n_tiles) {
-            nxt = locate(next_tile);
-            if (kPrefetch) prefetch(nxt);
-        }
+        if (next_tile < meta.n_tiles && kPrefetch) prefetch(nxt);
 
         // ---- a half-warp per frame, two frames per warp at a time: 512-point real FFT = 256-point complex FFT (z[m] = x[2m] +
         // i x[2m+1]) as 16 x 16: radix-16 in registers over m1 (m = 16 m1 + lane), twiddle W256^(lane k1), transpose through
@@ -398,14 +402,18 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
                 const double2 t = tw256[k1 * 16 + hl];
                 a[k1] = cmul(a[k1], cplx{t.x, t.y});
             }
+            // 16 x 16 transpose through shared memory, real parts then imaginary parts (half the buffer of a complex exchange)
 #pragma unroll
-            for (int k1 = 0; k1 < 16; ++k1) myx[k1 * TLD + hl] = make_double2(a[k1].x, a[k1].y);
+            for (int k1 = 0; k1 < 16; ++k1) myx[k1 * TLD + hl] = a[k1].x;
             __syncwarp();
 #pragma unroll
-            for (int m2 = 0; m2 < 16; ++m2) {
-                const double2 t = myx[hl * TLD + m2];
-                a[m2] = cplx{t.x, t.y};
-            }
+            for (int m2 = 0; m2 < 16; ++m2) a[m2].x = myx[hl * TLD + m2];
+            __syncwarp();
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) myx[k1 * TLD + hl] = a[k1].y;
+            __syncwarp();
+#pragma unroll
+            for (int m2 = 0; m2 < 16; ++m2) a[m2].y = myx[hl * TLD + m2];
             dft16(a);  // Z[hl + 16 k2] = sum_m2 (...) W16^(m2 k2), already halved by the window scale
             __syncwarp();
             // X[k] = E + W512^k O, X[256-k] = conj(E - W512^k O) with E = Z[k] + conj Z[256-k], O = (Z[k] - conj Z[256-k]) / i.
@@ -443,38 +451,59 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
         }
         __syncthreads();  // all power spectra of the tile are in shared memory; the staging buffer is dead (outt may overwrite it)
 
-        // ---- mel reduction, a lane per frame: every power bin is one conflict-free load (row stride 257) at an immediate offset,
-        // every weight an FFMA immediate; warp w owns a contiguous range of filters of equal modelled cost ----
+        // ---- mel reduction, a lane per frame.  Filters come in groups of four with a common walk (FrontendTables::grp): every
+        // table access is warp-uniform (one L1 wavefront, broadcast), every power bin one conflict-free shared-memory load (row
+        // stride 257), four independent FFMA chains per step.  A rolled loop on purpose: the fully unrolled form (504 FFMA with
+        // immediate weights) was instruction-fetch bound — each warp ran 2.4 KB of straight-line code once per tile ----
         if (!(meta.debug & 2)) {
             const float *prow = pw + lane * P_LD;  // lanes >= nf read stale-but-finite spectra; their results are not used
-            float *outcol = outt + lane;
-            constexpr int S0 = mel128::kSplit[0], S1 = mel128::kSplit[1], S2 = mel128::kSplit[2], S3 = mel128::kSplit[3], S4 = mel128::kSplit[4];
-            if (warp == 0) mel_warp<S0, S1>(prow, outcol);
-            else if (warp == 1) mel_warp<S1, S2>(prow, outcol);
-            else if (warp == 2) mel_warp<S2, S3>(prow, outcol);
-            else mel_warp<S3, S4>(prow, outcol);
+            const int g_end = __ldg(&tab->warp_group[warp + 1]);
+            for (int g = __ldg(&tab->warp_group[warp]); g < g_end; ++g) {
+                const int4 ga = __ldg(reinterpret_cast<const int4 *>(&tab->grp[g]));       // m0, nf, steps, woff
+                const int4 gk = __ldg(reinterpret_cast<const int4 *>(&tab->grp[g]) + 1);   // k0[4]
+                const float4 *wv = reinterpret_cast<const float4 *>(tab->mel_w + ga.w);
+                const float *p0 = prow + gk.x, *p1 = prow + gk.y, *p2 = prow + gk.z, *p3 = prow + gk.w;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 2
+                for (int st = 0; st < ga.z; ++st) {
+                    const float4 w4 = __ldg(wv + st);
+                    a0 = fmaf(w4.x, p0[st], a0);
+                    a1 = fmaf(w4.y, p1[st], a1);
+                    a2 = fmaf(w4.z, p2[st], a2);
+                    a3 = fmaf(w4.w, p3[st], a3);
+                }
+                float *o = outt + ga.x * OUT_LD + lane;
+                o[0] = logf(a0 + 5.9604644775390625e-08f);  // log(mel + 2^-24)
+                if (ga.y > 1) o[OUT_LD] = logf(a1 + 5.9604644775390625e-08f);
+                if (ga.y > 2) o[2 * OUT_LD] = logf(a2 + 5.9604644775390625e-08f);
+                if (ga.y > 3) o[3 * OUT_LD] = logf(a3 + 5.9604644775390625e-08f);
+            }
         }
         __syncthreads();
 
-        // ---- per-tile statistics (one thread per mel row) + coalesced store of the tile ----
+        // ---- per-tile statistics (two threads per mel row, 16 frames each) + coalesced store of the tile ----
         {
-            const int m = tid;  // FE_THREADS == kMel
-            // mean in fp64 (it is subtracted from values of magnitude ~10 whose spread may be 1e-2), M2 in fp32 relative to it;
-            // four independent chains each
+            static_assert(FE_THREADS == 2 * kMel && TF == 32, "two threads per mel row");
+            const int m = tid >> 1, fb0 = (tid & 1) * 16, fe = min(nf, fb0 + 16);
+            // mean in fp64 (it is subtracted from values of magnitude ~10 whose spread may be 1e-2), M2 in fp32 relative to it
             const float *orow = outt + m * OUT_LD;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int f = 0;
-            for (; f + 3 < nf; f += 4) { s0 += (double)orow[f]; s1 += (double)orow[f + 1]; s2 += (double)orow[f + 2]; s3 += (double)orow[f + 3]; }
-            for (; f < nf; ++f) s0 += (double)orow[f];
-            const double mean = ((s0 + s1) + (s2 + s3)) / nf;
+            double s0 = 0.0, s1 = 0.0;
+            int f = fb0;
+            for (; f + 1 < fe; f += 2) { s0 += (double)orow[f]; s1 += (double)orow[f + 1]; }
+            if (f < fe) s0 += (double)orow[f];
+            double sum = s0 + s1;
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            const double mean = sum / nf;
             const float mf = (float)mean, ml = (float)(mean - (double)mf);
-            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-            for (f = 0; f + 3 < nf; f += 4) {
-                const float d0 = (orow[f] - mf) - ml, d1 = (orow[f + 1] - mf) - ml, d2 = (orow[f + 2] - mf) - ml, d3 = (orow[f + 3] - mf) - ml;
-                q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+            float q0 = 0.f, q1 = 0.f;
+            for (f = fb0; f + 1 < fe; f += 2) {
+                const float d0 = (orow[f] - mf) - ml, d1 = (orow[f + 1] - mf) - ml;
+                q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
             }
-            for (; f < nf; ++f) { const float d = (orow[f] - mf) - ml; q0 = fmaf(d, d, q0); }
-            partials[(size_t)tile * kMel + m] = make_double2(mean, (double)((q0 + q1) + (q2 + q3)));
+            if (f < fe) { const float d = (orow[f] - mf) - ml; q0 = fmaf(d, d, q0); }
+            float q = q0 + q1;
+            q += __shfl_xor_sync(0xffffffffu, q, 1);
+            if (!(tid & 1)) partials[(size_t)tile * kMel + m] = make_double2(mean, (double)q);
         }
         // row stride: t_stride (padded layout) or, packed (t_stride == 0), the utterance's own frame count
         const int64_t ld = t_stride > 0 ? t_stride : L;
@@ -482,37 +511,23 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
         for (int m = warp; m < kMel; m += FE_WARPS)
             if (lane < nf) dst[(size_t)m * ld + lane] = outt[m * OUT_LD + lane];
 
-        // ---- the CTA that finishes the LAST tile of the utterance normalises it, from L2 ----
+        // ---- completion of the utterance: count this tile; the answer (am I the last?) is consumed during the NEXT tile, so the
+        // atomic's round trip is off the per-tile critical path ----
         __syncthreads();  // every thread's feature and partial stores are ordered before thread 0's fence below (cumulativity)
         if (tid == 0) {
             __threadfence();
-            s_last = atomicAdd(meta.done + b, 1) == meta.tile_cnt[b] - 1;
+            pend_old = atomicAdd(meta.done + b, 1);
         }
-        __syncthreads();
-        if (s_last && !(meta.debug & 1)) {
-            __threadfence();  // acquire side of the counter: every other CTA's stores of this utterance are visible
-            {   // Chan et al. merge of the per-tile (count, mean, M2), one thread per mel row
-                const int m = tid, t0 = meta.tile_pfx[b], nt = meta.tile_cnt[b];
-                double cn = 0.0, cmean = 0.0, cm2 = 0.0;
-                for (int t = 0; t < nt; ++t) {
-                    const double2 q = __ldcg(partials + (size_t)(t0 + t) * kMel + m);
-                    const double n2 = (double)min((int64_t)TF, L - (int64_t)t * TF), nt2 = cn + n2, d = q.x - cmean;
-                    cmean += d * (n2 / nt2);
-                    cm2 += q.y + d * d * (cn * n2 / nt2);
-                    cn = nt2;
-                }
-                const double sd = L > 1 ? sqrt(cm2 / (double)(L - 1)) : 0.0;
-                s_mu[m] = (float)cmean;
-                s_inv[m] = (float)(1.0 / (sd + 1e-5));
-            }
-            __syncthreads();
-            float *ub = features + foff_b;
-            for (int m = warp; m < kMel; m += FE_WARPS) normalize_row(ub + (int64_t)m * ld, ld, L, s_mu[m], s_inv[m], lane);
-        }
+        pend_b = b; pend_L = L; pend_ld = ld; pend_foff = foff_b;
         cur = nxt;
         tile = next_tile;
         next_tile = after_next;
     }
+    // the last tile this CTA worked on
+    __syncthreads();
+    if (tid == 0) s_last = pend_b >= 0 && pend_old == meta.tile_cnt[pend_b] - 1;
+    __syncthreads();
+    normalize_pending();
 }
 
 __global__ void bytes_to_f32_kernel(const uint8_t *__restrict__ in, size_t n_bytes, int drop_odd, float *__restrict__ out) {
@@ -552,26 +567,16 @@ __global__ void bytes_to_f32_kernel(const uint8_t *__restrict__ in, size_t n_byt
 
 template <typename RawT>
 size_t fe_smem_bytes() {
-    return sizeof(double2) * (FE_HALVES * TBUF + 256 + 130 + 256) + sizeof(typename Stage<RawT>::T) * SPAN + sizeof(float) * TF * P_LD +
+    return sizeof(double) * FE_HALVES * TBUF + sizeof(double2) * (256 + 130 + 256) + sizeof(typename Stage<RawT>::T) * SPAN + sizeof(float) * TF * P_LD +
            (sizeof(RawT) == 2 ? ((RAW_CAP * sizeof(RawT) + 15) & ~(size_t)15) : 0);  // raw2 (16-bit input: prefetched staging)
 }
 
 }  // namespace
 
-// the compile-time mel filterbank of the kernel (include/amira_mel128.h) must be the table tables.cpp builds (and the oracle checks)
-cudaError_t frontend_upload_tables(const FrontendTables *t) {
-    std::vector<float> fb((size_t)kMel * kNbin);
-    build_mel_filterbank(fb.data());
-    int o = 0;
-    for (int m = 0; m < kMel; ++m) {
-        if (t->kstart[m] != mel128::kStart[m] || t->kcnt[m] != mel128::kCount[m] || mel128::kOffset[m] != o) return cudaErrorInvalidValue;
-        for (int r = 0; r < t->kcnt[m]; ++r, ++o) {
-            uint32_t bits;
-            std::memcpy(&bits, &fb[(size_t)m * kNbin + t->kstart[m] + r], sizeof(bits));
-            if (bits != mel128::kWeightBits[o]) return cudaErrorInvalidValue;
-        }
-    }
-    return o == mel128::kNonZero ? cudaSuccess : cudaErrorInvalidValue;
+cudaError_t frontend_upload_tables(const FrontendTables *t) {  // sanity of the grouped mel tables (tables.cpp)
+    int n = 0;
+    for (int g = 0; g < t->n_groups; ++g) n += t->grp[g].nf;
+    return (t->n_groups > 0 && t->n_groups <= kMelGroupsMax && n == kMel && t->warp_group[kFeWarps] == t->n_groups) ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const int64_t *starts_host,

@@ -52,21 +52,51 @@ void build_frontend_tables(FrontendTables *t) {
         t->kstart[m] = first < 0 ? 0 : first;
         t->kcnt[m] = first < 0 ? 0 : last - first + 1;
     }
-    int row = 0;
-    for (int g = 0; g < 4; ++g) {
-        t->melRow[g] = row;
-        int mx = 0;
-        for (int l = 0; l < 32; ++l) mx = t->kcnt[g * 32 + l] > mx ? t->kcnt[g * 32 + l] : mx;
-        for (int j = 0; j < mx; ++j)
-            for (int l = 0; l < 32; ++l) {
-                const int m = g * 32 + l;
-                // clamp the bin index inside the spectrum; padded rows carry weight 0
-                t->melw_t[row + j][l] = j < t->kcnt[m] ? fb[m * kNbin + t->kstart[m] + j] : 0.0f;
-            }
-        row += mx;
+    // contiguous filter ranges per warp with equal modelled cost (2 per non-zero weight + 26 per filter: log + store), then
+    // groups of four inside each range
+    long total = 0;
+    for (int m = 0; m < kMel; ++m) total += 2 * t->kcnt[m] + 26;
+    int split[kFeWarps + 1];
+    split[0] = 0;
+    long run = 0;
+    int m = 0;
+    for (int w = 1; w < kFeWarps; ++w) {
+        while (m < kMel && run + (2 * t->kcnt[m] + 26) / 2 < total * w / kFeWarps) run += 2 * t->kcnt[m++] + 26;
+        split[w] = m;
     }
-    t->melRow[4] = row;
-    if (row > kMelRowsMax) std::fprintf(stderr, "amira_b200: mel table overflow (%d rows)\n", row);
+    split[kFeWarps] = kMel;
+    int g = 0, woff = 0;
+    for (int w = 0; w < kFeWarps; ++w) {
+        t->warp_group[w] = g;
+        for (int m0 = split[w]; m0 < split[w + 1]; m0 += 4) {
+            if (g >= kMelGroupsMax) { std::fprintf(stderr, "amira_b200: mel group table overflow\n"); return; }
+            MelGroup &G = t->grp[g];
+            G.m0 = m0;
+            G.nf = split[w + 1] - m0 < 4 ? split[w + 1] - m0 : 4;
+            G.steps = 0;
+            for (int j = 0; j < G.nf; ++j) G.steps = t->kcnt[m0 + j] > G.steps ? t->kcnt[m0 + j] : G.steps;
+            G.woff = woff;
+            for (int j = 0; j < 4; ++j) {
+                const int mj = j < G.nf ? m0 + j : m0;
+                // a filter shorter than the group's walk reads a few bins past its support with zero weights: keep them inside the row
+                G.k0[j] = t->kstart[mj] + G.steps <= kNbin ? t->kstart[mj] : kNbin - G.steps;
+            }
+            if (woff + 4 * G.steps > kMelWeightsMax) { std::fprintf(stderr, "amira_b200: mel weight table overflow\n"); return; }
+            for (int s2 = 0; s2 < G.steps; ++s2)
+                for (int j = 0; j < 4; ++j) {
+                    float wv = 0.0f;
+                    if (j < G.nf) {
+                        const int k = G.k0[j] + s2, r = k - t->kstart[m0 + j];
+                        if (r >= 0 && r < t->kcnt[m0 + j]) wv = fb[(m0 + j) * kNbin + k];
+                    }
+                    t->mel_w[woff + 4 * s2 + j] = wv;
+                }
+            woff += 4 * G.steps;
+            ++g;
+        }
+    }
+    t->warp_group[kFeWarps] = g;
+    t->n_groups = g;
 }
 
 BlobLayout blob_layout() {

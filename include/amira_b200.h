@@ -70,6 +70,10 @@ typedef struct {
 /* replaces get_cuda_device_count_ffi (src/cuda/cuda_helper.cu:23-30, src/cuda/mod.rs:372) */
 int32_t amira_device_count(int32_t *count);
 int32_t amira_config_default(amira_config *cfg);
+/* Recovery from a sticky device error (a kernel watchdog trap, any device-side fault): after one, every call on every context of
+ * that device fails with AMIRA_ERR_UNKNOWN.  Destroy those contexts, call this (cudaDeviceReset), create new ones.  The reference
+ * has no counterpart: its CUDA path never launches a kernel (src/cuda/cuda_helper.cu). */
+int32_t amira_device_reset(int32_t device_id);
 /* replaces CudaAsrPipeline::new + CudaSharedMemoryRegionCreate (src/asr/cuda_pipeline.rs:41-103,
  * src/cuda/cuda_helper.cu:63-110) */
 int32_t amira_ctx_create(const amira_config *cfg, amira_ctx **out);
