@@ -37,6 +37,7 @@ constexpr int FE_WARPS = FE_THREADS / 32;
 static_assert(FE_WARPS == kFeWarps, "the mel tables are split for this many warps");
 constexpr int SPAN = (TF - 1) * kHop + kNfft;      // 5472 padded samples per tile
 constexpr int RAW_CAP = SPAN + 16;                 // raw samples staged per tile (+ previous sample, alignment slack)
+constexpr int kMelWeightsSmem = 704;                // floats of FrontendTables::mel_w kept in shared memory (>= the table in use)
 constexpr int P_LD = kNbin;                        // power spectrum row stride (257: odd, so a lane per frame is conflict-free)
 constexpr int OUT_LD = TF + 1;
 constexpr int FE_HALVES = 2 * FE_WARPS;            // a half-warp (16 lanes) transforms one frame
@@ -185,9 +186,14 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
     // tile of this CTA while the current tile's frames are transformed
     constexpr bool kPrefetch = sizeof(RawT) == 2;
     RawT *raw2 = reinterpret_cast<RawT *>(pw + TF * P_LD);  // [RAW_CAP], 16-byte aligned
+    constexpr size_t kRaw2Bytes = kPrefetch ? ((RAW_CAP * sizeof(RawT) + 15) & ~(size_t)15) : 0;
+    // the grouped mel tables (FrontendTables::grp / mel_w / warp_group), copied once per CTA: walked by every warp for every tile
+    int4 *s_grp = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(raw2) + kRaw2Bytes);   // [n_groups][2]
+    float4 *s_melw = reinterpret_cast<float4 *>(s_grp + 2 * kMelGroupsMax);                         // [kMelWeightsSmem / 4]
     __shared__ int s_tile[2];   // tile being processed / next tile of this CTA
     __shared__ int s_last;      // this CTA finished the last tile of the utterance
-    __shared__ float s_mu[kMel], s_inv[kMel];
+    __shared__ int s_wg[kFeWarps + 1];
+    float *s_mu = reinterpret_cast<float *>(ystage), *s_inv = s_mu + kMel;  // normalisation runs while the staging buffer is idle
     static_assert(sizeof(float) * kMel * OUT_LD <= sizeof(StT) * SPAN, "the log-mel tile must fit the staging buffer it aliases");
     static_assert((TF * P_LD * 4) % 16 == 0 && (SPAN * 4) % 16 == 0 && (FE_HALVES * TBUF * 8) % 16 == 0, "alignment of the carve-up");
     static_assert(sizeof(RawT) * RAW_CAP <= sizeof(double) * FE_HALVES * TBUF, "raw staging aliases the exchange buffers");
@@ -208,6 +214,9 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
         sincospi(-2.0 * (double)i / 512.0, &sn, &cs);
         tw512[i] = make_double2(cs, sn);
     }
+    for (int i = tid; i < 2 * kMelGroupsMax; i += FE_THREADS) s_grp[i] = reinterpret_cast<const int4 *>(tab->grp)[i];
+    for (int i = tid; i < kMelWeightsSmem / 4; i += FE_THREADS) s_melw[i] = reinterpret_cast<const float4 *>(tab->mel_w)[i];
+    if (tid <= kFeWarps) s_wg[tid] = tab->warp_group[tid];
     double *myx = xbuf + (warp * 2 + half) * TBUF;
     int32_t *tile_counter = meta.done + meta.B;
 
@@ -290,6 +299,7 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
             __syncthreads();
             float *ub = features + pend_foff;
             for (int m = warp; m < kMel; m += FE_WARPS) normalize_row(ub + (int64_t)m * pend_ld, pend_ld, pend_L, s_mu[m], s_inv[m], lane);
+            __syncthreads();  // s_mu / s_inv alias the staging buffer the caller writes next
         }
     };
 
@@ -452,21 +462,21 @@ fe_fused_kernel(const RawT *__restrict__ wave, FeMeta meta, const FrontendTables
         __syncthreads();  // all power spectra of the tile are in shared memory; the staging buffer is dead (outt may overwrite it)
 
         // ---- mel reduction, a lane per frame.  Filters come in groups of four with a common walk (FrontendTables::grp): every
-        // table access is warp-uniform (one L1 wavefront, broadcast), every power bin one conflict-free shared-memory load (row
+        // table access is warp-uniform (one shared-memory wavefront, broadcast), every power bin one conflict-free shared-memory load (row
         // stride 257), four independent FFMA chains per step.  A rolled loop on purpose: the fully unrolled form (504 FFMA with
         // immediate weights) was instruction-fetch bound — each warp ran 2.4 KB of straight-line code once per tile ----
         if (!(meta.debug & 2)) {
             const float *prow = pw + lane * P_LD;  // lanes >= nf read stale-but-finite spectra; their results are not used
-            const int g_end = __ldg(&tab->warp_group[warp + 1]);
-            for (int g = __ldg(&tab->warp_group[warp]); g < g_end; ++g) {
-                const int4 ga = __ldg(reinterpret_cast<const int4 *>(&tab->grp[g]));       // m0, nf, steps, woff
-                const int4 gk = __ldg(reinterpret_cast<const int4 *>(&tab->grp[g]) + 1);   // k0[4]
-                const float4 *wv = reinterpret_cast<const float4 *>(tab->mel_w + ga.w);
+            const int g_end = s_wg[warp + 1];
+            for (int g = s_wg[warp]; g < g_end; ++g) {
+                const int4 ga = s_grp[2 * g];       // m0, nf, steps, woff
+                const int4 gk = s_grp[2 * g + 1];   // k0[4]
+                const float4 *wv = s_melw + (ga.w >> 2);
                 const float *p0 = prow + gk.x, *p1 = prow + gk.y, *p2 = prow + gk.z, *p3 = prow + gk.w;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 2
                 for (int st = 0; st < ga.z; ++st) {
-                    const float4 w4 = __ldg(wv + st);
+                    const float4 w4 = wv[st];
                     a0 = fmaf(w4.x, p0[st], a0);
                     a1 = fmaf(w4.y, p1[st], a1);
                     a2 = fmaf(w4.z, p2[st], a2);
@@ -568,7 +578,8 @@ __global__ void bytes_to_f32_kernel(const uint8_t *__restrict__ in, size_t n_byt
 template <typename RawT>
 size_t fe_smem_bytes() {
     return sizeof(double) * FE_HALVES * TBUF + sizeof(double2) * (256 + 130 + 256) + sizeof(typename Stage<RawT>::T) * SPAN + sizeof(float) * TF * P_LD +
-           (sizeof(RawT) == 2 ? ((RAW_CAP * sizeof(RawT) + 15) & ~(size_t)15) : 0);  // raw2 (16-bit input: prefetched staging)
+           (sizeof(RawT) == 2 ? ((RAW_CAP * sizeof(RawT) + 15) & ~(size_t)15) : 0) +  // raw2 (16-bit input: prefetched staging)
+           sizeof(int4) * 2 * kMelGroupsMax + sizeof(float) * kMelWeightsSmem;         // grouped mel tables
 }
 
 }  // namespace
@@ -576,7 +587,9 @@ size_t fe_smem_bytes() {
 cudaError_t frontend_upload_tables(const FrontendTables *t) {  // sanity of the grouped mel tables (tables.cpp)
     int n = 0;
     for (int g = 0; g < t->n_groups; ++g) n += t->grp[g].nf;
-    return (t->n_groups > 0 && t->n_groups <= kMelGroupsMax && n == kMel && t->warp_group[kFeWarps] == t->n_groups) ? cudaSuccess : cudaErrorInvalidValue;
+    const MelGroup &last = t->grp[t->n_groups > 0 ? t->n_groups - 1 : 0];
+    return (t->n_groups > 0 && t->n_groups <= kMelGroupsMax && n == kMel && t->warp_group[kFeWarps] == t->n_groups &&
+            last.woff + 4 * last.steps <= kMelWeightsSmem) ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const int64_t *starts_host,
