@@ -36,7 +36,8 @@ EXPORTS = ["amira_device_count", "amira_config_default", "amira_ctx_create", "am
            "amira_stream_group_process_chunks", "amira_stream_group_transcript", "amira_stream_group_tokens",
            "amira_stream_group_audio_length", "amira_stream_group_process_batch", "amira_stream_group_stats", "amira_ctx_fork", "amira_device_alloc",
            "amira_device_free", "amira_ipc_export", "amira_ipc_import", "amira_ipc_close", "amira_wire_classify_frame",
-           "amira_wire_parse_batch_request", "amira_wire_format_response", "amira_device_reset"]
+           "amira_wire_parse_batch_request", "amira_wire_format_response", "amira_device_reset", "amira_logmel_pcm16_packed",
+           "amira_greedy_decode_resume", "amira_stream_group_set_incremental", "amira_stream_group_flush", "amira_stream_group_progress"]
 
 
 class AmiraError(RuntimeError):
@@ -101,6 +102,11 @@ def load_library():
     L.amira_preprocess_pcm16.argtypes = [vp, vp, vp, i32, vp, i64, vp]
     L.amira_preprocess_f32.argtypes = [vp, vp, i64, vp, i32, vp, i64, vp]
     L.amira_preprocess_pcm16_packed.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    L.amira_logmel_pcm16_packed.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    L.amira_greedy_decode_resume.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.amira_stream_group_set_incremental.argtypes = [vp, i32]
+    L.amira_stream_group_flush.argtypes = [vp, i32, vp, vp]
+    L.amira_stream_group_progress.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     L.amira_greedy_decode_packed.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.amira_preprocess_f32_packed.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     L.amira_weave_transcript_segs.argtypes = [C.c_char_p, C.c_char_p, C.c_float, C.c_float, vp, C.c_size_t, C.POINTER(i32)]
@@ -385,6 +391,38 @@ class Context:
         feats = np.empty(max(int(foff[B]), 1), dtype=np.float32)
         self._check(self._L.amira_preprocess_pcm16_packed(self._h, _ptr(pcm), _ptr(offsets), B, _ptr(feats), _ptr(foff), _ptr(lens)))
         return [feats[foff[b]:foff[b + 1]].reshape(N_MELS, -1) for b in range(B)], lens
+
+    def logmel_pcm16_packed(self, pcm: np.ndarray, offsets):
+        """Un-normalised log-mel (amira_logmel_pcm16_packed): a list of B [128, features_len_b] arrays and features_lens."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        B = offsets.size - 1
+        lens = np.zeros(B, dtype=np.int64)
+        foff = np.zeros(B + 1, dtype=np.int64)
+        for b in range(B):
+            foff[b + 1] = foff[b] + N_MELS * features_len(int(offsets[b + 1] - offsets[b]))
+        feats = np.empty(max(int(foff[B]), 1), dtype=np.float32)
+        self._check(self._L.amira_logmel_pcm16_packed(self._h, _ptr(pcm), _ptr(offsets), B, _ptr(feats), _ptr(foff), _ptr(lens)))
+        return [feats[foff[b]:foff[b + 1]].reshape(N_MELS, -1) for b in range(B)], lens
+
+    def greedy_decode_resume(self, encoder_outputs: list, state: "DecoderState", last_tokens):
+        """amira_greedy_decode_resume: like greedy_decode_packed, with the last emitted token of every stream carried in and out.
+        Returns (tokens per stream, DecoderState, last_tokens [B], n_steps)."""
+        B = len(encoder_outputs)
+        lens = np.array([int(e.shape[-1]) for e in encoder_outputs], dtype=np.int64)
+        eoff = np.zeros(B + 1, dtype=np.int64)
+        eoff[1:] = np.cumsum(lens * ENC_DIM)
+        enc = np.empty(max(int(eoff[B]), 1), dtype=np.float32)
+        for b, e in enumerate(encoder_outputs):
+            enc[eoff[b]:eoff[b + 1]] = np.ascontiguousarray(e, dtype=np.float32).reshape(-1)
+        st = DecoderState(np.ascontiguousarray(state.states_1, np.float32).copy(), np.ascontiguousarray(state.states_2, np.float32).copy())
+        last = np.ascontiguousarray(last_tokens, dtype=np.int32).copy()
+        toks = np.zeros((B, self.max_total_tokens), dtype=np.int32)
+        ntok = np.zeros(B, dtype=np.int32)
+        nsteps = np.zeros(B, dtype=np.int32)
+        self._check(self._L.amira_greedy_decode_resume(self._h, _ptr(enc), _ptr(eoff), B, _ptr(lens), _ptr(st.states_1), _ptr(st.states_2),
+                                                       _ptr(last), _ptr(toks), _ptr(ntok), _ptr(nsteps)))
+        return [toks[b, :max(int(ntok[b]), 0)].tolist() for b in range(B)], st, last, nsteps
 
     def preprocess_pcm16_packed_raw(self, pcm_ptr: int, offsets: np.ndarray, B: int, features_ptr: int, feat_offsets: np.ndarray,
                                     lens_out: np.ndarray):

@@ -428,7 +428,7 @@ int32_t amira_features_len(int64_t n_samples, int64_t *features_len) {
 
 static int32_t preprocess_common(amira_ctx *c, const void *wave, bool pcm16, const int64_t *starts, const int64_t *lens,
                                  int64_t total_elems, int32_t B, float *features, int64_t t_stride,
-                                 int64_t *features_lens, const int64_t *feat_offsets = nullptr) {
+                                 int64_t *features_lens, const int64_t *feat_offsets = nullptr, bool normalize = true) {
     // feat_offsets != nullptr: packed output — utterance b is a [128][features_len_b] block at features + feat_offsets[b]
     int64_t max_len = 0;
     for (int b = 0; b < B; ++b) {
@@ -481,7 +481,7 @@ static int32_t preprocess_common(amira_ctx *c, const void *wave, bool pcm16, con
         const int b0 = (int)((int64_t)B * k / n_chunks), b1 = (int)((int64_t)B * (k + 1) / n_chunks);
         if (b1 > b0)
             CK(launch_frontend(c, wave_dev, pcm16, starts + b0, lens + b0, b1 - b0, feat_offsets ? feat_dev : feat_dev + feat_elem(b0), t_stride,
-                               k, 1, feat_offsets ? feat_offsets + b0 : nullptr),
+                               k, 1, feat_offsets ? feat_offsets + b0 : nullptr, normalize),
                "front-end metadata");
     }
     for (int k = 0; k < n_chunks; ++k) {
@@ -497,7 +497,7 @@ static int32_t preprocess_common(amira_ctx *c, const void *wave, bool pcm16, con
             if (dbg) cudaEventRecord(dbg_ev[1 + 3 * k], c->h2d_stream);
         }
         CK(launch_frontend(c, wave_dev, pcm16, starts + b0, lens + b0, b1 - b0, feat_offsets ? feat_dev : feat_dev + feat_elem(b0), t_stride, k,
-                           n_chunks > 1 ? 2 : 0, feat_offsets ? feat_offsets + b0 : nullptr),
+                           n_chunks > 1 ? 2 : 0, feat_offsets ? feat_offsets + b0 : nullptr, normalize),
            "front-end launch");
         if (feat_host) {
             CK(cudaEventRecord(c->ev_pool[2 * k + 1], c->stream), "event");
@@ -550,6 +550,23 @@ int32_t amira_preprocess_pcm16_packed(amira_ctx *c, const int16_t *pcm, const in
         if (lens[b] < 0 || offsets[b] < 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "offsets must be non-decreasing");
     }
     return preprocess_common(c, pcm, true, offsets, lens.data(), offsets[B], B, features, 0, features_lens, feat_offsets);
+    API_END(c)
+}
+
+// Un-normalised log-mel, ragged layout: log(mel + 2^-24) of every frame, the tensor the preprocessor holds before its per-feature
+// normalisation.  The incremental streaming path normalises it with running statistics (host_stream.cpp).
+int32_t amira_logmel_pcm16_packed(amira_ctx *c, const int16_t *pcm, const int64_t *offsets, int32_t B, float *features,
+                                  const int64_t *feat_offsets, int64_t *features_lens) {
+    API_BEGIN(c)
+    if (B < 0 || !offsets || !features || !feat_offsets || (B > 0 && !pcm && offsets[B] > 0))
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_logmel_pcm16_packed: bad arguments");
+    if (B == 0) return AMIRA_OK;
+    std::vector<int64_t> lens((size_t)B);
+    for (int b = 0; b < B; ++b) {
+        lens[b] = offsets[b + 1] - offsets[b];
+        if (lens[b] < 0 || offsets[b] < 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "offsets must be non-decreasing");
+    }
+    return preprocess_common(c, pcm, true, offsets, lens.data(), offsets[B], B, features, 0, features_lens, feat_offsets, false);
     API_END(c)
 }
 
@@ -650,7 +667,8 @@ int32_t amira_decoder_joint(amira_ctx *c, const float *encoder_outputs, int32_t 
 // ---------------------------------------------------------------------------------------------- greedy decode
 static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t B, int32_t T,
                              const int64_t *encoded_lengths, const int32_t *slots_host, float *states_1, float *states_2,
-                             int32_t *tokens, int32_t *n_tokens, int32_t *n_steps, const int64_t *enc_offsets = nullptr) {
+                             int32_t *tokens, int32_t *n_tokens, int32_t *n_steps, const int64_t *enc_offsets = nullptr,
+                             int32_t *last_tokens = nullptr) {
     // enc_offsets != nullptr: packed encoder outputs — stream b is a [1024][encoded_lengths[b]] block at encoder_outputs + enc_offsets[b]
     if (c->shared && c->shared->version != c->weights_version) decoder_adopt_shared(c);  // a sibling lane loaded weights
     if (!c->has_weights) return fail(c, AMIRA_ERR_NO_WEIGHTS, "greedy decode: no weights loaded");
@@ -716,13 +734,26 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
     } else if (!slots_host && (states_1 || states_2)) {
         return fail(c, AMIRA_ERR_INVALID_VALUE, "states_1 and states_2 must both be given or both be null");
     }
+    // resume form: the token each stream emitted last (the LSTM input of its first step) in, the one it emitted last now out
+    int32_t *last_dev = nullptr;
+    bool last_h = false;
+    if (last_tokens) {
+        if (c->cfg.decode_engine == 1) return fail(c, AMIRA_ERR_INVALID_VALUE, "the resume form needs the tcgen05 decode engine");
+        CK(stage_out<int32_t>(c, 6, last_tokens, (size_t)B, &last_dev, &last_h), "last_tokens staging");
+        if (last_h) {
+            for (int b = 0; b < B; ++b)
+                if (last_tokens[b] < 0 || last_tokens[b] >= kEmbRows) return fail(c, AMIRA_ERR_INVALID_VALUE, "last_tokens outside the embedding table");
+            CK(cudaMemcpyAsync(last_dev, last_tokens, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, c->stream), "last_tokens H2D");
+        }
+    }
     int32_t *tok_dev, *nt_dev, *ns_dev;
     bool tok_h, nt_h, ns_h;
     CK(stage_out<int32_t>(c, 3, tokens, (size_t)B * cap, &tok_dev, &tok_h), "tokens staging");
     CK(stage_out<int32_t>(c, 4, n_tokens, (size_t)B, &nt_dev, &nt_h), "n_tokens staging");
     CK(stage_out<int32_t>(c, 5, n_steps, (size_t)B, &ns_dev, &ns_h), "n_steps staging");
-    CK(launch_greedy_decode(c, enc_dev, enc_host, B, T, lens_dev, h_lens, slots_dev, s1_dev, s2_dev, tok_dev, nt_dev, ns_dev, enc_offsets),
+    CK(launch_greedy_decode(c, enc_dev, enc_host, B, T, lens_dev, h_lens, slots_dev, s1_dev, s2_dev, tok_dev, nt_dev, ns_dev, enc_offsets, last_dev),
        "greedy decode launch");
+    CK(finish_out<int32_t>(c, last_tokens, last_dev, (size_t)B, last_h), "last_tokens D2H");
     CK(finish_out<int32_t>(c, tokens, tok_dev, (size_t)B * cap, tok_h), "tokens D2H");
     CK(finish_out<int32_t>(c, n_tokens, nt_dev, (size_t)B, nt_h), "n_tokens D2H");
     CK(finish_out<int32_t>(c, n_steps, ns_dev, (size_t)B, ns_h), "n_steps D2H");
@@ -759,6 +790,26 @@ int32_t amira_greedy_decode_packed(amira_ctx *c, const float *encoder_outputs, c
     }
     return greedy_common(c, encoder_outputs, B, (int32_t)T, encoded_lengths, nullptr, states_1, states_2, tokens, n_tokens, n_steps,
                          enc_offsets);
+    API_END(c)
+}
+
+// The loop resumed where an earlier call left it: besides the LSTM state, the token emitted last is carried (last_tokens [B],
+// in/out, host or device; AMIRA_BLANK_ID for a fresh stream), so chunk-by-chunk decoding of one stream emits exactly the
+// tokens of one call over the concatenated frames.  The reference carries the state only (src/asr/decoder_optimized.rs:78: every
+// call starts from blank); this is the "carry state + last token" of a truly incremental decoder.
+int32_t amira_greedy_decode_resume(amira_ctx *c, const float *encoder_outputs, const int64_t *enc_offsets, int32_t B,
+                                   const int64_t *encoded_lengths, float *states_1, float *states_2, int32_t *last_tokens,
+                                   int32_t *tokens, int32_t *n_tokens, int32_t *n_steps) {
+    API_BEGIN(c)
+    if (B < 0 || (B > 0 && (!enc_offsets || !encoded_lengths || !last_tokens)))
+        return fail(c, AMIRA_ERR_INVALID_VALUE, "amira_greedy_decode_resume: bad arguments");
+    int64_t T = 0;
+    for (int b = 0; b < B; ++b) {
+        if (encoded_lengths[b] < 0 || encoded_lengths[b] > 0x7fffffff) return fail(c, AMIRA_ERR_INVALID_VALUE, "encoded_lengths out of range");
+        T = encoded_lengths[b] > T ? encoded_lengths[b] : T;
+    }
+    return greedy_common(c, encoder_outputs, B, (int32_t)T, encoded_lengths, nullptr, states_1, states_2, tokens, n_tokens, n_steps,
+                         enc_offsets, last_tokens);
     API_END(c)
 }
 

@@ -192,7 +192,7 @@ struct ProfScope {  // RAII: records begin/end events around one launch when pro
 // element of utterance b's [128][features_len_b] block relative to features_dev.
 cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const int64_t *starts_host,
                             const int64_t *lens_host, int B, float *features_dev, int64_t t_stride, int slot = 0, int phase = 0,
-                            const int64_t *foff_host = nullptr);
+                            const int64_t *foff_host = nullptr, bool normalize = true);
 cudaError_t launch_bytes_to_f32(Ctx *c, const uint8_t *bytes_dev, size_t n_bytes, bool drop_odd, float *out_dev);
 cudaError_t frontend_upload_tables(const FrontendTables *t);  // mel filterbank -> constant memory of the current device
 
@@ -206,7 +206,7 @@ void decoder_release(Ctx *c);                 // this context's workspace only; 
 // chunk on c->h2d_stream and overlaps the upload with the encoder projection of the chunks already on the device.
 cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, const float *enc_host, int B, int T, const int32_t *lens_dev,
                                  const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev,
-                                 int32_t *ntok_dev, int32_t *nsteps_dev, const int64_t *enc_off_host = nullptr);
+                                 int32_t *ntok_dev, int32_t *nsteps_dev, const int64_t *enc_off_host = nullptr, int32_t *last_dev = nullptr);
 const int32_t *decoder_fail_count_dev(Ctx *c);  // failed-stream counter of the last greedy launch
 cudaError_t launch_decoder_joint(Ctx *c, const float *enc_dev, int B, int T, const int32_t *targets_dev, int U,
                                  const int32_t *tlen_dev, const float *in_s1, const float *in_s2, float *outputs,
@@ -218,7 +218,8 @@ cudaError_t decoder_tc_prepare_weights(Ctx *c);
 void decoder_tc_free(TcWeights *w);
 cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *enc_host, int B, int T, const int32_t *lens_dev,
                                     const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev,
-                                    int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev, const int64_t *enc_off_host = nullptr);
+                                    int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev, const int64_t *enc_off_host = nullptr,
+                                    int32_t *last_dev = nullptr);
 cudaError_t launch_tc_gemm(Ctx *c, const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_lo, const __nv_bfloat16 *w_hi,
                            const __nv_bfloat16 *w_lo, const float *bias, float *C, long long ldc, int M, int N, int K);
 cudaError_t launch_split_rows(Ctx *c, const float *x, size_t ldx, __nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t ldo,
@@ -233,6 +234,6 @@ cudaError_t decoder_ws_prepare(Ctx *c, TcWeights *w);
 // work == nullptr: size query (*work_bytes receives the workspace size).  E [B*T][640] and perm_dev [Mpad] from the caller.
 cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t *lens_dev, const int *perm_dev,
                              const int *eoff_dev, const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
-                             int32_t *nsteps_dev, char *work, size_t *work_bytes);
+                             int32_t *nsteps_dev, char *work, size_t *work_bytes, int32_t *last_dev = nullptr);
 
 }  // namespace amira

@@ -643,13 +643,13 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, const float *enc_host, int B, int T, const int32_t *lens_dev,
                                  const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev,
-                                 int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev, const int64_t *enc_off_host) {
+                                 int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev, const int64_t *enc_off_host, int32_t *last_dev) {
     // decode_engine: 1 = fp32 CUDA-core persistent kernel (this file, the numerics anchor); 0 = auto = 4 = tcgen05 split-bf16
     // weight-stationary dataflow kernel (decoder_ws.cu, launched from decoder_tc.cu)
     if (c->cfg.decode_engine != 1)
         return launch_greedy_decode_tc(c, enc_dev, enc_host, B, T, lens_dev, lens_host, slots_dev, s1_dev, s2_dev, tokens_dev, ntok_dev,
-                                       nsteps_dev, enc_off_host);
-    if (enc_off_host) return cudaErrorNotSupported;  // packed encoder outputs: tcgen05 engines only
+                                       nsteps_dev, enc_off_host, last_dev);
+    if (enc_off_host || last_dev) return cudaErrorNotSupported;  // packed encoder outputs: tcgen05 engines only
     DecoderPriv *d = c->dec;
     if (enc_host) {  // fp32 reference engine: plain upload
         cudaError_t eu = cudaMemcpyAsync(const_cast<float *>(enc_dev), enc_host, sizeof(float) * (size_t)B * kEnc * T, cudaMemcpyHostToDevice, c->stream);

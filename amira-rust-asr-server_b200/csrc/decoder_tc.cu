@@ -332,7 +332,7 @@ static size_t tc_align(size_t x) { return (x + 1023) & ~(size_t)1023; }
 
 cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *enc_host, int B, int T, const int32_t *lens_dev,
                                     const int32_t *lens_host, const int32_t *slots_dev, float *s1_dev, float *s2_dev,
-                                    int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev, const int64_t *enc_off_host) {
+                                    int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev, const int64_t *enc_off_host, int32_t *last_dev) {
     // enc_off_host != nullptr: packed encoder outputs — stream b is a [1024][lens[b]] block at enc + enc_off_host[b]
     DecoderPriv *d = c->dec;
     TcWeights *w = d->tc;
@@ -399,7 +399,7 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
         }
     }
     return launch_greedy_ws(c, E, B, T, lens_dev, reinterpret_cast<int *>(base + operm), eoff_dev, slots_dev, s1_dev, s2_dev,
-                            tokens_dev, ntok_dev, nsteps_dev, base + ows, &ws_bytes);
+                            tokens_dev, ntok_dev, nsteps_dev, base + ows, &ws_bytes, last_dev);
 }
 
 }  // namespace amira

@@ -94,6 +94,7 @@ struct WsParams {
     int *tile_active, *cnt_d, *cnt_a, *cnt_b, *cnt_c, *dead_at, *part_ready /* [MT][40] */, *fail_count, *live_tiles;
     float *s1, *s2;
     int *tokens, *ntok, *nsteps;
+    int *last_io;       // nullable [B]: the token each stream emitted last, in (first LSTM input) and out (amira_greedy_decode_resume)
     int max_sym, max_total, blank, relu;
     int norot;          // debug: all CTAs walk the k-chunks in the same order (bit-identical logits across slices)
     int nrows;          // stream rows a unit loads and multiplies (32 / 64 when a single M-tile holds that few streams, else 128)
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
     for (int row = blockIdx.x * blockDim.x + tid; row < p.Mpad; row += gridDim.x * blockDim.x) {
         const int act = (row < p.B && p.lens[p.perm[row]] > 0) ? 1 : 0;
         int4 *dstc = reinterpret_cast<int4 *>(p.ctl + (size_t)(W_R - 1) * p.Mpad + row);  // the control row of "tick -1"
-        dstc[0] = make_int4(0, 0, 0, p.blank);
+        dstc[0] = make_int4(0, 0, 0, (p.last_io && row < p.B) ? p.last_io[p.perm[row]] : p.blank);
         dstc[1] = make_int4(act, 0, 0, 0);
         const int prow_ = row < p.B ? p.perm[row] : 0;
         p.rowinfo[row] = make_int4(prow_, row < p.B ? p.lens[prow_] : 0, row < p.B ? p.eoff[prow_] : 0, 0);
@@ -601,6 +602,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     if (fin_ver >= 0 && row < p.B) {  // this stream's results
                         p.ntok[ri.x] = failed ? -1 : c.total;
                         if (p.nsteps) p.nsteps[ri.x] = c.nsteps;
+                        if (p.last_io) p.last_io[ri.x] = c.last;
                         if (failed) atomicAdd(p.fail_count, 1);
                     }
                 }
@@ -830,7 +832,7 @@ cudaError_t decoder_ws_prepare(Ctx *c, TcWeights *w) {
 // produced by the caller (decoder_tc.cu).
 cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t *lens_dev, const int *perm_dev,
                              const int *eoff_dev, const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
-                             int32_t *nsteps_dev, char *work, size_t *work_bytes) {
+                             int32_t *nsteps_dev, char *work, size_t *work_bytes, int32_t *last_dev) {
     DecoderPriv *d = c->dec;
     TcWeights *w = d->tc;
     const int MT = (B + W_BM - 1) / W_BM, Mpad = MT * W_BM;
@@ -890,7 +892,7 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     p.dead_at = cnt + 5 * MT; p.part_ready = cnt + 6 * MT; p.tinfo = cnt + 6 * MT + MT * W_NG;
     p.fail_count = cnt + 6 * MT + MT * W_NG + MT * W_R; p.live_tiles = p.fail_count + 1;
     if (slots_dev) { p.s1 = c->slot_s1; p.s2 = c->slot_s2; } else { p.s1 = s1_dev; p.s2 = s2_dev; }
-    p.tokens = tokens_dev; p.ntok = ntok_dev; p.nsteps = nsteps_dev;
+    p.tokens = tokens_dev; p.ntok = ntok_dev; p.nsteps = nsteps_dev; p.last_io = last_dev;
     p.max_sym = c->cfg.max_symbols_per_step; p.max_total = c->cfg.max_total_tokens; p.blank = c->cfg.blank_id;
     p.relu = c->cfg.joint_activation;
     d->fail_count_dev = p.fail_count;

@@ -54,8 +54,8 @@ struct FeMeta {
     int32_t *done;           // [B] tiles finished per utterance (zero at launch); [B] = the tile counter
     int B;
     int n_tiles;
-    int debug;               // AMIRA_FE_DEBUG bit mask (timing attribution only): 1 skip the normalisation, 2 skip the mel phase,
-                             // 8 skip the transforms
+    int debug;               // bit 0: leave the log-mel un-normalised (amira_logmel_pcm16_packed); AMIRA_FE_DEBUG adds bits for
+                             // timing attribution only: 2 skip the mel phase, 8 skip the transforms
 };
 
 __device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
@@ -594,7 +594,7 @@ cudaError_t frontend_upload_tables(const FrontendTables *t) {  // sanity of the 
 
 cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const int64_t *starts_host,
                             const int64_t *lens_host, int B, float *features_dev, int64_t t_stride, int slot, int phase,
-                            const int64_t *foff_host) {
+                            const int64_t *foff_host, bool normalize) {
     if (B <= 0) return cudaSuccess;
     if (slot < 0 || slot >= Ctx::kMaxChunks) return cudaErrorInvalidValue;
     DevBuf &fe_meta = c->fe_meta[slot], &fe_partials = c->fe_partials[slot];
@@ -655,6 +655,7 @@ cudaError_t launch_frontend(Ctx *c, const void *wave_dev, bool is_pcm16, const i
     meta.B = B;
     meta.n_tiles = (int)tiles;
     meta.debug = getenv("AMIRA_FE_DEBUG") ? atoi(getenv("AMIRA_FE_DEBUG")) : 0;
+    if (!normalize) meta.debug |= 1;  // un-normalised log-mel (the incremental streaming path normalises with running statistics)
 
     ProfScope prof(c, PK_FE_LOGMEL);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)c->sm_count * 2));

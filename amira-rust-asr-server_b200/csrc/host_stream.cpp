@@ -249,6 +249,16 @@ struct Session {
     float acc_mean_amplitude = 0.0f;
     std::vector<float> s1, s2;        // DecoderState [2][1][640] (types.rs:159-183)
     float chunk_size = 2.0f;
+    // ---- incremental mode: what a stream carries between chunks ----
+    std::vector<int16_t> hist;        // audio tail: samples [hist_start, n_total) of the stream
+    int64_t hist_start = 0, n_total = 0;
+    int64_t t_next = 0;               // first log-mel frame not emitted yet
+    int64_t enc_frames = 0;
+    bool flushed = false;
+    std::vector<double> st_mean = std::vector<double>(AMIRA_N_MELS, 0.0), st_m2 = std::vector<double>(AMIRA_N_MELS, 0.0);  // running
+                                      // per-feature statistics over the st_count frames emitted so far
+    int64_t st_count = 0;
+    int32_t last_token = AMIRA_BLANK_ID;
     void reset_state() { s1.assign(2 * AMIRA_STATE_SIZE, 0.0f); s2.assign(2 * AMIRA_STATE_SIZE, 0.0f); }
     void clear() {  // incremental.rs:99-103
         audio.clear();
@@ -256,6 +266,12 @@ struct Session {
         transcript.clear();
         acc_mean_amplitude = 0.0f;
         reset_state();
+        hist.clear();
+        hist_start = n_total = t_next = enc_frames = st_count = 0;
+        flushed = false;
+        st_mean.assign(AMIRA_N_MELS, 0.0);
+        st_m2.assign(AMIRA_N_MELS, 0.0);
+        last_token = AMIRA_BLANK_ID;
     }
 };
 
@@ -278,6 +294,9 @@ struct amira_stream_group {
     std::mutex mu;
     std::string err;
     int64_t n_pipeline_calls = 0, n_rounds = 0;
+    bool incremental = false;
+    std::vector<int16_t> pcm;       // incremental mode: the segments of one round, back to back
+    std::vector<int32_t> last;
     // batch scratch
     std::vector<float> wave, features, enc, s1, s2;
     std::vector<int64_t> woff, foff, eoff, flens, elens;
@@ -437,6 +456,165 @@ int32_t process_buffered(amira_stream_group *g, const std::vector<Session *> &ac
     return AMIRA_OK;
 }
 
+// ---- incremental mode (amira_b200.h: amira_stream_group_set_incremental) ----
+constexpr int64_t kHopS = 160, kHalfWin = 200, kCtxHops = 2;  // a frame's window covers +-200 samples around its centre 160 t
+
+// Frames [t_next, t_end) of every listed session, in one front-end launch, the injected encoder and one resumed decode launch.
+// A session's segment starts at sample 160 A, A = max(0, t_next - 2): local frame t' = t - A.  For A > 0 the local frames 0 and 1
+// see the segment's artificial left edge (reflect padding, missing pre-emphasis partner) and are dropped — t_next - A = 2 is the
+// first local frame whose 400 window samples and their predecessors are all real.  For A = 0 the left edge is the true start of
+// the stream.  The right edge is real audio (frames are only emitted once complete) or, on flush, the true end of the stream.
+int32_t incremental_round(amira_stream_group *g, const std::vector<Session *> &ss, const std::vector<int64_t> &t_end, std::vector<int32_t> &rcs) {
+    amira_pipeline *p = g->p;
+    std::lock_guard<std::mutex> plock(p->mu);
+    const int B = (int)ss.size();
+    if (B == 0) return AMIRA_OK;
+    g->n_rounds++;
+    g->n_pipeline_calls += B;
+    std::vector<int64_t> A((size_t)B), nloc((size_t)B), lloc((size_t)B);
+    g->woff.assign((size_t)B + 1, 0);
+    g->foff.assign((size_t)B + 1, 0);
+    for (int i = 0; i < B; ++i) {
+        Session &s = *ss[(size_t)i];
+        A[(size_t)i] = std::max<int64_t>(0, s.t_next - kCtxHops);
+        nloc[(size_t)i] = s.n_total - kHopS * A[(size_t)i];
+        lloc[(size_t)i] = nloc[(size_t)i] / kHopS + 1;
+        g->woff[(size_t)i + 1] = g->woff[(size_t)i] + nloc[(size_t)i];
+        g->foff[(size_t)i + 1] = g->foff[(size_t)i] + (int64_t)AMIRA_N_MELS * lloc[(size_t)i];
+    }
+    g->pcm.resize((size_t)std::max<int64_t>(g->woff[(size_t)B], 1));
+    for (int i = 0; i < B; ++i) {
+        const Session &s = *ss[(size_t)i];
+        const int64_t a = kHopS * A[(size_t)i] - s.hist_start;  // >= 0: the history keeps two hops of left context
+        std::memcpy(g->pcm.data() + g->woff[(size_t)i], s.hist.data() + a, sizeof(int16_t) * (size_t)nloc[(size_t)i]);
+    }
+    g->features.resize((size_t)std::max<int64_t>(g->foff[(size_t)B], 1));
+    g->flens.assign((size_t)B, 0);
+    int32_t rc = amira_logmel_pcm16_packed(p->ctx, g->pcm.data(), g->woff.data(), B, g->features.data(), g->foff.data(), g->flens.data());
+    if (rc) { g->err = amira_last_error(p->ctx); for (auto &r : rcs) r = rc; return rc; }
+    // running normalisation + encoder, per stream
+    g->eoff.assign((size_t)B + 1, 0);
+    g->elens.assign((size_t)B, 0);
+    g->enc.clear();
+    std::vector<float> chunk;
+    for (int i = 0; i < B; ++i) {
+        Session &s = *ss[(size_t)i];
+        const int64_t n_new = t_end[(size_t)i] - s.t_next, f_first = s.t_next - A[(size_t)i], L = lloc[(size_t)i];
+        const float *src = g->features.data() + g->foff[(size_t)i];  // [128][L]
+        chunk.assign((size_t)AMIRA_N_MELS * (size_t)n_new, 0.f);
+        for (int m = 0; m < AMIRA_N_MELS; ++m) {
+            // Chan merge of the new frames into the running (count, mean, M2) of this feature, then (x - mean) / (std + 1e-5) of the
+            // new frames with the merged statistics (sample variance, like the utterance-level rule of the preprocessor)
+            double bm = 0.0, b2 = 0.0;
+            for (int64_t f = 0; f < n_new; ++f) bm += (double)src[(size_t)m * L + f_first + f];
+            bm /= (double)n_new;
+            for (int64_t f = 0; f < n_new; ++f) { const double d = (double)src[(size_t)m * L + f_first + f] - bm; b2 += d * d; }
+            const double na = (double)s.st_count, nb = (double)n_new, nt = na + nb, d = bm - s.st_mean[(size_t)m];
+            const double mean = s.st_mean[(size_t)m] + d * (nb / nt), m2 = s.st_m2[(size_t)m] + b2 + d * d * (na * nb / nt);
+            s.st_mean[(size_t)m] = mean;
+            s.st_m2[(size_t)m] = m2;
+            const double sd = nt > 1.0 ? std::sqrt(m2 / (nt - 1.0)) : 0.0;
+            const float mu = (float)mean, inv = (float)(1.0 / (sd + 1e-5));
+            for (int64_t f = 0; f < n_new; ++f) chunk[(size_t)m * n_new + f] = (src[(size_t)m * L + f_first + f] - mu) * inv;
+        }
+        s.st_count += n_new;
+        s.t_next = t_end[(size_t)i];
+        const float *e = nullptr;
+        int64_t el = 0;
+        if (!p->encoder || p->encoder(p->encoder_user, chunk.data(), n_new, &e, &el) != 0 || el < 0 || (el > 0 && !e)) {
+            rcs[(size_t)i] = p->encoder ? AMIRA_ERR_UNKNOWN : AMIRA_ERR_NOT_READY;
+            el = 0;
+        }
+        if (el > 0) g->enc.insert(g->enc.end(), e, e + (size_t)AMIRA_ENC_DIM * (size_t)el);
+        g->elens[(size_t)i] = el;
+        g->eoff[(size_t)i + 1] = g->eoff[(size_t)i] + (int64_t)AMIRA_ENC_DIM * el;
+    }
+    // resumed greedy loop: state and last token in and out
+    int32_t cap = AMIRA_MAX_TOTAL_TOKENS;
+    amira_ctx_max_total_tokens(p->ctx, &cap);
+    const size_t H = AMIRA_STATE_SIZE;
+    g->s1.resize(2 * (size_t)B * H);
+    g->s2.resize(2 * (size_t)B * H);
+    g->last.resize((size_t)B);
+    for (int i = 0; i < B; ++i) {
+        for (int l = 0; l < 2; ++l) {
+            std::memcpy(g->s1.data() + ((size_t)l * B + i) * H, ss[(size_t)i]->s1.data() + (size_t)l * H, sizeof(float) * H);
+            std::memcpy(g->s2.data() + ((size_t)l * B + i) * H, ss[(size_t)i]->s2.data() + (size_t)l * H, sizeof(float) * H);
+        }
+        g->last[(size_t)i] = ss[(size_t)i]->last_token;
+    }
+    g->tokens.assign((size_t)B * (size_t)cap, 0);
+    g->ntok.assign((size_t)B, 0);
+    if (g->eoff[(size_t)B] > 0) {
+        rc = amira_greedy_decode_resume(p->ctx, g->enc.data(), g->eoff.data(), B, g->elens.data(), g->s1.data(), g->s2.data(), g->last.data(),
+                                        g->tokens.data(), g->ntok.data(), nullptr);
+        if (rc && rc != AMIRA_ERR_DECODE_STEP) { g->err = amira_last_error(p->ctx); for (auto &r : rcs) r = rc; return rc; }
+    }
+    for (int i = 0; i < B; ++i) {
+        Session &s = *ss[(size_t)i];
+        if (rcs[(size_t)i]) continue;
+        if (g->ntok[(size_t)i] < 0) { rcs[(size_t)i] = AMIRA_ERR_DECODE_STEP; continue; }
+        if (g->elens[(size_t)i] > 0) {
+            for (int l = 0; l < 2; ++l) {
+                std::memcpy(s.s1.data() + (size_t)l * H, g->s1.data() + ((size_t)l * B + i) * H, sizeof(float) * H);
+                std::memcpy(s.s2.data() + (size_t)l * H, g->s2.data() + ((size_t)l * B + i) * H, sizeof(float) * H);
+            }
+            s.last_token = g->last[(size_t)i];
+            s.enc_frames += g->elens[(size_t)i];
+        }
+        const int32_t *tk = g->tokens.data() + (size_t)i * (size_t)cap;
+        s.token_ids.insert(s.token_ids.end(), tk, tk + g->ntok[(size_t)i]);
+        s.transcript = decode_utf8(p->vocab.decode(s.token_ids.data(), (int32_t)s.token_ids.size()).c_str());
+    }
+    return AMIRA_OK;
+}
+
+// push the new audio of the listed streams, then emit whatever has become complete (or, on flush, everything that is left)
+int32_t incremental_step(amira_stream_group *g, int32_t n, const int32_t *streams, const uint8_t *const *audio_bytes, const size_t *n_bytes,
+                         bool flush, int32_t *status) {
+    std::vector<Session *> ss;
+    std::vector<int64_t> t_end;
+    std::vector<int32_t> idx;
+    for (int32_t i = 0; i < n; ++i) {
+        Session &s = *g->sessions[(size_t)streams[i]];
+        if (status) status[i] = AMIRA_OK;
+        if (s.flushed) { if (status) status[i] = AMIRA_ERR_INVALID_VALUE; continue; }  // a flushed stream takes no more audio (clear it first)
+        if (!flush && n_bytes[i]) {
+            const size_t ns = n_bytes[i] / 2;  // an odd trailing byte is dropped (audio.rs:18-26)
+            const size_t o = s.hist.size();
+            s.hist.resize(o + ns);
+            std::memcpy(s.hist.data() + o, audio_bytes[i], 2 * ns);  // little-endian i16, as the wire carries it
+            s.n_total += (int64_t)ns;
+        }
+        int64_t te;
+        if (flush) {
+            s.flushed = true;
+            te = s.n_total > 0 ? s.n_total / kHopS + 1 : 0;  // features_lens of the whole stream
+        } else {
+            te = s.n_total >= kHalfWin ? (s.n_total - kHalfWin) / kHopS + 1 : 0;  // frames whose window lies inside the audio so far
+        }
+        if (te > s.t_next) { ss.push_back(&s); t_end.push_back(te); idx.push_back(i); }
+    }
+    std::vector<int32_t> rcs(ss.size(), AMIRA_OK);
+    incremental_round(g, ss, t_end, rcs);
+    int32_t worst = AMIRA_OK;
+    for (size_t a = 0; a < ss.size(); ++a) {
+        Session &s = *ss[a];
+        // keep two hops of left context before the next frame (and one more sample: the pre-emphasis partner lies inside them)
+        const int64_t keep_from = std::max<int64_t>(0, kHopS * (s.t_next - kCtxHops));
+        if (keep_from > s.hist_start) {
+            s.hist.erase(s.hist.begin(), s.hist.begin() + (keep_from - s.hist_start));
+            s.hist_start = keep_from;
+        }
+        if (status) status[idx[a]] = rcs[a];
+        if (rcs[a] && !worst) worst = rcs[a];
+    }
+    if (status)
+        for (int32_t i = 0; i < n; ++i)
+            if (status[i] && !worst) worst = status[i];
+    return worst;
+}
+
 void copy_text(const std::string &s, char *text, size_t cap, int32_t *len) {
     if (len) *len = (int32_t)s.size();
     if (text && cap) {
@@ -562,6 +740,7 @@ int32_t amira_stream_group_process_chunks(amira_stream_group *g, int32_t n, cons
             seen[(size_t)streams[i]] = 1;
             if (n_bytes[i] && !audio_bytes[i]) return gfail(g, AMIRA_ERR_INVALID_VALUE, "process_chunks: null audio");
         }
+        if (g->incremental) return incremental_step(g, n, streams, audio_bytes, n_bytes, false, status);
         std::vector<Session *> active;
         std::vector<int32_t> idx;
         std::vector<float> samples;
@@ -645,6 +824,42 @@ int32_t amira_stream_group_process_batch(amira_stream_group *g, int32_t stream, 
         copy_text(encode_utf8(s.transcript), text, text_cap, &out->text_len);
         return AMIRA_OK;
     HS_CATCH(g)
+}
+
+int32_t amira_stream_group_set_incremental(amira_stream_group *g, int32_t enable) {
+    if (!g) return AMIRA_ERR_INVALID_VALUE;
+    std::lock_guard<std::mutex> lock(g->mu);
+    for (auto &s : g->sessions)
+        if (s->audio.length != 0 || s->n_total != 0) return gfail(g, AMIRA_ERR_INVALID_VALUE, "set_incremental: a stream already holds audio (clear it first)");
+    g->incremental = enable != 0;
+    return AMIRA_OK;
+}
+
+int32_t amira_stream_group_flush(amira_stream_group *g, int32_t n, const int32_t *streams, int32_t *status) {
+    if (!g) return AMIRA_ERR_INVALID_VALUE;
+    std::lock_guard<std::mutex> lock(g->mu);
+    if (!g->incremental) return gfail(g, AMIRA_ERR_INVALID_VALUE, "flush: the group is not in incremental mode");
+    if (n < 0 || (n > 0 && !streams)) return gfail(g, AMIRA_ERR_INVALID_VALUE, "flush: bad arguments");
+    if (!g->p->ctx) return gfail(g, AMIRA_ERR_NO_DEVICE, "pipeline was created without a GPU context");
+    HS_TRY
+        std::vector<char> seen(g->sessions.size(), 0);
+        for (int32_t i = 0; i < n; ++i) {
+            if (streams[i] < 0 || (size_t)streams[i] >= g->sessions.size() || seen[(size_t)streams[i]])
+                return gfail(g, AMIRA_ERR_INVALID_VALUE, "flush: stream id out of range or repeated");
+            seen[(size_t)streams[i]] = 1;
+        }
+        return incremental_step(g, n, streams, nullptr, nullptr, true, status);
+    HS_CATCH(g)
+}
+
+int32_t amira_stream_group_progress(amira_stream_group *g, int32_t stream, int64_t *samples, int64_t *frames, int64_t *encoder_frames) {
+    if (!g || stream < 0 || (size_t)stream >= g->sessions.size()) return AMIRA_ERR_INVALID_VALUE;
+    std::lock_guard<std::mutex> lock(g->mu);
+    const Session &s = *g->sessions[(size_t)stream];
+    if (samples) *samples = s.n_total;
+    if (frames) *frames = s.t_next;
+    if (encoder_frames) *encoder_frames = s.enc_frames;
+    return AMIRA_OK;
 }
 
 int32_t amira_stream_group_stats(amira_stream_group *g, int64_t *n_pipeline_calls, int64_t *n_rounds) {

@@ -102,6 +102,28 @@ class StreamGroup:
         self.last_status = status[:n].tolist()
         return [self.transcript(int(s)) for s in ids]
 
+    # -- incremental mode (amira_b200.h: amira_stream_group_set_incremental): each chunk costs its own frames
+    def set_incremental(self, enable: bool = True):
+        rc = self._L.amira_stream_group_set_incremental(self._h, int(enable))
+        if rc:
+            raise AmiraError(rc, self._err())
+
+    def flush(self, streams, raise_on_error: bool = True):
+        """End of the listed streams: the remaining frames (reflect padding of the true end); returns their transcripts."""
+        ids = np.ascontiguousarray(streams, dtype=np.int32)
+        status = np.zeros(max(ids.size, 1), np.int32)
+        rc = self._L.amira_stream_group_flush(self._h, int(ids.size), ids.ctypes.data, status.ctypes.data)
+        if rc and raise_on_error:
+            raise AmiraError(rc, self._err())
+        self.last_status = status[:ids.size].tolist()
+        return [self.transcript(int(s)) for s in ids]
+
+    def progress(self, stream: int):
+        """(samples received, log-mel frames emitted, encoder frames decoded) of one stream."""
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        _check(self._L.amira_stream_group_progress(self._h, stream, C.byref(a), C.byref(b), C.byref(c)), "progress")
+        return int(a.value), int(b.value), int(c.value)
+
     def transcript(self, stream: int) -> str:
         n = C.c_int32(0)
         _check(self._L.amira_stream_group_transcript(self._h, stream, None, 0, C.byref(n)), "transcript")

@@ -140,6 +140,11 @@ int32_t amira_preprocess_f32(amira_ctx *ctx, const float *waveforms, int64_t n_s
  * streaming path, src/asr/incremental.rs:139-160), features as in amira_preprocess_pcm16_packed. */
 int32_t amira_preprocess_f32_packed(amira_ctx *ctx, const float *waveforms, const int64_t *wave_offsets, int32_t B,
                                     float *features, const int64_t *feat_offsets, int64_t *features_lens);
+/* Un-normalised log-mel, ragged layout as amira_preprocess_pcm16_packed: log(mel + 2^-24) of every frame — the tensor the
+ * preprocessor holds before its per-feature normalisation.  Used by the incremental streaming path, which normalises with running
+ * statistics because the statistics of the whole utterance do not exist yet. */
+int32_t amira_logmel_pcm16_packed(amira_ctx *ctx, const int16_t *pcm, const int64_t *offsets, int32_t B, float *features,
+                                  const int64_t *feat_offsets, int64_t *features_lens);
 /* replaces performance_opts::audio::bytes_to_f32_optimized (src/performance_opts.rs:14-31), including the
  * odd-trailing-byte rule; drop_odd != 0 gives bytes_to_f32_samples (src/asr/audio.rs:18-26) /
  * simd::bytes_to_f32_optimized (src/asr/simd.rs:222-248).  bytes, out: host or device. */
@@ -170,6 +175,15 @@ int32_t amira_greedy_decode(amira_ctx *ctx, const float *encoder_outputs, int32_
 int32_t amira_greedy_decode_packed(amira_ctx *ctx, const float *encoder_outputs, const int64_t *enc_offsets, int32_t B,
                                    const int64_t *encoded_lengths, float *states_1, float *states_2, int32_t *tokens,
                                    int32_t *n_tokens, int32_t *n_steps);
+
+/* The loop resumed where an earlier call left a stream: besides the LSTM state, the token emitted last is carried (last_tokens
+ * [B] in/out, host or device; AMIRA_BLANK_ID for a fresh stream), so decoding a stream chunk by chunk emits exactly the tokens of
+ * one call over the concatenated frames (up to max_total_tokens per call).  The reference carries the state only — every call
+ * starts from blank (src/asr/decoder_optimized.rs:78) — and re-decodes overlapping windows instead (src/asr/incremental.rs:136-171);
+ * this entry is the "carry state + last token" decoder of SURVEY 8 f1.  Ragged input as amira_greedy_decode_packed. */
+int32_t amira_greedy_decode_resume(amira_ctx *ctx, const float *encoder_outputs, const int64_t *enc_offsets, int32_t B,
+                                   const int64_t *encoded_lengths, float *states_1, float *states_2, int32_t *last_tokens,
+                                   int32_t *tokens, int32_t *n_tokens, int32_t *n_steps);
 
 /* ---- WebSocket path: device-resident per-stream LSTM state (replaces the DecoderState carried by
  * IncrementalAsr, src/asr/incremental.rs:45-51,101-105, and process_stream_* in src/asr/pipeline.rs:384-431) */
@@ -266,6 +280,20 @@ int32_t amira_stream_group_process_batch(amira_stream_group *g, int32_t stream, 
                                          amira_transcription *out, int32_t *tokens, int32_t tokens_cap, char *text,
                                          size_t text_cap);
 int32_t amira_stream_group_stats(amira_stream_group *g, int64_t *n_pipeline_calls, int64_t *n_rounds);
+/* INCREMENTAL mode of a stream group: every chunk costs its own frames instead of every window of a 10 s buffer.
+ * Per stream the group carries (a) the audio tail the next STFT frames still need (at most two hops of left context + the
+ * samples after the last complete frame), (b) running per-feature statistics (count, mean, M2) for the normalisation,
+ * (c) the LSTM state and the last emitted token.  amira_stream_group_process_chunks then pushes the new audio, computes the
+ * log-mel frames that have become complete (a frame is complete when its 400-sample window lies inside the received audio;
+ * they are bit-identical to the frames of the whole recording), normalises them with the statistics of all frames so far, runs the
+ * injected encoder on the new frames only and resumes the greedy loop (amira_greedy_decode_resume); tokens are appended, no
+ * weaving takes place.  amira_stream_group_flush ends a stream: the remaining frames, with the reflect padding of the true end.
+ * The literal mode above remains the parity anchor of the reference's IncrementalAsr; this mode is an extension with its own
+ * definition of the normalisation (running instead of per-utterance statistics). */
+int32_t amira_stream_group_set_incremental(amira_stream_group *g, int32_t enable); /* before the first audio of every stream */
+int32_t amira_stream_group_flush(amira_stream_group *g, int32_t n, const int32_t *streams, int32_t *status);
+/* samples received, log-mel frames emitted and encoder frames decoded so far (incremental mode) */
+int32_t amira_stream_group_progress(amira_stream_group *g, int32_t stream, int64_t *samples, int64_t *frames, int64_t *encoder_frames);
 /* configured max_total_tokens of a context (row stride of the tokens output of the decode entries) */
 int32_t amira_ctx_max_total_tokens(amira_ctx *ctx, int32_t *value);
 

@@ -372,6 +372,56 @@ int orc_greedy_decode(const float *enc, size_t enc_len, int64_t encoded_len, flo
     float *logits = (float *)malloc(sizeof(float) * (size_t)cap);
     int32_t *targets = (int32_t *)malloc(sizeof(int32_t) * (size_t)(cfg->max_total_tokens + 2));
     int total = 0, rc = 0;
+    if (cfg->single_step && (cfg->state_update_on_nonblank_only || cfg->tdt_durations)) {
+        /* NON-REFERENCE variants (see amira_oracle.h): canonical state rule and/or TDT durations.  Same limits, same first-max
+         * argmax; the token argmax of the TDT reading runs over outputs [0, blank] only. */
+        float keep1[2 * ORC_H], keep2[2 * ORC_H];
+        const int n_tok = cfg->tdt_durations ? cfg->blank + 1 : ORC_VOCAB;
+        size_t t = 0;
+        while (t < T && total < cfg->max_total_tokens) {
+            if (orc_extract_frame_into(enc, enc_len, shape, 3, t, frame, features) != features) { rc = -2; break; }
+            st.frames_visited++;
+            int symbols = 0, advance = 1;
+            for (;;) {
+                symbols += 1;
+                if (symbols > cfg->max_symbols_per_step) { advance = 1; break; }
+                targets[0] = total > 0 ? tokens[total - 1] : cfg->initial_last;
+                memcpy(keep1, states_1, sizeof(keep1));
+                memcpy(keep2, states_2, sizeof(keep2));
+                const int nl = step(user, frame, (int)features, targets, 1, states_1, states_2, logits, cap);
+                if (nl < 0) { rc = -1; goto done; }
+                st.n_steps++;
+                size_t k;
+                float kv;
+                orc_argmax_zero_copy(logits, (size_t)(nl < n_tok ? nl : n_tok), &k, &kv);
+                int skip = -1;
+                if (cfg->tdt_durations && nl >= ORC_VOCAB) {
+                    size_t d;
+                    float dv;
+                    orc_argmax_zero_copy(logits + cfg->blank + 1, (size_t)(ORC_VOCAB - cfg->blank - 1), &d, &dv);
+                    skip = (int)d;
+                    if ((int32_t)k == cfg->blank && skip == 0) skip = 1;
+                }
+                const int is_blank = (int32_t)k == cfg->blank;
+                if (is_blank && cfg->state_update_on_nonblank_only) {  /* canonical: a blank leaves the prediction net where it was */
+                    memcpy(states_1, keep1, sizeof(keep1));
+                    memcpy(states_2, keep2, sizeof(keep2));
+                }
+                if (!is_blank) {
+                    tokens[total++] = (int32_t)k;
+                    if (total >= cfg->max_total_tokens) break;
+                }
+                if (skip >= 0) {  /* TDT: the duration decides; 0 = more symbols on this frame */
+                    if (skip > 0) { advance = skip; break; }
+                } else if (is_blank) {
+                    advance = 1;
+                    break;
+                }
+            }
+            t += (size_t)advance;
+        }
+        goto done;
+    }
     for (size_t t = 0; t < T; ++t) {                                /* :88 */
         if (total >= cfg->max_total_tokens) break;                  /* :89-95 */
         if (orc_extract_frame_into(enc, enc_len, shape, 3, t, frame, features) != features) { rc = -2; break; } /* :98-130 */
@@ -382,7 +432,7 @@ int orc_greedy_decode(const float *enc, size_t enc_len, int64_t encoded_len, flo
             if (symbols > cfg->max_symbols_per_step) break;         /* :133-137 */
             int U;
             if (cfg->single_step) {                                 /* north_star "one prediction-net step" */
-                targets[0] = total > 0 ? tokens[total - 1] : cfg->blank;
+                targets[0] = total > 0 ? tokens[total - 1] : cfg->initial_last;
                 U = 1;
             } else {                                                /* :140-142 — [blank] ++ tokens of THIS call */
                 targets[0] = cfg->blank;

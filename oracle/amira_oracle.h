@@ -102,6 +102,16 @@ typedef struct {
     int max_total_tokens;     /* 200 */
     int blank;                /* 1024 */
     int single_step;          /* 1: targets=[last] (U=1, north_star); 0: literal refeed [blank]++tokens */
+    /* NON-REFERENCE options, both off by default; single_step only:
+     * state_update_on_nonblank_only: the canonical RNN-T rule — the prediction-net state advances only when a token is emitted
+     *   (the reference replaces it after every step, blank included: src/asr/decoder_optimized.rs:154);
+     * tdt_durations: Token-and-Duration-Transducer reading of the 1030 outputs the model-repo config declares — outputs
+     *   [0, 1024] are token logits (1024 = blank), outputs [1025, 1029] duration logits for skips 0..4; the frame index advances
+     *   by the predicted duration (a blank with duration 0 advances by 1), as in NeMo's greedy TDT decoding; compare
+     *   src/triton_backends/k2_decoder/k2_decoder_backend.cc:114-253 for the reference's only other decoder. */
+    int state_update_on_nonblank_only;
+    int tdt_durations;
+    int initial_last;         /* single_step: the LSTM input of the first step (blank for a fresh call; amira_greedy_decode_resume) */
 } orc_decode_cfg;
 
 typedef struct {

@@ -60,7 +60,8 @@ class _Model(C.Structure):
 
 class _Cfg(C.Structure):
     _fields_ = [("max_symbols_per_step", C.c_int), ("max_total_tokens", C.c_int), ("blank", C.c_int),
-                ("single_step", C.c_int)]
+                ("single_step", C.c_int), ("state_update_on_nonblank_only", C.c_int), ("tdt_durations", C.c_int),
+                ("initial_last", C.c_int)]
 
 
 class _Stats(C.Structure):
@@ -306,13 +307,15 @@ class DecodeResult:
 
 def greedy_decode(enc: np.ndarray, encoded_len: int, model: Model | None = None, step=None, states=None,
                   single_step: bool = True, max_symbols: int = MAX_SYMBOLS_PER_STEP,
-                  max_total: int = MAX_TOTAL_TOKENS, blank: int = BLANK) -> DecodeResult:
+                  max_total: int = MAX_TOTAL_TOKENS, blank: int = BLANK, state_update_on_nonblank_only: bool = False,
+                  tdt_durations: bool = False, initial_last: int | None = None) -> DecodeResult:
     """src/asr/decoder_optimized.rs:24-200 for one utterance.  `step` is an optional Python mock with the
     signature step(frame, targets, states_1, states_2) -> (logits, states_1, states_2) or None for failure."""
     enc = np.ascontiguousarray(enc, dtype=np.float32).ravel()
     s1 = np.zeros(2 * H, np.float32) if states is None else np.ascontiguousarray(states[0], np.float32).ravel().copy()
     s2 = np.zeros(2 * H, np.float32) if states is None else np.ascontiguousarray(states[1], np.float32).ravel().copy()
-    cfg = _Cfg(max_symbols, max_total, blank, 1 if single_step else 0)
+    cfg = _Cfg(max_symbols, max_total, blank, 1 if single_step else 0, int(state_update_on_nonblank_only), int(tdt_durations),
+               blank if initial_last is None else int(initial_last))
     toks = np.zeros(max(max_total, 1) + 1, dtype=np.int32)
     st = _Stats()
     cap = (max_total + max(int(encoded_len), 0)) + 8
@@ -358,7 +361,7 @@ def greedy_decode_batch(model: Model, enc: np.ndarray, enc_lens=None, states=Non
     if states is not None:
         s1 = np.ascontiguousarray(states[0], np.float32).copy()
         s2 = np.ascontiguousarray(states[1], np.float32).copy()
-    cfg = _Cfg(max_symbols, max_total, blank, 1 if single_step else 0)
+    cfg = _Cfg(max_symbols, max_total, blank, 1 if single_step else 0, 0, 0, blank)
     toks = np.zeros((B, max(max_total, 1)), dtype=np.int32)
     ntok = np.zeros(B, np.int32)
     nstep = np.zeros(B, np.int32)
