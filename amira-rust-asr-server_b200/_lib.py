@@ -343,8 +343,8 @@ class Context:
         return C_
 
     def debug_ws_trace(self, n_its: int = 512) -> np.ndarray:
-        """[n_its][32] globaltimer stamps (ns) of M-tile 0 from the last weight-stationary greedy launch (AMIRA_WS_TRACE=1)."""
-        out = np.zeros((n_its, 32), np.int64)
+        """[n_its][8 M-tiles][32] globaltimer stamps (ns) of the last weight-stationary greedy launch (AMIRA_WS_TRACE=1)."""
+        out = np.zeros((n_its, 8, 32), np.int64)
         self._check(self._L.amira_debug_ws_trace(self._h, _ptr(out), n_its))
         return out
 

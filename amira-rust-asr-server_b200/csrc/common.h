@@ -231,9 +231,17 @@ cudaError_t launch_split_transpose_enc(Ctx *c, const float *enc, int B, int T, c
 // decoder_ws.cu (weight-stationary dataflow engine, decode_engine = 4) ------------------------------------------
 bool decoder_ws_supported(const Ctx *c);
 cudaError_t decoder_ws_prepare(Ctx *c, TcWeights *w);
-// work == nullptr: size query (*work_bytes receives the workspace size).  E [B*T][640] and perm_dev [Mpad] from the caller.
-cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t *lens_dev, const int *perm_dev,
-                             const int *eoff_dev, const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
+// The lane plan of a batch: MT M-tiles of 128 lanes; lane r decodes the streams rowinfo[lane_first[r] .. lane_first[r+1]).
+struct WsPlan {
+    int MT = 1, Mpad = 128;
+};
+constexpr int kWsMaxTiles = 256;
+// fills rowinfo [B] {stream, encoded length, first row of E, 0} and lane_first [Mpad + 1 <= B + 129] (host memory)
+WsPlan ws_plan_lanes(const int32_t *lens, const int *eoff, int B, int4 *rowinfo, int *lane_first);
+// work == nullptr: size query (*work_bytes receives the workspace size for MT M-tiles).  E [sum of lengths][640], the plan's
+// lane_first and rowinfo (device copies) from the caller.
+cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int MT, int T, const int *lane_first_dev, const int4 *rowinfo_dev,
+                             const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
                              int32_t *nsteps_dev, char *work, size_t *work_bytes, int32_t *last_dev = nullptr);
 
 }  // namespace amira

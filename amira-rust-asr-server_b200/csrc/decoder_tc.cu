@@ -337,37 +337,34 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
     DecoderPriv *d = c->dec;
     TcWeights *w = d->tc;
     const int Tq = T > 0 ? T : 1;
-    constexpr int BM = 128;  // streams per M-tile of the decode kernel
-    const int MT = (B + BM - 1) / BM, Mpad = MT * BM;
     if (!decoder_ws_supported(c)) return cudaErrorNotSupported;  // the weight-stationary kernel needs 147 co-resident CTAs
+    cudaError_t e;
+    // metadata block (pinned, one upload): rowinfo[B] int4 | src_off[B+1] (packed input) | eoff[B+1] | lane_first[<= B + 129]
+    const size_t m_ri = 0, m_soff = m_ri + sizeof(int4) * (size_t)B, m_eoff = m_soff + sizeof(long long) * ((size_t)B + 1);
+    const size_t m_lane = m_eoff + sizeof(int) * ((size_t)B + 1), meta_bytes = m_lane + sizeof(int) * ((size_t)B + 129);
+    if ((e = c->pin[1].reserve(meta_bytes)) != cudaSuccess) return e;
+    char *h_meta = c->pin[1].as<char>();
+    long long *h_soff = reinterpret_cast<long long *>(h_meta + m_soff);
+    for (int i = 0; i <= B; ++i) h_soff[i] = enc_off_host ? (long long)enc_off_host[i] : 0;
+    int *h_eoff = reinterpret_cast<int *>(h_meta + m_eoff);  // first packed row of each stream's valid frames in E
+    h_eoff[0] = 0;
+    for (int i = 0; i < B; ++i) h_eoff[i + 1] = h_eoff[i] + lens_host[i];
+    // the streams packed into lanes of (almost) equal frame counts: every M-tile lives for the whole kernel
+    const WsPlan plan = ws_plan_lanes(lens_host, h_eoff, B, reinterpret_cast<int4 *>(h_meta + m_ri), reinterpret_cast<int *>(h_meta + m_lane));
+
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += tc_align(bytes); return o; };
     const size_t oE = take(sizeof(float) * (size_t)B * Tq * kH);
     const size_t oeh = take(2 * (size_t)B * Tq * kEnc), oel = take(2 * (size_t)B * Tq * kEnc);
-    const size_t meta_bytes = sizeof(long long) * ((size_t)B + 1) + sizeof(int) * ((size_t)Mpad + (size_t)B + 1);
-    const size_t ometa = take(meta_bytes);  // src_off[B+1] (packed input), perm[Mpad], eoff[B+1]
-    const size_t operm = ometa + sizeof(long long) * ((size_t)B + 1);
+    const size_t ometa = take(meta_bytes);
     size_t ws_bytes = 0;
-    cudaError_t e;
-    if ((e = launch_greedy_ws(c, nullptr, B, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &ws_bytes)) != cudaSuccess) return e;
+    if ((e = launch_greedy_ws(c, nullptr, B, plan.MT, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &ws_bytes)) != cudaSuccess) return e;
     const size_t ows = take(ws_bytes);
     if ((e = d->work.reserve(off)) != cudaSuccess) return e;
     char *base = d->work.as<char>();
-
-    // rows sorted by encoded length (descending, stable): active rows stay a prefix, whole M-tiles retire early
-    if ((e = c->pin[1].reserve(meta_bytes)) != cudaSuccess) return e;
-    long long *h_soff = c->pin[1].as<long long>();
-    for (int i = 0; i <= B; ++i) h_soff[i] = enc_off_host ? (long long)enc_off_host[i] : 0;
-    int *h_perm = reinterpret_cast<int *>(h_soff + B + 1);
-    int *h_eoff = h_perm + Mpad;  // first packed row of each stream's valid frames in E
-    h_eoff[0] = 0;
-    for (int i = 0; i < B; ++i) h_eoff[i + 1] = h_eoff[i] + lens_host[i];
-    for (int i = 0; i < B; ++i) h_perm[i] = i;
-    std::stable_sort(h_perm, h_perm + B, [&](int a, int b2) { return lens_host[a] > lens_host[b2]; });
-    for (int i = B; i < Mpad; ++i) h_perm[i] = 0;
-    if ((e = cudaMemcpyAsync(base + ometa, h_soff, meta_bytes, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return e;
-    const long long *soff_dev = enc_off_host ? reinterpret_cast<const long long *>(base + ometa) : nullptr;
-    const int *eoff_dev = reinterpret_cast<int *>(base + operm) + Mpad;
+    if ((e = cudaMemcpyAsync(base + ometa, h_meta, meta_bytes, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return e;
+    const long long *soff_dev = enc_off_host ? reinterpret_cast<const long long *>(base + ometa + m_soff) : nullptr;
+    const int *eoff_dev = reinterpret_cast<const int *>(base + ometa + m_eoff);
 
     float *E = reinterpret_cast<float *>(base + oE);
     if (T > 0) {  // hoisted encoder projection on tcgen05: E[(b,t)][:] = W_enc enc[b][:, t] + b_enc + b_pred
@@ -398,8 +395,9 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
             if ((e = launch_tc_gemm(c, eh + ro * kEnc, el + ro * kEnc, w->we_hi, w->we_lo, d->bjoint, E + ro * kH, kH, rows, kH, kEnc)) != cudaSuccess) return e;
         }
     }
-    return launch_greedy_ws(c, E, B, T, lens_dev, reinterpret_cast<int *>(base + operm), eoff_dev, slots_dev, s1_dev, s2_dev,
-                            tokens_dev, ntok_dev, nsteps_dev, base + ows, &ws_bytes, last_dev);
+    return launch_greedy_ws(c, E, B, plan.MT, T, reinterpret_cast<const int *>(base + ometa + m_lane),
+                            reinterpret_cast<const int4 *>(base + ometa + m_ri), slots_dev, s1_dev, s2_dev, tokens_dev, ntok_dev, nsteps_dev,
+                            base + ows, &ws_bytes, last_dev);
 }
 
 }  // namespace amira

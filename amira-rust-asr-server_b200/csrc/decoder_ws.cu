@@ -25,6 +25,14 @@
 // emitted tokens, step counts and final states are exactly those of the sequential loop: speculation only changes WHEN a
 // step is computed, never its inputs.  d is chosen per M-tile and tick: 0 while many M-tiles are alive (the machine is
 // throughput-bound and wasted ticks would cost real time), W_DMAX once few are left (latency-bound).
+//
+// Lanes (round 2).  A row of an M-tile is a LANE that decodes a queue of streams back to back: the host packs the batch's
+// streams into n x 128 lanes with (almost) equal numbers of encoder frames (longest-processing-time first) and picks n so that
+// n units per tick fill the step chain's latency.  With one stream per row the M-tiles of a mixed-length batch end one after the
+// other and the longest streams finish alone on an idle machine, one chain latency per step; with lanes every M-tile lives for
+// the whole kernel and the tick count is that of the longest lane.  When a lane's stream ends, its results are written, and the
+// next tick is a LOAD: the lane's recurrent state becomes the next stream's initial state (the caller's DecoderState or zeros).
+// A stream's tokens do not depend on the lane or M-tile it runs in (rows of an MMA are independent).
 // Spin loops carry a cycle-count watchdog that traps instead of hanging the GPU.
 #include <cooperative_groups.h>
 #include <cuda.h>
@@ -34,6 +42,9 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <queue>
+#include <utility>
+#include <vector>
 
 #include "common.h"
 #include "tc_common.cuh"
@@ -63,33 +74,36 @@ constexpr int W_EPI_WARPS = 8, W_EPI_THREADS = W_EPI_WARPS * 32;
 constexpr int W_THREADS = (4 + W_EPI_WARPS) * 32;           // 384: warp 0 TMA, 1 MMA, 2 scheduler, 3 signal, 4..11 epilogue
 constexpr int W_MAX_MT = 256;
 constexpr long long W_SPIN_LIMIT = 6000000000LL;            // ~3 s of SM clocks
-constexpr int W_TRACE_ITS = 512;
+constexpr int W_TRACE_ITS = 512, W_TRACE_MT = 8;          // debug trace: ticks x M-tiles recorded
 constexpr int W_DMAX = 3;                                   // deepest blank speculation (ticks of unresolved results)
 constexpr int W_V = W_DMAX + 2;                             // versions of the recurrent state (by tick)
 constexpr int W_R = 8;                                      // ring of control rows / argmax keys / tile info (by tick; > W_DMAX + 2)
 
 enum { R_A = 0, R_BI = 1, R_BH = 2, R_C = 3, R_D = 4 };
-enum { OP_IDLE = 0, OP_STEP = 1, OP_COPY = 2 };
+enum { OP_IDLE = 0, OP_STEP = 1, OP_COPY = 2, OP_LOAD = 3 };
 
-// per-stream control row of one tick (32 bytes).  flags: bit 0 active, bit 1 failed.  spec: bits 0-7 = ticks (index & 7) whose
-// STEP result has not been consumed yet; bits 8-9 = this tick's op; bits 12-14 = source version of a COPY.  tuse: the encoder
-// frame this tick's STEP reads.
+// per-lane control row of one tick (48 bytes).  flags: bit 0 active, bit 1 failed.  spec: bits 0-7 = ticks (index & 7) whose
+// STEP result has not been consumed yet; bits 8-9 = this tick's op; bits 12-14 = source version of a COPY.  tuse: the row of E
+// (absolute: ebase + frame) this tick's STEP reads.
 struct WCtl {
     int t, sym, total, last, flags, nsteps, spec, tuse;
+    int sidx, len, ebase, cur;  // the lane's current stream: index in the batch, encoded length, first packed row of E, chain position
 };
+static_assert(sizeof(WCtl) == 48, "three 16-byte words");
 
 struct WsParams {
     CUtensorMap h0_hi, h0_lo, h1_hi, h1_lo, z_hi, z_lo;   // activations [W_V versions][Mpad][640], box {64 k, nrows}
     const __nv_bfloat16 *g_whh0_hi, *g_whh0_lo, *g_w1_hi, *g_w1_lo, *g_wp_hi, *g_wp_lo, *g_wo_hi, *g_wo_lo;
     const float *g0p, *b1p, *boutp, *E;
     int B, Mpad, MT, T;
-    const int *lens, *slots, *perm, *eoff;
+    const int *slots;
+    const int *lane_first;   // [Mpad + 1]: lane r decodes the streams rowinfo[lane_first[r] .. lane_first[r + 1]) in that order
+    const int4 *rowinfo;     // [streams with frames] {stream index, encoded length, first packed row of E, 0}, grouped by lane
     __nv_bfloat16 *h0b_hi, *h0b_lo, *h1b_hi, *h1b_lo, *zb_hi, *zb_lo;   // [W_V][Mpad][640]
     float *h0f, *h1f, *c0, *c1;                                          // [W_V][Mpad][640]
     float *part;        // [MT][40 slices][2 column groups][128 rows][32] fp32: h1(t-1) W_hh1 partial sums
     unsigned long long *amax;  // [W_R ticks][Mpad] packed (orderable logit << 32 | ~column): atomicMax = first-max argmax
     WCtl *ctl;          // [W_R ticks][Mpad]
-    int4 *rowinfo;      // [Mpad] {stream index, encoded length, first packed row of E, 0}
     int *tinfo;         // [MT][W_R]: res(it) = the last tick whose vocabulary results the layer-0 epilogue of tick `it` consumes
     int *tile_active, *cnt_d, *cnt_a, *cnt_b, *cnt_c, *dead_at, *part_ready /* [MT][40] */, *fail_count, *live_tiles;
     float *s1, *s2;
@@ -156,10 +170,11 @@ __device__ __forceinline__ long long gtime() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// debug trace: slice 0 of every role stamps its events for M-tile 0
+// debug trace: slice 0 of every role stamps its events for the first W_TRACE_MT M-tiles
 #define WS_TRACE(ev)                                                                                   \
     do {                                                                                               \
-        if (p.trace && slice == 0 && mt == 0 && it < W_TRACE_ITS) p.trace[it * 32 + role * 6 + (ev)] = gtime(); \
+        if (p.trace && slice == 0 && mt < W_TRACE_MT && it < W_TRACE_ITS)                              \
+            p.trace[(it * W_TRACE_MT + mt) * 32 + role * 6 + (ev)] = gtime();                         \
     } while (0)
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
@@ -201,9 +216,11 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
     }
 }
 __device__ __forceinline__ WCtl load_ctl(const WCtl *q) {  // L1-bypassing: written by another SM's control update
-    const int4 a = __ldcg(reinterpret_cast<const int4 *>(q)), b = __ldcg(reinterpret_cast<const int4 *>(q) + 1);
+    const int4 a = __ldcg(reinterpret_cast<const int4 *>(q)), b = __ldcg(reinterpret_cast<const int4 *>(q) + 1),
+               d = __ldcg(reinterpret_cast<const int4 *>(q) + 2);
     WCtl c;
     c.t = a.x; c.sym = a.y; c.total = a.z; c.last = a.w; c.flags = b.x; c.nsteps = b.y; c.spec = b.z; c.tuse = b.w;
+    c.sidx = d.x; c.len = d.y; c.ebase = d.z; c.cur = d.w;
     return c;
 }
 __device__ __forceinline__ size_t ws_state_off(const WsParams &p, int layer, int b) {
@@ -285,7 +302,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
     const size_t v_init = (size_t)(W_V - 1) * n_state;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < n_state; i += (size_t)gridDim.x * blockDim.x) {
         const int row = (int)(i / kH), j = (int)(i % kH);
-        const int b = row < p.B ? p.perm[row] : -1;
+        const int lf = p.lane_first[row];
+        const int b = lf < p.lane_first[row + 1] ? p.rowinfo[lf].x : -1;  // the lane's first stream
         const float h0 = (b >= 0 && p.s1) ? p.s1[ws_state_off(p, 0, b) + j] : 0.f;
         const float h1 = (b >= 0 && p.s1) ? p.s1[ws_state_off(p, 1, b) + j] : 0.f;
         p.h0f[v_init + i] = h0;
@@ -299,17 +317,18 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
         p.h1b_hi[v_init + i] = hh; p.h1b_lo[v_init + i] = hl;
     }
     for (int row = blockIdx.x * blockDim.x + tid; row < p.Mpad; row += gridDim.x * blockDim.x) {
-        const int act = (row < p.B && p.lens[p.perm[row]] > 0) ? 1 : 0;
+        const int lf = p.lane_first[row];
+        const int act = lf < p.lane_first[row + 1] ? 1 : 0;  // the host leaves streams without frames out of the lanes
+        const int4 ri = act ? p.rowinfo[lf] : make_int4(0, 0, 0, 0);
         int4 *dstc = reinterpret_cast<int4 *>(p.ctl + (size_t)(W_R - 1) * p.Mpad + row);  // the control row of "tick -1"
-        dstc[0] = make_int4(0, 0, 0, (p.last_io && row < p.B) ? p.last_io[p.perm[row]] : p.blank);
+        dstc[0] = make_int4(0, 0, 0, (p.last_io && act) ? p.last_io[ri.x] : p.blank);
         dstc[1] = make_int4(act, 0, 0, 0);
-        const int prow_ = row < p.B ? p.perm[row] : 0;
-        p.rowinfo[row] = make_int4(prow_, row < p.B ? p.lens[prow_] : 0, row < p.B ? p.eoff[prow_] : 0, 0);
+        dstc[2] = make_int4(ri.x, ri.y, ri.z, lf);
         if (act) atomicAdd(&p.tile_active[row / W_BM], 1);
-        if (row < p.B) {
-            p.ntok[p.perm[row]] = 0;
-            if (p.nsteps) p.nsteps[p.perm[row]] = 0;
-        }
+    }
+    for (int b = blockIdx.x * blockDim.x + tid; b < p.B; b += gridDim.x * blockDim.x) {
+        p.ntok[b] = 0;
+        if (p.nsteps) p.nsteps[b] = 0;
     }
     __threadfence();
     fence_proxy_async();
@@ -511,6 +530,24 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 split_bf16(hnew[j], vh[j], vl[j]);
             }
         };
+        // this thread's 8 hidden features of a stream's initial state into the current version of a layer's state
+        auto load_state = [&](int layer, int sidx, float *cdst, float *hdst, __nv_bfloat16 *bh, __nv_bfloat16 *bl) {
+            const size_t o = ws_state_off(p, layer, sidx) + nb / 4;
+            float4 hv[2], cv[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                hv[h] = p.s1 ? __ldcg(reinterpret_cast<const float4 *>(p.s1 + o) + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cv[h] = p.s2 ? __ldcg(reinterpret_cast<const float4 *>(p.s2 + o) + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+                reinterpret_cast<float4 *>(cdst)[h] = cv[h];
+                reinterpret_cast<float4 *>(hdst)[h] = hv[h];
+            }
+            const float h8[8] = {hv[0].x, hv[0].y, hv[0].z, hv[0].w, hv[1].x, hv[1].y, hv[1].z, hv[1].w};
+            __align__(16) __nv_bfloat16 vh[8], vl[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split_bf16(h8[j], vh[j], vl[j]);
+            *reinterpret_cast<uint4 *>(bh) = *reinterpret_cast<uint4 *>(vh);
+            *reinterpret_cast<uint4 *>(bl) = *reinterpret_cast<uint4 *>(vl);
+        };
         uint32_t qn = 0, tile = 0;
         for (;;) {
             const uint32_t slot = qn % W_Q;
@@ -540,7 +577,6 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 float4 ad[8], cold4[2];
                 cold4[0] = __ldcg(reinterpret_cast<const float4 *>(p.c0 + so_prev));  // loads that do not depend on the vocabulary
                 cold4[1] = __ldcg(reinterpret_cast<const float4 *>(p.c0 + so_prev) + 1);  // phase go out before the wait on it
-                const int4 ri = __ldg(p.rowinfo + row);
                 WCtl c = load_ctl(p.ctl + (size_t)((it + W_R - 1) & (W_R - 1)) * p.Mpad + row);  // control after tick it-1
                 const int res_prev = it > 0 ? __ldcg(p.tinfo + mt * W_R + ((it - 1) & (W_R - 1))) : -1;
                 const int res = __ldcg(p.tinfo + mt * W_R + (it & (W_R - 1)));
@@ -551,10 +587,10 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 if (etid == 0) WS_TRACE(5);
                 int &act_cnt = sm.act2[tile & 1];  // `tile` was advanced above: consecutive units alternate slots
                 int active = c.flags & 1, failed = (c.flags >> 1) & 1, kinds = c.spec & 0xff;
-                int op = OP_IDLE, src = vprev, fin_ver = -1;
+                int op = OP_IDLE, src = vprev, fin_ver = -1, fin_sidx = 0;
                 bool restore = false;
-                const int len = ri.y;
                 if (active) {
+                    const int len = c.len;
                     for (int j = res_prev + 1; j <= res; ++j) {
                         if (!((kinds >> (j & 7)) & 1)) continue;  // that tick was not a step of this stream (or was discarded)
                         kinds &= ~(1 << (j & 7));
@@ -566,7 +602,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                             c.t += 1; c.sym = 0;
                             if (c.t >= len) active = 0;
                         } else {
-                            if (slice == 0 && cgp == 0) p.tokens[(size_t)ri.x * p.max_total + c.total] = bi;   // :176
+                            if (slice == 0 && cgp == 0) p.tokens[(size_t)c.sidx * p.max_total + c.total] = bi;   // :176
                             c.total += 1;
                             c.last = bi;
                             if (c.total >= p.max_total) active = 0;                      // :179-188
@@ -584,13 +620,27 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                             break;
                         }
                     }
-                    if (active) {
-                        if (restore) op = OP_COPY;
-                        else {
-                            const int tspec = c.t + __popc(kinds);  // every unresolved step is assumed to emit blank
-                            if (tspec < len) { op = OP_STEP; c.tuse = tspec; kinds |= 1 << (it & 7); }
-                            else op = OP_COPY;                      // nothing left to speculate on: carry the state, wait for results
+                    if (fin_ver >= 0) {  // the lane's stream ended with tick fin_ver: its results, then the lane's next stream
+                        fin_sidx = c.sidx;
+                        if (slice == 0 && cgp == 0) {
+                            p.ntok[c.sidx] = failed ? -1 : c.total;
+                            if (p.nsteps) p.nsteps[c.sidx] = c.nsteps;
+                            if (p.last_io) p.last_io[c.sidx] = c.last;
+                            if (failed) atomicAdd(p.fail_count, 1);
                         }
+                        const int nxt = c.cur + 1;
+                        if (nxt < __ldg(p.lane_first + row + 1)) {
+                            const int4 ri = __ldg(p.rowinfo + nxt);
+                            c.t = 0; c.sym = 0; c.total = 0; c.nsteps = 0;
+                            c.last = p.last_io ? __ldcg(p.last_io + ri.x) : p.blank;
+                            c.sidx = ri.x; c.len = ri.y; c.ebase = ri.z; c.cur = nxt;
+                            active = 1; failed = 0; op = OP_LOAD;  // this tick installs the stream's initial state
+                        }
+                    } else if (restore) op = OP_COPY;
+                    else {
+                        const int tspec = c.t + __popc(kinds);  // every unresolved step is assumed to emit blank
+                        if (tspec < len) { op = OP_STEP; c.tuse = c.ebase + tspec; kinds |= 1 << (it & 7); }
+                        else op = OP_COPY;                      // nothing left to speculate on: carry the state, wait for results
                     }
                 }
                 c.flags = active | (failed << 1);
@@ -599,12 +649,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     int4 *dstc = reinterpret_cast<int4 *>(p.ctl + (size_t)(it & (W_R - 1)) * p.Mpad + row);
                     __stcg(dstc, make_int4(c.t, c.sym, c.total, c.last));
                     __stcg(dstc + 1, make_int4(c.flags, c.nsteps, c.spec, c.tuse));
-                    if (fin_ver >= 0 && row < p.B) {  // this stream's results
-                        p.ntok[ri.x] = failed ? -1 : c.total;
-                        if (p.nsteps) p.nsteps[ri.x] = c.nsteps;
-                        if (p.last_io) p.last_io[ri.x] = c.last;
-                        if (failed) atomicAdd(p.fail_count, 1);
-                    }
+                    __stcg(dstc + 2, make_int4(c.sidx, c.len, c.ebase, c.cur));
                 }
                 if (cgp == 0 && active) atomicAdd(&act_cnt, 1);
                 if (op == OP_STEP) {  // the token-dependent gather overlaps the barrier below
@@ -615,11 +660,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
 #pragma unroll
                     for (int j = 0; j < 8; ++j) ad[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                if (fin_ver >= 0 && p.s1 && p.s2 && row < p.B) {
+                if (fin_ver >= 0 && p.s1 && p.s2) {
                     // the stream ended at tick fin_ver: every layer's state of that tick is final and visible (its vocabulary
                     // phase was released after all of them); each layer-0 CTA hands back its 16 hidden features
-                    const size_t sf = ((size_t)fin_ver * p.Mpad + row) * kH + nb / 4, o0 = ws_state_off(p, 0, ri.x) + nb / 4,
-                                 o1 = ws_state_off(p, 1, ri.x) + nb / 4;
+                    const size_t sf = ((size_t)fin_ver * p.Mpad + row) * kH + nb / 4, o0 = ws_state_off(p, 0, fin_sidx) + nb / 4,
+                                 o1 = ws_state_off(p, 1, fin_sidx) + nb / 4;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         reinterpret_cast<float4 *>(p.s1 + o0)[h] = __ldcg(reinterpret_cast<const float4 *>(p.h0f + sf) + h);
@@ -631,7 +676,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 named_bar_sync(1, W_EPI_THREADS);
                 const bool live = act_cnt > 0;  // identical in every layer-0 CTA
                 if (etid == 0) sm.act2[(tile & 1) ^ 1] = 0;  // the next unit's slot: nobody touches it before that unit's barrier
-                if (etid == 0 && slice == 0 && p.trace && mt == 0 && it < W_TRACE_ITS) p.trace[it * 32 + 30] = gtime();
+                if (etid == 0 && slice == 0 && p.trace && mt < W_TRACE_MT && it < W_TRACE_ITS) p.trace[(it * W_TRACE_MT + mt) * 32 + 30] = gtime();
                 float *pre = reinterpret_cast<float *>(ad);
                 if (etid == 0) WS_TRACE(3);
                 gather_add(pre);  // accumulator (parked in the shared tile at the top of this unit) + G0[token] row
@@ -639,6 +684,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     if (slice == 0 && etid == 0) {
                         __threadfence();
                         st_release(p.dead_at + mt, it);
+                        if (p.trace && mt < W_TRACE_MT) p.trace[((W_TRACE_ITS - 1) * W_TRACE_MT + mt) * 32 + 31] = it;  // the tile's tick count
                         atomicSub(p.live_tiles, 1);
                     }
                     if (etid == 0) sm.sig_skip[(tile - 1) % W_Q] = 1;
@@ -672,6 +718,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     reinterpret_cast<float4 *>(p.h0f + so_cur)[0] = b0; reinterpret_cast<float4 *>(p.h0f + so_cur)[1] = b1;
                     *reinterpret_cast<uint4 *>(p.h0b_hi + so_cur) = uh;
                     *reinterpret_cast<uint4 *>(p.h0b_lo + so_cur) = ul;
+                } else if (op == OP_LOAD) {  // the lane's next stream starts from the caller's DecoderState (types.rs:159-183) or zeros
+                    load_state(0, c.sidx, p.c0 + so_cur, p.h0f + so_cur, p.h0b_hi + so_cur, p.h0b_lo + so_cur);
                 }
                 if (etid == 0) WS_TRACE(5);
                 mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);  // stores issued: the signal thread fences and publishes them
@@ -732,21 +780,22 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     reinterpret_cast<float4 *>(p.h1f + so_cur)[0] = b0; reinterpret_cast<float4 *>(p.h1f + so_cur)[1] = b1;
                     *reinterpret_cast<uint4 *>(p.h1b_hi + so_cur) = uh;
                     *reinterpret_cast<uint4 *>(p.h1b_lo + so_cur) = ul;
+                } else if (op == OP_LOAD) {
+                    load_state(1, c.sidx, p.c1 + so_cur, p.h1f + so_cur, p.h1b_hi + so_cur, p.h1b_lo + so_cur);
                 }
                 if (etid == 0) WS_TRACE(5);
                 mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);
             } else if (role == R_C) {
-                const int4 ri = __ldg(p.rowinfo + row);
                 const WCtl c = load_ctl(p.ctl + (size_t)(it & (W_R - 1)) * p.Mpad + row);
                 const bool step = ((c.spec >> 8) & 3) == OP_STEP;
                 float4 ev[8] = {};
                 if (step) {
-                    const float4 *ep = reinterpret_cast<const float4 *>(p.E + ((size_t)ri.z + c.tuse) * kH + nb);
+                    const float4 *ep = reinterpret_cast<const float4 *>(p.E + (size_t)c.tuse * kH + nb);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) ev[j] = __ldg(ep + j);
                     // E is streamed from HBM exactly once per (stream, frame): pull the next frame's 128 bytes into L2 now so
                     // that the load above finds them there when the stream advances (this load sits on the step chain)
-                    if (c.tuse + 1 < ri.y) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep + kH / 4));
+                    if (c.tuse + 1 < c.ebase + c.len) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep + kH / 4));
                 }
                 wait_acc(use);
                 if (etid == 0) WS_TRACE(3);
@@ -828,14 +877,70 @@ cudaError_t decoder_ws_prepare(Ctx *c, TcWeights *w) {
     return cudaSuccess;
 }
 
+// The lane plan: which streams each row of each M-tile decodes, in which order (see "Lanes" at the top of this file).
+// Longest-processing-time-first packing for every candidate number of M-tiles, scored with the two measured constants of the
+// kernel: a tick of n live M-tiles takes max(n x unit time, step-chain latency).  Streams without frames are left out (their
+// results are the zero counts the prologue writes).  rowinfo [B] and lane_first [plan.Mpad + 1] are filled for the choice.
+WsPlan ws_plan_lanes(const int32_t *lens, const int *eoff, int B, int4 *rowinfo, int *lane_first) {
+    std::vector<int> idx;
+    idx.reserve(B);
+    for (int i = 0; i < B; ++i)
+        if (lens[i] > 0) idx.push_back(i);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return lens[a] > lens[b]; });
+    const int nz = (int)idx.size();
+    const int mt_max = std::max(1, std::min(W_MAX_MT, (nz + W_BM - 1) / W_BM));
+    constexpr double kUnitUs = 6.7, kChainUs = 34.0;  // per unit with every SM busy / per step of a lone M-tile
+    constexpr int kSwitchTicks = 2;                   // a stream's end is seen one tick late, the next tick loads the state
+    auto pack = [&](int mt, std::vector<int> *lane_of) -> long long {  // returns the longest lane, in ticks
+        const int nl = std::min(mt * W_BM, std::max(nz, 1));
+        std::priority_queue<std::pair<long long, int>, std::vector<std::pair<long long, int>>, std::greater<std::pair<long long, int>>> q;
+        for (int l = 0; l < nl; ++l) q.push({0, l});
+        long long worst = 0;
+        for (int k = 0; k < nz; ++k) {
+            auto [load, l] = q.top();
+            q.pop();
+            load += lens[idx[k]] + kSwitchTicks;
+            worst = std::max(worst, load);
+            if (lane_of) (*lane_of)[k] = l;
+            q.push({load, l});
+        }
+        return worst;
+    };
+    int best_mt = mt_max;
+    if (const char *f = getenv("AMIRA_WS_TILES")) best_mt = std::max(1, std::min(mt_max, atoi(f)));  // A/B timing
+    else {
+        double best = 1e300;
+        for (int mt = 1; mt <= mt_max; ++mt) {
+            const double t = (double)pack(mt, nullptr) * std::max(mt * kUnitUs, kChainUs);
+            if (t < best * 0.999) { best = t; best_mt = mt; }
+        }
+    }
+    std::vector<int> lane_of(std::max(nz, 1));
+    pack(best_mt, &lane_of);
+    WsPlan plan;
+    plan.MT = best_mt;
+    plan.Mpad = best_mt * W_BM;
+    std::vector<int> cnt(plan.Mpad + 1, 0);
+    for (int k = 0; k < nz; ++k) cnt[lane_of[k]]++;
+    lane_first[0] = 0;
+    for (int l = 0; l < plan.Mpad; ++l) lane_first[l + 1] = lane_first[l] + cnt[l];
+    std::vector<int> fill(lane_first, lane_first + plan.Mpad);
+    for (int k = 0; k < nz; ++k) {  // idx is sorted by length: a lane decodes its longest stream first
+        const int s = idx[k];
+        rowinfo[fill[lane_of[k]]++] = make_int4(s, lens[s], eoff[s], 0);
+    }
+    for (int k = nz; k < B; ++k) rowinfo[k] = make_int4(0, 0, 0, 0);
+    return plan;
+}
+
 // E [sum of encoded lengths][640] fp32 (hoisted encoder projection, valid frames packed; stream b starts at row eoff[b]) is
-// produced by the caller (decoder_tc.cu).
-cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t *lens_dev, const int *perm_dev,
-                             const int *eoff_dev, const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
+// produced by the caller (decoder_tc.cu), and so is the lane plan (ws_plan_lanes, uploaded by the caller).
+cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int MT, int T, const int *lane_first_dev, const int4 *rowinfo_dev,
+                             const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
                              int32_t *nsteps_dev, char *work, size_t *work_bytes, int32_t *last_dev) {
     DecoderPriv *d = c->dec;
     TcWeights *w = d->tc;
-    const int MT = (B + W_BM - 1) / W_BM, Mpad = MT * W_BM;
+    const int Mpad = MT * W_BM;
     const size_t MH = (size_t)Mpad * kH, VMH = (size_t)W_V * MH;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += ws_align(bytes); return o; };
@@ -846,15 +951,14 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     const size_t opart = take(sizeof(float) * (size_t)MT * W_NG * 2 * W_BM * 32);
     const size_t oamax = take(sizeof(unsigned long long) * W_R * (size_t)Mpad);
     const size_t octl = take(sizeof(WCtl) * W_R * (size_t)Mpad);  // a ring by tick
-    const size_t ori = take(sizeof(int4) * (size_t)Mpad);
     const size_t n_cnt = 6 * (size_t)MT + (size_t)MT * W_NG + (size_t)MT * W_R + 8;
     const size_t ocnt = take(sizeof(int) * n_cnt);
-    const size_t otrace = take(sizeof(long long) * W_TRACE_ITS * 32);
+    const size_t otrace = take(sizeof(long long) * W_TRACE_ITS * W_TRACE_MT * 32);
     if (!work) {  // size query
         *work_bytes = off;
         return cudaSuccess;
     }
-    if (MT > W_MAX_MT || !w || !w->ws_ready) return cudaErrorInvalidValue;
+    if (MT < 1 || MT > W_MAX_MT || !w || !w->ws_ready) return cudaErrorInvalidValue;
     cudaError_t e;
     if ((e = cudaMemsetAsync(work + ocnt, 0, sizeof(int) * n_cnt, c->stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(work + oamax, 0, sizeof(unsigned long long) * W_R * (size_t)Mpad, c->stream)) != cudaSuccess) return e;
@@ -880,13 +984,12 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     p.g_whh0_hi = w->whh0_hi; p.g_whh0_lo = w->whh0_lo; p.g_w1_hi = w->w1_hi; p.g_w1_lo = w->w1_lo;
     p.g_wp_hi = w->wp_hi; p.g_wp_lo = w->wp_lo; p.g_wo_hi = w->wo_hi; p.g_wo_lo = w->wo_lo;
     p.B = B; p.Mpad = Mpad; p.MT = MT; p.T = T > 0 ? T : 1;
-    p.lens = lens_dev; p.slots = slots_dev; p.perm = perm_dev; p.eoff = eoff_dev;
+    p.slots = slots_dev; p.lane_first = lane_first_dev; p.rowinfo = rowinfo_dev;
     p.h0f = reinterpret_cast<float *>(work + oh0f); p.h1f = reinterpret_cast<float *>(work + oh1f);
     p.c0 = reinterpret_cast<float *>(work + oc0); p.c1 = reinterpret_cast<float *>(work + oc1);
     p.part = reinterpret_cast<float *>(work + opart);
     p.amax = reinterpret_cast<unsigned long long *>(work + oamax);
     p.ctl = reinterpret_cast<WCtl *>(work + octl);
-    p.rowinfo = reinterpret_cast<int4 *>(work + ori);
     int *cnt = reinterpret_cast<int *>(work + ocnt);
     p.tile_active = cnt; p.cnt_d = cnt + MT; p.cnt_a = cnt + 2 * MT; p.cnt_b = cnt + 3 * MT; p.cnt_c = cnt + 4 * MT;
     p.dead_at = cnt + 5 * MT; p.part_ready = cnt + 6 * MT; p.tinfo = cnt + 6 * MT + MT * W_NG;
@@ -919,7 +1022,7 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int T, const int32_t
     p.force_trap = getenv("AMIRA_DEBUG_FORCE_TRAP") ? 1 : 0;
     if (getenv("AMIRA_WS_TRACE")) {
         p.trace = reinterpret_cast<long long *>(work + otrace);
-        cudaMemsetAsync(p.trace, 0, sizeof(long long) * W_TRACE_ITS * 32, c->stream);
+        cudaMemsetAsync(p.trace, 0, sizeof(long long) * W_TRACE_ITS * W_TRACE_MT * 32, c->stream);
         d->ws_trace_dev = p.trace;
     }
 
@@ -941,6 +1044,6 @@ extern "C" int32_t amira_debug_ws_trace(amira_ctx *ctx, int64_t *out, int32_t n_
     if (!c->dec || !c->dec->ws_trace_dev) return AMIRA_ERR_NOT_READY;
     cudaSetDevice(c->device);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return AMIRA_ERR_UNKNOWN;
-    return cudaMemcpy(out, c->dec->ws_trace_dev, sizeof(int64_t) * 32 * (size_t)n_its, cudaMemcpyDeviceToHost) == cudaSuccess
+    return cudaMemcpy(out, c->dec->ws_trace_dev, sizeof(int64_t) * 32 * W_TRACE_MT * (size_t)n_its, cudaMemcpyDeviceToHost) == cudaSuccess
                ? AMIRA_OK : AMIRA_ERR_UNKNOWN;
 }

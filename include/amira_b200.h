@@ -105,7 +105,7 @@ int32_t amira_ctx_kernel_ms(amira_ctx *ctx, int32_t kernel, double *total_ms, in
 int32_t amira_debug_tc_gemm(amira_ctx *ctx, const float *A, const float *W, const float *bias, int32_t M, int32_t N,
                             int32_t K, float *C);
 
-/* diagnostics: per-tick globaltimer stamps [n_its][32] (n_its <= 512) of M-tile 0 from the last weight-stationary greedy launch
+/* diagnostics: per-tick globaltimer stamps [n_its][8 M-tiles][32] (n_its <= 512) of the last weight-stationary greedy launch
  * made with the environment variable AMIRA_WS_TRACE set (slot = role * 6 + event; slot 30 = control update done). */
 int32_t amira_debug_ws_trace(amira_ctx *ctx, int64_t *out, int32_t n_its);
 

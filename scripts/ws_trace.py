@@ -1,5 +1,6 @@
-"""Per-step critical-path breakdown of the weight-stationary decode engine (debug): runs the bench workload's decode once
-with AMIRA_WS_TRACE=1 and prints, for M-tile 0, the median time between consecutive events of one decode step."""
+"""Per-tick timeline of the weight-stationary decode engine (debug): runs the bench workload's decode once with
+AMIRA_WS_TRACE=1 and prints, per M-tile, when slice 0 of every role handled the tile's unit of a tick (offsets from the
+tick's start = the previous tick's control update of M-tile 0), plus the tick period.  AMIRA_WS_TILES / AMIRA_WS_SPEC apply."""
 import os
 import sys
 
@@ -27,21 +28,29 @@ ns = torch.zeros(B, dtype=torch.int32, device="cuda")
 for _ in range(2):
     ctx.greedy_decode_raw(enc.data_ptr(), B, T, elens, tok.data_ptr(), nt.data_ptr(), ns.data_ptr())
 torch.cuda.synchronize()
-tr = ctx.debug_ws_trace(512).astype(np.float64)
+tr = ctx.debug_ws_trace(512).astype(np.float64)  # [its][8][32]
 names = {0: "A", 1: "BI", 2: "BH", 3: "C", 4: "D"}
-ev = {0: "dep seen", 1: "1st TMA landed", 2: "MMAs issued", 3: "acc full seen", 4: "signalled", 5: "ctl seen (A)"}
-its = [i for i in range(4, 500) if tr[i, 30] > 0 and tr[i - 1, 30] > 0]
-print("steps traced", len(its), "median step period (ctl->ctl) us:", np.median([(tr[i, 30] - tr[i - 1, 30]) for i in its]) / 1e3)
-for lo, hi in ((4, 120), (140, 300), (380, 470)):
-    sel = [i for i in its if lo <= i < hi]
-    if not sel:
-        continue
-    print(f"--- steps {lo}..{hi}: period {np.median([(tr[i, 30] - tr[i - 1, 30]) for i in sel]) / 1e3:.2f} us; offsets from previous ctl (us):")
+ev = {0: "dep", 1: "tma1", 2: "mma", 3: "acc", 4: "sig", 5: "epi"}
+nt_ = int((tr[8, :, 30] > 0).sum())
+print("M-tiles traced:", nt_)
+print("ticks per M-tile:", [int(tr[511, m, 31]) for m in range(nt_)], " decode steps:", int(ns.sum().item()), " tokens:", int(nt.clamp(min=0).sum().item()),
+      " longest stream (steps):", int(ns.max().item()))
+for a_, b_ in ((4, 50), (50, 100), (100, 200), (200, 300), (300, 400), (400, 511)):
+    v = [tr[i, 0, 30] - tr[i - 1, 0, 30] for i in range(a_, b_) if tr[i, 0, 30] > 0 and tr[i - 1, 0, 30] > 0]
+    if v:
+        print(f"  ticks {a_}..{b_}: median period {np.median(v) / 1e3:.2f} us, mean {np.mean(v) / 1e3:.2f} us")
+lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (20, 200)
+its = [i for i in range(lo, hi) if tr[i, 0, 30] > 0 and tr[i - 1, 0, 30] > 0]
+per = np.median([tr[i, 0, 30] - tr[i - 1, 0, 30] for i in its]) / 1e3
+print(f"ticks {lo}..{hi}: tick period (M-tile 0, A control update to the next) = {per:.2f} us")
+print("offsets (us, medians) from the previous tick's control update of M-tile 0; events: dep = scheduler saw the dependency,"
+      " tma1 = first operand tile landed, mma = last MMA issued, acc = accumulator drained from, sig = unit published, epi = stores issued")
+for mt in range(nt_):
     for role in range(5):
         row = []
         for e in range(6):
-            v = [tr[i, role * 6 + e] - tr[i - 1, 30] for i in sel if tr[i, role * 6 + e] > 0]
+            v = [tr[i, mt, role * 6 + e] - tr[i - 1, 0, 30] for i in its if tr[i, mt, role * 6 + e] > 0]
             row.append(f"{ev[e]}={np.median(v) / 1e3:7.2f}" if v else f"{ev[e]}=   --  ")
-        print(f"  {names[role]:>2}: " + "  ".join(row))
-    v = [tr[i, 30] - tr[i - 1, 30] for i in sel]
-    print(f"  ctl done = {np.median(v) / 1e3:7.2f};  D-role MMA thread waited on TMA data {np.median([tr[i, 31] for i in sel]) / 1.965e3:.2f} us per unit (after the first chunk)")
+        print(f"  tile {mt} {names[role]:>2}: " + "  ".join(row))
+    v = [tr[i, mt, 30] - tr[i - 1, 0, 30] for i in its if tr[i, mt, 30] > 0]
+    print(f"  tile {mt} control update done = {np.median(v) / 1e3:7.2f}")
