@@ -231,16 +231,17 @@ cudaError_t launch_split_transpose_enc(Ctx *c, const float *enc, int B, int T, c
 // decoder_ws.cu (weight-stationary dataflow engine, decode_engine = 4) ------------------------------------------
 bool decoder_ws_supported(const Ctx *c);
 cudaError_t decoder_ws_prepare(Ctx *c, TcWeights *w);
-// The lane plan of a batch: MT M-tiles of 128 lanes; lane r decodes the streams rowinfo[lane_first[r] .. lane_first[r+1]).
+// The lane plan of a batch (decoder_ws.cu): MT M-tiles of 128 lanes share the batch's streams; rowinfo lists the streams with
+// frames, longest first: the first Mpad start in the lanes, the others are taken off the queue when a lane's stream ends.
 struct WsPlan {
-    int MT = 1, Mpad = 128;
+    int MT = 1, Mpad = 128, n_streams = 0;
+    int spec = 0;  // ticks of an M-tile overlap by blank speculation from the start
 };
-constexpr int kWsMaxTiles = 256;
-// fills rowinfo [B] {stream, encoded length, first row of E, 0} and lane_first [Mpad + 1 <= B + 129] (host memory)
-WsPlan ws_plan_lanes(const int32_t *lens, const int *eoff, int B, int4 *rowinfo, int *lane_first);
-// work == nullptr: size query (*work_bytes receives the workspace size for MT M-tiles).  E [sum of lengths][640], the plan's
-// lane_first and rowinfo (device copies) from the caller.
-cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int MT, int T, const int *lane_first_dev, const int4 *rowinfo_dev,
+// fills rowinfo [B] {stream, encoded length, first row of E, 0} (host memory)
+WsPlan ws_plan_lanes(const int32_t *lens, const int *eoff, int B, int4 *rowinfo);
+// work == nullptr: size query (*work_bytes receives the workspace size for plan.MT M-tiles).  E [sum of lengths][640] and the
+// device copy of the plan's rowinfo from the caller.
+cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, const WsPlan &plan, int T, const int4 *rowinfo_dev,
                              const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
                              int32_t *nsteps_dev, char *work, size_t *work_bytes, int32_t *last_dev = nullptr);
 

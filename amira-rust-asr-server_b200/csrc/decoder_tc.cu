@@ -339,9 +339,9 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
     const int Tq = T > 0 ? T : 1;
     if (!decoder_ws_supported(c)) return cudaErrorNotSupported;  // the weight-stationary kernel needs 147 co-resident CTAs
     cudaError_t e;
-    // metadata block (pinned, one upload): rowinfo[B] int4 | src_off[B+1] (packed input) | eoff[B+1] | lane_first[<= B + 129]
+    // metadata block (pinned, one upload): rowinfo[B] int4 | src_off[B+1] (packed input) | eoff[B+1]
     const size_t m_ri = 0, m_soff = m_ri + sizeof(int4) * (size_t)B, m_eoff = m_soff + sizeof(long long) * ((size_t)B + 1);
-    const size_t m_lane = m_eoff + sizeof(int) * ((size_t)B + 1), meta_bytes = m_lane + sizeof(int) * ((size_t)B + 129);
+    const size_t meta_bytes = m_eoff + sizeof(int) * ((size_t)B + 1);
     if ((e = c->pin[1].reserve(meta_bytes)) != cudaSuccess) return e;
     char *h_meta = c->pin[1].as<char>();
     long long *h_soff = reinterpret_cast<long long *>(h_meta + m_soff);
@@ -349,8 +349,8 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
     int *h_eoff = reinterpret_cast<int *>(h_meta + m_eoff);  // first packed row of each stream's valid frames in E
     h_eoff[0] = 0;
     for (int i = 0; i < B; ++i) h_eoff[i + 1] = h_eoff[i] + lens_host[i];
-    // the streams packed into lanes of (almost) equal frame counts: every M-tile lives for the whole kernel
-    const WsPlan plan = ws_plan_lanes(lens_host, h_eoff, B, reinterpret_cast<int4 *>(h_meta + m_ri), reinterpret_cast<int *>(h_meta + m_lane));
+    // the streams, longest first, share the lanes of plan.MT M-tiles: every M-tile lives for the whole kernel
+    const WsPlan plan = ws_plan_lanes(lens_host, h_eoff, B, reinterpret_cast<int4 *>(h_meta + m_ri));
 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += tc_align(bytes); return o; };
@@ -358,7 +358,7 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
     const size_t oeh = take(2 * (size_t)B * Tq * kEnc), oel = take(2 * (size_t)B * Tq * kEnc);
     const size_t ometa = take(meta_bytes);
     size_t ws_bytes = 0;
-    if ((e = launch_greedy_ws(c, nullptr, B, plan.MT, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &ws_bytes)) != cudaSuccess) return e;
+    if ((e = launch_greedy_ws(c, nullptr, B, plan, T, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &ws_bytes)) != cudaSuccess) return e;
     const size_t ows = take(ws_bytes);
     if ((e = d->work.reserve(off)) != cudaSuccess) return e;
     char *base = d->work.as<char>();
@@ -395,9 +395,8 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
             if ((e = launch_tc_gemm(c, eh + ro * kEnc, el + ro * kEnc, w->we_hi, w->we_lo, d->bjoint, E + ro * kH, kH, rows, kH, kEnc)) != cudaSuccess) return e;
         }
     }
-    return launch_greedy_ws(c, E, B, plan.MT, T, reinterpret_cast<const int *>(base + ometa + m_lane),
-                            reinterpret_cast<const int4 *>(base + ometa + m_ri), slots_dev, s1_dev, s2_dev, tokens_dev, ntok_dev, nsteps_dev,
-                            base + ows, &ws_bytes, last_dev);
+    return launch_greedy_ws(c, E, B, plan, T, reinterpret_cast<const int4 *>(base + ometa + m_ri), slots_dev, s1_dev, s2_dev, tokens_dev,
+                            ntok_dev, nsteps_dev, base + ows, &ws_bytes, last_dev);
 }
 
 }  // namespace amira

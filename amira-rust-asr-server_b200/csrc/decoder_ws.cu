@@ -81,10 +81,12 @@ constexpr int W_R = 8;                                      // ring of control r
 
 enum { R_A = 0, R_BI = 1, R_BH = 2, R_C = 3, R_D = 4 };
 enum { OP_IDLE = 0, OP_STEP = 1, OP_COPY = 2, OP_LOAD = 3 };
+enum { F_ACTIVE = 1, F_FAILED = 2, F_PENDING = 4 };  // WCtl::flags
 
-// per-lane control row of one tick (48 bytes).  flags: bit 0 active, bit 1 failed.  spec: bits 0-7 = ticks (index & 7) whose
-// STEP result has not been consumed yet; bits 8-9 = this tick's op; bits 12-14 = source version of a COPY.  tuse: the row of E
-// (absolute: ebase + frame) this tick's STEP reads.
+// per-lane control row of one tick (48 bytes).  flags: bit 0 active, bit 1 failed, bit 2 pending (the row describes the lane's
+// NEXT stream, whose state the next tick loads).  spec: bits 0-7 = ticks (index & 7) whose STEP result has not been consumed yet;
+// bits 8-9 = this tick's op; bit 11 = the STEP starts from the state of version `src` instead of the previous tick's (redo after
+// a lost speculation); bits 12-14 = src.  tuse: the row of E (absolute: ebase + frame) this tick's STEP reads.
 struct WCtl {
     int t, sym, total, last, flags, nsteps, spec, tuse;
     int sidx, len, ebase, cur;  // the lane's current stream: index in the batch, encoded length, first packed row of E, chain position
@@ -97,11 +99,14 @@ struct WsParams {
     const float *g0p, *b1p, *boutp, *E;
     int B, Mpad, MT, T;
     const int *slots;
-    const int *lane_first;   // [Mpad + 1]: lane r decodes the streams rowinfo[lane_first[r] .. lane_first[r + 1]) in that order
-    const int4 *rowinfo;     // [streams with frames] {stream index, encoded length, first packed row of E, 0}, grouped by lane
+    const int4 *rowinfo;     // [streams with frames] {stream index, encoded length, first packed row of E, 0}, longest first
     __nv_bfloat16 *h0b_hi, *h0b_lo, *h1b_hi, *h1b_lo, *zb_hi, *zb_lo;   // [W_V][Mpad][640]
     float *h0f, *h1f, *c0, *c1;                                          // [W_V][Mpad][640]
-    float *part;        // [MT][40 slices][2 column groups][128 rows][32] fp32: h1(t-1) W_hh1 partial sums
+    float *part;        // [2 tick parities][MT][40 slices][2 column groups][128 rows][32] fp32: h1(t-1) W_hh1 partial sums
+    float4 *presave;    // [2 tick parities][MT][40 slices][8][256 threads]: the layer-0 recurrent products of the last two ticks
+    int *q_head;        // next unassigned entry of rowinfo (streams sorted by length, longest first)
+    int n_streams;      // streams with frames = entries of rowinfo
+    int spec_any;       // some speculation depth is non-zero: keep what a redo needs
     unsigned long long *amax;  // [W_R ticks][Mpad] packed (orderable logit << 32 | ~column): atomicMax = first-max argmax
     WCtl *ctl;          // [W_R ticks][Mpad]
     int *tinfo;         // [MT][W_R]: res(it) = the last tick whose vocabulary results the layer-0 epilogue of tick `it` consumes
@@ -114,6 +119,7 @@ struct WsParams {
     int nrows;          // stream rows a unit loads and multiplies (32 / 64 when a single M-tile holds that few streams, else 128)
     int spec_depth[8];  // 0..W_DMAX: speculation depth while n M-tiles are alive, n = 1..8 (index n-1); 0 beyond
     long long *trace;   // nullable: [W_TRACE_ITS][32] globaltimer stamps of M-tile 0 (debug)
+    int trace_mode, trace_role;
     int force_trap;     // test hook (AMIRA_DEBUG_FORCE_TRAP): take the watchdog's exit on purpose
 };
 
@@ -173,9 +179,16 @@ __device__ __forceinline__ long long gtime() {
 // debug trace: slice 0 of every role stamps its events for the first W_TRACE_MT M-tiles
 #define WS_TRACE(ev)                                                                                   \
     do {                                                                                               \
-        if (p.trace && slice == 0 && mt < W_TRACE_MT && it < W_TRACE_ITS)                              \
+        if (p.trace && p.trace_mode == 1 && slice == 0 && mt < W_TRACE_MT && it < W_TRACE_ITS)         \
             p.trace[(it * W_TRACE_MT + mt) * 32 + role * 6 + (ev)] = gtime();                         \
     } while (0)
+// AMIRA_WS_TRACE=2: stamps inside the epilogue of one role's slice 0 (AMIRA_WS_TRACE_ROLE, default 1 = layer-1 input half), slots 0..15
+#define WS_TRACE2(k)                                                                                   \
+    do {                                                                                               \
+        if (p.trace && p.trace_mode == 2 && role == p.trace_role && slice == 0 && etid == 0 && mt < W_TRACE_MT && it < W_TRACE_ITS) \
+            p.trace[(it * W_TRACE_MT + mt) * 32 + (k)] = gtime();                                     \
+    } while (0)
+#define WS_FORCE(x) asm volatile("" ::"f"(x))
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;
@@ -302,8 +315,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
     const size_t v_init = (size_t)(W_V - 1) * n_state;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < n_state; i += (size_t)gridDim.x * blockDim.x) {
         const int row = (int)(i / kH), j = (int)(i % kH);
-        const int lf = p.lane_first[row];
-        const int b = lf < p.lane_first[row + 1] ? p.rowinfo[lf].x : -1;  // the lane's first stream
+        const int b = row < p.n_streams ? p.rowinfo[row].x : -1;  // the lane's first stream
         const float h0 = (b >= 0 && p.s1) ? p.s1[ws_state_off(p, 0, b) + j] : 0.f;
         const float h1 = (b >= 0 && p.s1) ? p.s1[ws_state_off(p, 1, b) + j] : 0.f;
         p.h0f[v_init + i] = h0;
@@ -317,19 +329,19 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
         p.h1b_hi[v_init + i] = hh; p.h1b_lo[v_init + i] = hl;
     }
     for (int row = blockIdx.x * blockDim.x + tid; row < p.Mpad; row += gridDim.x * blockDim.x) {
-        const int lf = p.lane_first[row];
-        const int act = lf < p.lane_first[row + 1] ? 1 : 0;  // the host leaves streams without frames out of the lanes
-        const int4 ri = act ? p.rowinfo[lf] : make_int4(0, 0, 0, 0);
+        const int act = row < p.n_streams ? 1 : 0;  // the host leaves streams without frames out of the queue
+        const int4 ri = act ? p.rowinfo[row] : make_int4(0, 0, 0, 0);
         int4 *dstc = reinterpret_cast<int4 *>(p.ctl + (size_t)(W_R - 1) * p.Mpad + row);  // the control row of "tick -1"
         dstc[0] = make_int4(0, 0, 0, (p.last_io && act) ? p.last_io[ri.x] : p.blank);
         dstc[1] = make_int4(act, 0, 0, 0);
-        dstc[2] = make_int4(ri.x, ri.y, ri.z, lf);
+        dstc[2] = make_int4(ri.x, ri.y, ri.z, row);
         if (act) atomicAdd(&p.tile_active[row / W_BM], 1);
     }
     for (int b = blockIdx.x * blockDim.x + tid; b < p.B; b += gridDim.x * blockDim.x) {
         p.ntok[b] = 0;
         if (p.nsteps) p.nsteps[b] = 0;
     }
+    if (blockIdx.x == 0 && tid == 0) *p.q_head = min(p.n_streams, p.Mpad);  // the first Mpad streams start in the lanes
     __threadfence();
     fence_proxy_async();
     grid.sync();
@@ -467,6 +479,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 const int mt = sm.q[slot].mt, it = sm.q[slot].it;
                 if (mt < 0) { mbar_arrive(&sm.q_empty[slot]); break; }
                 mbar_wait_wd(&sm.sig_full[slot], (qn / W_Q) & 1);
+                if (p.trace && p.trace_mode == 2 && role == p.trace_role && slice == 0 && mt < W_TRACE_MT && it < W_TRACE_ITS)
+                    p.trace[(it * W_TRACE_MT + mt) * 32 + 8] = gtime();
                 const int skip = sm.sig_skip[slot];
                 sm.sig_skip[slot] = 0;
                 if (!skip) {
@@ -477,6 +491,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     else if (role == R_C) { fence_proxy_async(); atomicAdd(p.cnt_c + mt, 1); }
                     else atomicAdd(p.cnt_d + mt, 1);
                     WS_TRACE(4);
+                    if (p.trace && p.trace_mode == 2 && role == p.trace_role && slice == 0 && mt < W_TRACE_MT && it < W_TRACE_ITS)
+                        p.trace[(it * W_TRACE_MT + mt) * 32 + 9] = gtime();
                 }
                 mbar_arrive(&sm.q_empty[slot]);
                 ++qn;
@@ -588,8 +604,12 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 int &act_cnt = sm.act2[tile & 1];  // `tile` was advanced above: consecutive units alternate slots
                 int active = c.flags & 1, failed = (c.flags >> 1) & 1, kinds = c.spec & 0xff;
                 int op = OP_IDLE, src = vprev, fin_ver = -1, fin_sidx = 0;
-                bool restore = false;
-                if (active) {
+                bool restore = false, redo = false;
+                if (c.flags & F_PENDING) {
+                    // the lane's previous stream ended one tick ago and slice 0 took the next one off the queue (the row already
+                    // describes it): this tick installs its initial state
+                    op = OP_LOAD;
+                } else if (active) {
                     const int len = c.len;
                     for (int j = res_prev + 1; j <= res; ++j) {
                         if (!((kinds >> (j & 7)) & 1)) continue;  // that tick was not a step of this stream (or was discarded)
@@ -616,46 +636,70 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                             // the ticks speculated after j assumed "blank, and the stream goes on": discard them for this stream
                             kinds = 0;
                             if (!active) fin_ver = j % W_V;                              // final state = the state after tick j
+                            else if (j == it - 2) { redo = true; src = j % W_V; }        // one tick was lost: step again from tick j's state
                             else if (j < it - 1) { restore = true; src = j % W_V; }
                             break;
                         }
                     }
-                    if (fin_ver >= 0) {  // the lane's stream ended with tick fin_ver: its results, then the lane's next stream
+                    if (fin_ver >= 0) {  // the lane's stream ended with tick fin_ver: its results, then the next stream of the queue
                         fin_sidx = c.sidx;
                         if (slice == 0 && cgp == 0) {
                             p.ntok[c.sidx] = failed ? -1 : c.total;
                             if (p.nsteps) p.nsteps[c.sidx] = c.nsteps;
                             if (p.last_io) p.last_io[c.sidx] = c.last;
                             if (failed) atomicAdd(p.fail_count, 1);
+                            // longest streams first, whichever lane is free takes the next: every lane stays busy to the end
+                            const int nxt = atomicAdd(p.q_head, 1);
+                            if (nxt < p.n_streams) {
+                                const int4 ri = __ldg(p.rowinfo + nxt);
+                                c.t = 0; c.sym = 0; c.total = 0; c.nsteps = 0;
+                                c.last = p.last_io ? __ldcg(p.last_io + ri.x) : p.blank;
+                                c.sidx = ri.x; c.len = ri.y; c.ebase = ri.z; c.cur = nxt;
+                                active = 1 | F_PENDING;
+                            }
                         }
-                        const int nxt = c.cur + 1;
-                        if (nxt < __ldg(p.lane_first + row + 1)) {
-                            const int4 ri = __ldg(p.rowinfo + nxt);
-                            c.t = 0; c.sym = 0; c.total = 0; c.nsteps = 0;
-                            c.last = p.last_io ? __ldcg(p.last_io + ri.x) : p.blank;
-                            c.sidx = ri.x; c.len = ri.y; c.ebase = ri.z; c.cur = nxt;
-                            active = 1; failed = 0; op = OP_LOAD;  // this tick installs the stream's initial state
-                        }
+                        failed = 0;
                     } else if (restore) op = OP_COPY;
                     else {
                         const int tspec = c.t + __popc(kinds);  // every unresolved step is assumed to emit blank
                         if (tspec < len) { op = OP_STEP; c.tuse = c.ebase + tspec; kinds |= 1 << (it & 7); }
-                        else op = OP_COPY;                      // nothing left to speculate on: carry the state, wait for results
+                        else { op = OP_COPY; redo = false; }    // nothing left to speculate on: carry the state, wait for results
                     }
                 }
-                c.flags = active | (failed << 1);
-                c.spec = kinds | (op << 8) | (src << 12);
+                // a lane whose stream ended in this tick counts as alive: only slice 0 knows whether the queue had another stream
+                const int alive = (op != OP_IDLE) | (fin_ver >= 0);
+                c.flags = (op == OP_LOAD ? 1 : active) | (failed << 1);
+                c.spec = kinds | (op << 8) | ((redo ? 1 : 0) << 11) | (src << 12);
+                if (p.trace && slice == 0 && cgp == 0) {  // debug: lane-ticks by kind (slot 31 of the first rows of the trace)
+                    const int kind = op == OP_STEP ? (redo ? 1 : 0) : op == OP_COPY ? (restore ? 2 : 3) : op == OP_LOAD ? 5 : fin_ver >= 0 ? 4 : 6;
+                    atomicAdd(reinterpret_cast<unsigned long long *>(p.trace) + (kind * W_TRACE_MT) * 32 + 31, 1ull);
+                }
                 if (slice == 0 && cgp == 0) {  // the control rows of tick `it`, for every other role's epilogue
                     int4 *dstc = reinterpret_cast<int4 *>(p.ctl + (size_t)(it & (W_R - 1)) * p.Mpad + row);
                     __stcg(dstc, make_int4(c.t, c.sym, c.total, c.last));
                     __stcg(dstc + 1, make_int4(c.flags, c.nsteps, c.spec, c.tuse));
                     __stcg(dstc + 2, make_int4(c.sidx, c.len, c.ebase, c.cur));
                 }
-                if (cgp == 0 && active) atomicAdd(&act_cnt, 1);
+                if (cgp == 0 && alive) atomicAdd(&act_cnt, 1);
+                // the raw accumulator (W_hh0 h0 of the previous version) of every tick is kept for one tick: a redo steps from the
+                // state of tick it-2, whose product is the one tick it-1 saved ([parity][M-tile][slice][8][256 threads] float4)
+                const size_t sv_unit = ((size_t)mt * W_NG + slice) * 8 * W_EPI_THREADS + etid;
+                float4 *sv_w = p.presave + (size_t)(it & 1) * p.MT * W_NG * 8 * W_EPI_THREADS + sv_unit;
                 if (op == OP_STEP) {  // the token-dependent gather overlaps the barrier below
                     const float4 *addp = reinterpret_cast<const float4 *>(p.g0p + (size_t)c.last * kG + nb);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) ad[j] = __ldg(addp + j);
+                    if (redo) {
+                        const size_t ss = ((size_t)src * p.Mpad + row) * kH + nb / 4;
+                        cold4[0] = __ldcg(reinterpret_cast<const float4 *>(p.c0 + ss));
+                        cold4[1] = __ldcg(reinterpret_cast<const float4 *>(p.c0 + ss) + 1);
+                        const float4 *sv_r = p.presave + (size_t)((it + 1) & 1) * p.MT * W_NG * 8 * W_EPI_THREADS + sv_unit;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 v = __ldcg(sv_r + j * W_EPI_THREADS);
+                            ad[j].x += v.x; ad[j].y += v.y; ad[j].z += v.z; ad[j].w += v.w;
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) ad[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -676,10 +720,23 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 named_bar_sync(1, W_EPI_THREADS);
                 const bool live = act_cnt > 0;  // identical in every layer-0 CTA
                 if (etid == 0) sm.act2[(tile & 1) ^ 1] = 0;  // the next unit's slot: nobody touches it before that unit's barrier
-                if (etid == 0 && slice == 0 && p.trace && mt < W_TRACE_MT && it < W_TRACE_ITS) p.trace[(it * W_TRACE_MT + mt) * 32 + 30] = gtime();
-                float *pre = reinterpret_cast<float *>(ad);
+                if (etid == 0 && slice == 0 && p.trace && p.trace_mode == 1 && mt < W_TRACE_MT && it < W_TRACE_ITS) p.trace[(it * W_TRACE_MT + mt) * 32 + 30] = gtime();
                 if (etid == 0) WS_TRACE(3);
-                gather_add(pre);  // accumulator (parked in the shared tile at the top of this unit) + G0[token] row
+                {   // accumulator (parked in the shared tile at the top of this unit) + G0[token] row; a redo lane already holds
+                    // the saved product of the state it steps from
+                    const float *srct = ttile + (cgp * 32) * T_LD + r_in;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 raw;
+                        raw.x = srct[(4 * j4) * T_LD] + srct[(W_SL + 4 * j4) * T_LD];
+                        raw.y = srct[(4 * j4 + 1) * T_LD] + srct[(W_SL + 4 * j4 + 1) * T_LD];
+                        raw.z = srct[(4 * j4 + 2) * T_LD] + srct[(W_SL + 4 * j4 + 2) * T_LD];
+                        raw.w = srct[(4 * j4 + 3) * T_LD] + srct[(W_SL + 4 * j4 + 3) * T_LD];
+                        if (p.spec_any) __stcg(sv_w + j4 * W_EPI_THREADS, raw);
+                        if (!redo) { ad[j4].x += raw.x; ad[j4].y += raw.y; ad[j4].z += raw.z; ad[j4].w += raw.w; }
+                    }
+                    named_bar_sync(2, W_EPI_THREADS);  // the tile is free for the next unit
+                }
                 if (!live) {  // the M-tile has ended: tick `it` does not exist (uniform across the layer-0 CTAs)
                     if (slice == 0 && etid == 0) {
                         __threadfence();
@@ -725,7 +782,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);  // stores issued: the signal thread fences and publishes them
             } else if (role == R_BH) {
                 // partial sums of the layer-1 recurrent half, for the layer-1 input CTA of the same slice
-                float4 *dst = reinterpret_cast<float4 *>(p.part + ((((size_t)mt * W_NG + slice) * 2 + cgp) * W_BM + r_in) * 32);
+                float4 *dst = reinterpret_cast<float4 *>(p.part + (((((size_t)(it & 1) * p.MT + mt) * W_NG + slice) * 2 + cgp) * W_BM + r_in) * 32);
                 float4 z4[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) z4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -740,27 +797,39 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
             } else if (role == R_BI) {
                 // every load that does not depend on another is issued up front: control row + cell state go out together with the
                 // acquire of the recurrent partner's flag, the partial sums right after it
+                WS_TRACE2(0);
                 const WCtl c = load_ctl(p.ctl + (size_t)(it & (W_R - 1)) * p.Mpad + row);  // published by layer-0 slice 0
                 // every layer-0 epilogue of this tick has consumed the argmax keys it needed (that is what released this unit):
                 // clear the ring entry that the vocabulary phase of tick it+4 will use
                 if (slice == 0 && cgp == 0) __stcg(p.amax + (size_t)((it + 4) & (W_R - 1)) * p.Mpad + row, 0ull);
                 const int op = (c.spec >> 8) & 3, src = (c.spec >> 12) & 7;
+                const bool redo = (c.spec >> 11) & 1;  // step from the state of version src: its recurrent product is the previous tick's
                 float4 ad[8], cold4[2], pr[8];
-                cold4[0] = __ldcg(reinterpret_cast<const float4 *>(p.c1 + so_prev));
-                cold4[1] = __ldcg(reinterpret_cast<const float4 *>(p.c1 + so_prev) + 1);
-                spin_ge(p.part_ready + mt * W_NG + slice, it + 1);  // per thread: acquire orders the partial-sum loads below
+                WS_TRACE2(1);
                 {
-                    const float4 *srcp = reinterpret_cast<const float4 *>(p.part + ((((size_t)mt * W_NG + slice) * 2 + cgp) * W_BM + r_in) * 32);
+                    const size_t so_old = redo ? ((size_t)src * p.Mpad + row) * kH + nb / 4 : so_prev;
+                    cold4[0] = __ldcg(reinterpret_cast<const float4 *>(p.c1 + so_old));
+                    cold4[1] = __ldcg(reinterpret_cast<const float4 *>(p.c1 + so_old) + 1);
+                }
+                spin_ge(p.part_ready + mt * W_NG + slice, it + 1);  // per thread: acquire orders the partial-sum loads below
+                WS_TRACE2(2);
+                {
+                    const float4 *srcp = reinterpret_cast<const float4 *>(
+                        p.part + (((((size_t)((it + (redo ? 1 : 0)) & 1) * p.MT + mt) * W_NG + slice) * 2 + cgp) * W_BM + r_in) * 32);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) pr[j] = __ldcg(srcp + j);
                     const float4 *addp = reinterpret_cast<const float4 *>(p.b1p + nb);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) ad[j] = __ldg(addp + j);
                 }
+                if (p.trace_mode == 2) { WS_FORCE(pr[7].w); WS_FORCE(cold4[1].w); WS_TRACE2(3); }
                 wait_acc(use);
                 if (etid == 0) WS_TRACE(3);
+                WS_TRACE2(4);
                 drain_acc();
+                WS_TRACE2(5);
                 gather_add(reinterpret_cast<float *>(pr));  // (accumulator + recurrent partial sums) ...
+                WS_TRACE2(6);
                 if (op == OP_STEP) {
                     float cnew[8], hnew[8];
                     __align__(16) __nv_bfloat16 vh[8], vl[8];
@@ -783,6 +852,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 } else if (op == OP_LOAD) {
                     load_state(1, c.sidx, p.c1 + so_cur, p.h1f + so_cur, p.h1b_hi + so_cur, p.h1b_lo + so_cur);
                 }
+                WS_TRACE2(7);
                 if (etid == 0) WS_TRACE(5);
                 mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);
             } else if (role == R_C) {
@@ -877,70 +947,55 @@ cudaError_t decoder_ws_prepare(Ctx *c, TcWeights *w) {
     return cudaSuccess;
 }
 
-// The lane plan: which streams each row of each M-tile decodes, in which order (see "Lanes" at the top of this file).
-// Longest-processing-time-first packing for every candidate number of M-tiles, scored with the two measured constants of the
-// kernel: a tick of n live M-tiles takes max(n x unit time, step-chain latency).  Streams without frames are left out (their
-// results are the zero counts the prologue writes).  rowinfo [B] and lane_first [plan.Mpad + 1] are filled for the choice.
-WsPlan ws_plan_lanes(const int32_t *lens, const int *eoff, int B, int4 *rowinfo, int *lane_first) {
+// The lane plan (see "Lanes" at the top of this file): how many M-tiles (x 128 lanes) the batch's streams share and whether
+// the ticks of an M-tile overlap by blank speculation.  The streams, longest first, go into rowinfo: the first lanes x 128 start
+// in the lanes, the rest are taken off the queue by whichever lane ends a stream (list scheduling).  Candidates are scored with
+// the measured constants of the kernel: a tick of n live M-tiles takes max(chain latency / ticks in flight, n x unit time); a
+// speculated tick is lost whenever the step before it emitted a token.  Streams without frames are left out (their results
+// are the zero counts the prologue writes).
+WsPlan ws_plan_lanes(const int32_t *lens, const int *eoff, int B, int4 *rowinfo) {
     std::vector<int> idx;
     idx.reserve(B);
+    long long frames = 0;
     for (int i = 0; i < B; ++i)
-        if (lens[i] > 0) idx.push_back(i);
+        if (lens[i] > 0) { idx.push_back(i); frames += lens[i]; }
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return lens[a] > lens[b]; });
     const int nz = (int)idx.size();
-    const int mt_max = std::max(1, std::min(W_MAX_MT, (nz + W_BM - 1) / W_BM));
-    constexpr double kUnitUs = 6.7, kChainUs = 34.0;  // per unit with every SM busy / per step of a lone M-tile
-    constexpr int kSwitchTicks = 2;                   // a stream's end is seen one tick late, the next tick loads the state
-    auto pack = [&](int mt, std::vector<int> *lane_of) -> long long {  // returns the longest lane, in ticks
-        const int nl = std::min(mt * W_BM, std::max(nz, 1));
-        std::priority_queue<std::pair<long long, int>, std::vector<std::pair<long long, int>>, std::greater<std::pair<long long, int>>> q;
-        for (int l = 0; l < nl; ++l) q.push({0, l});
-        long long worst = 0;
-        for (int k = 0; k < nz; ++k) {
-            auto [load, l] = q.top();
-            q.pop();
-            load += lens[idx[k]] + kSwitchTicks;
-            worst = std::max(worst, load);
-            if (lane_of) (*lane_of)[k] = l;
-            q.push({load, l});
-        }
-        return worst;
-    };
-    int best_mt = mt_max;
-    if (const char *f = getenv("AMIRA_WS_TILES")) best_mt = std::max(1, std::min(mt_max, atoi(f)));  // A/B timing
-    else {
-        double best = 1e300;
-        for (int mt = 1; mt <= mt_max; ++mt) {
-            const double t = (double)pack(mt, nullptr) * std::max(mt * kUnitUs, kChainUs);
-            if (t < best * 0.999) { best = t; best_mt = mt; }
-        }
-    }
-    std::vector<int> lane_of(std::max(nz, 1));
-    pack(best_mt, &lane_of);
-    WsPlan plan;
-    plan.MT = best_mt;
-    plan.Mpad = best_mt * W_BM;
-    std::vector<int> cnt(plan.Mpad + 1, 0);
-    for (int k = 0; k < nz; ++k) cnt[lane_of[k]]++;
-    lane_first[0] = 0;
-    for (int l = 0; l < plan.Mpad; ++l) lane_first[l + 1] = lane_first[l] + cnt[l];
-    std::vector<int> fill(lane_first, lane_first + plan.Mpad);
-    for (int k = 0; k < nz; ++k) {  // idx is sorted by length: a lane decodes its longest stream first
-        const int s = idx[k];
-        rowinfo[fill[lane_of[k]]++] = make_int4(s, lens[s], eoff[s], 0);
-    }
+    for (int k = 0; k < nz; ++k) rowinfo[k] = make_int4(idx[k], lens[idx[k]], eoff[idx[k]], 0);
     for (int k = nz; k < B; ++k) rowinfo[k] = make_int4(0, 0, 0, 0);
+    const int mt_max = std::max(1, std::min(W_MAX_MT, (nz + W_BM - 1) / W_BM));
+    // profiles/r2_ws_trace.log: chain latency of a step 35 us alone, 41 us among other M-tiles; unit time 6.7 us, 7.2 us when
+    // speculating.  Tokens per frame are not known in advance: 0.2 on average, 0.45 for the stream that ends last.
+    constexpr double kChainUs = 41.0, kUnitUs = 6.7, kUnitSpecUs = 7.2, kTokMean = 0.2, kTokWorst = 0.45;
+    constexpr int kSwitchTicks = 3;  // end seen, next stream taken off the queue, state loaded
+    WsPlan plan;
+    double best = 1e300;
+    const int lmax = nz ? lens[idx[0]] : 0;
+    for (int d = 0; d <= 1; ++d) {
+        for (int mt = 1; mt <= mt_max; ++mt) {
+            const int lanes = std::min(mt * W_BM, std::max(nz, 1));
+            const double per_lane = ((double)frames * (1.0 + kTokMean * (1 + d)) + (double)kSwitchTicks * nz) / lanes;
+            const double ticks = std::max(per_lane, lmax * (1.0 + kTokWorst * (1 + d)));
+            const double period = std::max(kChainUs / (1 + d), mt * (d ? kUnitSpecUs : kUnitUs));
+            const double t = ticks * period;
+            if (t < best * 0.999) { best = t; plan.MT = mt; plan.spec = d; }
+        }
+    }
+    if (const char *f = getenv("AMIRA_WS_TILES"))
+        if (*f) plan.MT = std::max(1, std::min(mt_max, atoi(f)));  // A/B timing
+    plan.Mpad = plan.MT * W_BM;
+    plan.n_streams = nz;
     return plan;
 }
 
 // E [sum of encoded lengths][640] fp32 (hoisted encoder projection, valid frames packed; stream b starts at row eoff[b]) is
 // produced by the caller (decoder_tc.cu), and so is the lane plan (ws_plan_lanes, uploaded by the caller).
-cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int MT, int T, const int *lane_first_dev, const int4 *rowinfo_dev,
+cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, const WsPlan &plan, int T, const int4 *rowinfo_dev,
                              const int32_t *slots_dev, float *s1_dev, float *s2_dev, int32_t *tokens_dev, int32_t *ntok_dev,
                              int32_t *nsteps_dev, char *work, size_t *work_bytes, int32_t *last_dev) {
     DecoderPriv *d = c->dec;
     TcWeights *w = d->tc;
-    const int Mpad = MT * W_BM;
+    const int MT = plan.MT, Mpad = MT * W_BM;
     const size_t MH = (size_t)Mpad * kH, VMH = (size_t)W_V * MH;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += ws_align(bytes); return o; };
@@ -948,10 +1003,11 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int MT, int T, const
     const size_t ozh = take(2 * VMH), ozl = take(2 * VMH);
     const size_t oact_end = off;
     const size_t oh0f = take(4 * VMH), oh1f = take(4 * VMH), oc0 = take(4 * VMH), oc1 = take(4 * VMH);
-    const size_t opart = take(sizeof(float) * (size_t)MT * W_NG * 2 * W_BM * 32);
+    const size_t opart = take(sizeof(float) * 2 * (size_t)MT * W_NG * 2 * W_BM * 32);  // by tick parity
+    const size_t opresave = take(sizeof(float4) * 2 * (size_t)MT * W_NG * 8 * W_EPI_THREADS);
     const size_t oamax = take(sizeof(unsigned long long) * W_R * (size_t)Mpad);
     const size_t octl = take(sizeof(WCtl) * W_R * (size_t)Mpad);  // a ring by tick
-    const size_t n_cnt = 6 * (size_t)MT + (size_t)MT * W_NG + (size_t)MT * W_R + 8;
+    const size_t n_cnt = 6 * (size_t)MT + (size_t)MT * W_NG + (size_t)MT * W_R + 8;  // ... + fail_count, live_tiles, q_head
     const size_t ocnt = take(sizeof(int) * n_cnt);
     const size_t otrace = take(sizeof(long long) * W_TRACE_ITS * W_TRACE_MT * 32);
     if (!work) {  // size query
@@ -984,16 +1040,17 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int MT, int T, const
     p.g_whh0_hi = w->whh0_hi; p.g_whh0_lo = w->whh0_lo; p.g_w1_hi = w->w1_hi; p.g_w1_lo = w->w1_lo;
     p.g_wp_hi = w->wp_hi; p.g_wp_lo = w->wp_lo; p.g_wo_hi = w->wo_hi; p.g_wo_lo = w->wo_lo;
     p.B = B; p.Mpad = Mpad; p.MT = MT; p.T = T > 0 ? T : 1;
-    p.slots = slots_dev; p.lane_first = lane_first_dev; p.rowinfo = rowinfo_dev;
+    p.slots = slots_dev; p.rowinfo = rowinfo_dev; p.n_streams = plan.n_streams;
     p.h0f = reinterpret_cast<float *>(work + oh0f); p.h1f = reinterpret_cast<float *>(work + oh1f);
     p.c0 = reinterpret_cast<float *>(work + oc0); p.c1 = reinterpret_cast<float *>(work + oc1);
     p.part = reinterpret_cast<float *>(work + opart);
+    p.presave = reinterpret_cast<float4 *>(work + opresave);
     p.amax = reinterpret_cast<unsigned long long *>(work + oamax);
     p.ctl = reinterpret_cast<WCtl *>(work + octl);
     int *cnt = reinterpret_cast<int *>(work + ocnt);
     p.tile_active = cnt; p.cnt_d = cnt + MT; p.cnt_a = cnt + 2 * MT; p.cnt_b = cnt + 3 * MT; p.cnt_c = cnt + 4 * MT;
     p.dead_at = cnt + 5 * MT; p.part_ready = cnt + 6 * MT; p.tinfo = cnt + 6 * MT + MT * W_NG;
-    p.fail_count = cnt + 6 * MT + MT * W_NG + MT * W_R; p.live_tiles = p.fail_count + 1;
+    p.fail_count = cnt + 6 * MT + MT * W_NG + MT * W_R; p.live_tiles = p.fail_count + 1; p.q_head = p.fail_count + 2;
     if (slots_dev) { p.s1 = c->slot_s1; p.s2 = c->slot_s2; } else { p.s1 = s1_dev; p.s2 = s2_dev; }
     p.tokens = tokens_dev; p.ntok = ntok_dev; p.nsteps = nsteps_dev; p.last_io = last_dev;
     p.max_sym = c->cfg.max_symbols_per_step; p.max_total = c->cfg.max_total_tokens; p.blank = c->cfg.blank_id;
@@ -1001,14 +1058,13 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int MT, int T, const
     d->fail_count_dev = p.fail_count;
     p.norot = getenv("AMIRA_WS_NOROT") ? 1 : 0;
     // blank speculation depth by the number of M-tiles alive.  A speculated tick costs a unit of work on every SM whether its
-    // result is kept or not, so it only pays while the SMs would otherwise idle on the step chain.  Measured on B200 (DESIGN.md
-    // 4.3, profiles/r2_ab_spec.log): depth 1 while at most 3 M-tiles are alive is the best table — deeper speculation does not
-    // shorten a tick below two phases, because the layer-1 recurrence (input-half epilogue -> recurrent-half GEMM -> partial sums
-    // -> input-half epilogue) is itself two hand-offs long.  AMIRA_WS_SPEC="d1,d2,..." overrides the table for A/B timing
-    // ("0" = the strictly sequential schedule of round 1).
+    // result is kept or not, so it only pays while the SMs would otherwise idle on the step chain: always once at most three
+    // M-tiles are left, and from the start when the plan chose it.  Depth 1 = two ticks of an M-tile in flight; deeper
+    // speculation does not shorten a tick below two phases, because the layer-1 recurrence (input-half epilogue -> recurrent-
+    // half GEMM -> partial sums -> input-half epilogue) is itself two hand-offs long.  AMIRA_WS_SPEC="d1,d2,..." overrides the
+    // table for A/B timing ("0" = the strictly sequential schedule).
     {
-        const int dflt[8] = {1, 1, 1, 0, 0, 0, 0, 0};
-        for (int i = 0; i < 8; ++i) p.spec_depth[i] = dflt[i];
+        for (int i = 0; i < 8; ++i) p.spec_depth[i] = (i < 3 || (plan.spec && i < MT)) ? 1 : 0;
         if (const char *e_ = getenv("AMIRA_WS_SPEC")) {
             int i = 0;
             for (const char *q = e_; i < 8; ++i) {
@@ -1018,10 +1074,13 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, int MT, int T, const
                 q = nx + 1;
             }
         }
+        for (int i = 0; i < 8; ++i) p.spec_any |= p.spec_depth[i] > 0;
     }
     p.force_trap = getenv("AMIRA_DEBUG_FORCE_TRAP") ? 1 : 0;
     if (getenv("AMIRA_WS_TRACE")) {
         p.trace = reinterpret_cast<long long *>(work + otrace);
+        p.trace_mode = std::max(1, atoi(getenv("AMIRA_WS_TRACE")));
+        p.trace_role = getenv("AMIRA_WS_TRACE_ROLE") ? atoi(getenv("AMIRA_WS_TRACE_ROLE")) : 1;
         cudaMemsetAsync(p.trace, 0, sizeof(long long) * W_TRACE_ITS * W_TRACE_MT * 32, c->stream);
         d->ws_trace_dev = p.trace;
     }

@@ -35,6 +35,8 @@ nt_ = int((tr[8, :, 30] > 0).sum())
 print("M-tiles traced:", nt_)
 print("ticks per M-tile:", [int(tr[511, m, 31]) for m in range(nt_)], " decode steps:", int(ns.sum().item()), " tokens:", int(nt.clamp(min=0).sum().item()),
       " longest stream (steps):", int(ns.max().item()))
+print("lane-ticks by kind: step %d, redo step %d, copy (restore) %d, copy (waiting for results) %d, stream ended %d, load %d, idle %d"
+      % tuple(int(tr[k, 0, 31]) for k in range(7)))
 for a_, b_ in ((4, 50), (50, 100), (100, 200), (200, 300), (300, 400), (400, 511)):
     v = [tr[i, 0, 30] - tr[i - 1, 0, 30] for i in range(a_, b_) if tr[i, 0, 30] > 0 and tr[i - 1, 0, 30] > 0]
     if v:
