@@ -235,6 +235,7 @@ cudaError_t decoder_ws_prepare(Ctx *c, TcWeights *w);
 // frames, longest first: the first Mpad start in the lanes, the others are taken off the queue when a lane's stream ends.
 struct WsPlan {
     int MT = 1, Mpad = 128, n_streams = 0;
+    int e_rows = 0;  // rows of E the streams cover (max over streams of first row + length)
     int spec = 0;  // ticks of an M-tile overlap by blank speculation from the start
 };
 // fills rowinfo [B] {stream, encoded length, first row of E, 0} (host memory)

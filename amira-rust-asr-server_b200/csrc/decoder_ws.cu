@@ -118,11 +118,15 @@ struct WsParams {
     const __nv_bfloat16 *g_whh0_hi, *g_whh0_lo, *g_w1_hi, *g_w1_lo, *g_wp_hi, *g_wp_lo, *g_wo_hi, *g_wo_lo;
     const float *g0p, *b1p, *boutp, *E;
     int B, Mpad, MT, T;
+    int e_rows;         // rows of E (all streams' encoder frames)
     const int *slots;
     const int4 *rowinfo;     // [streams with frames] {stream index, encoded length, first packed row of E, 0}, longest first
     __nv_bfloat16 *h0b_hi, *h0b_lo, *h1b_hi, *h1b_lo, *zb_hi, *zb_lo;   // [W_V][Mpad][640]
     float *h0f, *h1f, *c0, *c1;                                          // [W_V][Mpad][640]
     float *part;        // [2 tick parities][MT][40 slices][2 column groups][128 rows][32] fp32: h1(t-1) W_hh1 partial sums
+    float4 *g0c;        // [MT][40 slices][2 column groups][8 float4][128 lanes]: each lane's current G0[last token] slice, kept in
+                        // the coalesced layout (a row of G0 per lane costs 32 lines per load instruction; the token changes on 13 % of the steps)
+    int *g0c_tok;       // [MT][40][2][128]: the token that slice belongs to (-1: none yet)
     float4 *presave;    // [2 tick parities][MT][40 slices][8][256 threads]: the layer-0 recurrent products of the last two ticks
     int *q_head;        // next unassigned entry of rowinfo (streams sorted by length, longest first)
     int n_streams;      // streams with frames = entries of rowinfo
@@ -684,6 +688,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
             const int r_in = tid - 128;
             const int hb = slice * (W_SL / 4);  // this CTA's 16 hidden features
             uint32_t qn = 0, unit = 0;
+            // the next unit's control row and result marks are requested while this one is worked on (its descriptor in the queue
+            // means that every layer-0 CTA has published the tick before it, control rows included)
+            bool pf_ok = false;
+            int pf_mt = 0, pf_it = 0, pf_rp = 0, pf_r = 0;
+            WCtl pfc;
             for (;;) {
                 const uint32_t slot = qn % W_Q;
                 mbar_wait_wd(&sm.q_full[slot], (qn / W_Q) & 1);
@@ -695,9 +704,26 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 const int mt = d.mt, it = d.it;
                 const int row = mt * W_BM + r_in;
                 const uint32_t cbuf = unit & 1;
-                WCtl c = load_ctl(p.ctl + (size_t)((it + W_R - 1) & (W_R - 1)) * p.Mpad + row);  // control after tick it-1
-                const int res_prev = it > 0 ? __ldcg(p.tinfo + mt * W_R + ((it - 1) & (W_R - 1))) : -1;
-                const int res = __ldcg(p.tinfo + mt * W_R + (it & (W_R - 1)));
+                WCtl c;
+                int res_prev, res;
+                if (pf_ok && pf_mt == mt && pf_it == it) { c = pfc; res_prev = pf_rp; res = pf_r; }
+                else {
+                    c = load_ctl(p.ctl + (size_t)((it + W_R - 1) & (W_R - 1)) * p.Mpad + row);  // control after tick it-1
+                    res_prev = it > 0 ? __ldcg(p.tinfo + mt * W_R + ((it - 1) & (W_R - 1))) : -1;
+                    res = __ldcg(p.tinfo + mt * W_R + (it & (W_R - 1)));
+                }
+                pf_ok = false;
+                {
+                    const uint32_t ns = qn % W_Q;
+                    int n_mt = -1, n_it = 0;
+                    if (mbar_test_wait(&sm.q_full[ns], (qn / W_Q) & 1)) { n_mt = sm.q[ns].mt; n_it = sm.q[ns].it; }
+                    if (n_mt >= 0 && n_mt != mt) {
+                        pfc = load_ctl(p.ctl + (size_t)((n_it + W_R - 1) & (W_R - 1)) * p.Mpad + n_mt * W_BM + r_in);
+                        pf_rp = n_it > 0 ? __ldcg(p.tinfo + n_mt * W_R + ((n_it - 1) & (W_R - 1))) : -1;
+                        pf_r = __ldcg(p.tinfo + n_mt * W_R + (n_it & (W_R - 1)));
+                        pf_ok = true; pf_mt = n_mt; pf_it = n_it;
+                    }
+                }
                 if (res > res_prev) {  // every vocabulary slice of ticks <= res has merged its argmax
                     if (r_in == 0) spin_ge(p.cnt_d + mt, ND * (res + 1));
                     named_bar_sync(3, W_CTL_THREADS);
@@ -925,11 +951,20 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
             if (role == R_A) {
                 // The recurrent GEMM ran ahead: park its result in the shared tile now, so the NEXT unit's GEMM can run while this
                 // unit waits for its control decisions (the control warps below derive them from the vocabulary results).
+                WS_TRACE2(0);
                 wait_acc(use);
+                WS_TRACE2(1);
                 drain_acc();
+                WS_TRACE2(2);
                 float4 ad[8], cold4[2];
                 cold4[0] = __ldcg(reinterpret_cast<const float4 *>(p.c0) + sf_prev);  // loads that do not depend on the decisions
                 cold4[1] = __ldcg(reinterpret_cast<const float4 *>(p.c0) + sf_prev + W_BM);  // go out before the wait for them
+                // ... and so does the lane's cached slice of G0[last token]: right unless the stream has just emitted a token
+                const size_t g0u = (((size_t)mt * W_NG + slice) * 2 + cgp) * W_BM + r_in;
+                float4 *g0cp = p.g0c + (((size_t)mt * W_NG + slice) * 2 + cgp) * 8 * W_BM + r_in;
+                const int g0tok = __ldcg(p.g0c_tok + g0u);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ad[j] = __ldcg(g0cp + j * W_BM);
                 const uint32_t cbuf = use & 1;
                 mbar_wait_wd(&sm.cb_full[cbuf], (use >> 1) & 1);
                 const uint32_t dw = sm.dec[cbuf][r_in];
@@ -938,14 +973,20 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 const int op = dw & 3, src = (dw >> 3) & 7, last = (int)(dw >> 16);
                 const bool redo = (dw >> 2) & 1;
                 if (etid == 0) WS_TRACE(3);
+                WS_TRACE2(3);
                 // the raw accumulator (W_hh0 h0 of the previous version) of every tick is kept for one tick: a redo steps from the
                 // state of tick it-2, whose product is the one tick it-1 saved ([parity][M-tile][slice][8][256 threads] float4)
                 const size_t sv_unit = ((size_t)mt * W_NG + slice) * 8 * W_EPI_THREADS + etid;
                 float4 *sv_w = p.presave + (size_t)(it & 1) * p.MT * W_NG * 8 * W_EPI_THREADS + sv_unit;
                 if (op == OP_STEP) {
-                    const float4 *addp = reinterpret_cast<const float4 *>(p.g0p + (size_t)last * kG + nb);
+                    if (last != g0tok) {  // a new token (or a new stream): gather its row of G0 and keep it
+                        const float4 *addp = reinterpret_cast<const float4 *>(p.g0p + (size_t)last * kG + nb);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) ad[j] = __ldg(addp + j);
+                        for (int j = 0; j < 8; ++j) ad[j] = __ldg(addp + j);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) __stcg(g0cp + j * W_BM, ad[j]);
+                        __stcg(p.g0c_tok + g0u, last);
+                    }
                     if (redo) {
                         const size_t sfs = sfi(src, mt);
                         cold4[0] = __ldcg(reinterpret_cast<const float4 *>(p.c0) + sfs);
@@ -974,7 +1015,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                         if (p.spec_any) __stcg(sv_w + j4 * W_EPI_THREADS, raw);
                         if (!redo) { ad[j4].x += raw.x; ad[j4].y += raw.y; ad[j4].z += raw.z; ad[j4].w += raw.w; }
                     }
+                    if (p.trace_mode == 2) { WS_FORCE(ad[7].w); WS_FORCE(cold4[1].w); WS_TRACE2(4); }
                     named_bar_sync(2, W_EPI_THREADS);  // the tile is free for the next unit
+                    WS_TRACE2(5);
                 }
                 if (!live) {  // the M-tile has ended: tick `it` does not exist (uniform across the layer-0 CTAs)
                     if (etid == 0) sm.sig_skip[(tile - 1) % W_Q] = 1;
@@ -1005,6 +1048,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     const int sidx = __ldcg(&p.ctl[(size_t)((it + W_R - 1) & (W_R - 1)) * p.Mpad + row].sidx);
                     load_state(0, sidx, reinterpret_cast<float4 *>(p.c0) + sf_cur, reinterpret_cast<float4 *>(p.h0f) + sf_cur, p.h0b_hi + so_cur, p.h0b_lo + so_cur);
                 }
+                WS_TRACE2(7);
                 if (etid == 0) { WS_TRACE(5); WS_TRACE3(2); }
                 mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);  // stores issued: the signal thread fences and publishes them
             } else if (role == R_BH) {
@@ -1113,74 +1157,80 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 if (etid == 0) { WS_TRACE(5); WS_TRACE3(2); }
                 mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);
             } else if (role == R_C) {
-                // control word -> row of E: two dependent round trips, issued for the next unit during this unit's arithmetic
-                bool step;
+                // Work items instead of a row per thread: item s of a thread = (lane 4 s + lane / 8 of this warp's 32, the four
+                // columns 4 (lane % 8) ..).  Eight lanes then cover a row's 128 bytes of E and its 64 + 64 bytes of z in ONE
+                // instruction (a row per thread costs 32 separate lines per instruction: the epilogues are bound by LSU requests,
+                // not bytes).  control word -> row of E: two dependent round trips, issued for the next unit during this one.
+                const int lr = lane >> 3, jj = lane & 7;
+                const int r0 = q * 32 + lr;  // the item's lane of the M-tile is r0 + 4 s
+                int stepm;
                 float4 ev[8];
+                auto load_words = [&](int mt_, int it_, int2 *w) {  // (spec, tuse) of the 8 items' lanes
+                    const WCtl *crow = p.ctl + (size_t)(it_ & (W_R - 1)) * p.Mpad + mt_ * W_BM + r0;
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; ++s8) w[s8] = __ldcg(reinterpret_cast<const int2 *>(&crow[4 * s8].spec));
+                };
+                auto load_e = [&](const int2 *w, float4 *dstv) -> int {
+                    int m = 0;
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; ++s8) {
+                        if (((w[s8].x >> 8) & 3) == OP_STEP) {
+                            m |= 1 << s8;
+                            const float4 *ep = reinterpret_cast<const float4 *>(p.E + (size_t)w[s8].y * kH + nb) + jj;
+                            dstv[s8] = __ldg(ep);
+                            // E is streamed from HBM exactly once per (stream, frame): pull the next frame's 128 bytes into L2
+                            // now so that the load finds them there when the stream advances (this load sits on the step chain)
+                            if (jj == 0 && w[s8].y + 1 < p.e_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep + kH / 4));
+                        } else dstv[s8] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    return m;
+                };
                 if (pf_ok && pf_mt == mt && pf_it == it) {
-                    step = pf_spec != 0;
+                    stepm = pf_spec;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) ev[j] = pf_v[j];
                 } else {
-                    const int4 *crow = reinterpret_cast<const int4 *>(p.ctl + (size_t)(it & (W_R - 1)) * p.Mpad + row);
-                    const int4 cb = __ldcg(crow + 1), cd = __ldcg(crow + 2);  // (flags, nsteps, spec, tuse), (sidx, len, ebase, cur)
-                    step = ((cb.z >> 8) & 3) == OP_STEP;
-                    if (step) {
-                        const float4 *ep = reinterpret_cast<const float4 *>(p.E + (size_t)cb.w * kH + nb);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) ev[j] = __ldg(ep + j);
-                        // E is streamed from HBM exactly once per (stream, frame): pull the next frame's 128 bytes into L2 now so
-                        // that the load finds them there when the stream advances
-                        if (cb.w + 1 < cd.z + cd.y) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep + kH / 4));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) ev[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    int2 w[8];
+                    load_words(mt, it, w);
+                    stepm = load_e(w, ev);
                 }
                 pf_ok = false;
                 int n_mt = -1, n_it = 0;
-                int4 ncb = make_int4(0, 0, 0, 0), ncd = make_int4(0, 0, 0, 0);
+                int2 nw[8];
                 {
                     const uint32_t ns = qn % W_Q;
                     if (mbar_test_wait(&sm.q_full[ns], (qn / W_Q) & 1)) { n_mt = sm.q[ns].mt; n_it = sm.q[ns].it; }
-                    if (n_mt >= 0) {
-                        const int4 *crow = reinterpret_cast<const int4 *>(p.ctl + (size_t)(n_it & (W_R - 1)) * p.Mpad + n_mt * W_BM + r_in);
-                        ncb = __ldcg(crow + 1);
-                        ncd = __ldcg(crow + 2);
-                    }
+                    if (n_mt >= 0) load_words(n_mt, n_it, nw);
                 }
                 wait_acc(use);
                 if (etid == 0) WS_TRACE(3);
                 drain_acc();
                 if (n_mt >= 0) {
-                    const bool nstep = ((ncb.z >> 8) & 3) == OP_STEP;
-                    if (nstep) {
-                        const float4 *ep = reinterpret_cast<const float4 *>(p.E + (size_t)ncb.w * kH + nb);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) pf_v[j] = __ldg(ep + j);
-                        if (ncb.w + 1 < ncd.z + ncd.y) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep + kH / 4));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) pf_v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    pf_ok = true; pf_mt = n_mt; pf_it = n_it; pf_spec = nstep ? 1 : 0;
+                    pf_spec = load_e(nw, pf_v);
+                    pf_ok = true; pf_mt = n_mt; pf_it = n_it;
                 }
-                gather_add(reinterpret_cast<float *>(ev));
-                if (step) {
-                    const size_t zo = ((size_t)vcur * p.Mpad + row) * kH + nb;
-                    __nv_bfloat16 *bh = p.zb_hi + zo, *bl = p.zb_lo + zo;
+                {   // gather: hi-part row + lo-part row of each of the item's four columns (conflict-free: bank = column + lane)
+                    const float *srct = ttile + (cgp * 32 + 4 * jj) * T_LD + r0;
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        __align__(16) __nv_bfloat16 vh[8], vl[8];
-                        const float e8[8] = {ev[2 * j8].x, ev[2 * j8].y, ev[2 * j8].z, ev[2 * j8].w,
-                                             ev[2 * j8 + 1].x, ev[2 * j8 + 1].y, ev[2 * j8 + 1].z, ev[2 * j8 + 1].w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float v = e8[j];
-                            split_bf16(p.relu ? fmaxf(v, 0.f) : ftanh(v), vh[j], vl[j]);
-                        }
-                        reinterpret_cast<uint4 *>(bh)[j8] = *reinterpret_cast<uint4 *>(vh);
-                        reinterpret_cast<uint4 *>(bl)[j8] = *reinterpret_cast<uint4 *>(vl);
+                    for (int s8 = 0; s8 < 8; ++s8) {
+                        const float *t = srct + 4 * s8;
+                        ev[s8].x += t[0] + t[W_SL * T_LD];
+                        ev[s8].y += t[T_LD] + t[(W_SL + 1) * T_LD];
+                        ev[s8].z += t[2 * T_LD] + t[(W_SL + 2) * T_LD];
+                        ev[s8].w += t[3 * T_LD] + t[(W_SL + 3) * T_LD];
                     }
+                    named_bar_sync(2, W_EPI_THREADS);  // the tile is free for the next unit
+                }
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8) {
+                    if (!((stepm >> s8) & 1)) continue;
+                    const size_t zo = ((size_t)vcur * p.Mpad + mt * W_BM + r0 + 4 * s8) * kH + nb + 4 * jj;
+                    const float e4[4] = {ev[s8].x, ev[s8].y, ev[s8].z, ev[s8].w};
+                    __align__(8) __nv_bfloat16 vh[4], vl[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) split_bf16(p.relu ? fmaxf(e4[j], 0.f) : ftanh(e4[j]), vh[j], vl[j]);
+                    *reinterpret_cast<uint2 *>(p.zb_hi + zo) = *reinterpret_cast<uint2 *>(vh);
+                    *reinterpret_cast<uint2 *>(p.zb_lo + zo) = *reinterpret_cast<uint2 *>(vl);
                 }
                 if (etid == 0) { WS_TRACE(5); WS_TRACE3(2); }
                 mbar_arrive(&sm.sig_full[(tile - 1) % W_Q]);
@@ -1287,9 +1337,10 @@ WsPlan ws_plan_lanes(const int32_t *lens, const int *eoff, int B, int4 *rowinfo)
     for (int k = 0; k < nz; ++k) rowinfo[k] = make_int4(idx[k], lens[idx[k]], eoff[idx[k]], 0);
     for (int k = nz; k < B; ++k) rowinfo[k] = make_int4(0, 0, 0, 0);
     const int mt_max = std::max(1, std::min(W_MAX_MT, (nz + W_BM - 1) / W_BM));
-    // profiles/r2_ws_trace.log: chain latency of a step 35 us alone, 41 us among other M-tiles; unit time 6.7 us, 7.2 us when
-    // speculating.  Tokens per frame are not known in advance: 0.2 on average, 0.45 for the stream that ends last.
-    constexpr double kChainUs = 41.0, kUnitUs = 6.7, kUnitSpecUs = 7.2, kTokMean = 0.2, kTokWorst = 0.45;
+    // profiles/r2_ws_trace_pair.log: chain latency of a step 36 us alone, 47 us among other M-tiles (two ticks of an M-tile share
+    // it when speculating); unit time 5.8 us, 6.0 us when speculating.  Tokens per frame are not known in advance: 0.2 on
+    // average, 0.45 for the stream that ends last.
+    constexpr double kChainUs = 47.0, kUnitUs = 5.8, kUnitSpecUs = 6.0, kTokMean = 0.2, kTokWorst = 0.45;
     constexpr int kSwitchTicks = 3;  // end seen, next stream taken off the queue, state loaded
     WsPlan plan;
     double best = 1e300;
@@ -1308,6 +1359,11 @@ WsPlan ws_plan_lanes(const int32_t *lens, const int *eoff, int B, int4 *rowinfo)
         if (*f) plan.MT = std::max(1, std::min(mt_max, atoi(f)));  // A/B timing
     plan.Mpad = plan.MT * W_BM;
     plan.n_streams = nz;
+    {
+        long long er = 0;
+        for (int i = 0; i < B; ++i) er = std::max(er, (long long)eoff[i] + std::max(lens[i], 0));
+        plan.e_rows = (int)er;
+    }
     return plan;
 }
 
@@ -1328,6 +1384,8 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, const WsPlan &plan, 
     const size_t oh0f = take(4 * VMH), oh1f = take(4 * VMH), oc0 = take(4 * VMH), oc1 = take(4 * VMH);
     const size_t opart = take(sizeof(float) * 2 * (size_t)MT * W_NG * 2 * W_BM * 32);  // by tick parity
     const size_t opresave = take(sizeof(float4) * 2 * (size_t)MT * W_NG * 8 * W_EPI_THREADS);
+    const size_t og0c = take(sizeof(float4) * (size_t)MT * W_NG * 2 * 8 * W_BM);
+    const size_t og0t = take(sizeof(int) * (size_t)MT * W_NG * 2 * W_BM);
     const size_t oamax = take(sizeof(unsigned long long) * W_R * (size_t)Mpad);
     const size_t octl = take(sizeof(WCtl) * W_R * (size_t)Mpad);  // a ring by tick
     const size_t n_cnt = 6 * (size_t)MT + (size_t)MT * W_NG + (size_t)MT * W_R + 8;  // ... + fail_count, live_tiles, q_head
@@ -1340,6 +1398,7 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, const WsPlan &plan, 
     if (MT < 1 || MT > W_MAX_MT || !w || !w->ws_ready) return cudaErrorInvalidValue;
     cudaError_t e;
     if ((e = cudaMemsetAsync(work + ocnt, 0, sizeof(int) * n_cnt, c->stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(work + og0t, 0xFF, sizeof(int) * (size_t)MT * W_NG * 2 * W_BM, c->stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(work + oamax, 0, sizeof(unsigned long long) * W_R * (size_t)Mpad, c->stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(work + oh0h, 0, oact_end - oh0h, c->stream)) != cudaSuccess) return e;  // padding rows feed the MMA too
 
@@ -1361,11 +1420,14 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, const WsPlan &plan, 
     p.g_whh0_hi = w->whh0_hi; p.g_whh0_lo = w->whh0_lo; p.g_w1_hi = w->w1_hi; p.g_w1_lo = w->w1_lo;
     p.g_wp_hi = w->wp_hi; p.g_wp_lo = w->wp_lo; p.g_wo_hi = w->wo_hi; p.g_wo_lo = w->wo_lo;
     p.B = B; p.Mpad = Mpad; p.MT = MT; p.T = T > 0 ? T : 1;
+    p.e_rows = plan.e_rows;
     p.slots = slots_dev; p.rowinfo = rowinfo_dev; p.n_streams = plan.n_streams;
     p.h0f = reinterpret_cast<float *>(work + oh0f); p.h1f = reinterpret_cast<float *>(work + oh1f);
     p.c0 = reinterpret_cast<float *>(work + oc0); p.c1 = reinterpret_cast<float *>(work + oc1);
     p.part = reinterpret_cast<float *>(work + opart);
     p.presave = reinterpret_cast<float4 *>(work + opresave);
+    p.g0c = reinterpret_cast<float4 *>(work + og0c);
+    p.g0c_tok = reinterpret_cast<int *>(work + og0t);
     p.amax = reinterpret_cast<unsigned long long *>(work + oamax);
     p.ctl = reinterpret_cast<WCtl *>(work + octl);
     int *cnt = reinterpret_cast<int *>(work + ocnt);

@@ -29,7 +29,10 @@ for _ in range(2):
 torch.cuda.synchronize()
 tr = ctx.debug_ws_trace(512).astype(np.float64)  # [its][8][32]
 nt_ = int((tr[8, :, 0] > 0).sum())
-names = ["unit popped", "control row here", "partner flag seen", "partial sums + cell state here", "accumulator full", "drained",
+role = int(os.environ.get("AMIRA_WS_TRACE_ROLE", "1"))
+names0 = ["unit popped", "accumulator full", "drained", "decisions here", "loads here + gathered", "tile released", "-",
+          "arithmetic done, stores issued", "signal thread: all arrived", "signal thread: published"]
+names = names0 if role == 0 else ["unit popped", "control row here", "partner flag seen", "partial sums + cell state here", "accumulator full", "drained",
          "gathered", "arithmetic done, stores issued", "signal thread: all arrived", "signal thread: published"]
 lo, hi = 50, 400
 print("M-tiles:", nt_)
