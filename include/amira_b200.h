@@ -62,7 +62,7 @@ typedef struct {
     int32_t joint_activation;     /* 0 = tanh (north_star), 1 = relu */
     int32_t decode_engine;        /* 0 = auto (4); 1 = fp32 CUDA-core persistent kernel (numerics anchor); 4 = tcgen05 split-bf16
                                    * weight-stationary dataflow kernel (one 64-feature weight slice resident in the tensor
-                                   * memory of each of 147 SMs).  Other values are rejected. */
+                                   * memory of each SM: 148 CTAs in pairs, cta_group::2 MMAs).  Other values are rejected. */
     int32_t max_streams;          /* resident stream-state slots for the WebSocket path (default 1024) */
     int32_t reserved;
 } amira_config;
