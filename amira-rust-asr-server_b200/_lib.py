@@ -50,7 +50,7 @@ class AmiraError(RuntimeError):
 class _Config(C.Structure):
     _fields_ = [("device_id", C.c_int32), ("max_symbols_per_step", C.c_int32), ("max_total_tokens", C.c_int32),
                 ("blank_id", C.c_int32), ("joint_activation", C.c_int32), ("decode_engine", C.c_int32),
-                ("max_streams", C.c_int32), ("reserved", C.c_int32)]
+                ("max_streams", C.c_int32), ("decode_rule", C.c_int32)]
 
 
 _lib = None
@@ -241,13 +241,13 @@ class Context:
 
     def __init__(self, device_id: int = 0, max_symbols_per_step: int = MAX_SYMBOLS_PER_STEP,
                  max_total_tokens: int = MAX_TOTAL_TOKENS, blank_id: int = BLANK_ID, joint_activation: str = "tanh",
-                 decode_engine: int = 0, max_streams: int = 1024):
+                 decode_engine: int = 0, max_streams: int = 1024, decode_rule: int = 0):
         self._L = load_library()
         cfg = _Config()
         self._L.amira_config_default(C.byref(cfg))
         cfg.device_id, cfg.max_symbols_per_step, cfg.max_total_tokens = device_id, max_symbols_per_step, max_total_tokens
         cfg.blank_id, cfg.joint_activation = blank_id, 1 if joint_activation == "relu" else 0
-        cfg.decode_engine, cfg.max_streams = decode_engine, max_streams
+        cfg.decode_engine, cfg.max_streams, cfg.decode_rule = decode_engine, max_streams, decode_rule
         self.max_total_tokens = max_total_tokens
         self._h = C.c_void_p()
         rc = self._L.amira_ctx_create(C.byref(cfg), C.byref(self._h))

@@ -188,7 +188,8 @@ int32_t amira_ctx_create(const amira_config *cfg, amira_ctx **out) {
     amira_config_default(&dflt);
     if (!cfg) cfg = &dflt;
     if (cfg->max_symbols_per_step <= 0 || cfg->max_total_tokens <= 0 || cfg->blank_id < 0 || cfg->blank_id >= kV ||
-        cfg->max_streams < 0 || cfg->joint_activation < 0 || cfg->joint_activation > 1 || (cfg->decode_engine != 0 && cfg->decode_engine != 1 && cfg->decode_engine != 4))
+        cfg->max_streams < 0 || cfg->joint_activation < 0 || cfg->joint_activation > 1 || (cfg->decode_engine != 0 && cfg->decode_engine != 1 && cfg->decode_engine != 4) ||
+        cfg->decode_rule < 0 || cfg->decode_rule > (AMIRA_RULE_STATE_ON_NONBLANK | AMIRA_RULE_TDT_DURATIONS) || (cfg->decode_rule != 0 && cfg->decode_engine == 4))
         return fail(nullptr, AMIRA_ERR_INVALID_VALUE, "invalid amira_config");
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -704,7 +705,8 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
     }
     unmark(B);
     if (enc_offsets) {
-        if (c->cfg.decode_engine == 1) return fail(c, AMIRA_ERR_INVALID_VALUE, "packed encoder outputs need a tcgen05 decode engine");
+        if (c->cfg.decode_engine == 1 || c->cfg.decode_rule != 0)
+            return fail(c, AMIRA_ERR_INVALID_VALUE, "packed encoder outputs need a tcgen05 decode engine (and the reference's decode rule)");
         if (enc_offsets[0] < 0) return fail(c, AMIRA_ERR_INVALID_VALUE, "enc_offsets must be non-negative");
         for (int b = 0; b < B; ++b)
             if (enc_offsets[b + 1] - enc_offsets[b] < (int64_t)kEnc * h_lens[b])
@@ -738,7 +740,8 @@ static int32_t greedy_common(amira_ctx *c, const float *encoder_outputs, int32_t
     int32_t *last_dev = nullptr;
     bool last_h = false;
     if (last_tokens) {
-        if (c->cfg.decode_engine == 1) return fail(c, AMIRA_ERR_INVALID_VALUE, "the resume form needs the tcgen05 decode engine");
+        if (c->cfg.decode_engine == 1 || c->cfg.decode_rule != 0)
+            return fail(c, AMIRA_ERR_INVALID_VALUE, "the resume form needs the tcgen05 decode engine (and the reference's decode rule)");
         CK(stage_out<int32_t>(c, 6, last_tokens, (size_t)B, &last_dev, &last_h), "last_tokens staging");
         if (last_h) {
             for (int b = 0; b < B; ++b)

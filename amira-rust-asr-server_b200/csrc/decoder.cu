@@ -55,7 +55,7 @@ struct DecArgs {
     const int *lens;      // [B]
     const int *slots;     // nullable
     float *h0, *h1;       // [2][B][640] ping-pong by row parity
-    float *c0, *c1;       // [B][640]
+    float *c0, *c1;       // [2][B][640] ping-pong by row parity, like h0 / h1 (a step that is not carried leaves no trace)
     float *z;             // [B][640]
     float *pval;          // [B][NT_OUT]
     int *pidx;            // [B][NT_OUT]
@@ -64,6 +64,8 @@ struct DecArgs {
     float *s1, *s2;       // in/out states (nullable); batch layout [2][B][640] or slot layout [slot][2][640]
     int *tokens, *ntok, *nsteps;
     int max_sym, max_total, blank, relu;
+    int rule;             // AMIRA_RULE_* bits (0 = the reference's literal loop)
+    float *dur;           // [B][8] duration logits (outputs blank+1 .. 1029) of the last step, TDT reading only
 };
 
 struct TileSmem {
@@ -120,10 +122,10 @@ __device__ __forceinline__ void gemm_tile(TileSmem &s, int nseg, const float *__
 }
 
 // LSTM cell update for one (row, unit): gates pre-activation in a[4] (i, f, g, o)
-__device__ __forceinline__ void lstm_cell(const float (&a)[4], float *c_ptr, float *h_ptr) {
+__device__ __forceinline__ void lstm_cell(const float (&a)[4], const float *c_old, float *c_new, float *h_ptr) {
     const float ig = sigmoidf_(a[0]), fg = sigmoidf_(a[1]), gg = tanhf(a[2]), og = sigmoidf_(a[3]);
-    const float cn = fg * (*c_ptr) + ig * gg;
-    *c_ptr = cn;
+    const float cn = fg * (*c_old) + ig * gg;
+    *c_new = cn;
     *h_ptr = og * tanhf(cn);
 }
 
@@ -178,20 +180,36 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) greedy_persistent_kernel(DecAr
                             const float v = a.pval[(size_t)row * NT_OUT + q];
                             if (v > bv) { bv = v; bi = a.pidx[(size_t)row * NT_OUT + q]; }
                         }
+                        // One rule set for the reference's loop and the two non-reference variants of SURVEY 8(f4) (a.rule):
+                        // literal (rule 0): state carried unconditionally, blank advances one frame; AMIRA_RULE_STATE_ON_NONBLANK: a
+                        // blank leaves the prediction net where it was (the step's results stay in the other parity and are
+                        // overwritten); AMIRA_RULE_TDT_DURATIONS: the token is the first max over outputs [0, blank], the frame
+                        // advance the first max over the duration outputs (blank with duration 0 advances one frame).
+                        const bool is_blank = bi == a.blank;
                         c.nsteps += 1;
-                        c.par ^= 1;      // state carried unconditionally (decoder_optimized.rs:154)
+                        if (!(is_blank && (a.rule & AMIRA_RULE_STATE_ON_NONBLANK))) c.par ^= 1;  // decoder_optimized.rs:154 when literal
                         c.sym += 1;      // :133
+                        int skip = -1;
+                        if (a.rule & AMIRA_RULE_TDT_DURATIONS) {
+                            const float *dv = a.dur + (size_t)row * 8;
+                            float best = dv[0];
+                            skip = 0;
+                            for (int q = 1; q < kV - a.blank - 1 && q < 8; ++q)
+                                if (dv[q] > best) { best = dv[q]; skip = q; }
+                            if (is_blank && skip == 0) skip = 1;
+                        }
                         const int len = a.lens[row];
-                        if (bi == a.blank) {                        // :171-173
-                            c.t += 1; c.sym = 0;
-                            if (c.t >= len) c.active = 0;
-                        } else {
+                        if (!is_blank) {
                             if (nt == 0) a.tokens[(size_t)row * a.max_total + c.total] = bi;   // :176
                             c.total += 1;
                             c.last = bi;
                             if (c.total >= a.max_total) c.active = 0;                           // :179-188
-                            else if (c.sym >= a.max_sym) {                                      // :133-137
-                                c.t += 1; c.sym = 0;
+                        }
+                        if (c.active) {
+                            int adv = skip >= 0 ? skip : (is_blank ? 1 : 0);                    // :171-173
+                            if (adv == 0 && c.sym >= a.max_sym) adv = 1;                        // :133-137
+                            if (adv) {
+                                c.t += adv; c.sym = 0;
                                 if (c.t >= len) c.active = 0;
                             }
                             // an id outside the embedding table fails the next step call ("Decode step failed", :148-152)
@@ -226,7 +244,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) greedy_persistent_kernel(DecAr
                 if (row < B && c.active) {
                     const float4 g = __ldg(reinterpret_cast<const float4 *>(a.w.g0p + (size_t)c.last * kG + nt * TN + tx * 4));
                     const float pre[4] = {acc[i][0] + g.x, acc[i][1] + g.y, acc[i][2] + g.z, acc[i][3] + g.w};
-                    lstm_cell(pre, a.c0 + (size_t)row * kH + u, a.h0 + (size_t)(c.par ^ 1) * BH + (size_t)row * kH + u);
+                    lstm_cell(pre, a.c0 + (size_t)c.par * BH + (size_t)row * kH + u, a.c0 + (size_t)(c.par ^ 1) * BH + (size_t)row * kH + u,
+                              a.h0 + (size_t)(c.par ^ 1) * BH + (size_t)row * kH + u);
                 }
             }
         }
@@ -262,7 +281,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) greedy_persistent_kernel(DecAr
                 const Ctl c = s.ctl[r];
                 if (row < B && c.active) {
                     const float pre[4] = {acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w};
-                    lstm_cell(pre, a.c1 + (size_t)row * kH + u, a.h1 + (size_t)(c.par ^ 1) * BH + (size_t)row * kH + u);
+                    lstm_cell(pre, a.c1 + (size_t)c.par * BH + (size_t)row * kH + u, a.c1 + (size_t)(c.par ^ 1) * BH + (size_t)row * kH + u,
+                              a.h1 + (size_t)(c.par ^ 1) * BH + (size_t)row * kH + u);
                 }
             }
         }
@@ -326,6 +346,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) greedy_persistent_kernel(DecAr
             gemm_tile(s, 1, a.w.woutp + (size_t)nt * TN * kH, kH, acc);
             const float4 bb = __ldg(reinterpret_cast<const float4 *>(a.w.boutp + nt * TN + tx * 4));
             const float bbv[4] = {bb.x, bb.y, bb.z, bb.w};
+            const int n_tok = (a.rule & AMIRA_RULE_TDT_DURATIONS) ? a.blank + 1 : kV;  // outputs that compete for the token
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float bv = -INFINITY;
@@ -335,7 +356,12 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) greedy_persistent_kernel(DecAr
                     const int n = nt * TN + tx * 4 + j;
                     const float v = acc[i][j] + bbv[j];
                     // zero_copy.rs:190-232: seed (logits[0], 0), replace on strict '>': NaN is returned only from index 0
-                    if (n < kV && (n == 0 || v > bv || (bi == 0x7fffffff && v == v))) { bv = v; bi = n; }
+                    if (n < n_tok && (n == 0 || v > bv || (bi == 0x7fffffff && v == v))) { bv = v; bi = n; }
+                    // TDT reading: the outputs behind blank are duration logits, kept for the control update
+                    if (n >= n_tok && n < kV && n - n_tok < 8) {
+                        const int r_ = ty * 4 + i, row_ = mt * TM + r_;
+                        if (row_ < B && s.ctl[r_].active) a.dur[(size_t)row_ * 8 + (n - n_tok)] = v;
+                    }
                 }
 #pragma unroll
                 for (int o = 8; o >= 1; o >>= 1) {
@@ -367,8 +393,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) greedy_persistent_kernel(DecAr
             const int par = fin[b].par;
             a.s1[state_off(a, 0, b) + j] = a.h0[(size_t)par * BH + i];
             a.s1[state_off(a, 1, b) + j] = a.h1[(size_t)par * BH + i];
-            a.s2[state_off(a, 0, b) + j] = a.c0[i];
-            a.s2[state_off(a, 1, b) + j] = a.c1[i];
+            a.s2[state_off(a, 0, b) + j] = a.c0[(size_t)par * BH + i];
+            a.s2[state_off(a, 1, b) + j] = a.c1[(size_t)par * BH + i];
         }
     }
 }
@@ -534,7 +560,7 @@ __global__ void __launch_bounds__(DEC_THREADS) lstm_step_kernel(StepArgs q) {
             add[0] = g.x; add[1] = g.y; add[2] = g.z; add[3] = g.w;
         }
         const float pre[4] = {acc[i][0] + add[0], acc[i][1] + add[1], acc[i][2] + add[2], acc[i][3] + add[3]};
-        lstm_cell(pre, q.c + (size_t)row * kH + un, hn);
+        lstm_cell(pre, q.c + (size_t)row * kH + un, q.c + (size_t)row * kH + un, hn);
     }
 }
 
@@ -646,7 +672,8 @@ cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, const float *enc_
                                  int32_t *tokens_dev, int32_t *ntok_dev, int32_t *nsteps_dev, const int64_t *enc_off_host, int32_t *last_dev) {
     // decode_engine: 1 = fp32 CUDA-core persistent kernel (this file, the numerics anchor); 0 = auto = 4 = tcgen05 split-bf16
     // weight-stationary dataflow kernel (decoder_ws.cu, launched from decoder_tc.cu)
-    if (c->cfg.decode_engine != 1)
+    // The non-reference decode rules of SURVEY 8(f4) (canonical state rule, TDT durations) run on the fp32 engine.
+    if (c->cfg.decode_engine != 1 && c->cfg.decode_rule == 0)
         return launch_greedy_decode_tc(c, enc_dev, enc_host, B, T, lens_dev, lens_host, slots_dev, s1_dev, s2_dev, tokens_dev, ntok_dev,
                                        nsteps_dev, enc_off_host, last_dev);
     if (enc_off_host || last_dev) return cudaErrorNotSupported;  // packed encoder outputs: tcgen05 engines only
@@ -663,7 +690,8 @@ cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, const float *enc_
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
     const size_t oE = take(sizeof(float) * (size_t)B * Tq * kH);
     const size_t oh0 = take(sizeof(float) * 2 * BH), oh1 = take(sizeof(float) * 2 * BH);
-    const size_t oc0 = take(sizeof(float) * BH), oc1 = take(sizeof(float) * BH), oz = take(sizeof(float) * BH);
+    const size_t oc0 = take(sizeof(float) * 2 * BH), oc1 = take(sizeof(float) * 2 * BH), oz = take(sizeof(float) * BH);
+    const size_t odur = take(sizeof(float) * 8 * (size_t)B);
     const size_t opv = take(sizeof(float) * (size_t)B * NT_OUT), opi = take(sizeof(int) * (size_t)B * NT_OUT);
     const size_t octl = take(sizeof(Ctl) * 2 * (size_t)B), oact = take(sizeof(int) * 4);
     cudaError_t e;
@@ -696,6 +724,8 @@ cudaError_t launch_greedy_decode(Ctx *c, const float *enc_dev, const float *enc_
     a.tokens = tokens_dev; a.ntok = ntok_dev; a.nsteps = nsteps_dev;
     a.max_sym = c->cfg.max_symbols_per_step; a.max_total = c->cfg.max_total_tokens; a.blank = c->cfg.blank_id;
     a.relu = c->cfg.joint_activation;
+    a.rule = c->cfg.decode_rule;
+    a.dur = reinterpret_cast<float *>(base + odur);
 
     const int MT = (B + TM - 1) / TM;
     int grid = std::min(d->coop_blocks_per_sm * c->sm_count, MT * NT_GATES);

@@ -64,8 +64,14 @@ typedef struct {
                                    * weight-stationary dataflow kernel (one 64-feature weight slice resident in the tensor
                                    * memory of each SM: 148 CTAs in pairs, cta_group::2 MMAs).  Other values are rejected. */
     int32_t max_streams;          /* resident stream-state slots for the WebSocket path (default 1024) */
-    int32_t reserved;
+    int32_t decode_rule;          /* 0 = the reference's literal loop (src/asr/decoder_optimized.rs:54-200: state carried unconditionally,
+                                   * flat argmax over all 1030 outputs).  AMIRA_RULE_* bits select the NON-REFERENCE variants of
+                                   * SURVEY 8(f4), what the model family was trained for: they run on the fp32 engine (decode_engine
+                                   * 0 or 1; 4 is rejected) through amira_greedy_decode / amira_stream_decode. */
 } amira_config;
+#define AMIRA_RULE_STATE_ON_NONBLANK 1 /* canonical RNN-T: a blank step leaves the prediction-net state where it was */
+#define AMIRA_RULE_TDT_DURATIONS 2     /* outputs 1025..1029 are duration logits: token = first max over [0, blank], frame advance
+                                        * = first max over the durations (0 = another symbol on this frame; blank advances >= 1) */
 
 /* replaces get_cuda_device_count_ffi (src/cuda/cuda_helper.cu:23-30, src/cuda/mod.rs:372) */
 int32_t amira_device_count(int32_t *count);

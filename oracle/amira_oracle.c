@@ -395,13 +395,28 @@ int orc_greedy_decode(const float *enc, size_t enc_len, int64_t encoded_len, flo
                 float kv;
                 orc_argmax_zero_copy(logits, (size_t)(nl < n_tok ? nl : n_tok), &k, &kv);
                 int skip = -1;
+                float mg = INFINITY;  /* smallest top-1 / top-2 margin of the decisions taken at this step */
+                {
+                    const int nk = nl < n_tok ? nl : n_tok;
+                    float second = -INFINITY;
+                    for (int i = 0; i < nk; ++i)
+                        if ((size_t)i != k && logits[i] > second) second = logits[i];
+                    if (nk > 1) mg = kv - second;
+                }
                 if (cfg->tdt_durations && nl >= ORC_VOCAB) {
                     size_t d;
                     float dv;
-                    orc_argmax_zero_copy(logits + cfg->blank + 1, (size_t)(ORC_VOCAB - cfg->blank - 1), &d, &dv);
+                    const int nd = ORC_VOCAB - cfg->blank - 1;
+                    orc_argmax_zero_copy(logits + cfg->blank + 1, (size_t)nd, &d, &dv);
+                    float second = -INFINITY;
+                    for (int i = 0; i < nd; ++i)
+                        if ((size_t)i != d && logits[cfg->blank + 1 + i] > second) second = logits[cfg->blank + 1 + i];
+                    if (nd > 1 && dv - second < mg) mg = dv - second;
                     skip = (int)d;
                     if ((int32_t)k == cfg->blank && skip == 0) skip = 1;
                 }
+                if (mg < st.min_margin) st.min_margin = mg;
+                if (margins && st.n_steps <= margins_cap) margins[st.n_steps - 1] = mg;
                 const int is_blank = (int32_t)k == cfg->blank;
                 if (is_blank && cfg->state_update_on_nonblank_only) {  /* canonical: a blank leaves the prediction net where it was */
                     memcpy(states_1, keep1, sizeof(keep1));

@@ -51,7 +51,7 @@ impl Ctx {
     pub fn new(device_id: i32, limits: DecodeLimits, max_streams: usize) -> B200Result<Self> {
         let mut cfg = AmiraConfig {
             device_id: 0, max_symbols_per_step: 0, max_total_tokens: 0, blank_id: 0, joint_activation: 0, decode_engine: 0,
-            max_streams: 0, reserved: 0,
+            max_streams: 0, decode_rule: 0,
         };
         unsafe { amira_config_default(&mut cfg) };
         cfg.device_id = device_id;

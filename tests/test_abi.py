@@ -65,3 +65,13 @@ def test_status_codes_keep_reference_meaning():
     for name, val in (("AMIRA_VOCAB_SIZE", 1030), ("AMIRA_BLANK_ID", 1024), ("AMIRA_MAX_SYMBOLS_PER_STEP", 30),
                       ("AMIRA_MAX_TOTAL_TOKENS", 200), ("AMIRA_STATE_SIZE", 640)):  # src/constants.rs:133-137
         assert re.search(rf"#define {name} {val}\b", src), name
+
+
+def test_decode_rule_is_validated_before_any_device_is_touched():
+    """amira_config.decode_rule (SURVEY 8(f4) variants): unknown bits and the combination with the tcgen05 engine are rejected
+    with AMIRA_ERR_INVALID_VALUE — on a box without a GPU too, because the configuration is checked first."""
+    import amira_b200 as A
+    for kw in (dict(decode_rule=4), dict(decode_rule=-1), dict(decode_engine=4, decode_rule=1)):
+        with pytest.raises(A.AmiraError) as e:
+            A.Context(device_id=0, **kw)
+        assert e.value.code == 1, kw

@@ -47,7 +47,7 @@ def test_struct_layouts_match():
     rust = open(os.path.join(ROOT, "rust", "amira-b200-sys", "src", "lib.rs")).read()
     cfg = re.search(r"pub struct AmiraConfig \{(.*?)\}", rust, flags=re.S).group(1)
     assert re.findall(r"pub (\w+): i32", cfg) == ["device_id", "max_symbols_per_step", "max_total_tokens", "blank_id", "joint_activation",
-                                                  "decode_engine", "max_streams", "reserved"]
+                                                  "decode_engine", "max_streams", "decode_rule"]
     tr = re.search(r"pub struct AmiraTranscription \{(.*?)\}", rust, flags=re.S).group(1)
     assert re.findall(r"pub (\w+): (\w+)", tr) == [("audio_length_samples", "i64"), ("features_length", "i64"), ("encoded_length", "i64"),
                                                    ("n_tokens", "i32"), ("text_len", "i32")]
