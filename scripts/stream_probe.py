@@ -29,4 +29,4 @@ print("steps max/mean", int(nst_d.max()), float(nst_d.float().mean()))
 ctx.profile(True)
 ctx.stream_decode_raw(slots, enc_d.data_ptr(), T, None, tok_d.data_ptr(), ntok_d.data_ptr(), nst_d.data_ptr())
 ctx.preprocess_pcm16_raw(pcm_d.data_ptr(), offsets, n, feats_d.data_ptr(), 32, flens)
-print({k: ctx.kernel_ms(k) for k in ("fe_logmel", "fe_normalize", "enc_proj", "greedy")})
+print({k: ctx.kernel_ms(k) for k in ("fe_logmel", "enc_proj", "greedy")})

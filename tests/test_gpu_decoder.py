@@ -375,3 +375,41 @@ def test_watchdog_trap_is_reported_and_contained(tmp_path):
     assert after.returncode == 0, after.stderr[-1500:]
     tok = lambda out: [l for l in out.splitlines() if l.startswith("TOKENS")][0]
     assert tok(after.stdout) == tok(ref.stdout) == tok(r.stdout)
+
+
+def test_literal_refeed_loop_over_the_contract_op(amira, oracle):
+    """The reference's loop AS WRITTEN re-sends [blank] ++ tokens of the call on every step and takes the argmax over the whole
+    flattened [U,1030] output (src/asr/decoder_optimized.rs:140-163, src/triton/model.rs:713; SURVEY finding 5).  Here the
+    oracle's restatement of that loop drives the GPU contract op (amira_decoder_joint, one call per step, [1,1024,1] frame, U
+    targets, carried state — exactly the RPC of src/asr/pipeline.rs:323-348) and must produce what it produces around the
+    CPU model: same tokens (flat indices included), same step count, same failure behaviour."""
+    blob = calibrated_weights(oracle, blank_bias=1.0)  # a blank-shy model: the refeed rows get to compete
+    model = oracle.Model(blob=blob)
+    rng = np.random.default_rng(21)
+    with amira.Context(device_id=0) as c:
+        c.load_weights(blob)
+        calls = []
+
+        def gpu_step(frame, targets, s1, s2):
+            calls.append(len(targets))
+            try:
+                out, _, st = c.decoder_joint(frame.reshape(1, 1024, 1), targets.reshape(1, -1),
+                                             state=amira.DecoderState(s1.reshape(2, 1, 640), s2.reshape(2, 1, 640)))
+            except amira.AmiraError as e:
+                assert e.code == 6  # "Decode step failed": a target outside the embedding table
+                return None
+            return out.reshape(-1), st.states_1.reshape(-1), st.states_2.reshape(-1)
+
+        n_same = n_multi = 0
+        for k in range(6):
+            T = 5
+            enc = (0.5 * rng.standard_normal((1024, T))).astype(np.float32)
+            calls.clear()
+            got = oracle.greedy_decode(enc, T, step=gpu_step, single_step=False)
+            ref = oracle.greedy_decode(enc, T, model, single_step=False)
+            n_multi += max(calls, default=1) > 1
+            if (got.rc, got.tokens, got.n_steps) == (ref.rc, ref.tokens, ref.n_steps):
+                n_same += 1
+            else:
+                assert ref.margins.size and ref.margins.min() < NEAR_TIE, (k, got.tokens, ref.tokens)
+        assert n_same >= 5 and n_multi >= 1  # at least one utterance re-fed U > 1 targets
