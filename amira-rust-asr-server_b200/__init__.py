@@ -17,10 +17,10 @@ from __future__ import annotations
 from ._lib import (AMIRA_N_PARAMS, BLANK_ID, ENC_DIM, MAX_SYMBOLS_PER_STEP, MAX_TOTAL_TOKENS, N_MELS, STATE_SIZE,
                    VOCAB_SIZE, AmiraError, Context, DecoderState, EXPORTS, device_count, device_reset, features_len, lib_path,
                    load_library, random_weights, synthetic_weights, blob_views, SYNTH_SCALE, SYNTH_BLANK_BIAS)
-from .pipeline import B200AsrPipeline, Batcher, Transcription, Vocabulary, shard_utterances
+from .pipeline import B200AsrPipeline, Batcher, NativeEncoder, Transcription, Vocabulary, shard_utterances
 from . import streaming
 from .streaming import IncrementalAsr, StreamGroup
 
-__all__ = ["AMIRA_N_PARAMS", "BLANK_ID", "ENC_DIM", "MAX_SYMBOLS_PER_STEP", "MAX_TOTAL_TOKENS", "N_MELS", "STATE_SIZE",
+__all__ = ["NativeEncoder", "AMIRA_N_PARAMS", "BLANK_ID", "ENC_DIM", "MAX_SYMBOLS_PER_STEP", "MAX_TOTAL_TOKENS", "N_MELS", "STATE_SIZE",
            "VOCAB_SIZE", "AmiraError", "Context", "DecoderState", "EXPORTS", "device_count", "device_reset", "features_len", "lib_path",
            "load_library", "random_weights", "synthetic_weights", "blob_views", "SYNTH_SCALE", "SYNTH_BLANK_BIAS", "B200AsrPipeline", "Batcher", "Transcription", "Vocabulary", "shard_utterances", "streaming", "IncrementalAsr", "StreamGroup"]

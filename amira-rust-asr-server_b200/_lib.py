@@ -429,6 +429,11 @@ class Context:
         self._check(self._L.amira_preprocess_pcm16_packed(self._h, _ptr(pcm_ptr), _ptr(offsets), B, _ptr(features_ptr),
                                                           _ptr(feat_offsets), _ptr(lens_out)))
 
+    def logmel_pcm16_packed_raw(self, pcm_ptr: int, offsets: np.ndarray, B: int, features_ptr: int, feat_offsets: np.ndarray,
+                                lens_out: np.ndarray):
+        self._check(self._L.amira_logmel_pcm16_packed(self._h, _ptr(pcm_ptr), _ptr(offsets), B, _ptr(features_ptr),
+                                                      _ptr(feat_offsets), _ptr(lens_out)))
+
     def greedy_decode_packed_raw(self, enc_ptr: int, enc_offsets: np.ndarray, B: int, lens: np.ndarray, tokens_ptr: int, ntok_ptr: int,
                                  nsteps_ptr: int | None = None, s1_ptr: int | None = None, s2_ptr: int | None = None):
         self._check(self._L.amira_greedy_decode_packed(self._h, _ptr(enc_ptr), _ptr(enc_offsets), B, _ptr(lens), _ptr(s1_ptr),

@@ -11,11 +11,17 @@
 // Rust semantics kept literally: str::len() is bytes while chars() are Unicode scalars; all float arithmetic is f32;
 // usize arithmetic wraps as in a release build (window_sequence's short-last-window branch, audio.rs:112-115).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <cuda_runtime_api.h>
 
 #include "host_common.h"
 
@@ -259,6 +265,7 @@ struct Session {
                                       // per-feature statistics over the st_count frames emitted so far
     int64_t st_count = 0;
     int32_t last_token = AMIRA_BLANK_ID;
+    bool transcript_stale = false;    // incremental mode: `transcript` is rebuilt from token_ids when somebody asks for it
     void reset_state() { s1.assign(2 * AMIRA_STATE_SIZE, 0.0f); s2.assign(2 * AMIRA_STATE_SIZE, 0.0f); }
     void clear() {  // incremental.rs:99-103
         audio.clear();
@@ -272,6 +279,7 @@ struct Session {
         st_mean.assign(AMIRA_N_MELS, 0.0);
         st_m2.assign(AMIRA_N_MELS, 0.0);
         last_token = AMIRA_BLANK_ID;
+        transcript_stale = false;
     }
 };
 
@@ -288,6 +296,57 @@ struct Job {  // one process_stream_samples call of one session
 
 }  // namespace
 
+// Host scratch of the incremental rounds in page-locked memory: the library copies pinned host buffers asynchronously at the
+// link's rate, pageable ones through the driver's bounce buffer (measured on a 1024-stream tick: front end 1.5 -> 0.8 ms, resumed
+// decode 3.9 -> 2.6 ms).  Falls back to pageable memory where cudaMallocHost fails.  Contents survive growth.
+template <class T>
+struct PinVec {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    bool pinned = false;
+    PinVec() = default;
+    PinVec(const PinVec &) = delete;
+    PinVec &operator=(const PinVec &) = delete;
+    ~PinVec() { release(p, pinned); }
+    static void release(T *q, bool pin) {
+        if (!q) return;
+        if (pin) { cudaFreeHost(q); cudaGetLastError(); }
+        else std::free(q);
+    }
+    void resize(size_t m) {
+        if (m > cap) {
+            const size_t want = m + m / 4 + 64;
+            T *q = nullptr;
+            bool pin = cudaMallocHost(reinterpret_cast<void **>(&q), want * sizeof(T)) == cudaSuccess;
+            if (!pin) {
+                cudaGetLastError();
+                q = static_cast<T *>(std::malloc(want * sizeof(T)));
+                if (!q) throw std::bad_alloc();
+            }
+            if (n) std::memcpy(q, p, n * sizeof(T));
+            release(p, pinned);
+            p = q; cap = want; pinned = pin;
+        }
+        n = m;
+    }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    size_t size() const { return n; }
+};
+
+// f(lo, hi) over [0, n) on up to 16 host threads (the sessions of a round are independent); the body must not throw
+template <class F>
+void parallel_for(int n, int min_per_thread, F f) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int T = std::max(1, std::min(std::min(n / std::max(min_per_thread, 1), (int)(hw ? hw : 1)), 16));
+    if (T <= 1) { f(0, n); return; }
+    std::vector<std::thread> th;
+    th.reserve((size_t)T - 1);
+    for (int t = 1; t < T; ++t) th.emplace_back(f, (int)((long long)n * t / T), (int)((long long)n * (t + 1) / T));
+    f(0, (int)((long long)n / T));
+    for (auto &x : th) x.join();
+}
+
 struct amira_stream_group {
     amira_pipeline *p = nullptr;
     std::vector<std::unique_ptr<Session>> sessions;
@@ -295,8 +354,15 @@ struct amira_stream_group {
     std::string err;
     int64_t n_pipeline_calls = 0, n_rounds = 0;
     bool incremental = false;
-    std::vector<int16_t> pcm;       // incremental mode: the segments of one round, back to back
-    std::vector<int32_t> last;
+    // incremental mode: page-locked scratch of a round — the segments back to back, their log-mel blocks, the new frames of every
+    // stream normalised (what the encoder reads), the encoder outputs packed, decoder states [2][B][640] x 2, last tokens, results
+    PinVec<int16_t> pcm;
+    PinVec<float> ifeat, ichunks, ienc, is1, is2;
+    PinVec<int32_t> last, itokens, intok;
+    std::vector<int64_t> coff;
+    // the streams whose decoder state lives in is1 / is2 (row i = resident[i]) instead of their Session: as long as consecutive
+    // rounds list the same streams in the same order the state never moves (1024 streams: 2 x 10.5 MB of memcpy per tick otherwise)
+    std::vector<Session *> resident;
     // batch scratch
     std::vector<float> wave, features, enc, s1, s2;
     std::vector<int64_t> woff, foff, eoff, flens, elens;
@@ -459,6 +525,23 @@ int32_t process_buffered(amira_stream_group *g, const std::vector<Session *> &ac
 // ---- incremental mode (amira_b200.h: amira_stream_group_set_incremental) ----
 constexpr int64_t kHopS = 160, kHalfWin = 200, kCtxHops = 2;  // a frame's window covers +-200 samples around its centre 160 t
 
+// the decoder states that live in the group's batch-layout buffers go back to their sessions
+void flush_resident(amira_stream_group *g) {
+    const size_t B = g->resident.size(), H = AMIRA_STATE_SIZE;
+    for (size_t i = 0; i < B; ++i)
+        for (size_t l = 0; l < 2; ++l) {
+            std::memcpy(g->resident[i]->s1.data() + l * H, g->is1.data() + (l * B + i) * H, sizeof(float) * H);
+            std::memcpy(g->resident[i]->s2.data() + l * H, g->is2.data() + (l * B + i) * H, sizeof(float) * H);
+        }
+    g->resident.clear();
+}
+
+void refresh_transcript(amira_stream_group *g, Session &s) {
+    if (!s.transcript_stale) return;
+    s.transcript = decode_utf8(g->p->vocab.decode(s.token_ids.data(), (int32_t)s.token_ids.size()).c_str());
+    s.transcript_stale = false;
+}
+
 // Frames [t_next, t_end) of every listed session, in one front-end launch, the injected encoder and one resumed decode launch.
 // A session's segment starts at sample 160 A, A = max(0, t_next - 2): local frame t' = t - A.  For A > 0 the local frames 0 and 1
 // see the segment's artificial left edge (reflect padding, missing pre-emphasis partner) and are dropped — t_next - A = 2 is the
@@ -469,6 +552,12 @@ int32_t incremental_round(amira_stream_group *g, const std::vector<Session *> &s
     std::lock_guard<std::mutex> plock(p->mu);
     const int B = (int)ss.size();
     if (B == 0) return AMIRA_OK;
+    static const bool sg_trace = getenv("AMIRA_SG_TRACE") != nullptr;  // debug: wall clock of the phases of a round on stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_0 = now();
+    double t_ph[6] = {0, 0, 0, 0, 0, 0};
+    int ph = 0;
+    auto lap = [&]() { const auto t1 = now(); t_ph[ph++] = std::chrono::duration<double, std::milli>(t1 - t_0).count(); t_0 = t1; };
     g->n_rounds++;
     g->n_pipeline_calls += B;
     std::vector<int64_t> A((size_t)B), nloc((size_t)B), lloc((size_t)B);
@@ -483,89 +572,125 @@ int32_t incremental_round(amira_stream_group *g, const std::vector<Session *> &s
         g->foff[(size_t)i + 1] = g->foff[(size_t)i] + (int64_t)AMIRA_N_MELS * lloc[(size_t)i];
     }
     g->pcm.resize((size_t)std::max<int64_t>(g->woff[(size_t)B], 1));
-    for (int i = 0; i < B; ++i) {
-        const Session &s = *ss[(size_t)i];
-        const int64_t a = kHopS * A[(size_t)i] - s.hist_start;  // >= 0: the history keeps two hops of left context
-        std::memcpy(g->pcm.data() + g->woff[(size_t)i], s.hist.data() + a, sizeof(int16_t) * (size_t)nloc[(size_t)i]);
-    }
-    g->features.resize((size_t)std::max<int64_t>(g->foff[(size_t)B], 1));
+    parallel_for(B, 128, [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            const Session &s = *ss[(size_t)i];
+            const int64_t a = kHopS * A[(size_t)i] - s.hist_start;  // >= 0: the history keeps two hops of left context
+            std::memcpy(g->pcm.data() + g->woff[(size_t)i], s.hist.data() + a, sizeof(int16_t) * (size_t)nloc[(size_t)i]);
+        }
+    });
+    g->ifeat.resize((size_t)std::max<int64_t>(g->foff[(size_t)B], 1));
     g->flens.assign((size_t)B, 0);
-    int32_t rc = amira_logmel_pcm16_packed(p->ctx, g->pcm.data(), g->woff.data(), B, g->features.data(), g->foff.data(), g->flens.data());
+    lap();  // 0: segments gathered
+    int32_t rc = amira_logmel_pcm16_packed(p->ctx, g->pcm.data(), g->woff.data(), B, g->ifeat.data(), g->foff.data(), g->flens.data());
     if (rc) { g->err = amira_last_error(p->ctx); for (auto &r : rcs) r = rc; return rc; }
-    // running normalisation + encoder, per stream
+    lap();  // 1: front end
+    // running normalisation of the new frames, sessions in parallel: Chan merge of the new frames into the running (count, mean,
+    // M2) of each feature, then (x - mean) / (std + 1e-5) with the merged statistics (sample variance, like the utterance-level
+    // rule of the preprocessor)
+    g->coff.assign((size_t)B + 1, 0);
+    for (int i = 0; i < B; ++i) g->coff[(size_t)i + 1] = g->coff[(size_t)i] + (int64_t)AMIRA_N_MELS * (t_end[(size_t)i] - ss[(size_t)i]->t_next);
+    g->ichunks.resize((size_t)std::max<int64_t>(g->coff[(size_t)B], 1));
+    parallel_for(B, 32, [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            Session &s = *ss[(size_t)i];
+            const int64_t n_new = t_end[(size_t)i] - s.t_next, f_first = s.t_next - A[(size_t)i], L = lloc[(size_t)i];
+            const float *src = g->ifeat.data() + g->foff[(size_t)i];  // [128][L]
+            float *chunk = g->ichunks.data() + g->coff[(size_t)i];   // [128][n_new]
+            for (int m = 0; m < AMIRA_N_MELS; ++m) {
+                const float *row = src + (size_t)m * L + f_first;
+                double bm = 0.0, b2 = 0.0;
+                for (int64_t f = 0; f < n_new; ++f) bm += (double)row[f];
+                bm /= (double)n_new;
+                for (int64_t f = 0; f < n_new; ++f) { const double d = (double)row[f] - bm; b2 += d * d; }
+                const double na = (double)s.st_count, nb = (double)n_new, nt = na + nb, d = bm - s.st_mean[(size_t)m];
+                const double mean = s.st_mean[(size_t)m] + d * (nb / nt), m2 = s.st_m2[(size_t)m] + b2 + d * d * (na * nb / nt);
+                s.st_mean[(size_t)m] = mean;
+                s.st_m2[(size_t)m] = m2;
+                const double sd = nt > 1.0 ? std::sqrt(m2 / (nt - 1.0)) : 0.0;
+                const float mu = (float)mean, inv = (float)(1.0 / (sd + 1e-5));
+                for (int64_t f = 0; f < n_new; ++f) chunk[(size_t)m * n_new + f] = (row[f] - mu) * inv;
+            }
+            s.st_count += n_new;
+            s.t_next = t_end[(size_t)i];
+        }
+    });
+    // the injected encoder on the new frames, one stream at a time (its output buffer is only valid until its next call)
     g->eoff.assign((size_t)B + 1, 0);
     g->elens.assign((size_t)B, 0);
-    g->enc.clear();
-    std::vector<float> chunk;
     for (int i = 0; i < B; ++i) {
-        Session &s = *ss[(size_t)i];
-        const int64_t n_new = t_end[(size_t)i] - s.t_next, f_first = s.t_next - A[(size_t)i], L = lloc[(size_t)i];
-        const float *src = g->features.data() + g->foff[(size_t)i];  // [128][L]
-        chunk.assign((size_t)AMIRA_N_MELS * (size_t)n_new, 0.f);
-        for (int m = 0; m < AMIRA_N_MELS; ++m) {
-            // Chan merge of the new frames into the running (count, mean, M2) of this feature, then (x - mean) / (std + 1e-5) of the
-            // new frames with the merged statistics (sample variance, like the utterance-level rule of the preprocessor)
-            double bm = 0.0, b2 = 0.0;
-            for (int64_t f = 0; f < n_new; ++f) bm += (double)src[(size_t)m * L + f_first + f];
-            bm /= (double)n_new;
-            for (int64_t f = 0; f < n_new; ++f) { const double d = (double)src[(size_t)m * L + f_first + f] - bm; b2 += d * d; }
-            const double na = (double)s.st_count, nb = (double)n_new, nt = na + nb, d = bm - s.st_mean[(size_t)m];
-            const double mean = s.st_mean[(size_t)m] + d * (nb / nt), m2 = s.st_m2[(size_t)m] + b2 + d * d * (na * nb / nt);
-            s.st_mean[(size_t)m] = mean;
-            s.st_m2[(size_t)m] = m2;
-            const double sd = nt > 1.0 ? std::sqrt(m2 / (nt - 1.0)) : 0.0;
-            const float mu = (float)mean, inv = (float)(1.0 / (sd + 1e-5));
-            for (int64_t f = 0; f < n_new; ++f) chunk[(size_t)m * n_new + f] = (src[(size_t)m * L + f_first + f] - mu) * inv;
-        }
-        s.st_count += n_new;
-        s.t_next = t_end[(size_t)i];
+        const int64_t n_new = (g->coff[(size_t)i + 1] - g->coff[(size_t)i]) / AMIRA_N_MELS;
         const float *e = nullptr;
         int64_t el = 0;
-        if (!p->encoder || p->encoder(p->encoder_user, chunk.data(), n_new, &e, &el) != 0 || el < 0 || (el > 0 && !e)) {
+        if (!p->encoder || p->encoder(p->encoder_user, g->ichunks.data() + g->coff[(size_t)i], n_new, &e, &el) != 0 || el < 0 || (el > 0 && !e)) {
             rcs[(size_t)i] = p->encoder ? AMIRA_ERR_UNKNOWN : AMIRA_ERR_NOT_READY;
             el = 0;
         }
-        if (el > 0) g->enc.insert(g->enc.end(), e, e + (size_t)AMIRA_ENC_DIM * (size_t)el);
-        g->elens[(size_t)i] = el;
         g->eoff[(size_t)i + 1] = g->eoff[(size_t)i] + (int64_t)AMIRA_ENC_DIM * el;
+        if (el > 0) {
+            g->ienc.resize((size_t)g->eoff[(size_t)i + 1]);
+            std::memcpy(g->ienc.data() + g->eoff[(size_t)i], e, sizeof(float) * (size_t)AMIRA_ENC_DIM * (size_t)el);
+        }
+        g->elens[(size_t)i] = el;
     }
-    // resumed greedy loop: state and last token in and out
+    lap();  // 2: running normalisation + encoder
+    // resumed greedy loop: state and last token in and out.  The states of the round's streams stay in the group's batch-layout
+    // buffers from round to round while the list of streams does not change.
     int32_t cap = AMIRA_MAX_TOTAL_TOKENS;
     amira_ctx_max_total_tokens(p->ctx, &cap);
     const size_t H = AMIRA_STATE_SIZE;
-    g->s1.resize(2 * (size_t)B * H);
-    g->s2.resize(2 * (size_t)B * H);
+    if (g->resident != ss) {
+        flush_resident(g);
+        g->is1.resize(2 * (size_t)B * H);
+        g->is2.resize(2 * (size_t)B * H);
+        parallel_for(B, 128, [&](int lo, int hi) {
+            for (int i = lo; i < hi; ++i)
+                for (int l = 0; l < 2; ++l) {
+                    std::memcpy(g->is1.data() + ((size_t)l * B + i) * H, ss[(size_t)i]->s1.data() + (size_t)l * H, sizeof(float) * H);
+                    std::memcpy(g->is2.data() + ((size_t)l * B + i) * H, ss[(size_t)i]->s2.data() + (size_t)l * H, sizeof(float) * H);
+                }
+        });
+        g->resident = ss;
+    }
     g->last.resize((size_t)B);
-    for (int i = 0; i < B; ++i) {
-        for (int l = 0; l < 2; ++l) {
-            std::memcpy(g->s1.data() + ((size_t)l * B + i) * H, ss[(size_t)i]->s1.data() + (size_t)l * H, sizeof(float) * H);
-            std::memcpy(g->s2.data() + ((size_t)l * B + i) * H, ss[(size_t)i]->s2.data() + (size_t)l * H, sizeof(float) * H);
-        }
-        g->last[(size_t)i] = ss[(size_t)i]->last_token;
-    }
-    g->tokens.assign((size_t)B * (size_t)cap, 0);
-    g->ntok.assign((size_t)B, 0);
+    for (int i = 0; i < B; ++i) g->last.data()[i] = ss[(size_t)i]->last_token;
+    g->itokens.resize((size_t)B * (size_t)cap);
+    g->intok.resize((size_t)B);
+    std::memset(g->intok.data(), 0, sizeof(int32_t) * (size_t)B);
+    lap();  // 3: states gathered
     if (g->eoff[(size_t)B] > 0) {
-        rc = amira_greedy_decode_resume(p->ctx, g->enc.data(), g->eoff.data(), B, g->elens.data(), g->s1.data(), g->s2.data(), g->last.data(),
-                                        g->tokens.data(), g->ntok.data(), nullptr);
-        if (rc && rc != AMIRA_ERR_DECODE_STEP) { g->err = amira_last_error(p->ctx); for (auto &r : rcs) r = rc; return rc; }
+        rc = amira_greedy_decode_resume(p->ctx, g->ienc.data(), g->eoff.data(), B, g->elens.data(), g->is1.data(), g->is2.data(), g->last.data(),
+                                        g->itokens.data(), g->intok.data(), nullptr);
+        if (rc && rc != AMIRA_ERR_DECODE_STEP) {
+            g->resident.clear();  // the buffers may hold a partial download: the sessions keep the states of their last flush
+            g->err = amira_last_error(p->ctx);
+            for (auto &r : rcs) r = rc;
+            return rc;
+        }
     }
+    lap();  // 4: decode
     for (int i = 0; i < B; ++i) {
         Session &s = *ss[(size_t)i];
         if (rcs[(size_t)i]) continue;
-        if (g->ntok[(size_t)i] < 0) { rcs[(size_t)i] = AMIRA_ERR_DECODE_STEP; continue; }
+        const int32_t nt = g->intok.data()[i];
+        if (nt < 0) { rcs[(size_t)i] = AMIRA_ERR_DECODE_STEP; continue; }
         if (g->elens[(size_t)i] > 0) {
-            for (int l = 0; l < 2; ++l) {
-                std::memcpy(s.s1.data() + (size_t)l * H, g->s1.data() + ((size_t)l * B + i) * H, sizeof(float) * H);
-                std::memcpy(s.s2.data() + (size_t)l * H, g->s2.data() + ((size_t)l * B + i) * H, sizeof(float) * H);
-            }
-            s.last_token = g->last[(size_t)i];
+            s.last_token = g->last.data()[i];
             s.enc_frames += g->elens[(size_t)i];
         }
-        const int32_t *tk = g->tokens.data() + (size_t)i * (size_t)cap;
-        s.token_ids.insert(s.token_ids.end(), tk, tk + g->ntok[(size_t)i]);
-        s.transcript = decode_utf8(p->vocab.decode(s.token_ids.data(), (int32_t)s.token_ids.size()).c_str());
+        if (nt > 0) {
+            const int32_t *tk = g->itokens.data() + (size_t)i * (size_t)cap;
+            s.token_ids.insert(s.token_ids.end(), tk, tk + nt);
+            s.transcript_stale = true;  // rebuilt on demand (amira_stream_group_transcript): decoding every stream's whole history
+                                        // on every tick cost more than the GPU work of the tick
+        }
     }
+    lap();  // 5: results scattered
+    if (sg_trace)
+        fprintf(stderr, "[stream group] B=%d gather %.2f | front end %.2f | normalise+encoder %.2f | states %.2f | decode %.2f | scatter %.2f ms"
+                " (pcm %.1f MB %s, features %.1f MB %s, encoder outputs %.1f MB %s)\n", B,
+                t_ph[0], t_ph[1], t_ph[2], t_ph[3], t_ph[4], t_ph[5], g->pcm.size() * 2e-6, g->pcm.pinned ? "pinned" : "pageable",
+                g->ifeat.size() * 4e-6, g->ifeat.pinned ? "pinned" : "pageable", g->ienc.size() * 4e-6, g->ienc.pinned ? "pinned" : "pageable");
     return AMIRA_OK;
 }
 
@@ -721,6 +846,7 @@ const char *amira_stream_group_last_error(amira_stream_group *g) { return g ? g-
 int32_t amira_stream_group_clear(amira_stream_group *g, int32_t stream) {
     if (!g || stream < 0 || (size_t)stream >= g->sessions.size()) return AMIRA_ERR_INVALID_VALUE;
     std::lock_guard<std::mutex> lock(g->mu);
+    flush_resident(g);  // the other streams' decoder states go back to their sessions before this one is reset
     g->sessions[(size_t)stream]->clear();
     return AMIRA_OK;
 }
@@ -772,6 +898,7 @@ int32_t amira_stream_group_transcript(amira_stream_group *g, int32_t stream, cha
     if (!g || stream < 0 || (size_t)stream >= g->sessions.size()) return AMIRA_ERR_INVALID_VALUE;
     std::lock_guard<std::mutex> lock(g->mu);
     HS_TRY
+    refresh_transcript(g, *g->sessions[(size_t)stream]);
     copy_text(encode_utf8(g->sessions[(size_t)stream]->transcript), text, text_cap, text_len);
     return AMIRA_OK;
     HS_CATCH(g)
@@ -798,6 +925,7 @@ int32_t amira_stream_group_process_batch(amira_stream_group *g, int32_t stream, 
                                          amira_transcription *out, int32_t *tokens, int32_t tokens_cap, char *text, size_t text_cap) {
     if (!g || stream < 0 || (size_t)stream >= g->sessions.size() || !out || (n_bytes && !audio_bytes)) return AMIRA_ERR_INVALID_VALUE;
     std::lock_guard<std::mutex> lock(g->mu);
+    flush_resident(g);
     Session &s = *g->sessions[(size_t)stream];
     s.clear();
     const size_t ns = n_bytes / 2;
@@ -831,6 +959,7 @@ int32_t amira_stream_group_set_incremental(amira_stream_group *g, int32_t enable
     std::lock_guard<std::mutex> lock(g->mu);
     for (auto &s : g->sessions)
         if (s->audio.length != 0 || s->n_total != 0) return gfail(g, AMIRA_ERR_INVALID_VALUE, "set_incremental: a stream already holds audio (clear it first)");
+    flush_resident(g);
     g->incremental = enable != 0;
     return AMIRA_OK;
 }

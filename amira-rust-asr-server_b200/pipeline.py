@@ -65,10 +65,21 @@ def shard_utterances(costs, n_shards: int) -> np.ndarray:
     return out
 
 
+class NativeEncoder:
+    """An encoder that is already a C function with the `amira_encoder_fn` signature (what the Rust server would install): the
+    address of the function and its user pointer go to the pipeline as they are, no Python frame per call."""
+
+    def __init__(self, fn_address: int, user_address: int | None = None, keepalive=None):
+        self.fn = C.cast(fn_address, _ENCODER_FN)
+        self.user = C.c_void_p(user_address)
+        self.keepalive = keepalive  # whatever owns the code and the user object
+
+
 class B200AsrPipeline:
     """impl AsrPipeline (src/asr/pipeline.rs:20-67) backed by libamira_b200.so.
 
-    encoder(features [128, L] f32) -> encoder outputs [1024, T] f32; stays whatever the deployment uses."""
+    encoder(features [128, L] f32) -> encoder outputs [1024, T] f32; stays whatever the deployment uses (a Python callable, or a
+    NativeEncoder wrapping a C function)."""
 
     def __init__(self, ctx: Context, vocab_path: str | None, encoder):
         self._L = load_library()
@@ -76,6 +87,14 @@ class B200AsrPipeline:
         self._ctx = ctx
         self._encoder = encoder
         self._keep = None
+        if isinstance(encoder, NativeEncoder):
+            self._cb = encoder.fn
+            self._h = C.c_void_p()
+            rc = self._L.amira_pipeline_create(ctx.handle, os.fsencode(vocab_path) if vocab_path else None, self._cb, encoder.user,
+                                               C.byref(self._h))
+            if rc:
+                raise AmiraError(rc, (self._L.amira_pipeline_last_error(None) or b"").decode())
+            return
 
         def _cb(_user, feats, flen, out_ptr, out_len):
             try:

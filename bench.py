@@ -268,6 +268,72 @@ def run_streaming(A, torch, dev, ctx, n_streams: int, ticks: int, warm: int):
             "audio_s_per_s": float(n_streams * 0.16 / (np.mean(lat) / 1e3)), "tokens_last_tick": int(ntok.numpy().clip(min=0).sum())}
 
 
+def run_stream_group(A, ctx, n_streams: int, ticks: int, warm: int):
+    """BASELINE config 4 through the ORCHESTRATOR (amira_stream_group_*, csrc/host_stream.cpp) in incremental mode: what the WebSocket
+    handler of the reference does per connection (IncrementalAsr::process_chunk, src/asr/incremental.rs:111-129) for n_streams
+    connections per tick.  One tick = every stream's 160 ms chunk (host bytes, as the wire carries them) through one C-ABI call:
+    carried audio tail -> one ragged front-end launch -> running normalisation -> the injected encoder (a C stub: the model is out
+    of scope) on the new frames -> one resumed greedy decode (state + last token carried) -> token history and transcript per
+    stream.  Wall clock per tick around that call; the chunk of a stream repeats from tick to tick (timing only)."""
+    import ctypes as C
+    import tempfile
+    so = os.path.join(ROOT, "bench_support", "libsynth_encoder.so")
+    if not os.path.exists(so):
+        import __graft_entry__ as G
+        G.build_bench_support()
+    S = C.CDLL(so)
+    S.synth_encoder_create.restype = C.c_void_p
+    S.synth_encoder_create.argtypes = [C.c_uint64]
+    S.synth_encoder_destroy.argtypes = [C.c_void_p]
+    S.synth_encoder_calls.restype = C.c_int64
+    S.synth_encoder_calls.argtypes = [C.c_void_p]
+    enc_obj = S.synth_encoder_create(77)
+    fn_addr = C.cast(S.synth_encoder_fn, C.c_void_p).value
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False, encoding="utf-8") as f:
+        for i in range(1024):
+            f.write(f"{'▁' if i % 3 == 0 else ''}t{i} {i}\n")
+        f.write("<blk> 1024\n")
+        vocab_path = f.name
+    chunk = 2560
+    rng = np.random.default_rng(98)
+    pcm = (rng.standard_normal((n_streams, chunk)) * 3000).astype(np.int16)
+    pipe = A.B200AsrPipeline(ctx, vocab_path, A.NativeEncoder(fn_addr, enc_obj, keepalive=S))
+    grp = A.StreamGroup(pipe, n_streams, chunk_size=0.16)
+    grp.set_incremental(True)
+    L = grp._L
+    ids = np.arange(n_streams, dtype=np.int32)
+    ptrs = (C.c_void_p * n_streams)(*[pcm[i].ctypes.data for i in range(n_streams)])
+    lens = (C.c_size_t * n_streams)(*([2 * chunk] * n_streams))
+    status = np.zeros(n_streams, np.int32)
+    lat = []
+    n_prof = 5  # extra ticks with per-kernel events switched on, after the timed ones: the device share of a tick
+    for i in range(warm + ticks + n_prof):
+        if i == warm + ticks:
+            ctx.profile(True)
+        t0 = time.perf_counter()
+        rc = L.amira_stream_group_process_chunks(grp._h, n_streams, ids.ctypes.data, ptrs, lens, status.ctypes.data)
+        dt = (time.perf_counter() - t0) * 1e3
+        assert rc == 0 and not status.any(), (rc, grp._err())
+        if warm <= i < warm + ticks:
+            lat.append(dt)
+    k_fe, k_dec, k_proj = ctx.kernel_ms("fe_logmel"), ctx.kernel_ms("greedy"), ctx.kernel_ms("enc_proj")
+    ctx.profile(False)
+    samples, frames, enc_frames = grp.progress(0)
+    n_tok = sum(len(grp.tokens(s_)) for s_ in range(0, n_streams, 64))
+    calls = int(S.synth_encoder_calls(enc_obj))
+    grp.close()
+    pipe.close()
+    S.synth_encoder_destroy(enc_obj)
+    os.unlink(vocab_path)
+    lat = np.array(lat)
+    gpu_ms = (k_fe[0] + k_dec[0] + k_proj[0]) / n_prof
+    return {"workload": f"cfg4 through the stream group (incremental mode): {n_streams} streams x 160 ms chunks, {ticks} ticks, one C-ABI call per tick, host bytes in",
+            "p50_chunk_ms": float(np.percentile(lat, 50)), "p99_chunk_ms": float(np.percentile(lat, 99)),
+            "audio_s_per_s": float(n_streams * 0.16 / (np.mean(lat) / 1e3)), "kernel_ms_per_tick": gpu_ms,
+            "frames_per_stream": int(frames), "encoder_frames_per_stream": int(enc_frames), "encoder_calls": calls,
+            "tokens_of_16_streams": int(n_tok)}
+
+
 # ------------------------------------------------------------------------------------------------ cfg2 / cfg3 stand-alone
 def run_extras(A, torch, dev, ctx, stream, hbm_peak, tf_peak):
     """BASELINE configs 2 and 3 on their own (device-resident inputs, CUDA events on the launching stream), so the driver's
@@ -609,6 +675,7 @@ def main():
     streaming = None
     if not args.no_stream and rank == 0:
         streaming = run_streaming(A, torch, dev, ctx, 1024, args.stream_ticks, 5)
+        streaming["stream_group"] = run_stream_group(A, ctx, 1024, args.stream_ticks, 5)
 
     if rank != 0:
         if world > 1:

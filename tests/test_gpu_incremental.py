@@ -179,3 +179,43 @@ def test_many_streams_at_once_equal_each_alone(gpu, amira):
     assert g.progress(0)[0] == 4000
     g.close()
     pipe.close()
+
+
+def test_decoder_state_follows_its_stream_when_the_round_changes(gpu, amira):
+    """The group keeps the decoder states of a round in batch layout while consecutive rounds list the same streams in the same
+    order (csrc/host_stream.cpp: `resident`).  Whatever the rounds look like — a subset, another order, a stream cleared and
+    restarted in between, transcripts read mid-way — every stream's tokens are those of the stream processed alone."""
+    n = 6
+    pcms = [synth_pcm(1.2 + 0.11 * i, 900 + i) for i in range(n)]
+    step = 3200
+    alone = [_run_stream(amira, gpu, pcms[i], [step] * (pcms[i].size // step) + [pcms[i].size % step])[1] for i in range(n)]
+    enc = FrameEncoder()
+    pipe = amira.B200AsrPipeline(gpu, VOCAB, enc)
+    g = amira.StreamGroup(pipe, n)
+    g.set_incremental(True)
+    pos = [0] * n
+    rng = np.random.default_rng(3)
+    k = 0
+    while any(pos[i] < pcms[i].size for i in range(n)):
+        live = [i for i in range(n) if pos[i] < pcms[i].size]
+        if k % 3 == 0:
+            ids = live                                   # the same list as the round before last: states stay where they are
+        elif k % 3 == 1:
+            ids = list(reversed(live))                   # another order
+        else:
+            ids = [i for i in live if rng.random() < 0.6] or live[:1]   # a subset
+        g.process_chunks(ids, [pcms[i][pos[i]:pos[i] + step].tobytes() for i in ids])
+        for i in ids:
+            pos[i] += step
+        if k == 4:                                       # stream 2 starts over: its state is reset, the others' must survive
+            g.clear(2)
+            pos[2] = 0
+        if k == 6:
+            _ = g.transcript(1)                          # reading a transcript mid-stream changes nothing
+        k += 1
+    g.flush(list(range(n)))
+    for i in range(n):
+        assert g.tokens(i) == alone[i], i
+        assert g.transcript(i) == pipe.decode_tokens(alone[i]), i
+    g.close()
+    pipe.close()
