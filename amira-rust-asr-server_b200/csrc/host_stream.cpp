@@ -17,6 +17,8 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <condition_variable>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -334,17 +336,96 @@ struct PinVec {
     size_t size() const { return n; }
 };
 
-// f(lo, hi) over [0, n) on up to 16 host threads (the sessions of a round are independent); the body must not throw
+// device memory of the group (the decoder states of the resident streams): the decode entries use device pointers in place
+struct DevVec {
+    float *p = nullptr;
+    size_t cap = 0;
+    DevVec() = default;
+    DevVec(const DevVec &) = delete;
+    DevVec &operator=(const DevVec &) = delete;
+    ~DevVec() { if (p) { cudaFree(p); cudaGetLastError(); } }
+    bool reserve(size_t n) {  // false: no device memory (the caller falls back to the host buffers)
+        if (n <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(reinterpret_cast<void **>(&p), (n + n / 4) * sizeof(float)) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
+        cap = n + n / 4;
+        return true;
+    }
+};
+
+// A small pool of host threads for the per-session work of a round (sessions are independent).  The workers live as long as the
+// library and sleep between rounds: starting fifteen threads per call cost more than the work they did, and the churn slowed
+// the CUDA calls that followed on the calling thread (measured on a 1024-stream tick).  run(n, min_per_thread, f) calls
+// f(lo, hi) over [0, n) split in up to 1 + workers pieces and returns when all are done; f must not throw.  One round at a time.
+class HostPool {
+  public:
+    static HostPool &get() {
+        static HostPool pool;
+        return pool;
+    }
+    template <class F>
+    void run(int n, int min_per_thread, F f) {
+        const int T = std::max(1, std::min(n / std::max(min_per_thread, 1), (int)workers_.size() + 1));
+        if (T <= 1) { f(0, n); return; }
+        std::unique_lock<std::mutex> round(round_mu_);  // callers of different groups take turns
+        std::function<void(int, int)> fn = f;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; n_ = n; pieces_ = T; next_ = 1; pending_ = T - 1;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        f(0, (int)((long long)n / T));
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    HostPool() {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int n = std::max(0, std::min((int)(hw ? hw : 1), 16) - 1);
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || (epoch_ != seen && next_ < pieces_); });
+            if (stop_) return;
+            while (fn_ && next_ < pieces_) {
+                const int t = next_++;
+                const int lo = (int)((long long)n_ * t / pieces_), hi = (int)((long long)n_ * (t + 1) / pieces_);
+                const std::function<void(int, int)> *fn = fn_;
+                lk.unlock();
+                (*fn)(lo, hi);
+                lk.lock();
+                if (--pending_ == 0) done_.notify_all();
+            }
+            seen = epoch_;
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, round_mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, int)> *fn_ = nullptr;
+    int n_ = 0, pieces_ = 0, next_ = 0, pending_ = 0;
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
+};
+
 template <class F>
 void parallel_for(int n, int min_per_thread, F f) {
-    const unsigned hw = std::thread::hardware_concurrency();
-    const int T = std::max(1, std::min(std::min(n / std::max(min_per_thread, 1), (int)(hw ? hw : 1)), 16));
-    if (T <= 1) { f(0, n); return; }
-    std::vector<std::thread> th;
-    th.reserve((size_t)T - 1);
-    for (int t = 1; t < T; ++t) th.emplace_back(f, (int)((long long)n * t / T), (int)((long long)n * (t + 1) / T));
-    f(0, (int)((long long)n / T));
-    for (auto &x : th) x.join();
+    HostPool::get().run(n, min_per_thread, f);
 }
 
 struct amira_stream_group {
@@ -363,6 +444,8 @@ struct amira_stream_group {
     // the streams whose decoder state lives in is1 / is2 (row i = resident[i]) instead of their Session: as long as consecutive
     // rounds list the same streams in the same order the state never moves (1024 streams: 2 x 10.5 MB of memcpy per tick otherwise)
     std::vector<Session *> resident;
+    DevVec ds1, ds2;                // ... and, when device memory is to be had, on the DEVICE: a tick then moves no state over PCIe
+    bool resident_on_device = false;
     // batch scratch
     std::vector<float> wave, features, enc, s1, s2;
     std::vector<int64_t> woff, foff, eoff, flens, elens;
@@ -528,6 +611,13 @@ constexpr int64_t kHopS = 160, kHalfWin = 200, kCtxHops = 2;  // a frame's windo
 // the decoder states that live in the group's batch-layout buffers go back to their sessions
 void flush_resident(amira_stream_group *g) {
     const size_t B = g->resident.size(), H = AMIRA_STATE_SIZE;
+    if (B && g->resident_on_device) {
+        amira_ctx_synchronize(g->p->ctx);
+        const bool ok = cudaMemcpy(g->is1.data(), g->ds1.p, sizeof(float) * 2 * B * H, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                        cudaMemcpy(g->is2.data(), g->ds2.p, sizeof(float) * 2 * B * H, cudaMemcpyDeviceToHost) == cudaSuccess;
+        g->resident_on_device = false;
+        if (!ok) { cudaGetLastError(); g->resident.clear(); return; }  // a dead device: the sessions keep the states of their last flush
+    }
     for (size_t i = 0; i < B; ++i)
         for (size_t l = 0; l < 2; ++l) {
             std::memcpy(g->resident[i]->s1.data() + l * H, g->is1.data() + (l * B + i) * H, sizeof(float) * H);
@@ -651,6 +741,10 @@ int32_t incremental_round(amira_stream_group *g, const std::vector<Session *> &s
                 }
         });
         g->resident = ss;
+        g->resident_on_device = g->ds1.reserve(2 * (size_t)B * H) && g->ds2.reserve(2 * (size_t)B * H) &&
+                                cudaMemcpy(g->ds1.p, g->is1.data(), sizeof(float) * 2 * (size_t)B * H, cudaMemcpyHostToDevice) == cudaSuccess &&
+                                cudaMemcpy(g->ds2.p, g->is2.data(), sizeof(float) * 2 * (size_t)B * H, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!g->resident_on_device) cudaGetLastError();
     }
     g->last.resize((size_t)B);
     for (int i = 0; i < B; ++i) g->last.data()[i] = ss[(size_t)i]->last_token;
@@ -659,10 +753,11 @@ int32_t incremental_round(amira_stream_group *g, const std::vector<Session *> &s
     std::memset(g->intok.data(), 0, sizeof(int32_t) * (size_t)B);
     lap();  // 3: states gathered
     if (g->eoff[(size_t)B] > 0) {
-        rc = amira_greedy_decode_resume(p->ctx, g->ienc.data(), g->eoff.data(), B, g->elens.data(), g->is1.data(), g->is2.data(), g->last.data(),
-                                        g->itokens.data(), g->intok.data(), nullptr);
+        rc = amira_greedy_decode_resume(p->ctx, g->ienc.data(), g->eoff.data(), B, g->elens.data(), g->resident_on_device ? g->ds1.p : g->is1.data(),
+                                        g->resident_on_device ? g->ds2.p : g->is2.data(), g->last.data(), g->itokens.data(), g->intok.data(), nullptr);
         if (rc && rc != AMIRA_ERR_DECODE_STEP) {
-            g->resident.clear();  // the buffers may hold a partial download: the sessions keep the states of their last flush
+            g->resident.clear();  // the buffers may hold a partial result: the sessions keep the states of their last flush
+            g->resident_on_device = false;
             g->err = amira_last_error(p->ctx);
             for (auto &r : rcs) r = rc;
             return rc;
