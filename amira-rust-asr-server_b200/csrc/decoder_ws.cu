@@ -251,6 +251,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+// one lane of a converged warp (elect.sync): tcgen05 / TMA issue under this predicate in warp-uniform control flow compiles to
+// straight uniform-datapath instructions
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ long long gtime() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -544,13 +551,17 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
             publish(-1, 0, qn);  // exit descriptor
         }
     } else if (warp == 0) {
-        if (lane == 0) {  // ===================== TMA producer =====================
+        {   // ===================== TMA producer =====================
+            // The whole warp walks the loop and one elected lane issues a unit's 20 loads (see the MMA issuer below: in warp-uniform
+            // control flow the UTMALDGs go out back to back instead of one ELECT / BRA.U.ANY loop each).
             const CUtensorMap *a_hi, *a_lo;
             if (role == R_A || role == R_BI) { a_hi = &p.h0_hi; a_lo = &p.h0_lo; }
             else if (role == R_BH || role == R_C) { a_hi = &p.h1_hi; a_lo = &p.h1_lo; }
             else { a_hi = &p.z_hi; a_lo = &p.z_lo; }
-            tma_prefetch_desc(a_hi);
-            tma_prefetch_desc(a_lo);
+            if (lane == 0) {
+                tma_prefetch_desc(a_hi);
+                tma_prefetch_desc(a_lo);
+            }
             // each CTA of the pair loads its 64 rows of every [128 rows][64 k] operand tile into its own ring; the bytes of both
             // loads are counted on the LEADER's full barrier (the leader issues the MMAs); a slot is free again in both CTAs when
             // the multicast commit of the MMAs that read it arrives
@@ -560,41 +571,48 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 const uint32_t slot = qn % W_Q;
                 mbar_wait_wd(&sm.q_full[slot], (qn / W_Q) & 1);
                 const int mt = sm.q[slot].mt, it = sm.q[slot].it;
-                q_release(slot);
+                __syncwarp();
+                if (lane == 0) q_release(slot);
                 ++qn;
                 if (mt < 0) break;
                 // the recurrent roles read the state version of tick it-1, the others the version of tick it
                 const int ver = (role == R_A || role == R_BH) ? (it + W_V - 1) % W_V : it % W_V;
                 const int a_row = ver * p.Mpad + mt * W_BM + (int)crank * K::BOX;
-                fence_proxy_async();  // the scheduler's acquire (through the queue barrier) before these async-proxy reads
-                for (int ki = 0; ki < W_KC; ++ki) {
-                    const int kc = (kc0 + ki) % W_KC;
+                if (elect_one()) {
+                    fence_proxy_async();  // the scheduler's acquire (through the queue barrier) before these async-proxy reads
+                    for (int ki = 0; ki < W_KC; ++ki) {
+                        const int kc = (kc0 + ki) % W_KC;
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        if constexpr (PAIR) {
-                            const uint32_t s = 2 * ki + half;  // 20 slots = one unit: the slot of (k-chunk, half) is fixed
-                            mbar_wait_wd(&sm.empty[s], (u & 1) ^ 1);
-                            if (leader) mbar_expect_tx(&sm.full[s], 2u * W_UNIT);
-                            tma_load_2d_pair(ring + s * W_UNIT, half ? a_lo : a_hi, lead_full0 + s * 8u, kc * BK, a_row);
-                        } else {
-                            const uint32_t j = 2 * ki + half, s = j % W_NRING;  // 20 loads on a 10-slot ring: two revolutions per unit
-                            mbar_wait_wd(&sm.empty[s], (j / W_NRING) ^ 1);
-                            mbar_expect_tx(&sm.full[s], (uint32_t)W_UNIT);
-                            tma_load_2d(ring + s * W_UNIT, half ? a_lo : a_hi, &sm.full[s], kc * BK, a_row);
+                        for (int half = 0; half < 2; ++half) {
+                            if constexpr (PAIR) {
+                                const uint32_t s = 2 * ki + half;  // 20 slots = one unit: the slot of (k-chunk, half) is fixed
+                                mbar_wait_wd(&sm.empty[s], (u & 1) ^ 1);
+                                if (leader) mbar_expect_tx(&sm.full[s], 2u * W_UNIT);
+                                tma_load_2d_pair(ring + s * W_UNIT, half ? a_lo : a_hi, lead_full0 + s * 8u, kc * BK, a_row);
+                            } else {
+                                const uint32_t j = 2 * ki + half, s = j % W_NRING;  // 20 loads on a 10-slot ring: two revolutions per unit
+                                mbar_wait_wd(&sm.empty[s], (j / W_NRING) ^ 1);
+                                mbar_expect_tx(&sm.full[s], (uint32_t)W_UNIT);
+                                tma_load_2d(ring + s * W_UNIT, half ? a_lo : a_hi, &sm.full[s], kc * BK, a_row);
+                            }
                         }
                     }
                 }
+                __syncwarp();
                 ++u;
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ===================== MMA issuer (the pair's leader; the peer only consumes its descriptors) =====================
+        {   // ===================== MMA issuer (the pair's leader; the peer only consumes its descriptors) =====================
             // A = both CTAs' slices [w_hi ; w_lo] in their tensor memories (M = 256; 32 columns per k-chunk), B = activation tile
             // (N = 128 stream rows, 64 in each CTA's ring): two instructions per k-step, a_hi then a_lo, both against all weight
-            // rows (w_lo x a_lo is a free 2^-18 term).  One thread issues all of it, and a lone thread retires an instruction
-            // only every few cycles: measured (scripts/bench_pipe.cu) ~150 instructions of bookkeeping per ring slot made the ISSUE
-            // loop, not the tensor pipe or shared memory, the limit of a unit.  Hence: the slot of every (k-chunk, half) is a
-            // compile-time constant of the fully unrolled loop; descriptors are one add; no watchdog here.
+            // rows (w_lo x a_lo is a free 2^-18 term).  The ISSUE loop, not the tensor pipe or shared memory, was the limit of a
+            // unit (80 MMAs in 3.7 us = 88 clk each against 64 clk of execution: profiles/r2_ws_trace_pair.log).  The WHOLE warp
+            // walks the loop and one elected lane (elect.sync) issues: in warp-uniform control flow the compiler keeps the
+            // descriptors in uniform registers and emits the UTCHMMAs back to back (one UIADD3 between them); under
+            // `if (lane == 0)` every tcgen05 instruction was wrapped in an ELECT / BRA.U.ANY loop with R2UR moves, nine
+            // instructions of a lone thread per MMA.  The slot of every (k-chunk, half) is a compile-time constant of the fully
+            // unrolled loop; no watchdog here.
             static_assert(W_NRING == (PAIR ? 2 : 1) * W_KC, "one ring revolution per unit (PAIR), two otherwise");
             const uint32_t ring_lo32 = sdesc_lo(smem_u32(ring));
             // PAIR: M = 2 x 128 weight rows (hi | lo of both slices); else M = 128; N = 128 streams
@@ -604,46 +622,47 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 const uint32_t slot = qn % W_Q;
                 mbar_wait_wd(&sm.q_full[slot], (qn / W_Q) & 1);
                 const int mt = sm.q[slot].mt, it = sm.q[slot].it;
-                q_release(slot);
+                __syncwarp();
+                if (lane == 0) q_release(slot);
                 ++qn;
                 if (mt < 0) break;
                 if (PAIR && !leader) continue;
                 mbar_wait_wd(&sm.acc_empty, (tile & 1) ^ 1);  // the epilogue (PAIR: of both CTAs) has drained the previous accumulator
                 tc_fence_after();
                 int kc = kc0;
-                // opaque per unit: every descriptor below is this base + an immediate, computed where it is used (hoisted out
-                // of the unit loop they would be 120 loop-invariant values, more than this thread's register budget)
-                uint32_t rb = ring_lo32, tb = tmem_base;
-                asm volatile("" : "+r"(rb), "+r"(tb));
+                const uint32_t rb = ring_lo32, tb = tmem_base;
                 const uint32_t acc = tb + W_ACC_COL0;
+                if (elect_one()) {
 #pragma unroll
-                for (int ki = 0; ki < W_KC; ++ki) {
-                    const uint32_t wa = tb + kc * 32;
+                    for (int ki = 0; ki < W_KC; ++ki) {
+                        const uint32_t wa = tb + kc * 32;
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const int j = 2 * ki + half, s = j % W_NRING;
-                        mbar_wait(&sm.full[s], PAIR ? (tile & 1) : (uint32_t)(j / W_NRING));
-                        if (j == 0) WS_TRACE(1);
-                        const uint32_t bd = rb + s * (W_UNIT >> 4);
-                        if constexpr (PAIR) {
-                            umma_bf16_ts2(acc, wa, bd, idesc_t, j != 0);
-                            umma_bf16_ts2(acc, wa + 8, bd + 2, idesc_t, 1);
-                            umma_bf16_ts2(acc, wa + 16, bd + 4, idesc_t, 1);
-                            umma_bf16_ts2(acc, wa + 24, bd + 6, idesc_t, 1);
-                            umma_commit2(&sm.empty[s]);
-                        } else {
-                            umma_bf16_ts(acc, wa, bd, idesc_t, j != 0);
-                            umma_bf16_ts(acc, wa + 8, bd + 2, idesc_t, 1);
-                            umma_bf16_ts(acc, wa + 16, bd + 4, idesc_t, 1);
-                            umma_bf16_ts(acc, wa + 24, bd + 6, idesc_t, 1);
-                            umma_commit(&sm.empty[s]);
+                        for (int half = 0; half < 2; ++half) {
+                            const int j = 2 * ki + half, s = j % W_NRING;
+                            mbar_wait(&sm.full[s], PAIR ? (tile & 1) : (uint32_t)(j / W_NRING));
+                            if (j == 0) WS_TRACE(1);
+                            const uint32_t bd = rb + s * (W_UNIT >> 4);
+                            if constexpr (PAIR) {
+                                umma_bf16_ts2(acc, wa, bd, idesc_t, j != 0);
+                                umma_bf16_ts2(acc, wa + 8, bd + 2, idesc_t, 1);
+                                umma_bf16_ts2(acc, wa + 16, bd + 4, idesc_t, 1);
+                                umma_bf16_ts2(acc, wa + 24, bd + 6, idesc_t, 1);
+                                umma_commit2(&sm.empty[s]);
+                            } else {
+                                umma_bf16_ts(acc, wa, bd, idesc_t, j != 0);
+                                umma_bf16_ts(acc, wa + 8, bd + 2, idesc_t, 1);
+                                umma_bf16_ts(acc, wa + 16, bd + 4, idesc_t, 1);
+                                umma_bf16_ts(acc, wa + 24, bd + 6, idesc_t, 1);
+                                umma_commit(&sm.empty[s]);
+                            }
                         }
+                        kc = kc + 1 == W_KC ? 0 : kc + 1;
                     }
-                    kc = kc + 1 == W_KC ? 0 : kc + 1;
+                    if constexpr (PAIR) umma_commit2(&sm.acc_full);
+                    else umma_commit(&sm.acc_full);
                 }
-                if constexpr (PAIR) umma_commit2(&sm.acc_full);
-                else umma_commit(&sm.acc_full);
-                WS_TRACE(2);
+                __syncwarp();
+                if (lane == 0) WS_TRACE(2);
                 ++tile;
             }
         }
