@@ -415,7 +415,8 @@ int32_t amira_ctx_load_weights_file(amira_ctx *c, const char *path) {
 // (a server runs many such threads on few cores; spinning ones starve the threads that feed the copy engines).  Small calls
 // (single requests, streaming ticks) keep the spinning wait and its microsecond wake-up.
 static cudaError_t wait_stream(Ctx *c, cudaStream_t s, bool blocking) {
-    if (!blocking) return cudaStreamSynchronize(s);
+    static const int spin_env = getenv("AMIRA_SPIN_WAIT") ? atoi(getenv("AMIRA_SPIN_WAIT")) : 0;  // A/B timing of the wake-up cost
+    if (!blocking || spin_env) return cudaStreamSynchronize(s);
     cudaError_t e = cudaEventRecord(c->ev_block, s);
     return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
 }

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
     const uint32_t tmem_acc = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer =====
+        {   // ===== TMA producer: the warp walks the loop converged, one elected lane issues (straight UTMALDGs, no ELECT / BRA loop each) =====
             uint32_t g = 0;  // k-chunks issued so far, across tiles: ring stage and phase
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int m0 = (tile / tiles_n) * G_BM, n0 = (tile % tiles_n) * G_BN;
@@ -163,16 +163,19 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
                     const uint32_t s = g % G_STAGES;
                     mbar_wait(&empty[s], ((g / G_STAGES) & 1) ^ 1);
                     unsigned char *st = smem + s * G_STAGE_BYTES;
-                    mbar_expect_tx(&full[s], G_STAGE_BYTES);
-                    tma_load_2d(st + 0 * G_TILE_BYTES, &p.a_hi, &full[s], kc * BK, m0);
-                    tma_load_2d(st + 1 * G_TILE_BYTES, &p.a_lo, &full[s], kc * BK, m0);
-                    tma_load_2d(st + 2 * G_TILE_BYTES, &p.w_hi, &full[s], kc * BK, n0);
-                    tma_load_2d(st + 3 * G_TILE_BYTES, &p.w_lo, &full[s], kc * BK, n0);
+                    if (elect_one_sync()) {
+                        mbar_expect_tx(&full[s], G_STAGE_BYTES);
+                        tma_load_2d(st + 0 * G_TILE_BYTES, &p.a_hi, &full[s], kc * BK, m0);
+                        tma_load_2d(st + 1 * G_TILE_BYTES, &p.a_lo, &full[s], kc * BK, m0);
+                        tma_load_2d(st + 2 * G_TILE_BYTES, &p.w_hi, &full[s], kc * BK, n0);
+                        tma_load_2d(st + 3 * G_TILE_BYTES, &p.w_lo, &full[s], kc * BK, n0);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer =====
+        {   // ===== MMA issuer: converged warp, one elected lane (the UTCHMMAs of a k-chunk go out back to back) =====
             constexpr uint32_t idesc = make_idesc_bf16(G_BM, G_BN);
             uint32_t g = 0, t = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
@@ -185,18 +188,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const __grid_cons
                     mbar_wait(&full[s], (g / G_STAGES) & 1);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + s * G_STAGE_BYTES);
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                        const uint32_t off = kk * UMMA_K * 2;  // bytes along the 128-byte swizzle row
-                        const uint64_t ah = make_sdesc_sw128(st + 0 * G_TILE_BYTES + off), al = make_sdesc_sw128(st + 1 * G_TILE_BYTES + off);
-                        const uint64_t wh = make_sdesc_sw128(st + 2 * G_TILE_BYTES + off), wl = make_sdesc_sw128(st + 3 * G_TILE_BYTES + off);
-                        umma_bf16(acc, al, wh, idesc, (kc | kk) != 0);
-                        umma_bf16(acc, ah, wl, idesc, 1);
-                        umma_bf16(acc, ah, wh, idesc, 1);
+                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                            const uint32_t off = kk * UMMA_K * 2;  // bytes along the 128-byte swizzle row
+                            const uint64_t ah = make_sdesc_sw128(st + 0 * G_TILE_BYTES + off), al = make_sdesc_sw128(st + 1 * G_TILE_BYTES + off);
+                            const uint64_t wh = make_sdesc_sw128(st + 2 * G_TILE_BYTES + off), wl = make_sdesc_sw128(st + 3 * G_TILE_BYTES + off);
+                            umma_bf16(acc, al, wh, idesc, (kc | kk) != 0);
+                            umma_bf16(acc, ah, wl, idesc, 1);
+                            umma_bf16(acc, ah, wh, idesc, 1);
+                        }
+                        umma_commit(&empty[s]);
                     }
-                    umma_commit(&empty[s]);
+                    __syncwarp();
                 }
-                umma_commit(&acc_full[buf]);
+                if (elect_one_sync()) umma_commit(&acc_full[buf]);
+                __syncwarp();
             }
         }
     } else {  // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====

@@ -251,13 +251,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
-// one lane of a converged warp (elect.sync): tcgen05 / TMA issue under this predicate in warp-uniform control flow compiles to
-// straight uniform-datapath instructions
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
 __device__ __forceinline__ long long gtime() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -578,7 +571,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 // the recurrent roles read the state version of tick it-1, the others the version of tick it
                 const int ver = (role == R_A || role == R_BH) ? (it + W_V - 1) % W_V : it % W_V;
                 const int a_row = ver * p.Mpad + mt * W_BM + (int)crank * K::BOX;
-                if (elect_one()) {
+                if (elect_one_sync()) {
                     fence_proxy_async();  // the scheduler's acquire (through the queue barrier) before these async-proxy reads
                     for (int ki = 0; ki < W_KC; ++ki) {
                         const int kc = (kc0 + ki) % W_KC;
@@ -632,7 +625,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 int kc = kc0;
                 const uint32_t rb = ring_lo32, tb = tmem_base;
                 const uint32_t acc = tb + W_ACC_COL0;
-                if (elect_one()) {
+                if (elect_one_sync()) {
 #pragma unroll
                     for (int ki = 0; ki < W_KC; ++ki) {
                         const uint32_t wa = tb + kc * 32;

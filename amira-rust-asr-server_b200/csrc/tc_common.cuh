@@ -21,6 +21,15 @@ constexpr int UMMA_K = 16;    // k per tcgen05.mma for 16-bit inputs
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp (elect.sync).  tcgen05 / TMA instructions issued under this predicate in warp-uniform control flow
+// compile to straight uniform-datapath instructions (UTCHMMA, UTMALDG back to back); under `if (lane == 0)` each one is wrapped in
+// an ELECT / BRA.U.ANY loop with R2UR moves.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
