@@ -413,3 +413,35 @@ def test_literal_refeed_loop_over_the_contract_op(amira, oracle):
             else:
                 assert ref.margins.size and ref.margins.min() < NEAR_TIE, (k, got.tokens, ref.tokens)
         assert n_same >= 5 and n_multi >= 1  # at least one utterance re-fed U > 1 targets
+
+
+def test_schedule_does_not_change_results(amira, monkeypatch):
+    """The lane plan (M-tiles), the blank-speculation table and the CTA-pair form decide WHEN the tcgen05 engine computes a step,
+    never its inputs: tokens, counts, step counts and final states of a mixed-length batch are bit-identical under every
+    schedule of one form of the kernel (the one-CTA form sums the k-chunks in another order: same tokens, states to 1e-4) (decoder_optimized.rs:54-200 is one sequential loop per stream; scripts/decode_soak.py is the long form)."""
+    rng = np.random.default_rng(77)
+    B, T = 320, 96
+    enc = (0.5 * rng.standard_normal((B, 1024, T))).astype(np.float32)
+    lens = rng.integers(8, T + 1, B).astype(np.int64)
+    ref = None
+    variants = [{}, {"AMIRA_WS_TILES": "1"}, {"AMIRA_WS_TILES": "3", "AMIRA_WS_SPEC": "0"}, {"AMIRA_WS_SPEC": "3,3,3"},
+                {"AMIRA_WS_SPEC": "2,2,2,2", "AMIRA_WS_TILES": "2"}, {"AMIRA_WS_PAIR": "0"}]
+    with amira.Context(device_id=0, decode_engine=4) as c:
+        c.load_weights(amira.synthetic_weights(3456))
+        for v in variants:
+            for k in ("AMIRA_WS_TILES", "AMIRA_WS_SPEC", "AMIRA_WS_PAIR"):
+                monkeypatch.delenv(k, raising=False)
+            for k, val in v.items():
+                monkeypatch.setenv(k, val)
+            for _ in range(2):
+                toks, st, steps = c.greedy_decode(enc, lens)
+                got = (toks, np.asarray(steps).tolist(), st.states_1.tobytes(), st.states_2.tobytes())
+                if ref is None:
+                    ref = got
+                    assert all(t is not None for t in toks) and sum(len(t) for t in toks) > 0
+                assert got[0] == ref[0] and got[1] == ref[1], v
+                if "AMIRA_WS_PAIR" in v:  # the one-CTA form walks the k-chunks in another order: fp32 sums differ in the last bits
+                    for k in (2, 3):
+                        np.testing.assert_allclose(np.frombuffer(got[k], np.float32), np.frombuffer(ref[k], np.float32), rtol=1e-4, atol=1e-4)
+                else:
+                    assert got[2] == ref[2] and got[3] == ref[3], v
