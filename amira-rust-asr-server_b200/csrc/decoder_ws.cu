@@ -132,6 +132,10 @@ struct WsParams {
     WCtl *ctl;          // [W_R ticks][Mpad]
     int *tinfo;         // [MT][W_R]: res(it) = the last tick whose vocabulary results the layer-0 epilogue of tick `it` consumes
     int *tile_active, *cnt_d, *cnt_a, *cnt_b, *cnt_c, *dead_at, *part_ready /* [MT][40] */, *fail_count, *live_tiles, *gbar;
+    // readiness per 64-feature k-chunk of h0 / h1 / z ([MT][10], monotonic like the per-M-tile counters): the four (z: one)
+    // producer slices of a chunk bump it, a consumer's TMA lanes start on the chunks that are there (chunked != 0, pair form)
+    int *cnt_ak, *cnt_bk, *cnt_ck;
+    int chunked;
     float *s1, *s2;
     int *tokens, *ntok, *nsteps;
     int *last_io;       // nullable [B]: the token each stream emitted last, in (first LSTM input) and out (amira_greedy_decode_resume)
@@ -374,6 +378,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
         else { role = R_D; slice = b - 3 * W_NG - W_NC; }
     }
     constexpr int ND = K::ND;
+    const bool chunked = PAIR && p.chunked != 0;
     // PAIR: the CTAs work in clusters of two (the two SMs of a TPC, neighbouring slices of one role).  A pair shares every
     // activation tile: each CTA loads 64 of its 128 stream rows, and one tcgen05.mma.cta_group::2 (M = 256: both weight slices)
     // issued by the pair's leader multiplies both halves in both SMs.  That halves what every SM pulls out of L2 per unit
@@ -529,10 +534,13 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     if (sm.dead[mt]) continue;
                     int st;
                     if (role == R_A) st = spin_ge_or_dead(p.cnt_a + mt, W_NG * it, p.dead_at + mt, it);              // h0(it-1)
-                    else if (role == R_BI) st = spin_ge_or_dead(p.cnt_a + mt, W_NG * (it + 1), p.dead_at + mt, it);  // h0(it)
+                    // chunked: the unit is published as soon as ONE producer slice has published the tick (the tick exists; every
+                    // other slice will follow): the TMA lanes wait per k-chunk, the MMAs per ring slot, and the operand chunks
+                    // of the slices that are on time are multiplied while the last slice is still in its epilogue
+                    else if (role == R_BI) st = spin_ge_or_dead(p.cnt_a + mt, chunked ? W_NG * it + 1 : W_NG * (it + 1), p.dead_at + mt, it);  // h0(it)
                     else if (role == R_BH) st = spin_ge_or_dead(p.cnt_b + mt, W_NG * it, p.dead_at + mt, it);        // h1(it-1)
-                    else if (role == R_C) st = spin_ge_or_dead(p.cnt_b + mt, W_NG * (it + 1), p.dead_at + mt, it);   // h1(it)
-                    else st = spin_ge_or_dead(p.cnt_c + mt, W_NC * (it + 1), p.dead_at + mt, it);                    // z(it)
+                    else if (role == R_C) st = spin_ge_or_dead(p.cnt_b + mt, chunked ? W_NG * it + 1 : W_NG * (it + 1), p.dead_at + mt, it);   // h1(it)
+                    else st = spin_ge_or_dead(p.cnt_c + mt, chunked ? W_NC * it + 1 : W_NC * (it + 1), p.dead_at + mt, it);                    // z(it)
                     if (st) { sm.dead[mt] = 1; continue; }
                     any = true;
                     WS_TRACE(0);
@@ -571,7 +579,26 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 // the recurrent roles read the state version of tick it-1, the others the version of tick it
                 const int ver = (role == R_A || role == R_BH) ? (it + W_V - 1) % W_V : it % W_V;
                 const int a_row = ver * p.Mpad + mt * W_BM + (int)crank * K::BOX;
-                if (elect_one_sync()) {
+                if (PAIR && chunked && (role == R_BI || role == R_C || role == R_D)) {
+                    // a lane per k-chunk: ring slots free, the chunk's producer slices published (acquire), proxy fence, two loads
+                    if constexpr (PAIR) {
+                        if (lane < W_KC) {
+                            const int ki = lane, kc = (kc0 + ki) % W_KC;
+                            const uint32_t s0 = 2 * ki;
+                            const int *ck = role == R_BI ? p.cnt_ak : role == R_C ? p.cnt_bk : p.cnt_ck;
+                            mbar_wait_wd(&sm.empty[s0], (u & 1) ^ 1);
+                            mbar_wait_wd(&sm.empty[s0 + 1], (u & 1) ^ 1);
+                            spin_ge(ck + mt * W_KC + kc, (role == R_D ? 1 : 4) * (it + 1));
+                            fence_proxy_async();
+                            if (leader) {
+                                mbar_expect_tx(&sm.full[s0], 2u * W_UNIT);
+                                mbar_expect_tx(&sm.full[s0 + 1], 2u * W_UNIT);
+                            }
+                            tma_load_2d_pair(ring + s0 * W_UNIT, a_hi, lead_full0 + s0 * 8u, kc * BK, a_row);
+                            tma_load_2d_pair(ring + (s0 + 1) * W_UNIT, a_lo, lead_full0 + (s0 + 1) * 8u, kc * BK, a_row);
+                        }
+                    }
+                } else if (elect_one_sync()) {
                     fence_proxy_async();  // the scheduler's acquire (through the queue barrier) before these async-proxy reads
                     for (int ki = 0; ki < W_KC; ++ki) {
                         const int kc = (kc0 + ki) % W_KC;
@@ -681,6 +708,11 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                     // fence + counter (release), the consumer scheduler's acquire and the fence.proxy.async its TMA thread executes
                     // before the loads; a second proxy fence here only cost time (cfg3: 7.4 -> 6.8 ms)
                     __threadfence();
+                    if (PAIR && p.chunked) {
+                        if (role == R_A) atomicAdd(p.cnt_ak + mt * W_KC + slice / 4, 1);
+                        else if (role == R_BI) atomicAdd(p.cnt_bk + mt * W_KC + slice / 4, 1);
+                        else if (role == R_C) atomicAdd(p.cnt_ck + mt * W_KC + slice, 1);
+                    }
                     if (role == R_A) atomicAdd(p.cnt_a + mt, 1);
                     else if (role == R_BI) atomicAdd(p.cnt_b + mt, 1);
                     else if (role == R_BH) st_release(p.part_ready + mt * W_NG + slice, it + 1);
@@ -1101,6 +1133,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
 #pragma unroll
                     for (int j = 0; j < 8; ++j) pr[j] = pf_v[j];
                 } else {
+                    if (chunked) spin_ge(p.cnt_a + mt, W_NG * (it + 1));  // the unit came early: every layer-0 slice (slice 0's control rows) first
                     spec_w = __ldcg(&p.ctl[(size_t)(it & (W_R - 1)) * p.Mpad + row].spec);  // published by layer-0 slice 0
                     const int src_ = (spec_w >> 12) & 7;
                     const bool redo_ = (spec_w >> 11) & 1;
@@ -1126,6 +1159,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) greedy_ws_kernel(const __grid_co
                 {
                     const uint32_t ns = qn % W_Q;
                     if (mbar_test_wait(&sm.q_full[ns], (qn / W_Q) & 1)) { n_mt = sm.q[ns].mt; n_it = sm.q[ns].it; }
+                    if (n_mt >= 0 && chunked && ld_acquire(p.cnt_a + n_mt) < W_NG * (n_it + 1)) n_mt = -1;  // not all of layer 0 yet
                     if (n_mt >= 0 && n_mt != mt) {
                         n_spec = __ldcg(&p.ctl[(size_t)(n_it & (W_R - 1)) * p.Mpad + n_mt * W_BM + r_in].spec);
                         n_flag = ld_acquire(p.part_ready + n_mt * W_NG + slice);
@@ -1417,7 +1451,7 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, const WsPlan &plan, 
     const size_t og0t = take(sizeof(int) * (size_t)MT * W_NG * 2 * W_BM);
     const size_t oamax = take(sizeof(unsigned long long) * W_R * (size_t)Mpad);
     const size_t octl = take(sizeof(WCtl) * W_R * (size_t)Mpad);  // a ring by tick
-    const size_t n_cnt = 6 * (size_t)MT + (size_t)MT * W_NG + (size_t)MT * W_R + 8;  // ... + fail_count, live_tiles, q_head
+    const size_t n_cnt = 6 * (size_t)MT + (size_t)MT * W_NG + (size_t)MT * W_R + 8 + 3 * (size_t)MT * W_KC;  // ... + fail_count, live_tiles, q_head, gbar | chunk counters
     const size_t ocnt = take(sizeof(int) * n_cnt);
     const size_t otrace = take(sizeof(long long) * W_TRACE_ITS * W_TRACE_MT * 32);
     if (!work) {  // size query
@@ -1464,6 +1498,8 @@ cudaError_t launch_greedy_ws(Ctx *c, const float *E, int B, const WsPlan &plan, 
     p.dead_at = cnt + 5 * MT; p.part_ready = cnt + 6 * MT; p.tinfo = cnt + 6 * MT + MT * W_NG;
     p.fail_count = cnt + 6 * MT + MT * W_NG + MT * W_R; p.live_tiles = p.fail_count + 1; p.q_head = p.fail_count + 2;
     p.gbar = p.fail_count + 3;
+    p.cnt_ak = p.fail_count + 8; p.cnt_bk = p.cnt_ak + MT * W_KC; p.cnt_ck = p.cnt_bk + MT * W_KC;
+    p.chunked = getenv("AMIRA_WS_CHUNK") ? atoi(getenv("AMIRA_WS_CHUNK")) : 1;  // AMIRA_WS_CHUNK=0: per-M-tile readiness only (A/B timing)
     if (slots_dev) { p.s1 = c->slot_s1; p.s2 = c->slot_s2; } else { p.s1 = s1_dev; p.s2 = s2_dev; }
     p.tokens = tokens_dev; p.ntok = ntok_dev; p.nsteps = nsteps_dev; p.last_io = last_dev;
     p.max_sym = c->cfg.max_symbols_per_step; p.max_total = c->cfg.max_total_tokens; p.blank = c->cfg.blank_id;

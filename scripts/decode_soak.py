@@ -10,7 +10,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = [{}, {"AMIRA_WS_TILES": "2"}, {"AMIRA_WS_TILES": "3"}, {"AMIRA_WS_TILES": "8", "AMIRA_WS_SPEC": "0"}, {"AMIRA_WS_SPEC": "1,1,1,1,1,1,1,1"},
-            {"AMIRA_WS_SPEC": "3,3,3,3"}, {"AMIRA_WS_PAIR": "0"}, {"AMIRA_WS_TILES": "6", "AMIRA_WS_SPEC": "2,2,2,2,2,2"}]
+            {"AMIRA_WS_SPEC": "3,3,3,3"}, {"AMIRA_WS_PAIR": "0"}, {"AMIRA_WS_CHUNK": "0"}, {"AMIRA_WS_TILES": "6", "AMIRA_WS_SPEC": "2,2,2,2,2,2"}]
 
 
 def child(runs):

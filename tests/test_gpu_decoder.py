@@ -416,7 +416,7 @@ def test_literal_refeed_loop_over_the_contract_op(amira, oracle):
 
 
 def test_schedule_does_not_change_results(amira, monkeypatch):
-    """The lane plan (M-tiles), the blank-speculation table and the CTA-pair form decide WHEN the tcgen05 engine computes a step,
+    """The lane plan (M-tiles), the blank-speculation table, readiness per k-chunk and the CTA-pair form decide WHEN the tcgen05 engine computes a step,
     never its inputs: tokens, counts, step counts and final states of a mixed-length batch are bit-identical under every
     schedule of one form of the kernel (the one-CTA form sums the k-chunks in another order: same tokens, states to 1e-4) (decoder_optimized.rs:54-200 is one sequential loop per stream; scripts/decode_soak.py is the long form)."""
     rng = np.random.default_rng(77)
@@ -425,11 +425,11 @@ def test_schedule_does_not_change_results(amira, monkeypatch):
     lens = rng.integers(8, T + 1, B).astype(np.int64)
     ref = None
     variants = [{}, {"AMIRA_WS_TILES": "1"}, {"AMIRA_WS_TILES": "3", "AMIRA_WS_SPEC": "0"}, {"AMIRA_WS_SPEC": "3,3,3"},
-                {"AMIRA_WS_SPEC": "2,2,2,2", "AMIRA_WS_TILES": "2"}, {"AMIRA_WS_PAIR": "0"}]
+                {"AMIRA_WS_SPEC": "2,2,2,2", "AMIRA_WS_TILES": "2"}, {"AMIRA_WS_CHUNK": "0"}, {"AMIRA_WS_PAIR": "0"}]
     with amira.Context(device_id=0, decode_engine=4) as c:
         c.load_weights(amira.synthetic_weights(3456))
         for v in variants:
-            for k in ("AMIRA_WS_TILES", "AMIRA_WS_SPEC", "AMIRA_WS_PAIR"):
+            for k in ("AMIRA_WS_TILES", "AMIRA_WS_SPEC", "AMIRA_WS_PAIR", "AMIRA_WS_CHUNK"):
                 monkeypatch.delenv(k, raising=False)
             for k, val in v.items():
                 monkeypatch.setenv(k, val)
