@@ -9,6 +9,7 @@
 //                         persistent decode kernel (decoder_ws.cu).
 #include <cooperative_groups.h>
 #include <cuda.h>
+#include <mutex>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -384,6 +385,15 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
         int by_bytes = (int)std::min<size_t>((size_t)2 * Ctx::kMaxChunks, enc_bytes / ((size_t)24 << 20));  // >= 24 MB per chunk
         if (const char *f = getenv("AMIRA_FORCE_CHUNKS")) by_bytes = std::min(2 * Ctx::kMaxChunks, atoi(f));  // tests: chunked path at small sizes
         const int n_chunks = enc_host ? std::max(1, std::min(by_bytes, B / 32)) : 1;
+        // Batch-sized uploads of the lanes of one GPU take turns, first come first served, instead of sharing the link chunk by
+        // chunk: with several batches in flight the call that came first gets its encoder outputs — and with them its decode
+        // kernel — first, and the SMs do not wait for an upload that is one of four advancing at a quarter of the rate (e2e leg of
+        // bench.py, four steps in flight, A/B on one box: 33.9 -> 32.1 ms per step, and the same from run to run).
+        // AMIRA_H2D_FIFO=0 restores the free-for-all.
+        static std::mutex upload_turn[64];
+        static const int fifo_env = getenv("AMIRA_H2D_FIFO") ? atoi(getenv("AMIRA_H2D_FIFO")) : 1;
+        std::unique_lock<std::mutex> turn;
+        if (fifo_env && enc_host && n_chunks > 3) turn = std::unique_lock<std::mutex>(upload_turn[c->device & 63]);
         for (int k = 0; k < n_chunks; ++k) {
             const int b0 = (int)((long long)B * k / n_chunks), b1 = (int)((long long)B * (k + 1) / n_chunks);
             if (b1 <= b0) continue;
