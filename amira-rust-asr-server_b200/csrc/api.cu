@@ -15,6 +15,16 @@
 
 using namespace amira;
 
+std::mutex &amira::upload_turn_mutex(int device) {
+    static std::mutex m[64];
+    return m[device & 63];
+}
+int amira::upload_fifo_mode() {
+    static const int mode = getenv("AMIRA_H2D_FIFO") ? atoi(getenv("AMIRA_H2D_FIFO")) : 1;
+    return mode;
+}
+
+
 struct amira_ctx : public amira::Ctx {};
 
 namespace {

@@ -123,6 +123,11 @@ struct DecoderPriv {  // per-context view of the shared weight tables + this con
     long long *ws_trace_dev = nullptr;  // decoder_ws.cu debug trace of the last launch (AMIRA_WS_TRACE=1)
 };
 
+// first-come-first-served turns of the batch-sized host -> device uploads of one GPU (decoder_tc.cu, api.cu)
+std::mutex &upload_turn_mutex(int device);
+int upload_fifo_mode();  // AMIRA_H2D_FIFO: 0 = off, 1 = the encoder-output uploads take turns (default; the front end's PCM uploads
+                         // taking turns as well measured the same: 32.0 vs 32.1 ms per e2e step)
+
 struct Ctx {
     amira_config cfg{};
     int device = 0;

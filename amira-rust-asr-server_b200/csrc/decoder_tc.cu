@@ -390,10 +390,9 @@ cudaError_t launch_greedy_decode_tc(Ctx *c, const float *enc_dev, const float *e
         // kernel — first, and the SMs do not wait for an upload that is one of four advancing at a quarter of the rate (e2e leg of
         // bench.py, four steps in flight, A/B on one box: 33.9 -> 32.1 ms per step, and the same from run to run).
         // AMIRA_H2D_FIFO=0 restores the free-for-all.
-        static std::mutex upload_turn[64];
-        static const int fifo_env = getenv("AMIRA_H2D_FIFO") ? atoi(getenv("AMIRA_H2D_FIFO")) : 1;
+        static const int fifo_env = upload_fifo_mode();
         std::unique_lock<std::mutex> turn;
-        if (fifo_env && enc_host && n_chunks > 3) turn = std::unique_lock<std::mutex>(upload_turn[c->device & 63]);
+        if (fifo_env && enc_host && n_chunks > 3) turn = std::unique_lock<std::mutex>(upload_turn_mutex(c->device));
         for (int k = 0; k < n_chunks; ++k) {
             const int b0 = (int)((long long)B * k / n_chunks), b1 = (int)((long long)B * (k + 1) / n_chunks);
             if (b1 <= b0) continue;
