@@ -92,16 +92,26 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.p.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """The timed region starts now: nvidia-smi was started before the warm-up (its start-up can take longer than a short timed
+        region), only samples from here on count."""
+        self.t_mark = time.perf_counter()
 
     def stop(self) -> dict:
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        t_end = time.perf_counter()
         time.sleep(0.15)
         self.p.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0 = getattr(self, "t_mark", 0.0)
+        inside = [r for (t, r) in self.rows if t0 <= t <= t_end + 0.05]
+        if not inside and self.rows:  # a timed region shorter than the sampling period: the sample nearest to it
+            inside = [min(self.rows, key=lambda tr: abs(tr[0] - t_end))[1]]
+        for r in inside:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -389,7 +399,7 @@ def run_extras(A, torch, dev, ctx, stream, hbm_peak, tf_peak):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--utterances", type=int, default=1024, help="utterances per GPU per step")
@@ -486,12 +496,13 @@ def main():
             ms = float(t.item())
         return ms
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     ctx.profile(True)
     l0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     ms_total = timed(step_device, args.steps)
     clocks = sampler.stop()
     launches = ctx.launch_count() - l0
